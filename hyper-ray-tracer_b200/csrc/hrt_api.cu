@@ -1,0 +1,407 @@
+// hrt_api.cu — C-ABI compute entry points: device upload of the flattened scene, render / resolve /
+// parity launches.  No CPU fallback: every function here returns HRT_ERR_CUDA when the CUDA runtime has no
+// usable device.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/hrt.h"
+#include "hrt_launch.h"
+#include "hrt_scene.hpp"
+
+namespace hrt {
+
+struct DeviceState {
+    int device = -1;
+    int num_sms = 0;
+    void* d_ops = nullptr;
+    void* d_ctxs = nullptr;
+    void* d_mats = nullptr;
+    void* d_texs = nullptr;
+    void* d_noise = nullptr;
+    std::vector<cudaArray_t> arrays;
+    std::vector<cudaTextureObject_t> texobjs;
+    unsigned long long* d_counters = nullptr;
+    // scratch for the host-buffer entry points
+    float* d_accum = nullptr;
+    float* d_rgba = nullptr;
+    size_t accum_pixels = 0;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    DeviceSceneHost view;
+};
+
+void release_device_state(DeviceState* d) {
+    if (!d) return;
+    int prev = 0;
+    if (cudaGetDevice(&prev) == cudaSuccess && cudaSetDevice(d->device) == cudaSuccess) {
+        for (auto t : d->texobjs) cudaDestroyTextureObject(t);
+        for (auto a : d->arrays) cudaFreeArray(a);
+        cudaFree(d->d_ops); cudaFree(d->d_ctxs); cudaFree(d->d_mats); cudaFree(d->d_texs); cudaFree(d->d_noise);
+        cudaFree(d->d_counters); cudaFree(d->d_accum); cudaFree(d->d_rgba);
+        for (auto e : d->ev) if (e) cudaEventDestroy(e);
+        cudaSetDevice(prev);
+    }
+    delete d;
+}
+
+static int32_t cuda_fail(cudaError_t e, const char* what) {
+    return fail(HRT_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define HRT_CUDA(call)                                      \
+    do {                                                    \
+        cudaError_t _e = (call);                            \
+        if (_e != cudaSuccess) return cuda_fail(_e, #call); \
+    } while (0)
+
+static int32_t upload_table(void** dst, const void* src, size_t bytes) {
+    if (bytes == 0) bytes = 16;  // keep pointers valid
+    HRT_CUDA(cudaMalloc(dst, bytes));
+    HRT_CUDA(cudaMemset(*dst, 0, bytes));
+    if (src) HRT_CUDA(cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice));
+    return HRT_OK;
+}
+
+static DeviceState* find_state(hrt_scene* s, int device) {
+    for (DeviceState* d : s->devices)
+        if (d && d->device == device) return d;
+    return nullptr;
+}
+
+static int32_t ensure_scratch(DeviceState* d, size_t pixels) {
+    if (d->accum_pixels >= pixels && d->d_accum) return HRT_OK;
+    cudaFree(d->d_accum); cudaFree(d->d_rgba);
+    d->d_accum = d->d_rgba = nullptr;
+    d->accum_pixels = 0;
+    HRT_CUDA(cudaMalloc((void**)&d->d_accum, pixels * 16));
+    HRT_CUDA(cudaMalloc((void**)&d->d_rgba, pixels * 16));
+    d->accum_pixels = pixels;
+    return HRT_OK;
+}
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    ~DevBuf() { cudaFree(p); }
+    cudaError_t alloc(size_t n) { return cudaMalloc((void**)&p, (n ? n : 1) * sizeof(T)); }
+};
+
+}  // namespace hrt
+
+using namespace hrt;
+
+extern "C" {
+
+int32_t hrt_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int32_t hrt_scene_upload(hrt_scene* s, int32_t device) {
+    if (!s) return fail(HRT_ERR_INVALID, "null scene");
+    if (!s->committed) return fail(HRT_ERR_STATE, "scene not committed");
+    if (find_state(s, device)) return HRT_OK;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(HRT_ERR_CUDA, std::string("no CUDA device available (there is no CPU fallback): ") +
+                                      (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+    if (device < 0 || device >= n) return fail(HRT_ERR_INVALID, "device index out of range");
+    HRT_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    HRT_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(HRT_ERR_CUDA, std::string("device '") + prop.name + "' is sm_" + std::to_string(prop.major) +
+                                      std::to_string(prop.minor) + "; this library ships sm_100a code only");
+    DeviceState* d = new DeviceState();
+    d->device = device;
+    d->num_sms = prop.multiProcessorCount;
+    s->devices.push_back(d);
+    int32_t rc;
+    if ((rc = upload_table(&d->d_ops, s->ops.data(), s->ops.size() * sizeof(Op))) != HRT_OK) return rc;
+    if ((rc = upload_table(&d->d_ctxs, s->ctxs.data(), s->ctxs.size() * sizeof(Ctx))) != HRT_OK) return rc;
+    if ((rc = upload_table(&d->d_mats, s->materials.data(), s->materials.size() * sizeof(Material))) != HRT_OK) return rc;
+    if ((rc = upload_table(&d->d_texs, s->textures.data(), s->textures.size() * sizeof(Texture))) != HRT_OK) return rc;
+    if ((rc = upload_table(&d->d_noise, s->noise_tables.data(), s->noise_tables.size() * sizeof(NoiseTable))) != HRT_OK) return rc;
+    HRT_CUDA(cudaMalloc((void**)&d->d_counters, 8 * sizeof(unsigned long long)));
+    for (auto& ev : d->ev) HRT_CUDA(cudaEventCreate(&ev));
+    std::memset(&d->view, 0, sizeof(d->view));
+    // Image textures: RGBA8 CUDA arrays bound as point-sampled, unnormalised texture objects
+    // (nearest texel, no filtering — image_texture.rs:44-62).
+    for (const ImageData& img : s->images) {
+        cudaChannelFormatDesc desc = cudaCreateChannelDesc<uchar4>();
+        cudaArray_t arr = nullptr;
+        HRT_CUDA(cudaMallocArray(&arr, &desc, img.width, img.height));
+        d->arrays.push_back(arr);
+        HRT_CUDA(cudaMemcpy2DToArray(arr, 0, 0, img.rgba.data(), (size_t)img.width * 4, (size_t)img.width * 4, img.height,
+                                     cudaMemcpyHostToDevice));
+        cudaResourceDesc rd;
+        std::memset(&rd, 0, sizeof(rd));
+        rd.resType = cudaResourceTypeArray;
+        rd.res.array.array = arr;
+        cudaTextureDesc td;
+        std::memset(&td, 0, sizeof(td));
+        td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+        td.filterMode = cudaFilterModePoint;
+        td.readMode = cudaReadModeElementType;
+        td.normalizedCoords = 0;
+        cudaTextureObject_t tex = 0;
+        HRT_CUDA(cudaCreateTextureObject(&tex, &rd, &td, nullptr));
+        d->texobjs.push_back(tex);
+    }
+    d->view.ops = d->d_ops; d->view.ctxs = d->d_ctxs; d->view.mats = d->d_mats; d->view.texs = d->d_texs;
+    d->view.noise = d->d_noise;
+    for (size_t i = 0; i < d->texobjs.size() && i < (size_t)kMaxImages; ++i) d->view.images[i] = d->texobjs[i];
+    d->view.n_ops = (int32_t)s->ops.size();
+    d->view.n_noise = (int32_t)s->noise_tables.size();
+    d->view.n_media = s->n_media;
+    d->view.ln_e = logf(2.71828182845904523536f);
+    return HRT_OK;
+}
+
+static int32_t get_state(hrt_scene* s, int32_t device, DeviceState** out) {
+    int32_t rc = hrt_scene_upload(s, device);
+    if (rc != HRT_OK) return rc;
+    *out = find_state(s, device);
+    HRT_CUDA(cudaSetDevice(device));
+    return HRT_OK;
+}
+
+static int32_t check_render_args(const hrt_scene* s, const hrt_camera_desc* cam, const hrt_render_desc* rd) {
+    if (!cam || !rd) return fail(HRT_ERR_INVALID, "null camera/render descriptor");
+    if (rd->width <= 0 || rd->height <= 0 || rd->samples <= 0 || rd->depth < 0)
+        return fail(HRT_ERR_INVALID, "render: width/height/samples must be positive, depth non-negative");
+    if (cam->width != rd->width || cam->height != rd->height)
+        return fail(HRT_ERR_INVALID, "render: camera size differs from render size (Camera::resize uses the image size)");
+    if ((long long)rd->width * rd->height > (1ll << 31) - 1) return fail(HRT_ERR_INVALID, "render: image too large");
+    (void)s;
+    return HRT_OK;
+}
+
+// The part every render variant shares: launch the path-trace kernel for [sample_begin, +count) into d_accum.
+static int32_t render_into(hrt_scene* s, DeviceState* d, const hrt_camera_desc* cam, const hrt_render_desc* rd,
+                           float* d_accum, cudaStream_t stream, bool want_stats, hrt_stats* stats) {
+    int32_t rc = check_render_args(s, cam, rd);
+    if (rc != HRT_OK) return rc;
+    RenderLaunch L;
+    std::memset(&L, 0, sizeof(L));
+    L.scene = d->view;
+    if ((rc = hrt_camera_init(cam, &L.cam)) != HRT_OK) return rc;
+    L.width = rd->width; L.height = rd->height; L.depth = rd->depth;
+    std::memcpy(L.background, rd->background, 12);
+    L.key0 = (uint32_t)rd->seed; L.key1 = (uint32_t)(rd->seed >> 32);
+    L.sample_begin = rd->sample_count > 0 ? rd->sample_begin : 0;
+    L.sample_count = rd->sample_count > 0 ? rd->sample_count : rd->samples;
+    if (L.sample_begin < 0 || L.sample_begin + L.sample_count > rd->samples)
+        return fail(HRT_ERR_INVALID, "render: sample slice outside [0, samples)");
+    // Moving-sphere boxes only cover the BVH build interval (moving_sphere.rs:98-110): a shutter outside it
+    // makes those boxes unsound, so fall back to the reference's own box test everywhere.
+    bool ref_boxes = (rd->flags & HRT_FLAG_REFERENCE_TRAVERSAL) != 0;
+    if (s->any_bvh && (std::fmin(cam->time0, cam->time1) < s->time_min || std::fmax(cam->time0, cam->time1) > s->time_max))
+        ref_boxes = true;
+    L.reference_boxes = ref_boxes ? 1 : 0;
+    L.counters = d->d_counters;
+    L.accum = d_accum;
+    L.chunk = 0;
+    HRT_CUDA(cudaMemsetAsync(d->d_counters, 0, 8 * sizeof(unsigned long long), stream));
+    if (want_stats) HRT_CUDA(cudaEventRecord(d->ev[0], stream));
+    cudaError_t e = (rd->flags & HRT_FLAG_EXACT_MATH) ? hrt_exact::launch_render(L, d->num_sms, stream)
+                                                      : hrt_fast::launch_render(L, d->num_sms, stream);
+    if (e != cudaSuccess) return cuda_fail(e, "render_kernel launch");
+    if (want_stats) HRT_CUDA(cudaEventRecord(d->ev[1], stream));
+    if (stats) {
+        stats->launches += 1;
+        stats->grid = L.grid;
+        stats->block = L.block;
+    }
+    return HRT_OK;
+}
+
+static int32_t finish_stats(DeviceState* d, cudaStream_t stream, hrt_stats* stats) {
+    if (!stats) return HRT_OK;
+    unsigned long long c[8];
+    HRT_CUDA(cudaMemcpyAsync(c, d->d_counters, sizeof(c), cudaMemcpyDeviceToHost, stream));
+    HRT_CUDA(cudaStreamSynchronize(stream));
+    stats->rays = c[1];
+    stats->paths = c[2];
+    float ms = 0.0f;
+    HRT_CUDA(cudaEventElapsedTime(&ms, d->ev[0], d->ev[1]));
+    stats->kernel_ms = ms;
+    return HRT_OK;
+}
+
+static int32_t render_host(hrt_scene* s, int32_t device, const hrt_camera_desc* cam, const hrt_render_desc* rd, float* out,
+                           hrt_stats* stats, bool resolve) {
+    if (!out) return fail(HRT_ERR_INVALID, "null output buffer");
+    DeviceState* d = nullptr;
+    int32_t rc = get_state(s, device, &d);
+    if (rc != HRT_OK) return rc;
+    if ((rc = check_render_args(s, cam, rd)) != HRT_OK) return rc;
+    const size_t pixels = (size_t)rd->width * rd->height;
+    if ((rc = ensure_scratch(d, pixels)) != HRT_OK) return rc;
+    hrt_stats local;
+    std::memset(&local, 0, sizeof(local));
+    cudaStream_t stream = 0;
+    HRT_CUDA(cudaMemsetAsync(d->d_accum, 0, pixels * 16, stream));
+    if ((rc = render_into(s, d, cam, rd, d->d_accum, stream, true, &local)) != HRT_OK) return rc;
+    const float* src = d->d_accum;
+    if (resolve) {
+        HRT_CUDA(cudaEventRecord(d->ev[2], stream));
+        cudaError_t e = hrt_fast::launch_resolve(d->d_accum, (int)pixels, rd->samples, d->d_rgba, stream);
+        if (e != cudaSuccess) return cuda_fail(e, "resolve_kernel launch");
+        HRT_CUDA(cudaEventRecord(d->ev[3], stream));
+        local.launches += 1;
+        src = d->d_rgba;
+    }
+    HRT_CUDA(cudaEventRecord(d->ev[4], stream));
+    HRT_CUDA(cudaMemcpyAsync(out, src, pixels * 16, cudaMemcpyDeviceToHost, stream));
+    HRT_CUDA(cudaEventRecord(d->ev[5], stream));
+    if ((rc = finish_stats(d, stream, &local)) != HRT_OK) return rc;
+    if (resolve) HRT_CUDA(cudaEventElapsedTime(&local.resolve_ms, d->ev[2], d->ev[3]));
+    HRT_CUDA(cudaEventElapsedTime(&local.d2h_ms, d->ev[4], d->ev[5]));
+    if (stats) *stats = local;
+    return HRT_OK;
+}
+
+int32_t hrt_render(hrt_scene* s, int32_t device, const hrt_camera_desc* cam, const hrt_render_desc* rd, float* out_rgba,
+                   hrt_stats* stats) {
+    return render_host(s, device, cam, rd, out_rgba, stats, true);
+}
+int32_t hrt_render_accum(hrt_scene* s, int32_t device, const hrt_camera_desc* cam, const hrt_render_desc* rd, float* out_sum,
+                         hrt_stats* stats) {
+    return render_host(s, device, cam, rd, out_sum, stats, false);
+}
+
+int32_t hrt_render_accum_device(hrt_scene* s, int32_t device, const hrt_camera_desc* cam, const hrt_render_desc* rd,
+                                void* d_accum, void* stream_ptr, hrt_stats* stats) {
+    if (!d_accum) return fail(HRT_ERR_INVALID, "null device accumulator");
+    DeviceState* d = nullptr;
+    int32_t rc = get_state(s, device, &d);
+    if (rc != HRT_OK) return rc;
+    cudaStream_t stream = (cudaStream_t)stream_ptr;
+    hrt_stats local;
+    std::memset(&local, 0, sizeof(local));
+    if ((rc = render_into(s, d, cam, rd, (float*)d_accum, stream, stats != nullptr, &local)) != HRT_OK) return rc;
+    if (stats) {
+        if ((rc = finish_stats(d, stream, &local)) != HRT_OK) return rc;
+        *stats = local;
+    }
+    return HRT_OK;
+}
+
+int32_t hrt_resolve_device(int32_t device, const void* d_accum, int32_t width, int32_t height, int32_t samples,
+                           void* d_out_rgba, void* stream_ptr) {
+    if (!d_accum || !d_out_rgba || width <= 0 || height <= 0 || samples <= 0)
+        return fail(HRT_ERR_INVALID, "resolve: bad argument");
+    HRT_CUDA(cudaSetDevice(device));
+    cudaError_t e = hrt_fast::launch_resolve((const float*)d_accum, width * height, samples, (float*)d_out_rgba,
+                                             (cudaStream_t)stream_ptr);
+    if (e != cudaSuccess) return cuda_fail(e, "resolve_kernel launch");
+    return HRT_OK;
+}
+
+// ---- parity entry points (host buffers in, host buffers out) -------------------------------------------
+int32_t hrt_trace_hits(hrt_scene* s, int32_t device, const hrt_ray* rays, int32_t n, const float* xi, hrt_hit* out,
+                       uint32_t flags) {
+    if (n < 0 || (n > 0 && (!rays || !out))) return fail(HRT_ERR_INVALID, "trace_hits: bad argument");
+    DeviceState* d = nullptr;
+    int32_t rc = get_state(s, device, &d);
+    if (rc != HRT_OK) return rc;
+    if (n == 0) return HRT_OK;
+    DevBuf<hrt_ray> dr;
+    DevBuf<float> dx;
+    DevBuf<hrt_hit> dh;
+    HRT_CUDA(dr.alloc(n));
+    HRT_CUDA(dh.alloc(n));
+    HRT_CUDA(cudaMemcpy(dr.p, rays, sizeof(hrt_ray) * (size_t)n, cudaMemcpyHostToDevice));
+    if (xi) {
+        HRT_CUDA(dx.alloc(n));
+        HRT_CUDA(cudaMemcpy(dx.p, xi, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice));
+    }
+    const int ref = (flags & HRT_FLAG_REFERENCE_TRAVERSAL) ? 1 : 0;
+    cudaError_t e = (flags & HRT_FLAG_EXACT_MATH) ? hrt_exact::launch_trace_hits(d->view, dr.p, n, dx.p, dh.p, ref, 0)
+                                                  : hrt_fast::launch_trace_hits(d->view, dr.p, n, dx.p, dh.p, ref, 0);
+    if (e != cudaSuccess) return cuda_fail(e, "trace_hits_kernel launch");
+    HRT_CUDA(cudaMemcpy(out, dh.p, sizeof(hrt_hit) * (size_t)n, cudaMemcpyDeviceToHost));
+    return HRT_OK;
+}
+
+int32_t hrt_tex_value(hrt_scene* s, int32_t device, int32_t tex, const float* uvp, int32_t n, float* out, uint32_t flags) {
+    if (!s || n < 0 || (n > 0 && (!uvp || !out))) return fail(HRT_ERR_INVALID, "tex_value: bad argument");
+    if (tex < 0 || (size_t)tex >= s->textures.size()) return fail(HRT_ERR_INVALID, "tex_value: unknown texture id");
+    DeviceState* d = nullptr;
+    int32_t rc = get_state(s, device, &d);
+    if (rc != HRT_OK) return rc;
+    if (n == 0) return HRT_OK;
+    DevBuf<float> di, dout;
+    HRT_CUDA(di.alloc((size_t)n * 5));
+    HRT_CUDA(dout.alloc((size_t)n * 3));
+    HRT_CUDA(cudaMemcpy(di.p, uvp, sizeof(float) * 5 * (size_t)n, cudaMemcpyHostToDevice));
+    cudaError_t e = (flags & HRT_FLAG_EXACT_MATH) ? hrt_exact::launch_tex_value(d->view, tex, di.p, n, dout.p, 0)
+                                                  : hrt_fast::launch_tex_value(d->view, tex, di.p, n, dout.p, 0);
+    if (e != cudaSuccess) return cuda_fail(e, "tex_value_kernel launch");
+    HRT_CUDA(cudaMemcpy(out, dout.p, sizeof(float) * 3 * (size_t)n, cudaMemcpyDeviceToHost));
+    return HRT_OK;
+}
+
+int32_t hrt_scatter(hrt_scene* s, int32_t device, const hrt_ray* rays, const hrt_hit* hits, const float* u4, int32_t n,
+                    hrt_scatter_out* out, uint32_t flags) {
+    if (!s || n < 0 || (n > 0 && (!rays || !hits || !u4 || !out))) return fail(HRT_ERR_INVALID, "scatter: bad argument");
+    for (int i = 0; i < n; ++i)
+        if (hits[i].hit && (hits[i].material_id < 0 || (size_t)hits[i].material_id >= s->materials.size()))
+            return fail(HRT_ERR_INVALID, "scatter: unknown material id");
+    DeviceState* d = nullptr;
+    int32_t rc = get_state(s, device, &d);
+    if (rc != HRT_OK) return rc;
+    if (n == 0) return HRT_OK;
+    DevBuf<hrt_ray> dr;
+    DevBuf<hrt_hit> dh;
+    DevBuf<float> du;
+    DevBuf<hrt_scatter_out> dout;
+    HRT_CUDA(dr.alloc(n)); HRT_CUDA(dh.alloc(n)); HRT_CUDA(du.alloc((size_t)n * 4)); HRT_CUDA(dout.alloc(n));
+    HRT_CUDA(cudaMemcpy(dr.p, rays, sizeof(hrt_ray) * (size_t)n, cudaMemcpyHostToDevice));
+    HRT_CUDA(cudaMemcpy(dh.p, hits, sizeof(hrt_hit) * (size_t)n, cudaMemcpyHostToDevice));
+    HRT_CUDA(cudaMemcpy(du.p, u4, sizeof(float) * 4 * (size_t)n, cudaMemcpyHostToDevice));
+    cudaError_t e = (flags & HRT_FLAG_EXACT_MATH) ? hrt_exact::launch_scatter(d->view, dr.p, dh.p, du.p, n, dout.p, 0)
+                                                  : hrt_fast::launch_scatter(d->view, dr.p, dh.p, du.p, n, dout.p, 0);
+    if (e != cudaSuccess) return cuda_fail(e, "scatter_kernel launch");
+    HRT_CUDA(cudaMemcpy(out, dout.p, sizeof(hrt_scatter_out) * (size_t)n, cudaMemcpyDeviceToHost));
+    return HRT_OK;
+}
+
+int32_t hrt_camera_rays(int32_t device, const hrt_camera_desc* cam, const float* stuuu, int32_t n, hrt_ray* out,
+                        uint32_t flags) {
+    if (!cam || n < 0 || (n > 0 && (!stuuu || !out))) return fail(HRT_ERR_INVALID, "camera_rays: bad argument");
+    int cnt = 0;
+    cudaError_t ce = cudaGetDeviceCount(&cnt);
+    if (ce != cudaSuccess || cnt == 0) return fail(HRT_ERR_CUDA, "no CUDA device available (there is no CPU fallback)");
+    HRT_CUDA(cudaSetDevice(device));
+    hrt_camera_state st;
+    int32_t rc = hrt_camera_init(cam, &st);
+    if (rc != HRT_OK) return rc;
+    if (n == 0) return HRT_OK;
+    DevBuf<float> di;
+    DevBuf<hrt_ray> dout;
+    HRT_CUDA(di.alloc((size_t)n * 5));
+    HRT_CUDA(dout.alloc(n));
+    HRT_CUDA(cudaMemcpy(di.p, stuuu, sizeof(float) * 5 * (size_t)n, cudaMemcpyHostToDevice));
+    cudaError_t e = (flags & HRT_FLAG_EXACT_MATH) ? hrt_exact::launch_camera_rays(st, di.p, n, dout.p, 0)
+                                                  : hrt_fast::launch_camera_rays(st, di.p, n, dout.p, 0);
+    if (e != cudaSuccess) return cuda_fail(e, "camera_rays_kernel launch");
+    HRT_CUDA(cudaMemcpy(out, dout.p, sizeof(hrt_ray) * (size_t)n, cudaMemcpyDeviceToHost));
+    return HRT_OK;
+}
+
+int32_t hrt_philox_uniforms(uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t bounce, uint32_t block, float out4[4]) {
+    if (!out4) return fail(HRT_ERR_INVALID, "null output");
+    hrt_fast::philox_uniforms(seed, pixel, sample, bounce, block, out4);
+    return HRT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,787 @@
+// hrt_device.cuh — device-side restatement of the reference hot path for sm_100a.
+//
+// Compiled TWICE from hrt_kernels.cu:
+//   * HRT_EXACT=1, nvcc --fmad=false  -> namespace hrt_exact : IEEE f32 in the reference's operation order,
+//     accurate libm.  t / point / normal / front_face come out bit-identical to the CPU oracle; used by the
+//     parity entry points (hrt_trace_hits & co.) and by HRT_FLAG_EXACT_MATH renders.
+//   * HRT_EXACT=0, default fmad      -> namespace hrt_fast  : FMA contraction, reciprocal multiplies,
+//     fast intrinsics where the image tolerance allows.  This is the production render path.
+//
+// Reference citations are /root/reference paths.
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "hrt_types.h"
+
+#ifndef HRT_EXACT
+#error "define HRT_EXACT to 0 or 1"
+#endif
+#if HRT_EXACT
+#define HRT_NS hrt_exact
+#else
+#define HRT_NS hrt_fast
+#endif
+
+namespace HRT_NS {
+
+using namespace hrt;
+
+#define HRT_PI 3.14159265358979323846f
+
+struct V3 {
+    float x, y, z;
+};
+__device__ __forceinline__ V3 v3(float x, float y, float z) { return V3{x, y, z}; }
+__device__ __forceinline__ V3 operator+(V3 a, V3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ V3 operator-(V3 a, V3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ V3 operator-(V3 a) { return v3(-a.x, -a.y, -a.z); }
+__device__ __forceinline__ V3 operator*(float s, V3 a) { return v3(s * a.x, s * a.y, s * a.z); }
+__device__ __forceinline__ V3 operator*(V3 a, float s) { return v3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ V3 operator*(V3 a, V3 b) { return v3(a.x * b.x, a.y * b.y, a.z * b.z); }
+__device__ __forceinline__ V3 operator/(V3 a, float s) { return v3(a.x / s, a.y / s, a.z / s); }
+// cgmath 0.18 dot: (x*x + y*y) + z*z
+__device__ __forceinline__ float dot(V3 a, V3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+__device__ __forceinline__ float length(V3 a) { return sqrtf(dot(a, a)); }
+// cgmath normalize: v * (1 / |v|)
+__device__ __forceinline__ V3 normalize(V3 a) {
+#if HRT_EXACT
+    return a * (1.0f / length(a));
+#else
+    return a * rsqrtf(dot(a, a));
+#endif
+}
+__device__ __forceinline__ float comp(V3 a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
+
+struct Ray {
+    V3 o, d;
+    float time;
+};
+__device__ __forceinline__ V3 ray_at(const Ray& r, float t) { return r.o + t * r.d; }  // ray.rs:25-27
+
+struct DeviceScene {
+    const float4* ops;     // 2 x float4 per record
+    const Ctx* ctxs;
+    const Material* mats;
+    const Texture* texs;
+    const NoiseTable* noise;
+    cudaTextureObject_t images[kMaxImages];
+    int32_t n_ops, n_noise, n_media;
+    float ln_e;            // logf(E_f32) as computed by the host libm (f32::log(self, E) = ln(x)/ln(E))
+};
+
+// ------------------------------------------------------------------------------------------------
+// Philox4x32-10 counter-based RNG (Salmon et al. 2011).  key = render seed; counter =
+// (pixel, sample, bounce<<8 | block, stream).  uniform = top 24 bits * 2^-24 in [0,1) — the same
+// distribution as rand 0.8.5's gen::<f32>().
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint32_t hrt_mulhi32(uint32_t a, uint32_t b) {
+#ifdef __CUDA_ARCH__
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32);
+#endif
+}
+struct U4 {
+    uint32_t x, y, z, w;
+};
+__host__ __device__ __forceinline__ U4 philox4x32_10(U4 c, uint32_t k0, uint32_t k1) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        uint32_t hi0 = hrt_mulhi32(M0, c.x), lo0 = M0 * c.x;
+        uint32_t hi1 = hrt_mulhi32(M1, c.z), lo1 = M1 * c.z;
+        U4 n;
+        n.x = hi1 ^ c.y ^ k0;
+        n.y = lo1;
+        n.z = hi0 ^ c.w ^ k1;
+        n.w = lo0;
+        c = n;
+        k0 += W0;
+        k1 += W1;
+    }
+    return c;
+}
+__host__ __device__ __forceinline__ float u32_to_unit(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
+
+enum { RNG_BLOCK_SCATTER = 0, RNG_BLOCK_MEDIA0 = 1, RNG_BLOCK_CAMERA = 255 };
+struct RngKey {
+    uint32_t k0, k1, pixel, sample;
+};
+__host__ __device__ __forceinline__ void rng_block(const RngKey& k, uint32_t bounce, uint32_t block, float out[4]) {
+    U4 c;
+    c.x = k.pixel; c.y = k.sample; c.z = (bounce << 8) | block; c.w = 0x68727421u;
+    U4 r = philox4x32_10(c, k.k0, k.k1);
+    out[0] = u32_to_unit(r.x); out[1] = u32_to_unit(r.y); out[2] = u32_to_unit(r.z); out[3] = u32_to_unit(r.w);
+}
+
+// Source of the one uniform a ConstantMedium draws (constant_medium.rs:59).
+struct MediumXi {
+    RngKey key;
+    uint32_t bounce;
+    float injected;   // used when inject
+    bool inject;
+    __device__ __forceinline__ float draw(int medium_index) const {
+        if (inject) return injected;
+        float u[4];
+        rng_block(key, bounce, RNG_BLOCK_MEDIA0 + ((uint32_t)medium_index >> 2), u);
+        int j = medium_index & 3;
+        return j == 0 ? u[0] : (j == 1 ? u[1] : (j == 2 ? u[2] : u[3]));
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Fixed-draw samplers of the distributions the reference rejection-samples (math.rs:12-40):
+// uniform on S^2, uniform in the unit ball, uniform in the unit disk.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void sincos_2pi(float u, float& s, float& c) {
+    float phi = (2.0f * HRT_PI) * u;
+#if HRT_EXACT
+    s = sinf(phi);
+    c = cosf(phi);
+#else
+    __sincosf(phi, &s, &c);
+#endif
+}
+__device__ __forceinline__ V3 sample_unit_vector(float u1, float u2) {
+    float z = 1.0f - 2.0f * u1;
+    float r = sqrtf(fmaxf(0.0f, 1.0f - z * z));
+    float s, c;
+    sincos_2pi(u2, s, c);
+    return v3(r * c, r * s, z);
+}
+__device__ __forceinline__ V3 sample_in_unit_sphere(float u1, float u2, float u3) {
+    return cbrtf(u3) * sample_unit_vector(u1, u2);
+}
+__device__ __forceinline__ V3 sample_in_unit_disk(float u1, float u2) {
+    float r = sqrtf(u1);
+    float s, c;
+    sincos_2pi(u2, s, c);
+    return v3(r * c, r * s, 0.0f);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Ray-space contexts
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_op(const DeviceScene& S, int pc, float4& A, float4& B) {
+    A = __ldg(S.ops + 2 * pc);
+    B = __ldg(S.ops + 2 * pc + 1);
+}
+
+// translation.rs:25-29
+__device__ __forceinline__ void apply_translate(Ray& r, float4 A) { r.o = r.o - v3(A.x, A.y, A.z); }
+// rotation.rs:103-116
+__device__ __forceinline__ void apply_rotate(Ray& r, float4 A) {
+    const float sn = A.x, cs = A.y;
+    const int axis = __float_as_int(A.z);
+    // (r,a,b): X -> (0,1,2), Y -> (1,2,0), Z -> (2,0,1)
+    float oa, ob, da, db;
+    if (axis == 1) { oa = r.o.z; ob = r.o.x; da = r.d.z; db = r.d.x; }
+    else if (axis == 0) { oa = r.o.y; ob = r.o.z; da = r.d.y; db = r.d.z; }
+    else { oa = r.o.x; ob = r.o.y; da = r.d.x; db = r.d.y; }
+    float noa = cs * oa + sn * ob, nob = (-sn) * oa + cs * ob;
+    float nda = cs * da + sn * db, ndb = (-sn) * da + cs * db;
+    if (axis == 1) { r.o.z = noa; r.o.x = nob; r.d.z = nda; r.d.x = ndb; }
+    else if (axis == 0) { r.o.y = noa; r.o.z = nob; r.d.y = nda; r.d.z = ndb; }
+    else { r.o.x = noa; r.o.y = nob; r.d.x = nda; r.d.y = ndb; }
+}
+// rotation.rs:119-131 (object -> parent space for a point or a normal)
+__device__ __forceinline__ V3 unrotate(V3 p, float4 A) {
+    const float sn = A.x, cs = A.y;
+    const int axis = __float_as_int(A.z);
+    float pa, pb;
+    if (axis == 1) { pa = p.z; pb = p.x; }
+    else if (axis == 0) { pa = p.y; pb = p.z; }
+    else { pa = p.x; pb = p.y; }
+    float na = cs * pa - sn * pb, nb = sn * pa + cs * pb;
+    if (axis == 1) { p.z = na; p.x = nb; }
+    else if (axis == 0) { p.y = na; p.z = nb; }
+    else { p.x = na; p.y = nb; }
+    return p;
+}
+// Map the world ray into context `ctx` by replaying its push records, outermost first.
+__device__ __noinline__ Ray ray_in_ctx(const DeviceScene& S, const Ray& world, int ctx) {
+    Ray r = world;
+    if (ctx == 0) return r;
+    const Ctx c = S.ctxs[ctx];
+    for (int i = 0; i < c.depth; ++i) {
+        float4 A, B;
+        load_op(S, c.op_pc[i], A, B);
+        if ((__float_as_uint(B.w) & 0xffu) == OP_TRANSLATE) apply_translate(r, A);
+        else apply_rotate(r, A);
+    }
+    return r;
+}
+
+// Per-context ray constants.
+struct RayK {
+    V3 inv;    // 1/d per component (aabb.rs:22)
+    float dd;  // d·d (sphere.rs:42)
+#if !HRT_EXACT
+    float inv_dd;
+#endif
+};
+__device__ __forceinline__ RayK make_rayk(const Ray& r) {
+    RayK k;
+    k.inv = v3(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z);
+    k.dd = dot(r.d, r.d);
+#if !HRT_EXACT
+    k.inv_dd = 1.0f / k.dd;
+#endif
+    return k;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Box tests
+// ------------------------------------------------------------------------------------------------
+// aabb.rs:20-47, verbatim semantics: per-axis interval vs (tmin,tmax), the three never intersected (Q1).
+__device__ __forceinline__ bool box_hit_reference(float4 A, float4 B, const Ray& r, const RayK& k, float tmin, float tmax) {
+    bool ok = true;
+    {
+        float t0 = (A.x - r.o.x) * k.inv.x, t1 = (B.x - r.o.x) * k.inv.x;
+        float lo = k.inv.x < 0.0f ? t1 : t0, hi = k.inv.x < 0.0f ? t0 : t1;
+        float a = lo > tmin ? lo : tmin, b = hi < tmax ? hi : tmax;
+        ok = ok && !(b <= a);
+    }
+    {
+        float t0 = (A.y - r.o.y) * k.inv.y, t1 = (B.y - r.o.y) * k.inv.y;
+        float lo = k.inv.y < 0.0f ? t1 : t0, hi = k.inv.y < 0.0f ? t0 : t1;
+        float a = lo > tmin ? lo : tmin, b = hi < tmax ? hi : tmax;
+        ok = ok && !(b <= a);
+    }
+    {
+        float t0 = (A.z - r.o.z) * k.inv.z, t1 = (B.z - r.o.z) * k.inv.z;
+        float lo = k.inv.z < 0.0f ? t1 : t0, hi = k.inv.z < 0.0f ? t0 : t1;
+        float a = lo > tmin ? lo : tmin, b = hi < tmax ? hi : tmax;
+        ok = ok && !(b <= a);
+    }
+    return ok;
+}
+// Intersected slab test: same per-axis arithmetic and NaN behaviour, intervals intersected across axes.
+// On a box that contains its contents it can never cull a hit the reference test would let through.
+__device__ __forceinline__ bool box_hit_tight(float4 A, float4 B, const Ray& r, const RayK& k, float tmin, float tmax) {
+    float t0x = (A.x - r.o.x) * k.inv.x, t1x = (B.x - r.o.x) * k.inv.x;
+    float t0y = (A.y - r.o.y) * k.inv.y, t1y = (B.y - r.o.y) * k.inv.y;
+    float t0z = (A.z - r.o.z) * k.inv.z, t1z = (B.z - r.o.z) * k.inv.z;
+    float lox = k.inv.x < 0.0f ? t1x : t0x, hix = k.inv.x < 0.0f ? t0x : t1x;
+    float loy = k.inv.y < 0.0f ? t1y : t0y, hiy = k.inv.y < 0.0f ? t0y : t1y;
+    float loz = k.inv.z < 0.0f ? t1z : t0z, hiz = k.inv.z < 0.0f ? t0z : t1z;
+    // `x > m ? x : m` == fmaxf(x, m) including NaN x (keeps m)
+    float lo = fmaxf(fmaxf(lox, loy), fmaxf(loz, tmin));
+    float hi = fminf(fminf(hix, hiy), fminf(hiz, tmax));
+    return !(hi <= lo);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Primitive tests (closest-hit form: accept tmin <= t <= closest, as the reference's range checks do)
+// ------------------------------------------------------------------------------------------------
+// sphere.rs:41-58 / moving_sphere.rs:62-79.  NaN discriminants/roots are accepted exactly as the reference
+// accepts them (Q15).
+__device__ __forceinline__ bool sphere_test(V3 center, float radius, const Ray& r, const RayK& k, float tmin, float closest,
+                                            float& t_out) {
+    V3 oc = r.o - center;
+    float a = k.dd;
+    float half_b = dot(oc, r.d);
+    float c = dot(oc, oc) - radius * radius;
+    float disc = half_b * half_b - a * c;
+    if (disc < 0.0f) return false;
+    float sqrtd = sqrtf(disc);
+#if HRT_EXACT
+    float root = (-half_b - sqrtd) / a;
+    if (root < tmin || closest < root) {
+        root = (-half_b + sqrtd) / a;
+        if (root < tmin || closest < root) return false;
+    }
+#else
+    float root = (-half_b - sqrtd) * k.inv_dd;
+    if (root < tmin || closest < root) {
+        root = (-half_b + sqrtd) * k.inv_dd;
+        if (root < tmin || closest < root) return false;
+    }
+#endif
+    t_out = root;
+    return true;
+}
+// moving_sphere.rs:53-57
+__device__ __forceinline__ V3 msphere_center(V3 c0, V3 c1, float t0, float t1, float time) {
+    return c0 + ((time - t0) / (t1 - t0)) * (c1 - c0);
+}
+// rect.rs:60-69 with (k,a,b) already resolved to scalars
+__device__ __forceinline__ bool rect_test(float ok, float dk, float invk, float oa, float da, float ob, float db, float a0,
+                                          float a1, float b0, float b1, float kk, float tmin, float closest, float& t_out) {
+#if HRT_EXACT
+    float t = (kk - ok) / dk;
+#else
+    float t = (kk - ok) * invk;
+#endif
+    if (t < tmin || t > closest) return false;
+    float a = oa + t * da;
+    float b = ob + t * db;
+    if (a < a0 || a > a1 || b < b0 || b > b1) return false;
+    t_out = t;
+    return true;
+}
+// cuboid.rs:30-96 + list.rs:20-31: six rects in construction order with closest-so-far narrowing.
+__device__ __forceinline__ bool cuboid_test(V3 mn, V3 mx, const Ray& r, const RayK& k, float tmin, float closest,
+                                            float& t_out, int& face_out) {
+    bool any = false;
+    float t;
+    // 0: XY @ max.z   1: XY @ min.z
+    if (rect_test(r.o.z, r.d.z, k.inv.z, r.o.x, r.d.x, r.o.y, r.d.y, mn.x, mx.x, mn.y, mx.y, mx.z, tmin, closest, t)) { closest = t; face_out = 0; any = true; }
+    if (rect_test(r.o.z, r.d.z, k.inv.z, r.o.x, r.d.x, r.o.y, r.d.y, mn.x, mx.x, mn.y, mx.y, mn.z, tmin, closest, t)) { closest = t; face_out = 1; any = true; }
+    // 2: ZX @ max.y   3: ZX @ min.y   (a = z, b = x)
+    if (rect_test(r.o.y, r.d.y, k.inv.y, r.o.z, r.d.z, r.o.x, r.d.x, mn.z, mx.z, mn.x, mx.x, mx.y, tmin, closest, t)) { closest = t; face_out = 2; any = true; }
+    if (rect_test(r.o.y, r.d.y, k.inv.y, r.o.z, r.d.z, r.o.x, r.d.x, mn.z, mx.z, mn.x, mx.x, mn.y, tmin, closest, t)) { closest = t; face_out = 3; any = true; }
+    // 4: YZ @ max.x   5: YZ @ min.x   (a = y, b = z)
+    if (rect_test(r.o.x, r.d.x, k.inv.x, r.o.y, r.d.y, r.o.z, r.d.z, mn.y, mx.y, mn.z, mx.z, mx.x, tmin, closest, t)) { closest = t; face_out = 4; any = true; }
+    if (rect_test(r.o.x, r.d.x, k.inv.x, r.o.y, r.d.y, r.o.z, r.d.z, mn.y, mx.y, mn.z, mx.z, mn.x, tmin, closest, t)) { closest = t; face_out = 5; any = true; }
+    t_out = closest;
+    return any;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Traversal: a forward-only interpreter over the op stream.
+// ------------------------------------------------------------------------------------------------
+struct Best {
+    float t;
+    int pc;    // record that produced the hit (-1: none)
+    int face;  // cuboid side
+    int ctx;   // ray space the record lives in
+};
+
+// Closest hit of the sub-stream [pc, pc_end) for t in [tmin, closest]; returns true and narrows `closest`
+// when something was hit.  kInner: boundary query of a ConstantMedium (only t is needed; media cannot
+// nest).  `world` is the world-space ray, `cur`/`cur_ctx` the ray in the space the sub-stream starts in.
+template <bool kInner>
+__device__ __forceinline__ bool traverse(const DeviceScene& S, int pc, const int pc_end, const Ray& world, Ray cur,
+                                         int cur_ctx, const float tmin, float& closest, Best& best,
+                                         const bool reference_boxes, const MediumXi& xi) {
+    RayK k = make_rayk(cur);
+    bool any = false;
+    while (pc < pc_end) {
+        float4 A, B;
+        load_op(S, pc, A, B);
+        const uint32_t w7 = __float_as_uint(B.w);
+        const uint32_t opc = w7 & 0xffu;
+        if (opc == OP_BOX || opc == OP_BOX_LOOSE) {
+            bool hit = (opc == OP_BOX_LOOSE || reference_boxes) ? box_hit_reference(A, B, cur, k, tmin, closest)
+                                                                : box_hit_tight(A, B, cur, k, tmin, closest);
+            pc = hit ? pc + 1 : (int)(w7 >> 8);
+            continue;
+        }
+        switch (opc) {
+            case OP_SPHERE: {
+                float t;
+                if (sphere_test(v3(A.x, A.y, A.z), A.w, cur, k, tmin, closest, t)) {
+                    closest = t; any = true;
+                    if (!kInner) { best.t = t; best.pc = pc; best.face = 0; best.ctx = cur_ctx; }
+                }
+                pc += 1;
+                break;
+            }
+            case OP_MSPHERE: {
+                float4 C, D;
+                load_op(S, pc + 1, C, D);
+                V3 ctr = msphere_center(v3(A.x, A.y, A.z), v3(C.x, C.y, C.z), C.w, D.x, cur.time);
+                float t;
+                if (sphere_test(ctr, A.w, cur, k, tmin, closest, t)) {
+                    closest = t; any = true;
+                    if (!kInner) { best.t = t; best.pc = pc; best.face = 0; best.ctx = cur_ctx; }
+                }
+                pc += 2;
+                break;
+            }
+            case OP_RECT_XY: case OP_RECT_YZ: case OP_RECT_ZX: {
+                float t;
+                bool h;
+                if (opc == OP_RECT_XY) h = rect_test(cur.o.z, cur.d.z, k.inv.z, cur.o.x, cur.d.x, cur.o.y, cur.d.y, A.x, A.y, A.z, A.w, B.x, tmin, closest, t);
+                else if (opc == OP_RECT_YZ) h = rect_test(cur.o.x, cur.d.x, k.inv.x, cur.o.y, cur.d.y, cur.o.z, cur.d.z, A.x, A.y, A.z, A.w, B.x, tmin, closest, t);
+                else h = rect_test(cur.o.y, cur.d.y, k.inv.y, cur.o.z, cur.d.z, cur.o.x, cur.d.x, A.x, A.y, A.z, A.w, B.x, tmin, closest, t);
+                if (h) {
+                    closest = t; any = true;
+                    if (!kInner) { best.t = t; best.pc = pc; best.face = 0; best.ctx = cur_ctx; }
+                }
+                pc += 1;
+                break;
+            }
+            case OP_CUBOID: {
+                float t;
+                int face = 0;
+                if (cuboid_test(v3(A.x, A.y, A.z), v3(B.x, B.y, B.z), cur, k, tmin, closest, t, face)) {
+                    closest = t; any = true;
+                    if (!kInner) { best.t = t; best.pc = pc; best.face = face; best.ctx = cur_ctx; }
+                }
+                pc += 1;
+                break;
+            }
+            case OP_TRANSLATE: {
+                apply_translate(cur, A);
+                cur_ctx = __float_as_int(A.w);
+                k = make_rayk(cur);
+                pc += 1;
+                break;
+            }
+            case OP_ROTATE: {
+                apply_rotate(cur, A);
+                cur_ctx = __float_as_int(A.w);
+                k = make_rayk(cur);
+                pc += 1;
+                break;
+            }
+            case OP_POP: {
+                cur_ctx = __float_as_int(A.w);
+                cur = ray_in_ctx(S, world, cur_ctx);
+                k = make_rayk(cur);
+                pc += 1;
+                break;
+            }
+            case OP_MEDIUM: {
+                const int end = (int)(w7 >> 8);
+                if (!kInner) {
+                    // constant_medium.rs:34-76
+                    Best dummy;
+                    float t1 = CUDART_INF_F;
+                    bool h1 = traverse<true>(S, pc + 1, end, world, cur, cur_ctx, -CUDART_INF_F, t1, dummy, reference_boxes, xi);
+                    if (h1) {
+                        float t2 = CUDART_INF_F;
+                        bool h2 = traverse<true>(S, pc + 1, end, world, cur, cur_ctx, t1 + 0.0001f, t2, dummy, reference_boxes, xi);
+                        if (h2) {
+                            if (t1 < tmin) t1 = tmin;
+                            if (t2 > closest) t2 = closest;
+                            if (!(t1 >= t2)) {
+                                if (t1 < 0.0f) t1 = 0.0f;
+                                float ray_length = sqrtf(k.dd);
+                                float dist_inside = (t2 - t1) * ray_length;
+                                float u = xi.draw(__float_as_int(A.z));
+#if HRT_EXACT
+                                float hit_distance = A.x * (logf(u) / S.ln_e);
+                                float t = t1 + hit_distance / ray_length;
+#else
+                                float hit_distance = A.x * __logf(u);
+                                float t = t1 + hit_distance * rsqrtf(k.dd);
+#endif
+                                if (!(hit_distance > dist_inside)) {
+                                    closest = t; any = true;
+                                    best.t = t; best.pc = pc; best.face = 0; best.ctx = cur_ctx;
+                                }
+                            }
+                        }
+                    }
+                }
+                pc = end;
+                break;
+            }
+            default:  // OP_END (or a stray AUX): stop
+                pc = pc_end;
+                break;
+        }
+    }
+    return any;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Hit record
+// ------------------------------------------------------------------------------------------------
+struct HitRec {
+    V3 p, n;
+    float t, u, v;
+    bool front_face;
+    int mat, prim, face;
+};
+
+// hit_record.rs:22-29
+__device__ __forceinline__ void set_face_normal(HitRec& h, V3 ray_d, V3 outward) {
+    h.front_face = dot(ray_d, outward) < 0.0f;
+    h.n = h.front_face ? outward : -outward;
+}
+// sphere.rs:31-36
+__device__ __forceinline__ void sphere_uv(V3 p, float& u, float& v) {
+    float theta = acosf(-p.y);
+    float phi = atan2f(-p.z, p.x) + HRT_PI;
+    u = phi / (2.0f * HRT_PI);
+    v = theta / HRT_PI;
+}
+
+// Rebuild the full reference HitRecord for the winning record: evaluate the primitive in its own ray space
+// at best.t, then undo the enclosing Rotation/Translation records innermost-first
+// (rotation.rs:119-131, translation.rs:33-34).
+__device__ __noinline__ void make_hit_record(const DeviceScene& S, const Ray& world, const Best& best, bool want_uv, HitRec& h) {
+    // forward: world -> local, remembering the direction seen by each push record
+    Ray r = world;
+    Ctx c;
+    c.depth = 0;
+    float4 PA[kMaxCtxDepth];
+    bool is_translate[kMaxCtxDepth];
+    if (best.ctx != 0) {
+        c = S.ctxs[best.ctx];
+        for (int i = 0; i < c.depth; ++i) {
+            float4 B;
+            load_op(S, c.op_pc[i], PA[i], B);
+            is_translate[i] = (__float_as_uint(B.w) & 0xffu) == OP_TRANSLATE;
+            if (is_translate[i]) apply_translate(r, PA[i]);
+            else apply_rotate(r, PA[i]);
+        }
+    }
+    float4 A, B;
+    load_op(S, best.pc, A, B);
+    const uint32_t w7 = __float_as_uint(B.w);
+    const uint32_t opc = w7 & 0xffu;
+    h.t = best.t;
+    h.u = 0.0f; h.v = 0.0f;
+    h.face = 0;
+    h.p = ray_at(r, best.t);
+    switch (opc) {
+        case OP_SPHERE: case OP_MSPHERE: {
+            V3 ctr = v3(A.x, A.y, A.z);
+            if (opc == OP_MSPHERE) {
+                float4 C, D;
+                load_op(S, best.pc + 1, C, D);
+                ctr = msphere_center(ctr, v3(C.x, C.y, C.z), C.w, D.x, r.time);
+            }
+            V3 outward = (h.p - ctr) / A.w;
+            h.mat = __float_as_int(B.x);
+            // sphere.rs:61 computes (u,v) on every hit; only image-textured materials ever read them
+            if (want_uv || (S.mats[h.mat].flags & MATF_NEEDS_UV)) sphere_uv(outward, h.u, h.v);
+            set_face_normal(h, r.d, outward);
+            h.prim = __float_as_int(B.y);
+            break;
+        }
+        case OP_RECT_XY: case OP_RECT_YZ: case OP_RECT_ZX: {
+            float a, b;
+            V3 outward;
+            if (opc == OP_RECT_XY) { a = h.p.x; b = h.p.y; outward = v3(0, 0, 1); }
+            else if (opc == OP_RECT_YZ) { a = h.p.y; b = h.p.z; outward = v3(1, 0, 0); }
+            else { a = h.p.z; b = h.p.x; outward = v3(0, 1, 0); }
+            h.u = (a - A.x) / (A.y - A.x);  // rect.rs:75-76
+            h.v = (b - A.z) / (A.w - A.z);
+            set_face_normal(h, r.d, outward);
+            h.mat = __float_as_int(B.y);
+            h.prim = __float_as_int(B.z);
+            break;
+        }
+        case OP_CUBOID: {
+            const V3 mn = v3(A.x, A.y, A.z), mx = v3(B.x, B.y, B.z);
+            const int f = best.face;
+            float a, b, a0, a1, b0, b1;
+            V3 outward;
+            if (f < 2) { a = h.p.x; b = h.p.y; a0 = mn.x; a1 = mx.x; b0 = mn.y; b1 = mx.y; outward = v3(0, 0, 1); }
+            else if (f < 4) { a = h.p.z; b = h.p.x; a0 = mn.z; a1 = mx.z; b0 = mn.x; b1 = mx.x; outward = v3(0, 1, 0); }
+            else { a = h.p.y; b = h.p.z; a0 = mn.y; a1 = mx.y; b0 = mn.z; b1 = mx.z; outward = v3(1, 0, 0); }
+            h.u = (a - a0) / (a1 - a0);
+            h.v = (b - b0) / (b1 - b0);
+            set_face_normal(h, r.d, outward);
+            h.mat = __float_as_int(A.w);
+            h.prim = (int)(w7 >> 8);
+            h.face = f;
+            break;
+        }
+        default: {  // OP_MEDIUM — constant_medium.rs:67-75
+            h.n = v3(0.0f, 0.0f, 0.0f);
+            h.front_face = false;
+            h.mat = __float_as_int(A.y);
+            h.prim = __float_as_int(A.w);
+            break;
+        }
+    }
+    // backward: local -> world.  After undoing record i the ray seen by the enclosing space has the
+    // direction that entered record i; Translation re-faces against ITS moved ray, whose direction equals
+    // the direction that entered it (translation.rs:25-34, Q4).
+    if (c.depth > 0) {
+        // directions entering each record: recompute by replaying (depth is tiny)
+        for (int i = c.depth - 1; i >= 0; --i) {
+            if (is_translate[i]) {
+                // direction of moved_ray == direction entering record i
+                Ray rr = world;
+                for (int j = 0; j < i; ++j) {
+                    if (is_translate[j]) apply_translate(rr, PA[j]);
+                    else apply_rotate(rr, PA[j]);
+                }
+                h.p = h.p + v3(PA[i].x, PA[i].y, PA[i].z);
+                set_face_normal(h, rr.d, h.n);
+            } else {
+                h.p = unrotate(h.p, PA[i]);
+                h.n = unrotate(h.n, PA[i]);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Textures (src/textures/*.rs, src/perlin_noise.rs)
+// ------------------------------------------------------------------------------------------------
+struct NoiseView {  // where the tables of noise texture `i` live (global or shared memory)
+    const float4* ranvec;
+    const uint8_t* perm;  // 3 x 256
+};
+
+// perlin_noise.rs:80-123 (Q6: smoothed u,v,w inside the weight vector too)
+__device__ __forceinline__ float perlin_noise(const NoiseView& N, V3 p) {
+    float fx = floorf(p.x), fy = floorf(p.y), fz = floorf(p.z);
+    int i = (int)fx, j = (int)fy, k = (int)fz;
+    float u = p.x - fx, v = p.y - fy, w = p.z - fz;
+    u = u * u * (3.0f - 2.0f * u);
+    v = v * v * (3.0f - 2.0f * v);
+    w = w * w * (3.0f - 2.0f * w);
+    uint32_t px0 = N.perm[(i)&255], px1 = N.perm[(i + 1) & 255];
+    uint32_t py0 = N.perm[256 + ((j)&255)], py1 = N.perm[256 + ((j + 1) & 255)];
+    uint32_t pz0 = N.perm[512 + ((k)&255)], pz1 = N.perm[512 + ((k + 1) & 255)];
+    float acc = 0.0f;
+#pragma unroll
+    for (int idx = 0; idx < 8; ++idx) {
+        const int x = idx >> 2, y = (idx >> 1) & 1, z = idx & 1;
+        float4 g = N.ranvec[(x ? px1 : px0) ^ (y ? py1 : py0) ^ (z ? pz1 : pz0)];
+        float wx = u - (float)x, wy = v - (float)y, wz = w - (float)z;
+        float bx = x ? u : (1.0f - u), by = y ? v : (1.0f - v), bz = z ? w : (1.0f - w);
+        // (x*u + (1-x)*(1-u)) reduces exactly to u or (1-u): the other term is an exact 0
+        acc += ((bx * by) * bz) * ((g.x * wx + g.y * wy) + g.z * wz);
+    }
+    return acc;
+}
+// perlin_noise.rs:66-78
+__device__ __forceinline__ float perlin_turbulence(const NoiseView& N, V3 p, int depth) {
+    float acc = 0.0f, weight = 1.0f;
+    for (int d = 0; d < depth; ++d) {
+        acc += weight * perlin_noise(N, p);
+        weight *= 0.5f;
+        p = p * 2.0f;
+    }
+    return fabsf(acc);
+}
+
+struct TexEnv {  // per-kernel texture environment
+    NoiseView noise[kMaxNoiseTablesShared];
+    int n_shared_noise;
+};
+__device__ __forceinline__ NoiseView noise_view(const DeviceScene& S, const TexEnv& E, int table) {
+    if (table < E.n_shared_noise) return E.noise[table];
+    NoiseView nv;
+    nv.ranvec = reinterpret_cast<const float4*>(S.noise[table].ranvec);
+    nv.perm = &S.noise[table].perm[0][0];
+    return nv;
+}
+
+__device__ __forceinline__ V3 texture_value(const DeviceScene& S, const TexEnv& E, int tex, float u, float v, V3 p) {
+    Texture T = S.texs[tex];
+    // checker_texture.rs:22-30 — select and descend (checkers may nest)
+    while (T.kind == TEX_CHECKER) {
+        float sines = sinf(10.0f * p.x) * sinf(10.0f * p.y) * sinf(10.0f * p.z);
+        T = S.texs[sines < 0.0f ? T.i0 : T.i1];
+    }
+    if (T.kind == TEX_SOLID) return v3(T.v[0], T.v[1], T.v[2]);  // solid_color.rs:21-23
+    if (T.kind == TEX_NOISE) {                                   // noise_texture.rs:25-31 (Q7)
+        const float scale = T.v[0];
+        NoiseView nv = noise_view(S, E, T.i0);
+        float arg = (scale * p.z) + (10.0f * perlin_turbulence(nv, scale * p, 7));
+        float s = sinf(arg);
+        float g = 0.5f * (1.0f + s);
+        return v3(g, g, g);
+    }
+    // image_texture.rs:36-63
+    if (T.i0 < 0) return v3(1.0f, 0.0f, 1.0f);
+    float uc = (u < 0.0f) ? 0.0f : ((u > 1.0f) ? 1.0f : u);  // f32::clamp keeps NaN
+    float vc = (v < 0.0f) ? 0.0f : ((v > 1.0f) ? 1.0f : v);
+    vc = 1.0f - vc;
+    const uint32_t W = (uint32_t)T.i1, H = (uint32_t)T.i2;
+    uint32_t i = __float2uint_rz(uc * (float)W);  // saturating, NaN -> 0: same as Rust `as u32`
+    uint32_t j = __float2uint_rz(vc * (float)H);
+    if (i >= W) i = W - 1;
+    if (j >= H) j = H - 1;
+    uchar4 c = tex2D<uchar4>(S.images[T.i0], (float)i + 0.5f, (float)j + 0.5f);
+    const float color_scale = 1.0f / 255.0f;
+    return v3(color_scale * (float)c.x, color_scale * (float)c.y, color_scale * (float)c.z);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Materials (src/materials/*.rs, src/math.rs)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool near_zero(V3 v) {  // math.rs:42-45
+    const float S = 1e-8f;
+    return (fabsf(v.x) < S) && (fabsf(v.y) < S) && (fabsf(v.z) < S);
+}
+__device__ __forceinline__ V3 reflect(V3 v, V3 n) { return v - (2.0f * dot(v, n)) * n; }  // math.rs:47-49
+__device__ __forceinline__ V3 refract(V3 uv, V3 n, float eta) {                            // math.rs:51-56
+    float cos_theta = fminf(dot(-uv, n), 1.0f);
+    V3 perp = eta * (uv + cos_theta * n);
+    V3 par = (-sqrtf(fabsf(1.0f - dot(perp, perp)))) * n;
+    return perp + par;
+}
+__device__ __forceinline__ float reflectance(float cosine, float ref_idx) {  // math.rs:58-62
+    float r0 = (1.0f - ref_idx) / (1.0f + ref_idx);
+    r0 = r0 * r0;
+#if HRT_EXACT
+    return r0 + (1.0f - r0) * powf(1.0f - cosine, 5.0f);
+#else
+    float m = 1.0f - cosine;
+    float m2 = m * m;
+    return r0 + (1.0f - r0) * (m2 * m2 * m);
+#endif
+}
+
+// Material::emitted (materials/mod.rs:18; only DiffuseLight is non-zero, diffuse_light.rs:25-27)
+__device__ __forceinline__ V3 material_emitted(const DeviceScene& S, const TexEnv& E, const Material& m, const HitRec& h) {
+    if (m.kind == MAT_DIFFUSE_LIGHT) return texture_value(S, E, m.tex, h.u, h.v, h.p);
+    return v3(0.0f, 0.0f, 0.0f);
+}
+// Material::scatter with uniforms u[0..3].  Returns false for "None".
+__device__ __forceinline__ bool material_scatter(const DeviceScene& S, const TexEnv& E, const Material& m, const Ray& ray,
+                                                 const HitRec& h, const float u[4], V3& attenuation, Ray& scattered) {
+    switch (m.kind) {
+        case MAT_LAMBERTIAN: {  // lambertian.rs:27-38
+            V3 dir = h.n + sample_unit_vector(u[0], u[1]);
+            if (near_zero(dir)) dir = h.n;
+            attenuation = texture_value(S, E, m.tex, h.u, h.v, h.p);
+            scattered = Ray{h.p, dir, ray.time};
+            return true;
+        }
+        case MAT_METAL: {  // metal.rs:29-42
+            V3 reflected = reflect(normalize(ray.d), h.n);
+            V3 dir = reflected + m.param * sample_in_unit_sphere(u[0], u[1], u[2]);
+            scattered = Ray{h.p, dir, ray.time};
+            if (dot(dir, h.n) > 0.0f) {
+                attenuation = v3(m.albedo[0], m.albedo[1], m.albedo[2]);
+                return true;
+            }
+            return false;
+        }
+        case MAT_DIELECTRIC: {  // dielectric.rs:31-55
+            float ratio = h.front_face ? (1.0f / m.param) : m.param;
+            V3 unit = normalize(ray.d);
+            float cos_theta = fminf(dot(-unit, h.n), 1.0f);
+            float sin_theta = sqrtf(1.0f - cos_theta * cos_theta);
+            bool cannot_refract = (ratio * sin_theta) > 1.0f;
+            V3 dir;
+            if (cannot_refract || reflectance(cos_theta, ratio) > u[0]) dir = reflect(unit, h.n);
+            else dir = refract(unit, h.n, ratio);
+            attenuation = v3(1.0f, 1.0f, 1.0f);
+            scattered = Ray{h.p, dir, ray.time};
+            return true;
+        }
+        case MAT_ISOTROPIC: {  // isotropic.rs:27-33
+            attenuation = texture_value(S, E, m.tex, h.u, h.v, h.p);
+            scattered = Ray{h.p, sample_in_unit_sphere(u[0], u[1], u[2]), ray.time};
+            return true;
+        }
+        default:  // MAT_DIFFUSE_LIGHT: diffuse_light.rs:21-23
+            return false;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Camera (src/camera.rs:85-95)
+// ------------------------------------------------------------------------------------------------
+struct CameraK {
+    V3 origin, lower_left_corner, horizontal, vertical, u, v;
+    float lens_radius, time0, time1;
+};
+__device__ __forceinline__ Ray camera_get_ray(const CameraK& c, float s, float t, float u_lens1, float u_lens2, float u_time) {
+    V3 rd = c.lens_radius * sample_in_unit_disk(u_lens1, u_lens2);
+    V3 offset = c.u * rd.x + c.v * rd.y;
+    Ray r;
+    r.o = c.origin + offset;
+    r.d = c.lower_left_corner + s * c.horizontal + t * c.vertical - c.origin - offset;
+    r.time = c.time0 + (c.time1 - c.time0) * u_time;
+    return r;
+}
+
+}  // namespace HRT_NS

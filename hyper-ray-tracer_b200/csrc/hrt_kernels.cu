@@ -1,0 +1,411 @@
+// hrt_kernels.cu — sm_100a kernels of the path-tracing hot path + their launchers.
+// Compiled twice (see hrt_device.cuh): -DHRT_EXACT=1 --fmad=false and -DHRT_EXACT=0.
+//
+//   render_kernel      replaces Application::render's sample loop + ray_color (src/application.rs:393-495):
+//                      persistent warps pull (8x4-pixel tile, sample-chunk) work items from a global cursor;
+//                      inside an item the 32 lanes draw path indices from a warp-local pool with
+//                      ballot/popc compaction, so a lane whose path ended is re-filled immediately and the
+//                      bounce "recursion" is one flat loop (one ray segment per lane per iteration).
+//   resolve_kernel     the gamma resolve sqrt(sum * 1/spp), alpha 1 (src/application.rs:451-456).
+//   trace_hits_kernel  world.hit() on explicit rays            (parity entry)
+//   tex_value_kernel   Texture::value                          (parity entry)
+//   scatter_kernel     Material::scatter / emitted             (parity entry)
+//   camera_rays_kernel Camera::get_ray                         (parity entry)
+#include "hrt_device.cuh"
+#include "hrt_launch.h"
+
+namespace HRT_NS {
+
+static_assert(sizeof(DeviceScene) == sizeof(hrt::DeviceSceneHost), "DeviceScene host/device mirror mismatch");
+
+constexpr int kBlock = 256;
+constexpr int kWarpsPerBlock = kBlock / 32;
+constexpr unsigned kFull = 0xffffffffu;
+
+struct RenderParams {
+    DeviceScene S;
+    CameraK cam;
+    int width, height, depth;
+    float bg[3];
+    uint32_t k0, k1;
+    int sample_begin, sample_count;
+    int chunk, n_chunks, tiles_x, tiles_y, n_tiles, n_items;
+    int reference_boxes;
+    unsigned long long* counters;
+    float4* accum;
+};
+
+__device__ __forceinline__ void stage_noise(const DeviceScene& S, NoiseTable* sh, TexEnv& E) {
+    E.n_shared_noise = S.n_noise < kMaxNoiseTablesShared ? S.n_noise : kMaxNoiseTablesShared;
+    const int words = E.n_shared_noise * (int)(sizeof(NoiseTable) / 16);
+    const uint4* src = reinterpret_cast<const uint4*>(S.noise);
+    uint4* dst = reinterpret_cast<uint4*>(sh);
+    for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = __ldg(src + i);
+    for (int i = 0; i < kMaxNoiseTablesShared; ++i) {
+        E.noise[i].ranvec = reinterpret_cast<const float4*>(sh[i].ranvec);
+        E.noise[i].perm = &sh[i].perm[0][0];
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kBlock, 2) render_kernel(const __grid_constant__ RenderParams P) {
+    __shared__ NoiseTable sh_noise[kMaxNoiseTablesShared];
+    __shared__ float sh_acc[kWarpsPerBlock][32][3];
+    TexEnv E;
+    stage_noise(P.S, sh_noise, E);
+
+    const DeviceScene& S = P.S;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const bool ref_boxes = P.reference_boxes != 0;
+    const V3 bg = v3(P.bg[0], P.bg[1], P.bg[2]);
+    const float div_w = (float)P.width - 1.0f, div_h = (float)P.height - 1.0f;  // application.rs:444-445
+    unsigned long long n_rays = 0, n_paths = 0;
+
+    for (;;) {
+        unsigned long long item = 0;
+        if (lane == 0) item = atomicAdd(P.counters, 1ULL);
+        item = __shfl_sync(kFull, item, 0);
+        if (item >= (unsigned long long)P.n_items) break;
+        const int tile = (int)(item % (unsigned long long)P.n_tiles);
+        const int chunk = (int)(item / (unsigned long long)P.n_tiles);
+        const int tx = tile % P.tiles_x, ty = tile / P.tiles_x;
+        const int s0 = P.sample_begin + chunk * P.chunk;
+        const int s_end = P.sample_begin + P.sample_count;
+        const int s_n = (s0 + P.chunk <= s_end) ? P.chunk : (s_end - s0);
+        const int pool_size = 32 * s_n;
+        int pool_next = 0;
+
+        sh_acc[warp][lane][0] = 0.0f;
+        sh_acc[warp][lane][1] = 0.0f;
+        sh_acc[warp][lane][2] = 0.0f;
+        __syncwarp();
+
+        bool active = false;
+        Ray ray;
+        V3 T = v3(1.0f, 1.0f, 1.0f);
+        uint32_t bounce = 0;
+        RngKey key;
+        key.k0 = P.k0; key.k1 = P.k1; key.pixel = 0; key.sample = 0;
+        int my_pl = lane;
+
+        for (;;) {
+            // ---- re-fill dead lanes from the warp-local pool (ballot + popc compaction) ----
+            const unsigned need = __ballot_sync(kFull, !active);
+            if (need) {
+                const int idx = pool_next + __popc(need & lt_mask);
+                pool_next += __popc(need);
+                if (!active && idx < pool_size) {
+                    const int pl = idx & 31;
+                    const int px = tx * 8 + (pl & 7), py = ty * 4 + (pl >> 3);
+                    if (px < P.width && py < P.height) {
+                        key.pixel = (uint32_t)(py * P.width + px);
+                        key.sample = (uint32_t)(s0 + (idx >> 5));
+                        float c4[4], t4[4];
+                        rng_block(key, 0, RNG_BLOCK_CAMERA, c4);
+                        rng_block(key, 0, RNG_BLOCK_CAMERA - 1, t4);
+                        const float u = ((float)px + c4[0]) / div_w;
+                        const float v = ((float)py + c4[1]) / div_h;
+                        ray = camera_get_ray(P.cam, u, v, c4[2], c4[3], t4[0]);
+                        T = v3(1.0f, 1.0f, 1.0f);
+                        bounce = 0;
+                        my_pl = pl;
+                        active = P.depth > 0;  // ray_color(depth == 0) is black (application.rs:478-480)
+                        n_paths++;
+                    }
+                }
+            }
+            if (!__any_sync(kFull, active)) {
+                if (pool_next >= pool_size) break;
+                continue;
+            }
+            // ---- one ray segment per live lane: world.hit + emitted + scatter (application.rs:477-495) ----
+            if (active) {
+                MediumXi xi;
+                xi.key = key; xi.bounce = bounce; xi.injected = 0.0f; xi.inject = false;
+                Best best;
+                best.pc = -1; best.t = 0.0f; best.face = 0; best.ctx = 0;
+                float closest = CUDART_INF_F;
+                const bool hit = traverse<false>(S, 0, S.n_ops, ray, ray, 0, 0.001f, closest, best, ref_boxes, xi);
+                n_rays++;
+                V3 add = v3(0.0f, 0.0f, 0.0f);
+                if (!hit) {
+                    add = T * bg;
+                    active = false;
+                } else {
+                    HitRec h;
+                    make_hit_record(S, ray, best, false, h);
+                    const Material m = S.mats[h.mat];
+                    if (m.kind == MAT_DIFFUSE_LIGHT) {
+                        add = T * material_emitted(S, E, m, h);
+                        active = false;  // DiffuseLight::scatter -> None
+                    } else {
+                        float u4[4];
+                        rng_block(key, bounce, RNG_BLOCK_SCATTER, u4);
+                        V3 att;
+                        Ray sc;
+                        if (material_scatter(S, E, m, ray, h, u4, att, sc)) {
+                            T = T * att;
+                            ray = sc;
+                            bounce++;
+                            if (bounce >= (uint32_t)P.depth) active = false;  // depth == 0 -> black
+                        } else {
+                            active = false;
+                        }
+                    }
+                }
+                if (add.x != 0.0f) atomicAdd(&sh_acc[warp][my_pl][0], add.x);
+                if (add.y != 0.0f) atomicAdd(&sh_acc[warp][my_pl][1], add.y);
+                if (add.z != 0.0f) atomicAdd(&sh_acc[warp][my_pl][2], add.z);
+            }
+        }
+        __syncwarp();
+        {
+            const int px = tx * 8 + (lane & 7), py = ty * 4 + (lane >> 3);
+            if (px < P.width && py < P.height) {
+                float* dst = reinterpret_cast<float*>(P.accum + (size_t)py * P.width + px);
+                atomicAdd(dst + 0, sh_acc[warp][lane][0]);
+                atomicAdd(dst + 1, sh_acc[warp][lane][1]);
+                atomicAdd(dst + 2, sh_acc[warp][lane][2]);
+                atomicAdd(dst + 3, (float)s_n);
+            }
+        }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        n_rays += __shfl_xor_sync(kFull, n_rays, o);
+        n_paths += __shfl_xor_sync(kFull, n_paths, o);
+    }
+    if (lane == 0) {
+        atomicAdd(P.counters + 1, n_rays);
+        atomicAdd(P.counters + 2, n_paths);
+    }
+}
+
+__global__ void __launch_bounds__(256) resolve_kernel(const float4* __restrict__ accum, int n_pixels, float scale,
+                                                      float4* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pixels) return;
+    float4 a = accum[i];
+    out[i] = make_float4(sqrtf(a.x * scale), sqrtf(a.y * scale), sqrtf(a.z * scale), 1.0f);
+}
+
+__global__ void __launch_bounds__(128) trace_hits_kernel(const __grid_constant__ DeviceScene S, const hrt_ray* __restrict__ rays,
+                                                         int n, const float* __restrict__ xi_in, hrt_hit* __restrict__ out,
+                                                         int reference_boxes) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    hrt_ray r = rays[i];
+    Ray ray;
+    ray.o = v3(r.o[0], r.o[1], r.o[2]);
+    ray.d = v3(r.d[0], r.d[1], r.d[2]);
+    ray.time = r.time;
+    MediumXi xi;
+    xi.key.k0 = 0; xi.key.k1 = 0; xi.key.pixel = 0; xi.key.sample = 0;
+    xi.bounce = 0;
+    xi.inject = true;
+    xi.injected = xi_in ? xi_in[i] : 0.5f;
+    Best best;
+    best.pc = -1; best.t = 0.0f; best.face = 0; best.ctx = 0;
+    float closest = r.tmax;
+    bool hit = traverse<false>(S, 0, S.n_ops, ray, ray, 0, r.tmin, closest, best, reference_boxes != 0, xi);
+    hrt_hit o;
+    o.hit = 0; o.t = 0.0f;
+    o.p[0] = o.p[1] = o.p[2] = 0.0f;
+    o.n[0] = o.n[1] = o.n[2] = 0.0f;
+    o.u = 0.0f; o.v = 0.0f;
+    o.front_face = 0; o.material_id = -1; o.prim_id = -1; o.face = 0;
+    if (hit) {
+        HitRec h;
+        make_hit_record(S, ray, best, true, h);
+        o.hit = 1;
+        o.t = h.t;
+        o.p[0] = h.p.x; o.p[1] = h.p.y; o.p[2] = h.p.z;
+        o.n[0] = h.n.x; o.n[1] = h.n.y; o.n[2] = h.n.z;
+        o.u = h.u; o.v = h.v;
+        o.front_face = h.front_face ? 1 : 0;
+        o.material_id = h.mat;
+        o.prim_id = h.prim;
+        o.face = h.face;
+    }
+    out[i] = o;
+}
+
+__global__ void __launch_bounds__(kBlock) tex_value_kernel(const __grid_constant__ DeviceScene S, int tex,
+                                                           const float* __restrict__ uvp, int n, float* __restrict__ out) {
+    __shared__ NoiseTable sh_noise[kMaxNoiseTablesShared];
+    TexEnv E;
+    stage_noise(S, sh_noise, E);
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* q = uvp + 5 * (size_t)i;
+    V3 c = texture_value(S, E, tex, q[0], q[1], v3(q[2], q[3], q[4]));
+    out[3 * (size_t)i + 0] = c.x;
+    out[3 * (size_t)i + 1] = c.y;
+    out[3 * (size_t)i + 2] = c.z;
+}
+
+__global__ void __launch_bounds__(kBlock) scatter_kernel(const __grid_constant__ DeviceScene S, const hrt_ray* __restrict__ rays,
+                                                         const hrt_hit* __restrict__ hits, const float* __restrict__ u4, int n,
+                                                         hrt_scatter_out* __restrict__ out) {
+    __shared__ NoiseTable sh_noise[kMaxNoiseTablesShared];
+    TexEnv E;
+    stage_noise(S, sh_noise, E);
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    hrt_scatter_out o;
+    o.scattered = 0;
+    for (int c = 0; c < 3; ++c) { o.attenuation[c] = 0.0f; o.o[c] = 0.0f; o.d[c] = 0.0f; o.emitted[c] = 0.0f; }
+    o.time = 0.0f;
+    const hrt_hit hh = hits[i];
+    if (hh.hit && hh.material_id >= 0) {
+        const hrt_ray r = rays[i];
+        Ray ray;
+        ray.o = v3(r.o[0], r.o[1], r.o[2]);
+        ray.d = v3(r.d[0], r.d[1], r.d[2]);
+        ray.time = r.time;
+        HitRec h;
+        h.p = v3(hh.p[0], hh.p[1], hh.p[2]);
+        h.n = v3(hh.n[0], hh.n[1], hh.n[2]);
+        h.t = hh.t; h.u = hh.u; h.v = hh.v;
+        h.front_face = hh.front_face != 0;
+        h.mat = hh.material_id; h.prim = hh.prim_id; h.face = hh.face;
+        const Material m = S.mats[h.mat];
+        V3 e = material_emitted(S, E, m, h);
+        o.emitted[0] = e.x; o.emitted[1] = e.y; o.emitted[2] = e.z;
+        float u[4] = {u4[4 * (size_t)i], u4[4 * (size_t)i + 1], u4[4 * (size_t)i + 2], u4[4 * (size_t)i + 3]};
+        V3 att;
+        Ray sc;
+        if (material_scatter(S, E, m, ray, h, u, att, sc)) {
+            o.scattered = 1;
+            o.attenuation[0] = att.x; o.attenuation[1] = att.y; o.attenuation[2] = att.z;
+            o.o[0] = sc.o.x; o.o[1] = sc.o.y; o.o[2] = sc.o.z;
+            o.d[0] = sc.d.x; o.d[1] = sc.d.y; o.d[2] = sc.d.z;
+            o.time = sc.time;
+        }
+    }
+    out[i] = o;
+}
+
+__global__ void __launch_bounds__(kBlock) camera_rays_kernel(const __grid_constant__ CameraK cam, const float* __restrict__ stuuu,
+                                                             int n, hrt_ray* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* q = stuuu + 5 * (size_t)i;
+    Ray r = camera_get_ray(cam, q[0], q[1], q[2], q[3], q[4]);
+    hrt_ray o;
+    o.o[0] = r.o.x; o.o[1] = r.o.y; o.o[2] = r.o.z;
+    o.d[0] = r.d.x; o.d[1] = r.d.y; o.d[2] = r.d.z;
+    o.time = r.time;
+    o.tmin = 0.001f;
+    o.tmax = CUDART_INF_F;
+    out[i] = o;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Launchers
+// ------------------------------------------------------------------------------------------------
+static DeviceScene to_device_scene(const hrt::DeviceSceneHost& h) {
+    DeviceScene S;
+    S.ops = reinterpret_cast<const float4*>(h.ops);
+    S.ctxs = reinterpret_cast<const Ctx*>(h.ctxs);
+    S.mats = reinterpret_cast<const Material*>(h.mats);
+    S.texs = reinterpret_cast<const Texture*>(h.texs);
+    S.noise = reinterpret_cast<const NoiseTable*>(h.noise);
+    for (int i = 0; i < kMaxImages; ++i) S.images[i] = h.images[i];
+    S.n_ops = h.n_ops; S.n_noise = h.n_noise; S.n_media = h.n_media;
+    S.ln_e = h.ln_e;
+    return S;
+}
+static CameraK to_camera(const hrt_camera_state& c) {
+    CameraK k;
+    k.origin = V3{c.origin[0], c.origin[1], c.origin[2]};
+    k.lower_left_corner = V3{c.lower_left_corner[0], c.lower_left_corner[1], c.lower_left_corner[2]};
+    k.horizontal = V3{c.horizontal[0], c.horizontal[1], c.horizontal[2]};
+    k.vertical = V3{c.vertical[0], c.vertical[1], c.vertical[2]};
+    k.u = V3{c.u[0], c.u[1], c.u[2]};
+    k.v = V3{c.v[0], c.v[1], c.v[2]};
+    k.lens_radius = c.lens_radius;
+    k.time0 = c.time0;
+    k.time1 = c.time1;
+    return k;
+}
+
+cudaError_t launch_render(hrt::RenderLaunch& L, int num_sms, cudaStream_t stream) {
+    RenderParams P;
+    P.S = to_device_scene(L.scene);
+    P.cam = to_camera(L.cam);
+    P.width = L.width; P.height = L.height; P.depth = L.depth;
+    P.bg[0] = L.background[0]; P.bg[1] = L.background[1]; P.bg[2] = L.background[2];
+    P.k0 = L.key0; P.k1 = L.key1;
+    P.sample_begin = L.sample_begin; P.sample_count = L.sample_count;
+    P.tiles_x = (L.width + 7) / 8;
+    P.tiles_y = (L.height + 3) / 4;
+    P.n_tiles = P.tiles_x * P.tiles_y;
+    int blocks_per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, render_kernel, kBlock, 0);
+    if (e != cudaSuccess) return e;
+    if (blocks_per_sm < 1) blocks_per_sm = 1;
+    const int grid = num_sms * blocks_per_sm;
+    // Samples per work item: large enough to amortise the per-item flush and the end-of-pool tail, small
+    // enough that the dynamic cursor balances the last wave (>= ~8 items per resident warp when possible).
+    int chunk = L.chunk;
+    if (chunk <= 0) {
+        chunk = 64;
+        const long long resident_warps = (long long)grid * kWarpsPerBlock;
+        while (chunk > 4 && (long long)P.n_tiles * ((L.sample_count + chunk - 1) / chunk) < 8 * resident_warps) chunk /= 2;
+    }
+    if (chunk > L.sample_count) chunk = L.sample_count;
+    if (chunk < 1) chunk = 1;
+    P.chunk = chunk;
+    P.n_chunks = (L.sample_count + chunk - 1) / chunk;
+    P.n_items = P.n_tiles * P.n_chunks;
+    P.reference_boxes = L.reference_boxes;
+    P.counters = L.counters;
+    P.accum = reinterpret_cast<float4*>(L.accum);
+    L.grid = grid;
+    L.block = kBlock;
+    L.chunk = chunk;
+    render_kernel<<<grid, kBlock, 0, stream>>>(P);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_trace_hits(const hrt::DeviceSceneHost& S, const hrt_ray* d_rays, int n, const float* d_xi, hrt_hit* d_out,
+                              int reference_boxes, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    trace_hits_kernel<<<(n + 127) / 128, 128, 0, stream>>>(to_device_scene(S), d_rays, n, d_xi, d_out, reference_boxes);
+    return cudaGetLastError();
+}
+cudaError_t launch_tex_value(const hrt::DeviceSceneHost& S, int tex, const float* d_uvp, int n, float* d_out,
+                             cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    tex_value_kernel<<<(n + kBlock - 1) / kBlock, kBlock, 0, stream>>>(to_device_scene(S), tex, d_uvp, n, d_out);
+    return cudaGetLastError();
+}
+cudaError_t launch_scatter(const hrt::DeviceSceneHost& S, const hrt_ray* d_rays, const hrt_hit* d_hits, const float* d_u4, int n,
+                           hrt_scatter_out* d_out, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    scatter_kernel<<<(n + kBlock - 1) / kBlock, kBlock, 0, stream>>>(to_device_scene(S), d_rays, d_hits, d_u4, n, d_out);
+    return cudaGetLastError();
+}
+cudaError_t launch_camera_rays(const hrt_camera_state& cam, const float* d_stuuu, int n, hrt_ray* d_out, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    camera_rays_kernel<<<(n + kBlock - 1) / kBlock, kBlock, 0, stream>>>(to_camera(cam), d_stuuu, n, d_out);
+    return cudaGetLastError();
+}
+cudaError_t launch_resolve(const float* d_accum, int n_pixels, int samples, float* d_out, cudaStream_t stream) {
+    if (n_pixels <= 0) return cudaSuccess;
+    const float scale = 1.0f / (float)samples;  // application.rs:403
+    resolve_kernel<<<(n_pixels + 255) / 256, 256, 0, stream>>>(reinterpret_cast<const float4*>(d_accum), n_pixels, scale,
+                                                              reinterpret_cast<float4*>(d_out));
+    return cudaGetLastError();
+}
+void philox_uniforms(uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t bounce, uint32_t block, float out[4]) {
+    RngKey k;
+    k.k0 = (uint32_t)seed; k.k1 = (uint32_t)(seed >> 32); k.pixel = pixel; k.sample = sample;
+    rng_block(k, bounce, block, out);
+}
+
+}  // namespace HRT_NS

@@ -1,0 +1,55 @@
+// hrt_launch.h — host-callable launchers exported by each compilation of hrt_kernels.cu
+// (namespace hrt_exact: --fmad=false parity build; namespace hrt_fast: production build).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/hrt.h"
+#include "hrt_types.h"
+
+namespace hrt {
+
+struct DeviceSceneHost {  // mirrors HRT_NS::DeviceScene field for field (checked by static_assert in the .cu)
+    const void* ops;
+    const void* ctxs;
+    const void* mats;
+    const void* texs;
+    const void* noise;
+    cudaTextureObject_t images[kMaxImages];
+    int32_t n_ops, n_noise, n_media;
+    float ln_e;
+};
+
+struct RenderLaunch {
+    DeviceSceneHost scene;
+    hrt_camera_state cam;
+    int32_t width, height, depth;
+    float background[3];
+    uint32_t key0, key1;
+    int32_t sample_begin, sample_count;
+    int32_t chunk;        // samples per work item
+    int32_t reference_boxes;
+    unsigned long long* counters;  // device: [0] work-item cursor, [1] rays, [2] paths
+    float* accum;                  // device: width*height*4 f32, added into
+    int32_t grid, block;           // out: launch configuration actually used
+};
+
+}  // namespace hrt
+
+#define HRT_DECLARE_LAUNCHERS(NS)                                                                                        \
+    namespace NS {                                                                                                       \
+    cudaError_t launch_render(hrt::RenderLaunch& L, int num_sms, cudaStream_t stream);                                        \
+    cudaError_t launch_trace_hits(const hrt::DeviceSceneHost& S, const hrt_ray* d_rays, int n, const float* d_xi,             \
+                                  hrt_hit* d_out, int reference_boxes, cudaStream_t stream);                             \
+    cudaError_t launch_tex_value(const hrt::DeviceSceneHost& S, int tex, const float* d_uvp, int n, float* d_out,             \
+                                 cudaStream_t stream);                                                                   \
+    cudaError_t launch_scatter(const hrt::DeviceSceneHost& S, const hrt_ray* d_rays, const hrt_hit* d_hits, const float* d_u4, \
+                               int n, hrt_scatter_out* d_out, cudaStream_t stream);                                      \
+    cudaError_t launch_camera_rays(const hrt_camera_state& cam, const float* d_stuuu, int n, hrt_ray* d_out,             \
+                                   cudaStream_t stream);                                                                 \
+    cudaError_t launch_resolve(const float* d_accum, int n_pixels, int samples, float* d_out, cudaStream_t stream);      \
+    void philox_uniforms(uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t bounce, uint32_t block, float out[4]); \
+    }
+
+HRT_DECLARE_LAUNCHERS(hrt_exact)
+HRT_DECLARE_LAUNCHERS(hrt_fast)

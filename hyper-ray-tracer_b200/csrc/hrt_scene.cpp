@@ -1,0 +1,755 @@
+// hrt_scene.cpp — C-ABI scene builder and the flattener ("host-side Rust flattener" of the north star,
+// delivered in C++ behind the C ABI because there is no Rust toolchain in this image).
+//
+// Builder calls mirror the reference constructors 1:1 (citations in include/hrt.h).  hrt_scene_commit()
+// reproduces, in f32 and in the reference's operation order, everything the reference computes at
+// construction time — every `bounding_box` (sphere.rs:77-83, moving_sphere.rs:98-110, rect.rs:88-103,
+// cuboid.rs:104-106, list.rs:33-44, translation.rs:39-48, rotation.rs:43-89, constant_medium.rs:78-80),
+// `Aabb::surrounding_box` (aabb.rs:49-63) and `BvhNode::new` (bvh_node.rs:27-100) — and then lowers the
+// tree to the stackless op stream described in hrt_types.h.
+//
+// Build with -ffp-contract=off (no FMA contraction): box coordinates must equal the reference's bit for bit.
+#include "hrt_scene.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+
+#include "../../include/hrt.h"
+
+namespace hrt {
+
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+int32_t fail(int32_t code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+
+static const float PI_F = 3.14159265358979323846f;
+static const float FMAX = std::numeric_limits<float>::max();
+
+static Box3 surrounding_box(const Box3& a, const Box3& b) {  // aabb.rs:49-63
+    Box3 o;
+    for (int i = 0; i < 3; ++i) {
+        o.mn[i] = std::fmin(a.mn[i], b.mn[i]);
+        o.mx[i] = std::fmax(a.mx[i], b.mx[i]);
+    }
+    return o;
+}
+static bool contains(const Box3& outer, const Box3& inner) {
+    for (int i = 0; i < 3; ++i)
+        if (!(outer.mn[i] <= inner.mn[i] && outer.mx[i] >= inner.mx[i])) return false;
+    return true;
+}
+
+static void rotation_axes(int axis, int& r, int& a, int& b) {  // rotation.rs:20-26
+    switch (axis) {
+        case 0: r = 0; a = 1; b = 2; break;
+        case 1: r = 1; a = 2; b = 0; break;
+        default: r = 2; a = 0; b = 1; break;
+    }
+}
+
+// rotation.rs:43-89 applied to an arbitrary input box
+static Box3 rotate_box(const Box3& bb, int axis, float sin_theta, float cos_theta) {
+    int r_axis, a_axis, b_axis;
+    rotation_axes(axis, r_axis, a_axis, b_axis);
+    Box3 o;
+    for (int i = 0; i < 3; ++i) { o.mn[i] = FMAX; o.mx[i] = -FMAX; }
+    for (int i = 0; i < 2; ++i)
+        for (int j = 0; j < 2; ++j)
+            for (int k = 0; k < 2; ++k) {
+                float r = (float)k * bb.mx[r_axis] + (float)(1 - k) * bb.mn[r_axis];
+                float a = (float)i * bb.mx[a_axis] + (float)(1 - i) * bb.mn[a_axis];
+                float b = (float)j * bb.mx[b_axis] + (float)(1 - j) * bb.mn[b_axis];
+                float new_a = cos_theta * a - sin_theta * b;
+                float new_b = sin_theta * a + cos_theta * b;
+                if (new_a < o.mn[a_axis]) o.mn[a_axis] = new_a;
+                if (new_b < o.mn[b_axis]) o.mn[b_axis] = new_b;
+                if (r < o.mn[r_axis]) o.mn[r_axis] = r;
+                if (new_a > o.mx[a_axis]) o.mx[a_axis] = new_a;
+                if (new_b > o.mx[b_axis]) o.mx[b_axis] = new_b;
+                if (r > o.mx[r_axis]) o.mx[r_axis] = r;
+            }
+    return o;
+}
+
+static void msphere_center(const Obj& o, float time, float out[3]) {  // moving_sphere.rs:53-57
+    float f = (time - o.t0) / (o.t1 - o.t0);
+    for (int i = 0; i < 3; ++i) out[i] = o.c0[i] + f * (o.c1[i] - o.c0[i]);
+}
+
+// `bounding_box(time_start, time_end)` of the reference, bit for bit.  `truth` = true returns instead the
+// box that actually contains the geometry hit() accepts (differs for ZX rects, Q2).
+static bool ref_box(const hrt_scene& s, int id, float ts, float te, bool truth, Box3& out) {
+    const Obj& o = s.objects[id];
+    switch (o.kind) {
+        case OBJ_SPHERE:
+            for (int i = 0; i < 3; ++i) { out.mn[i] = o.c0[i] - o.r; out.mx[i] = o.c0[i] + o.r; }
+            return true;
+        case OBJ_MSPHERE: {
+            float ca[3], cb[3];
+            msphere_center(o, ts, ca);
+            msphere_center(o, te, cb);
+            Box3 b0, b1;
+            for (int i = 0; i < 3; ++i) {
+                b0.mn[i] = ca[i] - o.r; b0.mx[i] = ca[i] + o.r;
+                b1.mn[i] = cb[i] - o.r; b1.mx[i] = cb[i] + o.r;
+            }
+            out = surrounding_box(b0, b1);
+            return true;
+        }
+        case OBJ_RECT: {
+            const float lo = o.k - 0.0001f, hi = o.k + 0.0001f;
+            switch (o.plane_or_axis) {
+                case HRT_PLANE_XY: out = Box3{{o.a0, o.b0, lo}, {o.a1, o.b1, hi}}; break;
+                case HRT_PLANE_YZ: out = Box3{{lo, o.a0, o.b0}, {hi, o.a1, o.b1}}; break;
+                default:
+                    if (truth) out = Box3{{o.b0, lo, o.a0}, {o.b1, hi, o.a1}};  // hit(): a is z, b is x (rect.rs:57)
+                    else       out = Box3{{o.a0, lo, o.b0}, {o.a1, hi, o.b1}};  // rect.rs:98-101 (axis-swapped)
+                    break;
+            }
+            return true;
+        }
+        case OBJ_CUBOID:
+            for (int i = 0; i < 3; ++i) { out.mn[i] = o.c0[i]; out.mx[i] = o.c1[i]; }
+            return true;
+        case OBJ_TRANSLATE: {
+            Box3 b;
+            if (!ref_box(s, o.child, ts, te, truth, b)) return false;
+            for (int i = 0; i < 3; ++i) { out.mn[i] = b.mn[i] + o.c0[i]; out.mx[i] = b.mx[i] + o.c0[i]; }
+            return true;
+        }
+        case OBJ_ROTATE: {
+            if (!truth) {
+                if (!o.has_rot_box) return false;
+                out = o.rot_box;
+                return true;
+            }
+            Box3 b;
+            if (!ref_box(s, o.child, 0.0f, 1.0f, true, b)) return false;
+            out = rotate_box(b, o.plane_or_axis, o.sin_theta, o.cos_theta);
+            return true;
+        }
+        case OBJ_MEDIUM:
+            return ref_box(s, o.child, ts, te, truth, out);
+        case OBJ_LIST: {
+            if (o.children.empty()) return false;
+            Box3 acc;
+            if (!ref_box(s, o.children[0], ts, te, truth, acc)) return false;
+            for (size_t i = 1; i < o.children.size(); ++i) {
+                Box3 b;
+                if (!ref_box(s, o.children[i], ts, te, truth, b)) return false;
+                acc = surrounding_box(acc, b);
+            }
+            out = acc;
+            return true;
+        }
+        case OBJ_BVH: {
+            if (!truth) {
+                out = o.bvh.nodes[o.bvh.root].box;
+                return true;
+            }
+            Box3 acc;
+            bool first = true;
+            for (const BvhTreeNode& n : o.bvh.nodes) {
+                if (n.leaf_obj < 0) continue;
+                Box3 b;
+                if (!ref_box(s, n.leaf_obj, o.t0, o.t1, true, b)) return false;
+                acc = first ? b : surrounding_box(acc, b);
+                first = false;
+            }
+            out = acc;
+            return !first;
+        }
+    }
+    return false;
+}
+
+// BvhNode::new (bvh_node.rs:27-63).  sort_unstable_by is an insertion sort for n <= 20 in rustc's
+// implementation (stable order); for larger n the tie order is toolchain-defined.  A stable sort is used
+// throughout; ties cannot change hit results on sound boxes.
+static int32_t build_bvh(const hrt_scene& s, BvhTree& tree, std::vector<int32_t> objs, float ts, float te) {
+    std::pair<int, float> ranges[3];
+    for (int axis = 0; axis < 3; ++axis) {  // axis_range, bvh_node.rs:83-100
+        float mn = FMAX, mx = -FMAX;
+        for (int32_t id : objs) {
+            Box3 b;
+            if (!ref_box(s, id, ts, te, false, b)) continue;
+            mn = std::fmin(mn, b.mn[axis]);
+            mx = std::fmax(mx, b.mx[axis]);
+        }
+        ranges[axis] = {axis, mx - mn};
+    }
+    std::stable_sort(ranges, ranges + 3,
+                     [](const std::pair<int, float>& a, const std::pair<int, float>& b) { return a.second > b.second; });
+    const int axis = ranges[0].first;
+    std::vector<std::pair<float, int32_t>> keyed;
+    keyed.reserve(objs.size());
+    for (int32_t id : objs) {  // box_compare key, bvh_node.rs:70-76
+        Box3 b;
+        ref_box(s, id, ts, te, false, b);
+        keyed.push_back({b.mn[axis] + b.mx[axis], id});
+    }
+    std::stable_sort(keyed.begin(), keyed.end(),
+                     [](const std::pair<float, int32_t>& a, const std::pair<float, int32_t>& b) { return a.first < b.first; });
+    const size_t len = keyed.size();
+    BvhTreeNode node;
+    if (len == 1) {
+        node.leaf_obj = keyed[0].second;
+        ref_box(s, node.leaf_obj, ts, te, false, node.box);
+        tree.nodes.push_back(node);
+        return (int32_t)tree.nodes.size() - 1;
+    }
+    std::vector<int32_t> l, r;
+    for (size_t i = 0; i < len / 2; ++i) l.push_back(keyed[i].second);
+    for (size_t i = len / 2; i < len; ++i) r.push_back(keyed[i].second);
+    int32_t ri = build_bvh(s, tree, std::move(r), ts, te);
+    int32_t li = build_bvh(s, tree, std::move(l), ts, te);
+    node.left = li;
+    node.right = ri;
+    node.box = surrounding_box(tree.nodes[li].box, tree.nodes[ri].box);
+    tree.nodes.push_back(node);
+    return (int32_t)tree.nodes.size() - 1;
+}
+
+static uint32_t count_of(const hrt_scene& s, int id) {
+    const Obj& o = s.objects[id];
+    switch (o.kind) {
+        case OBJ_SPHERE: case OBJ_MSPHERE: case OBJ_RECT: return 1;
+        case OBJ_CUBOID: return 6;                     // cuboid.rs:108-110 -> List::count over 6 rects
+        case OBJ_TRANSLATE: return count_of(s, o.child);
+        case OBJ_ROTATE: return 1;                     // rotation.rs:140-142
+        case OBJ_MEDIUM: return count_of(s, o.child);
+        case OBJ_LIST: { uint32_t n = 0; for (int c : o.children) n += count_of(s, c); return n; }
+        case OBJ_BVH: { uint32_t n = 0; for (auto& nd : o.bvh.nodes) if (nd.leaf_obj >= 0) n += count_of(s, nd.leaf_obj); return n; }
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Flattener
+// ------------------------------------------------------------------------------------------------
+struct Flattener {
+    hrt_scene& s;
+    std::string error;
+    bool in_medium = false;
+    explicit Flattener(hrt_scene& sc) : s(sc) {}
+
+    int32_t pc() const { return (int32_t)s.ops.size(); }
+    Op& push(uint32_t opcode) {
+        Op op;
+        std::memset(&op, 0, sizeof(op));
+        op.u[7] = opcode;
+        s.ops.push_back(op);
+        return s.ops.back();
+    }
+    int32_t new_ctx(int32_t parent, int32_t op_pc) {
+        Ctx c = s.ctxs[parent];
+        if (c.depth >= kMaxCtxDepth) { error = "Translation/Rotation nesting deeper than 6"; return -1; }
+        c.op_pc[c.depth] = op_pc;
+        c.depth += 1;
+        c.parent = parent;
+        s.ctxs.push_back(c);
+        s.max_ctx_depth = std::max(s.max_ctx_depth, c.depth);
+        return (int32_t)s.ctxs.size() - 1;
+    }
+
+    bool emit(int32_t id, int32_t ctx) {
+        const Obj& o = s.objects[id];
+        switch (o.kind) {
+            case OBJ_SPHERE: {
+                Op& op = push(OP_SPHERE);
+                op.f[0] = o.c0[0]; op.f[1] = o.c0[1]; op.f[2] = o.c0[2]; op.f[3] = o.r;
+                op.i[4] = o.mat; op.i[5] = id;
+                s.n_prim_ops++;
+                return true;
+            }
+            case OBJ_MSPHERE: {
+                Op& op = push(OP_MSPHERE);
+                op.f[0] = o.c0[0]; op.f[1] = o.c0[1]; op.f[2] = o.c0[2]; op.f[3] = o.r;
+                op.i[4] = o.mat; op.i[5] = id;
+                Op& aux = push(OP_MSPHERE_AUX);
+                aux.f[0] = o.c1[0]; aux.f[1] = o.c1[1]; aux.f[2] = o.c1[2]; aux.f[3] = o.t0; aux.f[4] = o.t1;
+                s.n_prim_ops++;
+                return true;
+            }
+            case OBJ_RECT: {
+                uint32_t opc = o.plane_or_axis == HRT_PLANE_XY ? OP_RECT_XY : (o.plane_or_axis == HRT_PLANE_YZ ? OP_RECT_YZ : OP_RECT_ZX);
+                Op& op = push(opc);
+                op.f[0] = o.a0; op.f[1] = o.a1; op.f[2] = o.b0; op.f[3] = o.b1; op.f[4] = o.k;
+                op.i[5] = o.mat; op.i[6] = id;
+                s.n_prim_ops++;
+                return true;
+            }
+            case OBJ_CUBOID: {
+                if (id >= (1 << 24)) { error = "more than 2^24 objects"; return false; }
+                Op& op = push(OP_CUBOID);
+                op.f[0] = o.c0[0]; op.f[1] = o.c0[1]; op.f[2] = o.c0[2]; op.i[3] = o.mat;
+                op.f[4] = o.c1[0]; op.f[5] = o.c1[1]; op.f[6] = o.c1[2];
+                op.u[7] = OP_CUBOID | ((uint32_t)id << 8);
+                s.n_prim_ops++;
+                return true;
+            }
+            case OBJ_TRANSLATE: {
+                int32_t at = pc();
+                int32_t nctx = new_ctx(ctx, at);
+                if (nctx < 0) return false;
+                Op& op = push(OP_TRANSLATE);
+                op.f[0] = o.c0[0]; op.f[1] = o.c0[1]; op.f[2] = o.c0[2]; op.i[3] = nctx;
+                if (!emit(o.child, nctx)) return false;
+                Op& pop = push(OP_POP);
+                pop.i[3] = ctx;
+                return true;
+            }
+            case OBJ_ROTATE: {
+                int32_t at = pc();
+                int32_t nctx = new_ctx(ctx, at);
+                if (nctx < 0) return false;
+                Op& op = push(OP_ROTATE);
+                op.f[0] = o.sin_theta; op.f[1] = o.cos_theta; op.i[2] = o.plane_or_axis; op.i[3] = nctx;
+                if (!emit(o.child, nctx)) return false;
+                Op& pop = push(OP_POP);
+                pop.i[3] = ctx;
+                return true;
+            }
+            case OBJ_MEDIUM: {
+                if (in_medium) { error = "ConstantMedium nested inside a ConstantMedium boundary is not supported"; return false; }
+                int32_t at = pc();
+                {
+                    Op& op = push(OP_MEDIUM);
+                    op.f[0] = o.neg_inv_density; op.i[1] = o.mat; op.i[2] = s.n_media; op.i[3] = id;
+                }
+                s.n_media++;
+                in_medium = true;
+                bool ok = emit(o.child, ctx);
+                in_medium = false;
+                if (!ok) return false;
+                if (pc() >= (1 << 24)) { error = "op stream longer than 2^24 records"; return false; }
+                s.ops[at].u[7] = OP_MEDIUM | ((uint32_t)pc() << 8);
+                return true;
+            }
+            case OBJ_LIST: {
+                // List::hit (list.rs:20-31): sequential closest-hit with narrowing, no box tests — exactly
+                // what falling through consecutive records does.
+                for (int32_t c : o.children)
+                    if (!emit(c, ctx)) return false;
+                return true;
+            }
+            case OBJ_BVH:
+                return emit_bvh(o, o.bvh.root, ctx);
+        }
+        return false;
+    }
+
+    bool emit_bvh(const Obj& bvh, int32_t node_index, int32_t ctx) {
+        const BvhTreeNode& n = bvh.bvh.nodes[node_index];
+        // Soundness: does the reference box contain everything hit() can accept beneath this node?
+        Box3 truth;
+        bool sound = true_extent(bvh, node_index, truth) && contains(n.box, truth);
+        int32_t at = pc();
+        {
+            Op& op = push(sound ? OP_BOX : OP_BOX_LOOSE);
+            op.f[0] = n.box.mn[0]; op.f[1] = n.box.mn[1]; op.f[2] = n.box.mn[2];
+            op.f[4] = n.box.mx[0]; op.f[5] = n.box.mx[1]; op.f[6] = n.box.mx[2];
+        }
+        s.n_box_ops++;
+        if (!sound) s.n_loose_boxes++;
+        if (n.leaf_obj >= 0) {
+            if (!emit(n.leaf_obj, ctx)) return false;
+        } else {
+            if (!emit_bvh(bvh, n.left, ctx)) return false;   // left first (bvh_node.rs:111)
+            if (!emit_bvh(bvh, n.right, ctx)) return false;
+        }
+        if (pc() >= (1 << 24)) { error = "op stream longer than 2^24 records"; return false; }
+        s.ops[at].u[7] = (s.ops[at].u[7] & 0xffu) | ((uint32_t)pc() << 8);
+        return true;
+    }
+
+    bool true_extent(const Obj& bvh, int32_t node_index, Box3& out) {
+        const BvhTreeNode& n = bvh.bvh.nodes[node_index];
+        if (n.leaf_obj >= 0) return ref_box(s, n.leaf_obj, bvh.t0, bvh.t1, true, out);
+        Box3 a, b;
+        if (!true_extent(bvh, n.left, a) || !true_extent(bvh, n.right, b)) return false;
+        out = surrounding_box(a, b);
+        return true;
+    }
+};
+
+}  // namespace hrt
+
+using namespace hrt;
+
+hrt_scene::~hrt_scene() {
+    for (DeviceState* d : devices)
+        if (d) release_device_state(d);
+}
+
+static bool tex_ok(const hrt_scene* s, int32_t i) { return i >= 0 && (size_t)i < s->textures.size(); }
+static bool mat_ok(const hrt_scene* s, int32_t i) { return i >= 0 && (size_t)i < s->materials.size(); }
+static bool obj_ok(const hrt_scene* s, int32_t i) { return i >= 0 && (size_t)i < s->objects.size(); }
+static bool tex_needs_uv(const hrt_scene* s, int32_t t) {
+    const Texture& x = s->textures[t];
+    if (x.kind == TEX_IMAGE) return true;
+    if (x.kind == TEX_CHECKER) return tex_needs_uv(s, x.i0) || tex_needs_uv(s, x.i1);
+    return false;
+}
+#define HRT_CHECK_SCENE(s)                                                        \
+    if (!(s)) return fail(HRT_ERR_INVALID, "null scene");                          \
+    if ((s)->committed) return fail(HRT_ERR_STATE, "scene is already committed (immutable)")
+
+static int32_t add_obj(hrt_scene* s, Obj&& o) {
+    s->objects.push_back(std::move(o));
+    return (int32_t)s->objects.size() - 1;
+}
+static int32_t add_mat(hrt_scene* s, const Material& m) {
+    s->materials.push_back(m);
+    return (int32_t)s->materials.size() - 1;
+}
+
+extern "C" {
+
+const char* hrt_last_error(void) { return g_last_error.c_str(); }
+int32_t hrt_abi_version(void) { return HRT_ABI_VERSION; }
+
+int32_t hrt_scene_create(hrt_scene** out) {
+    if (!out) return fail(HRT_ERR_INVALID, "null out pointer");
+    *out = new hrt_scene();
+    Ctx root;
+    std::memset(&root, 0, sizeof(root));
+    root.parent = -1;
+    (*out)->ctxs.push_back(root);
+    return HRT_OK;
+}
+void hrt_scene_destroy(hrt_scene* scene) { delete scene; }
+
+int32_t hrt_tex_solid(hrt_scene* s, const float rgb[3]) {
+    HRT_CHECK_SCENE(s);
+    if (!rgb) return fail(HRT_ERR_INVALID, "null rgb");
+    Texture t;
+    std::memset(&t, 0, sizeof(t));
+    t.kind = TEX_SOLID;
+    t.v[0] = rgb[0]; t.v[1] = rgb[1]; t.v[2] = rgb[2];
+    s->textures.push_back(t);
+    return (int32_t)s->textures.size() - 1;
+}
+int32_t hrt_tex_checker(hrt_scene* s, int32_t odd, int32_t even) {
+    HRT_CHECK_SCENE(s);
+    if (!tex_ok(s, odd) || !tex_ok(s, even)) return fail(HRT_ERR_INVALID, "checker: unknown texture id");
+    Texture t;
+    std::memset(&t, 0, sizeof(t));
+    t.kind = TEX_CHECKER;
+    t.i0 = odd; t.i1 = even;
+    s->textures.push_back(t);
+    return (int32_t)s->textures.size() - 1;
+}
+int32_t hrt_tex_noise(hrt_scene* s, float scale, const float* ranvec, const uint32_t* px, const uint32_t* py,
+                      const uint32_t* pz) {
+    HRT_CHECK_SCENE(s);
+    if (!ranvec || !px || !py || !pz) return fail(HRT_ERR_INVALID, "noise: null table");
+    NoiseTable nt;
+    std::memset(&nt, 0, sizeof(nt));
+    for (int i = 0; i < 256; ++i) {
+        nt.ranvec[i][0] = ranvec[3 * i]; nt.ranvec[i][1] = ranvec[3 * i + 1]; nt.ranvec[i][2] = ranvec[3 * i + 2];
+        if (px[i] > 255 || py[i] > 255 || pz[i] > 255) return fail(HRT_ERR_INVALID, "noise: permutation entry > 255");
+        nt.perm[0][i] = (uint8_t)px[i]; nt.perm[1][i] = (uint8_t)py[i]; nt.perm[2][i] = (uint8_t)pz[i];
+    }
+    s->noise_tables.push_back(nt);
+    Texture t;
+    std::memset(&t, 0, sizeof(t));
+    t.kind = TEX_NOISE;
+    t.v[0] = scale;
+    t.i0 = (int32_t)s->noise_tables.size() - 1;
+    s->textures.push_back(t);
+    return (int32_t)s->textures.size() - 1;
+}
+int32_t hrt_tex_image(hrt_scene* s, const uint8_t* data, uint32_t width, uint32_t height, uint32_t components) {
+    HRT_CHECK_SCENE(s);
+    Texture t;
+    std::memset(&t, 0, sizeof(t));
+    t.kind = TEX_IMAGE;
+    t.i0 = -1;
+    if (data && width && height) {
+        if (components != 3 && components != 4)
+            return fail(HRT_ERR_UNSUPPORTED, "image: components must be 3 or 4 (the reference reads 3 consecutive bytes per texel)");
+        if ((int)s->images.size() >= kMaxImages) return fail(HRT_ERR_UNSUPPORTED, "more than 8 image textures");
+        if (width > 32768 || height > 32768) return fail(HRT_ERR_UNSUPPORTED, "image larger than 32768 in a dimension");
+        ImageData img;
+        img.width = width; img.height = height;
+        img.rgba.resize((size_t)width * height * 4);
+        for (size_t p = 0; p < (size_t)width * height; ++p) {
+            img.rgba[4 * p + 0] = data[components * p + 0];
+            img.rgba[4 * p + 1] = data[components * p + 1];
+            img.rgba[4 * p + 2] = data[components * p + 2];
+            img.rgba[4 * p + 3] = 255;
+        }
+        s->images.push_back(std::move(img));
+        t.i0 = (int32_t)s->images.size() - 1;
+        t.i1 = (int32_t)width; t.i2 = (int32_t)height;
+    }
+    s->textures.push_back(t);
+    return (int32_t)s->textures.size() - 1;
+}
+
+int32_t hrt_mat_lambertian(hrt_scene* s, int32_t tex) {
+    HRT_CHECK_SCENE(s);
+    if (!tex_ok(s, tex)) return fail(HRT_ERR_INVALID, "lambertian: unknown texture id");
+    Material m;
+    std::memset(&m, 0, sizeof(m));
+    m.kind = MAT_LAMBERTIAN; m.tex = tex;
+    m.flags = tex_needs_uv(s, tex) ? MATF_NEEDS_UV : 0;
+    return add_mat(s, m);
+}
+int32_t hrt_mat_metal(hrt_scene* s, const float albedo[3], float fuzz) {
+    HRT_CHECK_SCENE(s);
+    if (!albedo) return fail(HRT_ERR_INVALID, "null albedo");
+    Material m;
+    std::memset(&m, 0, sizeof(m));
+    m.kind = MAT_METAL; m.tex = -1;
+    m.albedo[0] = albedo[0]; m.albedo[1] = albedo[1]; m.albedo[2] = albedo[2];
+    m.param = fuzz;
+    return add_mat(s, m);
+}
+int32_t hrt_mat_dielectric(hrt_scene* s, float ior) {
+    HRT_CHECK_SCENE(s);
+    Material m;
+    std::memset(&m, 0, sizeof(m));
+    m.kind = MAT_DIELECTRIC; m.tex = -1; m.param = ior;
+    return add_mat(s, m);
+}
+int32_t hrt_mat_diffuse_light(hrt_scene* s, int32_t tex) {
+    HRT_CHECK_SCENE(s);
+    if (!tex_ok(s, tex)) return fail(HRT_ERR_INVALID, "diffuse_light: unknown texture id");
+    Material m;
+    std::memset(&m, 0, sizeof(m));
+    m.kind = MAT_DIFFUSE_LIGHT; m.tex = tex;
+    m.flags = tex_needs_uv(s, tex) ? MATF_NEEDS_UV : 0;
+    return add_mat(s, m);
+}
+
+int32_t hrt_sphere(hrt_scene* s, const float c[3], float radius, int32_t mat) {
+    HRT_CHECK_SCENE(s);
+    if (!c || !mat_ok(s, mat)) return fail(HRT_ERR_INVALID, "sphere: bad argument");
+    Obj o;
+    o.kind = OBJ_SPHERE;
+    std::memcpy(o.c0, c, 12);
+    o.r = radius; o.mat = mat;
+    return add_obj(s, std::move(o));
+}
+int32_t hrt_moving_sphere(hrt_scene* s, const float c0[3], const float c1[3], float t0, float t1, float radius,
+                          int32_t mat) {
+    HRT_CHECK_SCENE(s);
+    if (!c0 || !c1 || !mat_ok(s, mat)) return fail(HRT_ERR_INVALID, "moving_sphere: bad argument");
+    Obj o;
+    o.kind = OBJ_MSPHERE;
+    std::memcpy(o.c0, c0, 12);
+    std::memcpy(o.c1, c1, 12);
+    o.t0 = t0; o.t1 = t1; o.r = radius; o.mat = mat;
+    return add_obj(s, std::move(o));
+}
+int32_t hrt_rect(hrt_scene* s, int32_t plane, float a0, float a1, float b0, float b1, float k, int32_t mat) {
+    HRT_CHECK_SCENE(s);
+    if (plane < 0 || plane > 2 || !mat_ok(s, mat)) return fail(HRT_ERR_INVALID, "rect: bad argument");
+    Obj o;
+    o.kind = OBJ_RECT;
+    o.plane_or_axis = plane; o.a0 = a0; o.a1 = a1; o.b0 = b0; o.b1 = b1; o.k = k; o.mat = mat;
+    return add_obj(s, std::move(o));
+}
+int32_t hrt_cuboid(hrt_scene* s, const float mn[3], const float mx[3], int32_t mat) {
+    HRT_CHECK_SCENE(s);
+    if (!mn || !mx || !mat_ok(s, mat)) return fail(HRT_ERR_INVALID, "cuboid: bad argument");
+    Obj o;
+    o.kind = OBJ_CUBOID;
+    std::memcpy(o.c0, mn, 12);
+    std::memcpy(o.c1, mx, 12);
+    o.mat = mat;
+    return add_obj(s, std::move(o));
+}
+int32_t hrt_translate(hrt_scene* s, int32_t child, const float d[3]) {
+    HRT_CHECK_SCENE(s);
+    if (!d || !obj_ok(s, child)) return fail(HRT_ERR_INVALID, "translate: bad argument");
+    Obj o;
+    o.kind = OBJ_TRANSLATE;
+    o.child = child;
+    std::memcpy(o.c0, d, 12);
+    return add_obj(s, std::move(o));
+}
+int32_t hrt_rotate(hrt_scene* s, int32_t axis, int32_t child, float degrees) {
+    HRT_CHECK_SCENE(s);
+    if (axis < 0 || axis > 2 || !obj_ok(s, child)) return fail(HRT_ERR_INVALID, "rotate: bad argument");
+    Obj o;
+    o.kind = OBJ_ROTATE;
+    o.child = child;
+    o.plane_or_axis = axis;
+    float radians = (PI_F / 180.0f) * degrees;  // rotation.rs:40-42
+    o.sin_theta = sinf(radians);
+    o.cos_theta = cosf(radians);
+    Box3 b;
+    o.has_rot_box = ref_box(*s, child, 0.0f, 1.0f, false, b);
+    if (o.has_rot_box) o.rot_box = rotate_box(b, axis, o.sin_theta, o.cos_theta);
+    return add_obj(s, std::move(o));
+}
+int32_t hrt_constant_medium(hrt_scene* s, int32_t boundary, float density, int32_t tex) {
+    HRT_CHECK_SCENE(s);
+    if (!obj_ok(s, boundary) || !tex_ok(s, tex)) return fail(HRT_ERR_INVALID, "constant_medium: bad argument");
+    Material m;
+    std::memset(&m, 0, sizeof(m));
+    m.kind = MAT_ISOTROPIC; m.tex = tex;
+    m.flags = tex_needs_uv(s, tex) ? MATF_NEEDS_UV : 0;
+    Obj o;
+    o.kind = OBJ_MEDIUM;
+    o.child = boundary;
+    o.neg_inv_density = -1.0f / density;  // constant_medium.rs:27
+    o.mat = add_mat(s, m);
+    return add_obj(s, std::move(o));
+}
+int32_t hrt_list(hrt_scene* s, const int32_t* children, int32_t n) {
+    HRT_CHECK_SCENE(s);
+    if (n < 0 || (n > 0 && !children)) return fail(HRT_ERR_INVALID, "list: bad argument");
+    Obj o;
+    o.kind = OBJ_LIST;
+    for (int i = 0; i < n; ++i) {
+        if (!obj_ok(s, children[i])) return fail(HRT_ERR_INVALID, "list: unknown object id");
+        o.children.push_back(children[i]);
+    }
+    return add_obj(s, std::move(o));
+}
+int32_t hrt_bvh(hrt_scene* s, const int32_t* children, int32_t n, float ts, float te) {
+    HRT_CHECK_SCENE(s);
+    if (n <= 0 || !children) return fail(HRT_ERR_INVALID, "bvh: no elements in scene");  // bvh_node.rs:38 panics
+    Obj o;
+    o.kind = OBJ_BVH;
+    o.t0 = ts; o.t1 = te;
+    for (int i = 0; i < n; ++i) {
+        if (!obj_ok(s, children[i])) return fail(HRT_ERR_INVALID, "bvh: unknown object id");
+        Box3 b;
+        if (!ref_box(*s, children[i], ts, te, false, b))
+            return fail(HRT_ERR_INVALID, "bvh: object without a bounding box");  // bvh_node.rs:41-43,77-79 panic
+        o.children.push_back(children[i]);
+    }
+    o.bvh.root = build_bvh(*s, o.bvh, o.children, ts, te);
+    return add_obj(s, std::move(o));
+}
+
+int32_t hrt_scene_commit(hrt_scene* s, int32_t root) {
+    HRT_CHECK_SCENE(s);
+    if (!obj_ok(s, root)) return fail(HRT_ERR_INVALID, "commit: unknown root id");
+    s->ops.clear();
+    s->ctxs.resize(1);
+    s->n_box_ops = s->n_loose_boxes = s->n_prim_ops = s->n_media = s->max_ctx_depth = 0;
+    s->any_bvh = false;
+    s->time_min = -FMAX;
+    s->time_max = FMAX;
+    for (const Obj& o : s->objects)
+        if (o.kind == OBJ_BVH) {  // harmless over-approximation: every BVH ever built bounds the valid shutter
+            s->any_bvh = true;
+            s->time_min = std::fmax(s->time_min, std::fmin(o.t0, o.t1));
+            s->time_max = std::fmin(s->time_max, std::fmax(o.t0, o.t1));
+        }
+    Flattener f(*s);
+    if (!f.emit(root, 0)) {
+        s->ops.clear();
+        return fail(HRT_ERR_UNSUPPORTED, "commit: " + f.error);
+    }
+    f.push(OP_END);
+    s->root = root;
+    s->committed = true;
+    return HRT_OK;
+}
+
+int32_t hrt_scene_count(const hrt_scene* s) {
+    if (!s || !s->committed) return fail(HRT_ERR_STATE, "scene not committed");
+    return (int32_t)count_of(*s, s->root);
+}
+
+int32_t hrt_scene_get_info(const hrt_scene* s, hrt_scene_info* out) {
+    if (!s || !out) return fail(HRT_ERR_INVALID, "null argument");
+    if (!s->committed) return fail(HRT_ERR_STATE, "scene not committed");
+    out->n_ops = (int32_t)s->ops.size();
+    out->n_box_ops = s->n_box_ops;
+    out->n_loose_boxes = s->n_loose_boxes;
+    out->n_prim_ops = s->n_prim_ops;
+    out->n_materials = (int32_t)s->materials.size();
+    out->n_textures = (int32_t)s->textures.size();
+    out->n_noise_tables = (int32_t)s->noise_tables.size();
+    out->n_images = (int32_t)s->images.size();
+    out->n_media = s->n_media;
+    out->n_contexts = (int32_t)s->ctxs.size();
+    out->max_context_depth = s->max_ctx_depth;
+    out->time_min = s->time_min;
+    out->time_max = s->time_max;
+    return HRT_OK;
+}
+int32_t hrt_scene_get_ops(const hrt_scene* s, void* out, int32_t cap_ops) {
+    if (!s) return fail(HRT_ERR_INVALID, "null scene");
+    if (!s->committed) return fail(HRT_ERR_STATE, "scene not committed");
+    int32_t n = (int32_t)s->ops.size();
+    if (out && cap_ops > 0) std::memcpy(out, s->ops.data(), sizeof(Op) * (size_t)std::min(n, cap_ops));
+    return n;
+}
+
+static void leaf_order(const BvhTree& t, int32_t node, std::vector<int32_t>& out) {
+    const BvhTreeNode& n = t.nodes[node];
+    if (n.leaf_obj >= 0) out.push_back(n.leaf_obj);
+    else { leaf_order(t, n.left, out); leaf_order(t, n.right, out); }
+}
+int32_t hrt_bvh_leaf_order(const hrt_scene* s, int32_t bvh, int32_t* out, int32_t cap) {
+    if (!s || !obj_ok(s, bvh) || s->objects[bvh].kind != OBJ_BVH) return fail(HRT_ERR_INVALID, "not a bvh object");
+    std::vector<int32_t> v;
+    leaf_order(s->objects[bvh].bvh, s->objects[bvh].bvh.root, v);
+    for (size_t i = 0; i < v.size() && (int32_t)i < cap; ++i) out[i] = v[i];
+    return (int32_t)v.size();
+}
+int32_t hrt_bounding_box(const hrt_scene* s, int32_t obj, float out6[6]) {
+    if (!s || !obj_ok(s, obj) || !out6) return fail(HRT_ERR_INVALID, "bounding_box: bad argument");
+    Box3 b;
+    if (!ref_box(*s, obj, 0.0f, 1.0f, false, b)) return fail(HRT_ERR_INVALID, "object has no bounding box");
+    for (int i = 0; i < 3; ++i) { out6[i] = b.mn[i]; out6[3 + i] = b.mx[i]; }
+    return HRT_OK;
+}
+
+// Camera::new + Camera::resize (src/camera.rs:34-83), f32, reference operation order.
+int32_t hrt_camera_init(const hrt_camera_desc* d, hrt_camera_state* out) {
+    if (!d || !out) return fail(HRT_ERR_INVALID, "null argument");
+    if (d->width <= 0 || d->height <= 0) return fail(HRT_ERR_INVALID, "camera: non-positive size");
+    auto dot3 = [](const float* a, const float* b) { return (a[0] * b[0] + a[1] * b[1]) + a[2] * b[2]; };
+    auto normalize3 = [&](const float* a, float* o) {
+        float inv = 1.0f / std::sqrt(dot3(a, a));
+        for (int i = 0; i < 3; ++i) o[i] = a[i] * inv;
+    };
+    auto cross3 = [](const float* a, const float* b, float* o) {
+        o[0] = a[1] * b[2] - a[2] * b[1];
+        o[1] = a[2] * b[0] - a[0] * b[2];
+        o[2] = a[0] * b[1] - a[1] * b[0];
+    };
+    float aspect_ratio = (float)d->width / (float)d->height;
+    float theta = d->vfov * (PI_F / 180.0f);
+    float h = tanf(theta / 2.0f);
+    float viewport_height = 2.0f * h;
+    float viewport_width = aspect_ratio * viewport_height;
+    float diff[3] = {d->look_from[0] - d->look_at[0], d->look_from[1] - d->look_at[1], d->look_from[2] - d->look_at[2]};
+    float w[3], u[3], v[3], c[3];
+    normalize3(diff, w);
+    const float vup[3] = {0.0f, 1.0f, 0.0f};
+    cross3(vup, w, c);
+    normalize3(c, u);
+    cross3(w, u, v);
+    const float fw = d->focus_dist * viewport_width, fh = d->focus_dist * viewport_height;
+    for (int i = 0; i < 3; ++i) {
+        out->origin[i] = d->look_from[i];
+        out->horizontal[i] = fw * u[i];
+        out->vertical[i] = fh * v[i];
+        out->u[i] = u[i]; out->v[i] = v[i]; out->w[i] = w[i];
+    }
+    for (int i = 0; i < 3; ++i)
+        out->lower_left_corner[i] =
+            ((out->origin[i] - out->horizontal[i] / 2.0f) - out->vertical[i] / 2.0f) - d->focus_dist * w[i];
+    out->lens_radius = d->aperture / 2.0f;
+    out->time0 = d->time0;
+    out->time1 = d->time1;
+    return HRT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,94 @@
+// hrt_types.h — flat scene tables shared by the host flattener (hrt_scene.cpp) and the CUDA kernels.
+//
+// The reference's world is a tree of `Box<dyn Hittable>` (src/hittable/mod.rs:19-25) walked by virtual
+// recursion.  Here the whole tree — every BvhNode of every (nested) BVH, every primitive, every
+// Translation/Rotation and every ConstantMedium — is flattened into ONE linear "op stream" of 32-byte
+// records laid out in the reference's own depth-first visit order (left before right,
+// src/hittable/bvh_node.rs:110-124).  Because that order is fixed (it does not depend on the ray), the
+// traversal needs no stack: a box record that is missed jumps to its `skip` index, anything else falls
+// through to pc+1.  Ray-space changes (Translation / Rotation) are push/pop records around the child's
+// sub-stream; a ConstantMedium record owns the sub-stream [pc+1, end) of its boundary.
+#pragma once
+#include <stdint.h>
+
+namespace hrt {
+
+enum Opcode : uint32_t {
+    OP_END = 0,
+    OP_BOX = 1,        // sound box: intersected ("tight") slab test is result-identical to the reference test
+    OP_BOX_LOOSE = 2,  // unsound box (Q2): MUST use the reference's per-axis test (src/aabb.rs:20-47)
+    OP_SPHERE = 3,
+    OP_MSPHERE = 4,    // followed by one OP_MSPHERE_AUX record
+    OP_MSPHERE_AUX = 5,
+    OP_RECT_XY = 6,
+    OP_RECT_YZ = 7,
+    OP_RECT_ZX = 8,
+    OP_CUBOID = 9,
+    OP_TRANSLATE = 10,  // enter child ray space
+    OP_ROTATE = 11,
+    OP_POP = 12,        // leave child ray space (restore context in w3)
+    OP_MEDIUM = 13,
+};
+
+// 32-byte record = two float4.  w7 (the .w of the second float4) = opcode | (payload << 8).
+//   BOX*        w0-2 min            w4-6 max                  w7 = op | skip_pc<<8
+//   SPHERE      w0-2 centre, w3 r   w4 mat, w5 prim_id        w7 = op
+//   MSPHERE     w0-2 c0, w3 r       w4 mat, w5 prim_id        w7 = op       (+AUX: w0-2 c1, w3 t0, w4 t1)
+//   RECT_*      w0-3 a0,a1,b0,b1    w4 k, w5 mat, w6 prim_id  w7 = op
+//   CUBOID      w0-2 min, w3 mat    w4-6 max                  w7 = op | prim_id<<8
+//   TRANSLATE   w0-2 d, w3 ctx                                 w7 = op
+//   ROTATE      w0 sin, w1 cos, w2 axis, w3 ctx                w7 = op
+//   POP         w3 ctx to restore                              w7 = op
+//   MEDIUM      w0 -1/density, w1 mat, w2 medium idx, w3 prim  w7 = op | end_pc<<8
+struct alignas(16) Op {
+    union {
+        float f[8];
+        uint32_t u[8];
+        int32_t i[8];
+    };
+};
+static_assert(sizeof(Op) == 32, "op record must be 32 bytes");
+
+constexpr int kMaxCtxDepth = 6;
+// A ray-space context = the chain of TRANSLATE/ROTATE records (outermost first) that maps the world ray
+// into it.  ctx 0 is world space.
+struct alignas(16) Ctx {
+    int32_t depth;
+    int32_t parent;
+    int32_t op_pc[kMaxCtxDepth];
+};
+static_assert(sizeof(Ctx) == 32, "ctx record must be 32 bytes");
+
+enum MaterialKind : int32_t { MAT_LAMBERTIAN = 0, MAT_METAL = 1, MAT_DIELECTRIC = 2, MAT_DIFFUSE_LIGHT = 3, MAT_ISOTROPIC = 4 };
+enum MaterialFlags : int32_t { MATF_NEEDS_UV = 1 };
+struct alignas(16) Material {
+    float albedo[3];  // metal
+    float param;      // metal fuzz | dielectric ior
+    int32_t kind;
+    int32_t tex;      // lambertian / isotropic albedo, diffuse-light emit
+    int32_t flags;
+    int32_t pad;
+};
+static_assert(sizeof(Material) == 32, "material record must be 32 bytes");
+
+enum TextureKind : int32_t { TEX_SOLID = 0, TEX_CHECKER = 1, TEX_NOISE = 2, TEX_IMAGE = 3 };
+struct alignas(16) Texture {
+    float v[4];   // solid: rgb | noise: scale
+    int32_t kind;
+    int32_t i0;   // checker: odd  | noise: table | image: image index (-1 = empty data)
+    int32_t i1;   // checker: even | image: width
+    int32_t i2;   //                 image: height
+};
+static_assert(sizeof(Texture) == 32, "texture record must be 32 bytes");
+
+// src/perlin_noise.rs:13-18: 256 gradient vectors + three 256-entry permutations (values < 256 -> u8).
+struct alignas(16) NoiseTable {
+    float ranvec[256][4];
+    uint8_t perm[3][256];
+};
+static_assert(sizeof(NoiseTable) == 4096 + 768, "noise table size");
+
+constexpr int kMaxImages = 8;
+constexpr int kMaxNoiseTablesShared = 2;  // staged in shared memory by the render kernel
+
+}  // namespace hrt

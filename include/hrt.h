@@ -1,0 +1,210 @@
+/*
+ * hrt.h — C ABI of libhrt.so: the B200-native (sm_100a CUDA) replacement for hyper-ray-tracer's
+ * per-pixel path-tracing hot path.
+ *
+ * The reference (SkillerRaptor/hyper-ray-tracer, Rust) has no FFI or plugin interface; the seam this ABI
+ * replaces is internal: `Application::render` + `Application::ray_color` (src/application.rs:393-495) and
+ * every `Hittable::hit` / `Material::scatter` / `Texture::value` beneath them.  `dyn Hittable` is opaque, so
+ * a flattener cannot introspect an existing tree: the front end *describes* the scene through builder calls
+ * that mirror the reference constructors 1:1, then commits it.  Each entry point below cites the reference
+ * interface it replaces.  INTEGRATION.md shows the Rust `extern "C"` block a maintainer would add.
+ *
+ * Conventions: plain C types only; ids are non-negative int32 handles into per-scene typed tables
+ * (textures, materials, hittables — three separate id spaces, allocated in call order); a negative return
+ * is an error code (hrt_status) and hrt_last_error() returns a thread-local message.  The library copies
+ * every input array; the caller keeps ownership.  A scene is immutable after hrt_scene_commit (the
+ * reference's world is an immutable Arc<Box<dyn Hittable>>, src/application.rs:68,228).  Calls on one
+ * scene must be serialised by the caller; different scenes are independent.
+ *
+ * There is NO CPU fallback: every compute entry point fails with HRT_ERR_CUDA when no sm_100 device or no
+ * CUDA runtime is available.
+ */
+#ifndef HRT_H
+#define HRT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HRT_ABI_VERSION 1
+
+typedef enum hrt_status {
+    HRT_OK = 0,
+    HRT_ERR_INVALID = -1,     /* bad argument / unknown id / wrong call order                         */
+    HRT_ERR_UNSUPPORTED = -2, /* scene shape outside what the flattener supports (message says which)  */
+    HRT_ERR_CUDA = -3,        /* CUDA runtime / device failure (message carries cudaGetErrorString)    */
+    HRT_ERR_STATE = -4        /* scene not committed / not uploaded                                    */
+} hrt_status;
+
+typedef struct hrt_scene hrt_scene; /* opaque */
+
+/* rect.rs:13-17  `enum Plane { XY, YZ, ZX }`; rotation.rs:13-17 `enum Axis { X, Y, Z }` */
+enum { HRT_PLANE_XY = 0, HRT_PLANE_YZ = 1, HRT_PLANE_ZX = 2 };
+enum { HRT_AXIS_X = 0, HRT_AXIS_Y = 1, HRT_AXIS_Z = 2 };
+
+/* Material kinds as reported in hit records / table dumps. */
+enum { HRT_MAT_LAMBERTIAN = 0, HRT_MAT_METAL = 1, HRT_MAT_DIELECTRIC = 2, HRT_MAT_DIFFUSE_LIGHT = 3,
+       HRT_MAT_ISOTROPIC = 4 };
+
+const char* hrt_last_error(void);
+int32_t hrt_abi_version(void);
+/* Number of CUDA devices usable by the library (0 when there is no driver/GPU; never fails). */
+int32_t hrt_device_count(void);
+
+/* ---- scene lifetime ------------------------------------------------------------------------------- */
+int32_t hrt_scene_create(hrt_scene** out);
+void hrt_scene_destroy(hrt_scene* scene);
+
+/* ---- textures (src/textures/ *.rs) ----------------------------------------------------------------- */
+/* SolidColor::new(color)                                   src/textures/solid_color.rs:15 */
+int32_t hrt_tex_solid(hrt_scene*, const float rgb[3]);
+/* CheckerTexture::new(odd, even)                           src/textures/checker_texture.rs:16 */
+int32_t hrt_tex_checker(hrt_scene*, int32_t odd_tex, int32_t even_tex);
+/* NoiseTexture::new(scale) + PerlinNoise::new()            src/textures/noise_texture.rs:16, src/perlin_noise.rs:23-64.
+ * The reference draws the tables from its own thread_rng; the front end passes them in:
+ * ranvec = 256 x 3 f32 (unit vectors), perm_* = 256 x u32 permutations of 0..255. */
+int32_t hrt_tex_noise(hrt_scene*, float scale, const float* ranvec, const uint32_t* perm_x, const uint32_t* perm_y,
+                      const uint32_t* perm_z);
+/* ImageTexture::new(path) — already-decoded bytes (the front end's `image` crate stays the decoder)
+ *                                                          src/textures/image_texture.rs:19-32.
+ * components must be 3 or 4; data may be NULL/empty (the reference then returns (1,0,1), :37-39). */
+int32_t hrt_tex_image(hrt_scene*, const uint8_t* data, uint32_t width, uint32_t height, uint32_t components);
+
+/* ---- materials (src/materials/ *.rs) --------------------------------------------------------------- */
+int32_t hrt_mat_lambertian(hrt_scene*, int32_t albedo_tex);          /* lambertian.rs:21 */
+int32_t hrt_mat_metal(hrt_scene*, const float albedo[3], float fuzz); /* metal.rs:23 (fuzz NOT clamped) */
+int32_t hrt_mat_dielectric(hrt_scene*, float index_of_refraction);    /* dielectric.rs:23 */
+int32_t hrt_mat_diffuse_light(hrt_scene*, int32_t emit_tex);          /* diffuse_light.rs:15 */
+
+/* ---- hittables (src/hittable/ *.rs) ---------------------------------------------------------------- */
+int32_t hrt_sphere(hrt_scene*, const float center[3], float radius, int32_t mat);                 /* sphere.rs:23 */
+int32_t hrt_moving_sphere(hrt_scene*, const float center0[3], const float center1[3], float time0, float time1,
+                          float radius, int32_t mat);                                             /* moving_sphere.rs:26 */
+int32_t hrt_rect(hrt_scene*, int32_t plane, float a0, float a1, float b0, float b1, float k, int32_t mat); /* rect.rs:31 */
+int32_t hrt_cuboid(hrt_scene*, const float box_min[3], const float box_max[3], int32_t mat);      /* cuboid.rs:30 */
+int32_t hrt_translate(hrt_scene*, int32_t child, const float displacement[3]);                    /* translation.rs:15 */
+int32_t hrt_rotate(hrt_scene*, int32_t axis, int32_t child, float angle_degrees);                 /* rotation.rs:38 */
+/* ConstantMedium::new(boundary, density, texture): allocates the next material id for its Isotropic phase
+ * function, exactly as the reference constructs one internally (constant_medium.rs:24-30). */
+int32_t hrt_constant_medium(hrt_scene*, int32_t boundary, float density, int32_t albedo_tex);
+int32_t hrt_list(hrt_scene*, const int32_t* children, int32_t n);                                 /* list.rs:14 */
+/* BvhNode::new(objects, time_start, time_end)  — reproduces the reference's axis choice, centroid sort,
+ * len/2 split and node boxes exactly (bvh_node.rs:27-100). */
+int32_t hrt_bvh(hrt_scene*, const int32_t* children, int32_t n, float time_start, float time_end);
+
+/* Flatten the tree under `root` into the device op stream + material/texture tables (host only). */
+int32_t hrt_scene_commit(hrt_scene*, int32_t root);
+
+/* `world.count()` as the reference logs it (src/application.rs:277; Rotation::count() == 1, rotation.rs:140). */
+int32_t hrt_scene_count(const hrt_scene*);
+
+/* ---- flattened-table introspection (tests, tools) -------------------------------------------------- */
+typedef struct hrt_scene_info {
+    int32_t n_ops;          /* 32-byte records in the op stream                              */
+    int32_t n_box_ops;      /* BVH node boxes                                                 */
+    int32_t n_loose_boxes;  /* boxes that must use the reference's per-axis test (unsound)    */
+    int32_t n_prim_ops;     /* sphere / moving sphere / rect / cuboid records                 */
+    int32_t n_materials, n_textures, n_noise_tables, n_images, n_media, n_contexts;
+    int32_t max_context_depth;
+    float time_min, time_max; /* BVH build interval (intersection over all hrt_bvh calls)      */
+} hrt_scene_info;
+int32_t hrt_scene_get_info(const hrt_scene*, hrt_scene_info* out);
+/* Copies up to cap_ops 32-byte records; returns n_ops. */
+int32_t hrt_scene_get_ops(const hrt_scene*, void* out, int32_t cap_ops);
+/* DFS left->right leaf object ids of a hrt_bvh object; returns leaf count. */
+int32_t hrt_bvh_leaf_order(const hrt_scene*, int32_t bvh, int32_t* out, int32_t cap);
+/* Reference bounding box of any hittable over time [0,1] (what `bounding_box(0.0, 1.0)` returns). */
+int32_t hrt_bounding_box(const hrt_scene*, int32_t obj, float out_min_max[6]);
+
+/* ---- camera (src/camera.rs) ------------------------------------------------------------------------ */
+typedef struct hrt_camera_desc { /* Camera::new arguments, camera.rs:34-44 */
+    float look_from[3], look_at[3];
+    float vfov, aperture, focus_dist, time0, time1;
+    int32_t width, height;
+} hrt_camera_desc;
+typedef struct hrt_camera_state { /* what Camera::resize derives, camera.rs:67-83 */
+    float origin[3], lower_left_corner[3], horizontal[3], vertical[3], u[3], v[3], w[3];
+    float lens_radius, time0, time1;
+} hrt_camera_state;
+int32_t hrt_camera_init(const hrt_camera_desc*, hrt_camera_state* out);
+
+/* ---- render (src/application.rs:393-495) ----------------------------------------------------------- */
+enum {
+    HRT_FLAG_REFERENCE_TRAVERSAL = 1, /* per-axis (loose) box test on every node, as aabb.rs:20-47        */
+    HRT_FLAG_EXACT_MATH = 2           /* no FMA contraction, IEEE div/sqrt, accurate libm (parity build) */
+};
+typedef struct hrt_render_desc {
+    int32_t width, height;
+    int32_t samples;     /* total samples per pixel of the whole job (--samples)                  */
+    int32_t depth;       /* --depth                                                               */
+    float background[3];
+    uint64_t seed;       /* Philox key                                                            */
+    int32_t sample_begin, sample_count; /* slice [begin, begin+count) rendered by THIS call (multi-GPU
+                                           sharding); count <= 0 means the whole range            */
+    uint32_t flags;
+} hrt_render_desc;
+typedef struct hrt_stats {
+    uint64_t paths;       /* camera samples traced by this call                                   */
+    uint64_t rays;        /* world.hit() calls issued from the bounce loop                        */
+    float kernel_ms;      /* path-trace kernel, CUDA events on the launch stream                   */
+    float resolve_ms;
+    float h2d_ms, d2h_ms;
+    int32_t launches;     /* kernels launched by this call                                         */
+    int32_t grid, block;
+} hrt_stats;
+
+/* Upload the committed scene to CUDA device `device` (idempotent per device). */
+int32_t hrt_scene_upload(hrt_scene*, int32_t device);
+
+/* Whole render on one device with HOST output: out_rgba = width*height*4 f32, rows bottom-up (row 0 is the
+ * bottom row, as the reference's GL upload expects), gamma-resolved sqrt(sum/samples), alpha 1.0 —
+ * byte-compatible with concatenated reference `Tile.pixels` (src/application.rs:46-52,451-456). Blocking. */
+int32_t hrt_render(hrt_scene*, int32_t device, const hrt_camera_desc*, const hrt_render_desc*, float* out_rgba,
+                   hrt_stats* stats);
+/* As hrt_render but returns the un-resolved linear sum (width*height*4 f32: r,g,b sums, w = samples). */
+int32_t hrt_render_accum(hrt_scene*, int32_t device, const hrt_camera_desc*, const hrt_render_desc*, float* out_sum,
+                         hrt_stats* stats);
+
+/* Device-resident variants for multi-GPU sample sharding: `d_accum` is a device pointer on `device` to
+ * width*height*4 f32 that the call ADDS into (zero it first); `stream` is a cudaStream_t (0 = default).
+ * Asynchronous w.r.t. the host except for the stats read-back when stats != NULL. */
+int32_t hrt_render_accum_device(hrt_scene*, int32_t device, const hrt_camera_desc*, const hrt_render_desc*,
+                                void* d_accum, void* stream, hrt_stats* stats);
+/* Gamma resolve (src/application.rs:451-456): d_out_rgba[i] = (sqrt(sum.rgb * (1/samples)), 1.0). */
+int32_t hrt_resolve_device(int32_t device, const void* d_accum, int32_t width, int32_t height, int32_t samples,
+                           void* d_out_rgba, void* stream);
+
+/* ---- parity entry points --------------------------------------------------------------------------- */
+typedef struct hrt_ray { float o[3], d[3], time, tmin, tmax; } hrt_ray;
+typedef struct hrt_hit {
+    int32_t hit;
+    float t, p[3], n[3], u, v;
+    int32_t front_face, material_id, prim_id, face;
+} hrt_hit;
+/* `world.hit(ray, tmin, tmax)` on explicit rays (host buffers).  xi[i] is the uniform returned by every
+ * ConstantMedium draw on ray i (constant_medium.rs:59); may be NULL (0.5). */
+int32_t hrt_trace_hits(hrt_scene*, int32_t device, const hrt_ray* rays, int32_t n, const float* xi, hrt_hit* out,
+                       uint32_t flags);
+/* `Texture::value(u, v, p)` on n tuples: uvp = n x 5 f32, out = n x 3 f32. */
+int32_t hrt_tex_value(hrt_scene*, int32_t device, int32_t tex, const float* uvp, int32_t n, float* out, uint32_t flags);
+/* `Material::scatter` + `emitted` under injected uniforms u4 (n x 4): the library's fixed-draw samplers. */
+typedef struct hrt_scatter_out {
+    int32_t scattered;
+    float attenuation[3], o[3], d[3], time, emitted[3];
+} hrt_scatter_out;
+int32_t hrt_scatter(hrt_scene*, int32_t device, const hrt_ray* rays, const hrt_hit* hits, const float* u4, int32_t n,
+                    hrt_scatter_out* out, uint32_t flags);
+/* `Camera::get_ray(s,t)` under injected uniforms: stuuu = n x 5 (s, t, lens u1, lens u2, time u). */
+int32_t hrt_camera_rays(int32_t device, const hrt_camera_desc*, const float* stuuu, int32_t n, hrt_ray* out,
+                        uint32_t flags);
+/* The first `n` uniforms the render kernel draws for (pixel, sample, bounce, block): Philox4x32-10 KAT. */
+int32_t hrt_philox_uniforms(uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t bounce, uint32_t block,
+                            float out4[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HRT_H */
