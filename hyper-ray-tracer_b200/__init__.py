@@ -7,7 +7,7 @@ Layout:
   scenes.py    the reference's eight scene generators, seeded
   renderer.py  `Application::render` drop-in: single-GPU and spp-sharded multi-GPU (torch.distributed/NCCL)
 """
-from . import native, scene, scenes  # noqa: F401
+from . import native, renderer, scene, scenes  # noqa: F401
 from .native import HrtBackend, HrtError  # noqa: F401
 from .scene import *  # noqa: F401,F403
 from .scenes import CONFIGS, SCENES, make_scene  # noqa: F401

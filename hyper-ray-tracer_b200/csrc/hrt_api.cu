@@ -165,6 +165,72 @@ int32_t hrt_scene_upload(hrt_scene* s, int32_t device) {
     return HRT_OK;
 }
 
+int32_t hrt_scene_evict(hrt_scene* s, int32_t device) {
+    if (!s) return fail(HRT_ERR_INVALID, "null scene");
+    for (size_t i = 0; i < s->devices.size(); ++i)
+        if (s->devices[i] && s->devices[i]->device == device) {
+            release_device_state(s->devices[i]);
+            s->devices.erase(s->devices.begin() + (long)i);
+            return HRT_OK;
+        }
+    return HRT_OK;
+}
+
+int64_t hrt_scene_device_bytes(const hrt_scene* s) {
+    if (!s || !s->committed) return fail(HRT_ERR_STATE, "scene not committed");
+    int64_t b = (int64_t)(s->ops.size() * sizeof(Op) + s->ctxs.size() * sizeof(Ctx) + s->materials.size() * sizeof(Material) +
+                          s->textures.size() * sizeof(Texture) + s->noise_tables.size() * sizeof(NoiseTable));
+    for (const ImageData& img : s->images) b += (int64_t)img.rgba.size();
+    return b;
+}
+
+int32_t hrt_measure_peaks(int32_t device, hrt_peaks* out) {
+    if (!out) return fail(HRT_ERR_INVALID, "null output");
+    int n = 0;
+    cudaError_t ce = cudaGetDeviceCount(&n);
+    if (ce != cudaSuccess || n == 0) return fail(HRT_ERR_CUDA, "no CUDA device available (there is no CPU fallback)");
+    HRT_CUDA(cudaSetDevice(device));
+    int sms = 0, khz = 0;
+    HRT_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    HRT_CUDA(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device));
+    DevBuf<float> sink;
+    DevBuf<float4> buf;
+    const size_t n_vec = (32u << 20) / sizeof(float4);
+    HRT_CUDA(sink.alloc(4));
+    HRT_CUDA(buf.alloc(n_vec));
+    HRT_CUDA(cudaMemset(buf.p, 0, n_vec * sizeof(float4)));
+    cudaEvent_t e0, e1;
+    HRT_CUDA(cudaEventCreate(&e0));
+    HRT_CUDA(cudaEventCreate(&e1));
+    const int grid = sms * 8, iters = 4096, repeats = 64;
+    float best_fma = 1e30f, best_l2 = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {  // first pass warms clocks / L2
+        float ms = 0.0f;
+        HRT_CUDA(cudaEventRecord(e0, 0));
+        HRT_CUDA(hrt_fast::launch_fma_peak(sink.p, grid, iters, 0));
+        HRT_CUDA(cudaEventRecord(e1, 0));
+        HRT_CUDA(cudaEventSynchronize(e1));
+        HRT_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best_fma) best_fma = ms;
+        HRT_CUDA(cudaEventRecord(e0, 0));
+        HRT_CUDA(hrt_fast::launch_l2_read(buf.p, n_vec, repeats, sink.p, grid, 0));
+        HRT_CUDA(cudaEventRecord(e1, 0));
+        HRT_CUDA(cudaEventSynchronize(e1));
+        HRT_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best_l2) best_l2 = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    const double flops = (double)grid * 256.0 * (double)iters * 64.0 * 2.0;
+    out->fp32_tflops = (float)(flops / (best_fma * 1e-3) / 1e12);
+    out->l2_read_gbs = (float)((double)n_vec * 16.0 * repeats / (best_l2 * 1e-3) / 1e9);
+    out->fma_ms = best_fma;
+    out->l2_ms = best_l2;
+    out->sm_count = sms;
+    out->clock_khz = khz;
+    return HRT_OK;
+}
+
 static int32_t get_state(hrt_scene* s, int32_t device, DeviceState** out) {
     int32_t rc = hrt_scene_upload(s, device);
     if (rc != HRT_OK) return rc;

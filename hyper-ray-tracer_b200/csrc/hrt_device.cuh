@@ -43,6 +43,7 @@ __device__ __forceinline__ V3 operator*(V3 a, V3 b) { return v3(a.x * b.x, a.y *
 __device__ __forceinline__ V3 operator/(V3 a, float s) { return v3(a.x / s, a.y / s, a.z / s); }
 // cgmath 0.18 dot: (x*x + y*y) + z*z
 __device__ __forceinline__ float dot(V3 a, V3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+__device__ __forceinline__ float dot_rn(V3 a, V3 b);
 __device__ __forceinline__ float length(V3 a) { return sqrtf(dot(a, a)); }
 // cgmath normalize: v * (1 / |v|)
 __device__ __forceinline__ V3 normalize(V3 a) {
@@ -180,8 +181,9 @@ __device__ __forceinline__ void apply_rotate(Ray& r, float4 A) {
     if (axis == 1) { oa = r.o.z; ob = r.o.x; da = r.d.z; db = r.d.x; }
     else if (axis == 0) { oa = r.o.y; ob = r.o.z; da = r.d.y; db = r.d.z; }
     else { oa = r.o.x; ob = r.o.y; da = r.d.x; db = r.d.y; }
-    float noa = cs * oa + sn * ob, nob = (-sn) * oa + cs * ob;
-    float nda = cs * da + sn * db, ndb = (-sn) * da + cs * db;
+    // individually rounded in both builds: with |o| ~ 1e3 an FMA-contracted rotation moves t by ~1e-4 relative
+    float noa = __fadd_rn(__fmul_rn(cs, oa), __fmul_rn(sn, ob)), nob = __fadd_rn(__fmul_rn(-sn, oa), __fmul_rn(cs, ob));
+    float nda = __fadd_rn(__fmul_rn(cs, da), __fmul_rn(sn, db)), ndb = __fadd_rn(__fmul_rn(-sn, da), __fmul_rn(cs, db));
     if (axis == 1) { r.o.z = noa; r.o.x = nob; r.d.z = nda; r.d.x = ndb; }
     else if (axis == 0) { r.o.y = noa; r.o.z = nob; r.d.y = nda; r.d.z = ndb; }
     else { r.o.x = noa; r.o.y = nob; r.d.x = nda; r.d.y = ndb; }
@@ -194,7 +196,7 @@ __device__ __forceinline__ V3 unrotate(V3 p, float4 A) {
     if (axis == 1) { pa = p.z; pb = p.x; }
     else if (axis == 0) { pa = p.y; pb = p.z; }
     else { pa = p.x; pb = p.y; }
-    float na = cs * pa - sn * pb, nb = sn * pa + cs * pb;
+    float na = __fsub_rn(__fmul_rn(cs, pa), __fmul_rn(sn, pb)), nb = __fadd_rn(__fmul_rn(sn, pa), __fmul_rn(cs, pb));
     if (axis == 1) { p.z = na; p.x = nb; }
     else if (axis == 0) { p.y = na; p.z = nb; }
     else { p.x = na; p.y = nb; }
@@ -218,17 +220,11 @@ __device__ __noinline__ Ray ray_in_ctx(const DeviceScene& S, const Ray& world, i
 struct RayK {
     V3 inv;    // 1/d per component (aabb.rs:22)
     float dd;  // d·d (sphere.rs:42)
-#if !HRT_EXACT
-    float inv_dd;
-#endif
 };
 __device__ __forceinline__ RayK make_rayk(const Ray& r) {
     RayK k;
     k.inv = v3(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z);
-    k.dd = dot(r.d, r.d);
-#if !HRT_EXACT
-    k.inv_dd = 1.0f / k.dd;
-#endif
+    k.dd = dot_rn(r.d, r.d);
     return k;
 }
 
@@ -278,34 +274,37 @@ __device__ __forceinline__ bool box_hit_tight(float4 A, float4 B, const Ray& r, 
 // ------------------------------------------------------------------------------------------------
 // sphere.rs:41-58 / moving_sphere.rs:62-79.  NaN discriminants/roots are accepted exactly as the reference
 // accepts them (Q15).
+__device__ __forceinline__ float dot_rn(V3 a, V3 b) {  // (x*x + y*y) + z*z with every op rounded (never contracted)
+    return __fadd_rn(__fadd_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)), __fmul_rn(a.z, b.z));
+}
 __device__ __forceinline__ bool sphere_test(V3 center, float radius, const Ray& r, const RayK& k, float tmin, float closest,
                                             float& t_out) {
-    V3 oc = r.o - center;
+    // The quadratic's coefficients are cancellation-prone (r = 1000 ground sphere, r = 5000 fog boundary, origins that
+    // lie ON the sphere): an FMA-contracted oc.oc - r^2 moves t by ~1e-5 relative.  They are therefore computed with
+    // individually rounded operations in BOTH builds (6 extra instructions), which keeps the production build's t within
+    // an ulp or two of the reference's.
+    V3 oc = v3(__fsub_rn(r.o.x, center.x), __fsub_rn(r.o.y, center.y), __fsub_rn(r.o.z, center.z));
     float a = k.dd;
-    float half_b = dot(oc, r.d);
-    float c = dot(oc, oc) - radius * radius;
-    float disc = half_b * half_b - a * c;
+    float half_b = dot_rn(oc, r.d);
+    float c = __fsub_rn(dot_rn(oc, oc), __fmul_rn(radius, radius));
+    float disc = __fsub_rn(__fmul_rn(half_b, half_b), __fmul_rn(a, c));
     if (disc < 0.0f) return false;
     float sqrtd = sqrtf(disc);
-#if HRT_EXACT
-    float root = (-half_b - sqrtd) / a;
+    // true divisions in both builds (only reached when the discriminant is non-negative): a reciprocal multiply is
+    // an ulp off, which is enough to flip `root < t_min` for rays that start on the sphere
+    float root = __fdiv_rn(-half_b - sqrtd, a);
     if (root < tmin || closest < root) {
-        root = (-half_b + sqrtd) / a;
+        root = __fdiv_rn(-half_b + sqrtd, a);
         if (root < tmin || closest < root) return false;
     }
-#else
-    float root = (-half_b - sqrtd) * k.inv_dd;
-    if (root < tmin || closest < root) {
-        root = (-half_b + sqrtd) * k.inv_dd;
-        if (root < tmin || closest < root) return false;
-    }
-#endif
     t_out = root;
     return true;
 }
 // moving_sphere.rs:53-57
 __device__ __forceinline__ V3 msphere_center(V3 c0, V3 c1, float t0, float t1, float time) {
-    return c0 + ((time - t0) / (t1 - t0)) * (c1 - c0);
+    const float f = __fdiv_rn(time - t0, t1 - t0);  // individually rounded in both builds (centre ~ 1e2..1e3 units)
+    return v3(__fadd_rn(c0.x, __fmul_rn(f, c1.x - c0.x)), __fadd_rn(c0.y, __fmul_rn(f, c1.y - c0.y)),
+              __fadd_rn(c0.z, __fmul_rn(f, c1.z - c0.z)));
 }
 // rect.rs:60-69 with (k,a,b) already resolved to scalars
 __device__ __forceinline__ bool rect_test(float ok, float dk, float invk, float oa, float da, float ob, float db, float a0,
@@ -458,8 +457,10 @@ __device__ __forceinline__ bool traverse(const DeviceScene& S, int pc, const int
                                 float hit_distance = A.x * (logf(u) / S.ln_e);
                                 float t = t1 + hit_distance / ray_length;
 #else
-                                float hit_distance = A.x * __logf(u);
-                                float t = t1 + hit_distance * rsqrtf(k.dd);
+                                // accurate logf here too: __logf's absolute error near u = 1 is a relative error of up to
+                                // ~1e-3 in the free-flight distance; one call per medium query is noise in the profile
+                                float hit_distance = A.x * logf(u);
+                                float t = t1 + hit_distance / ray_length;
 #endif
                                 if (!(hit_distance > dist_inside)) {
                                     closest = t; any = true;

@@ -304,6 +304,43 @@ __global__ void __launch_bounds__(kBlock) camera_rays_kernel(const __grid_consta
     out[i] = o;
 }
 
+#if !HRT_EXACT
+// Roofline microbenchmarks (hrt_measure_peaks): 8 independent FFMA chains per thread; L2-resident float4 reads.
+__global__ void __launch_bounds__(256) fma_peak_kernel(float* __restrict__ sink, int iters) {
+    float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.0f, a2 = a0 + 2.0f, a3 = a0 + 3.0f, a4 = a0 + 4.0f, a5 = a0 + 5.0f,
+          a6 = a0 + 6.0f, a7 = a0 + 7.0f;
+    const float m = 0.999f + blockIdx.x * 1e-9f, c = 1e-3f;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            a0 = fmaf(a0, m, c); a1 = fmaf(a1, m, c); a2 = fmaf(a2, m, c); a3 = fmaf(a3, m, c);
+            a4 = fmaf(a4, m, c); a5 = fmaf(a5, m, c); a6 = fmaf(a6, m, c); a7 = fmaf(a7, m, c);
+        }
+    }
+    float r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (r == 123.456f) sink[0] = r;
+}
+__global__ void __launch_bounds__(256) l2_read_kernel(const float4* __restrict__ buf, size_t n_vec, int repeats,
+                                                      float* __restrict__ sink) {
+    float acc = 0.0f;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (int r = 0; r < repeats; ++r)
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
+            float4 v = __ldcg(buf + i);
+            acc += (v.x + v.y) + (v.z + v.w);
+        }
+    if (acc == 123.456f) sink[0] = acc;
+}
+cudaError_t launch_fma_peak(float* d_sink, int grid, int iters, cudaStream_t stream) {
+    fma_peak_kernel<<<grid, 256, 0, stream>>>(d_sink, iters);
+    return cudaGetLastError();
+}
+cudaError_t launch_l2_read(const float4* d_buf, size_t n_vec, int repeats, float* d_sink, int grid, cudaStream_t stream) {
+    l2_read_kernel<<<grid, 256, 0, stream>>>(d_buf, n_vec, repeats, d_sink);
+    return cudaGetLastError();
+}
+#endif
+
 // ------------------------------------------------------------------------------------------------
 // Launchers
 // ------------------------------------------------------------------------------------------------

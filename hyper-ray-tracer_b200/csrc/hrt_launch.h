@@ -51,5 +51,10 @@ struct RenderLaunch {
     void philox_uniforms(uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t bounce, uint32_t block, float out[4]); \
     }
 
+namespace hrt_fast {
+cudaError_t launch_fma_peak(float* d_sink, int grid, int iters, cudaStream_t stream);
+cudaError_t launch_l2_read(const float4* d_buf, size_t n_vec, int repeats, float* d_sink, int grid, cudaStream_t stream);
+}
+
 HRT_DECLARE_LAUNCHERS(hrt_exact)
 HRT_DECLARE_LAUNCHERS(hrt_fast)

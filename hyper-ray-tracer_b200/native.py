@@ -46,6 +46,11 @@ class Stats(C.Structure):
                 ("block", C.c_int32)]
 
 
+class Peaks(C.Structure):
+    _fields_ = [("fp32_tflops", C.c_float), ("l2_read_gbs", C.c_float), ("fma_ms", C.c_float), ("l2_ms", C.c_float),
+                ("sm_count", C.c_int32), ("clock_khz", C.c_int32)]
+
+
 class SceneInfo(C.Structure):
     _fields_ = [("n_ops", C.c_int32), ("n_box_ops", C.c_int32), ("n_loose_boxes", C.c_int32), ("n_prim_ops", C.c_int32),
                 ("n_materials", C.c_int32), ("n_textures", C.c_int32), ("n_noise_tables", C.c_int32),
@@ -69,7 +74,8 @@ EXPORTS = [
     "hrt_constant_medium", "hrt_list", "hrt_bvh", "hrt_scene_commit", "hrt_scene_count", "hrt_scene_get_info",
     "hrt_scene_get_ops", "hrt_bvh_leaf_order", "hrt_bounding_box", "hrt_camera_init", "hrt_scene_upload", "hrt_render",
     "hrt_render_accum", "hrt_render_accum_device", "hrt_resolve_device", "hrt_trace_hits", "hrt_tex_value",
-    "hrt_scatter", "hrt_camera_rays", "hrt_philox_uniforms",
+    "hrt_scatter", "hrt_camera_rays", "hrt_philox_uniforms", "hrt_scene_evict", "hrt_scene_device_bytes",
+    "hrt_measure_peaks",
 ]
 
 _lib = None
@@ -129,10 +135,14 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.hrt_scatter.argtypes = [vp, i32, vp, vp, vp, i32, vp, C.c_uint32]
     lib.hrt_camera_rays.argtypes = [i32, C.POINTER(CameraDesc), vp, i32, vp, C.c_uint32]
     lib.hrt_philox_uniforms.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, f3]
+    lib.hrt_scene_evict.argtypes = [vp, i32]
+    lib.hrt_scene_device_bytes.argtypes = [vp]
+    lib.hrt_measure_peaks.argtypes = [i32, C.POINTER(Peaks)]
     for name in EXPORTS:
         fn = getattr(lib, name)
-        if name not in ("hrt_last_error", "hrt_scene_destroy"):
+        if name not in ("hrt_last_error", "hrt_scene_destroy", "hrt_scene_device_bytes"):
             fn.restype = i32
+    lib.hrt_scene_device_bytes.restype = C.c_int64
     if path is None:
         _lib = lib
     return lib
@@ -278,6 +288,12 @@ class HrtBackend:
     def upload(self, device: int = 0):
         self._check(self.lib.hrt_scene_upload(self.handle, device))
 
+    def evict(self, device: int = 0):
+        self._check(self.lib.hrt_scene_evict(self.handle, device))
+
+    def device_bytes(self) -> int:
+        return int(self._check(self.lib.hrt_scene_device_bytes(self.handle)))
+
     def _render_desc(self, width, height, samples, depth, background, seed, sample_begin, sample_count, flags):
         return RenderDesc(int(width), int(height), int(samples), int(depth), _arr3(background), int(seed), int(sample_begin),
                           int(sample_count), int(flags))
@@ -342,6 +358,15 @@ def philox_uniforms(seed, pixel, sample, bounce, block):
     out = (C.c_float * 4)()
     lib.hrt_philox_uniforms(int(seed), int(pixel), int(sample), int(bounce), int(block), out)
     return np.array(list(out), dtype=np.float32)
+
+
+def measure_peaks(device: int = 0) -> Peaks:
+    lib = load_library()
+    p = Peaks()
+    rc = lib.hrt_measure_peaks(device, C.byref(p))
+    if rc < 0:
+        raise HrtError(rc, (lib.hrt_last_error() or b"").decode())
+    return p
 
 
 def device_count() -> int:

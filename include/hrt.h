@@ -177,6 +177,22 @@ int32_t hrt_render_accum_device(hrt_scene*, int32_t device, const hrt_camera_des
 int32_t hrt_resolve_device(int32_t device, const void* d_accum, int32_t width, int32_t height, int32_t samples,
                            void* d_out_rgba, void* stream);
 
+/* Drop the device copy of the scene on `device` (next compute call uploads again). */
+int32_t hrt_scene_evict(hrt_scene*, int32_t device);
+/* Bytes hrt_scene_upload copies host->device (op stream + tables + image texels). */
+int64_t hrt_scene_device_bytes(const hrt_scene*);
+
+/* Roofline denominators measured on `device` with CUDA events (not in the reference): dependent-free FFMA
+ * chains on every SM (FP32 TFLOP/s, FMA = 2 flops) and a repeated coalesced read of an L2-resident buffer. */
+typedef struct hrt_peaks {
+    float fp32_tflops;   /* measured FFMA throughput                                   */
+    float l2_read_gbs;   /* measured L2-resident read bandwidth (32 MiB buffer)         */
+    float fma_ms, l2_ms; /* durations of the two microbenchmarks                        */
+    int32_t sm_count;
+    int32_t clock_khz;   /* cudaDevAttrClockRate (max SM clock)                         */
+} hrt_peaks;
+int32_t hrt_measure_peaks(int32_t device, hrt_peaks* out);
+
 /* ---- parity entry points --------------------------------------------------------------------------- */
 typedef struct hrt_ray { float o[3], d[3], time, tmin, tmax; } hrt_ray;
 typedef struct hrt_hit {

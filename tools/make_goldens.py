@@ -1,0 +1,59 @@
+"""Golden frames for image parity: the CPU oracle's own render of each BASELINE config at 4096 spp, depth 50.
+
+The reference cannot be built or run here (no Rust toolchain; it needs a GLFW window and writes no image), so "the
+reference's own render" is the oracle's.  The reference-faithful (loose-box) traversal runs at ~0.09 Mpaths/s on
+8 cores for `final`, so goldens are rendered at HALF the config's resolution (same scene instance, same camera,
+same spp and depth; a pixel just covers 4x the footprint) — full-res C5 alone would take > 8 h.
+
+Each golden is rendered as two independent 2048-spp halves (seeds A, B): their sum is the 4096-spp golden, their
+difference measures the oracle-vs-oracle noise floor.  Stored per config in tests/golden/<cfg>.npz:
+  img    float16 [h,w,3]  gamma-resolved golden  sqrt(sum/4096)        (application.rs:451-456)
+  sigma  float16 [h,w,3]  standard error of the LINEAR per-pixel mean  sqrt(var/4096)
+  meta   json: sizes, spp, seeds, MAE(A,B) of the two resolved halves, oracle counters, seconds
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as graft  # noqa: E402
+
+pkg = graft.load_package()
+orc = graft.load_oracle()
+SPP = 4096
+threads = int(os.environ.get("GOLDEN_THREADS", "7"))
+only = sys.argv[1:] or list(pkg.CONFIGS)
+for cfg in only:
+    scene, W, H, _, depth = pkg.CONFIGS[cfg]
+    w, h = W // 2, H // 2
+    dst = os.path.join(ROOT, "tests", "golden", f"{cfg}.npz")
+    if os.path.exists(dst):
+        print(cfg, "exists, skipping", flush=True)
+        continue
+    spec = pkg.make_scene(scene, 1)
+    ob = orc.OracleBackend()
+    pkg.scene.emit(spec.world, ob)
+    t0 = time.time()
+    halves = []
+    counters = None
+    for seed in (101, 202):
+        s, sq, c = ob.render(spec.camera, w, h, SPP // 2, depth, spec.background, seed=seed, threads=threads, want_sumsq=True)
+        halves.append((np.nan_to_num(s.astype(np.float64)), np.nan_to_num(sq.astype(np.float64))))
+        counters = c
+        print(cfg, "half", seed, f"{time.time() - t0:.0f}s", flush=True)
+    total = halves[0][0] + halves[1][0]
+    total_sq = halves[0][1] + halves[1][1]
+    mean = total / SPP
+    var = np.maximum(total_sq / SPP - mean * mean, 0.0)
+    img = np.sqrt(mean)
+    ia, ib = np.sqrt(halves[0][0] / (SPP // 2)), np.sqrt(halves[1][0] / (SPP // 2))
+    meta = {"config": cfg, "scene": scene, "width": w, "height": h, "full_width": W, "full_height": H, "spp": SPP,
+            "depth": depth, "scene_seed": 1, "seeds": [101, 202], "mae_half_vs_half": float(np.abs(ia - ib).mean()),
+            "psnr_half_vs_half": float(10 * np.log10(1.0 / max(1e-12, ((np.clip(ia, 0, 1) - np.clip(ib, 0, 1)) ** 2).mean()))),
+            "rays_per_path": counters.rays / counters.paths, "seconds": time.time() - t0, "threads": threads}
+    np.savez_compressed(dst, img=img.astype(np.float16), sigma=np.sqrt(var / SPP).astype(np.float16), meta=json.dumps(meta))
+    print(cfg, json.dumps(meta), flush=True)
