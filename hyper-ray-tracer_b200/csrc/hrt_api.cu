@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -129,7 +131,7 @@ int32_t hrt_scene_upload(hrt_scene* s, int32_t device) {
     if ((rc = upload_table(&d->d_mats, s->materials.data(), s->materials.size() * sizeof(Material))) != HRT_OK) return rc;
     if ((rc = upload_table(&d->d_texs, s->textures.data(), s->textures.size() * sizeof(Texture))) != HRT_OK) return rc;
     if ((rc = upload_table(&d->d_noise, s->noise_tables.data(), s->noise_tables.size() * sizeof(NoiseTable))) != HRT_OK) return rc;
-    HRT_CUDA(cudaMalloc((void**)&d->d_counters, 8 * sizeof(unsigned long long)));
+    HRT_CUDA(cudaMalloc((void**)&d->d_counters, 24 * sizeof(unsigned long long)));
     for (auto& ev : d->ev) HRT_CUDA(cudaEventCreate(&ev));
     std::memset(&d->view, 0, sizeof(d->view));
     // Image textures: RGBA8 CUDA arrays bound as point-sampled, unnormalised texture objects
@@ -272,10 +274,17 @@ static int32_t render_into(hrt_scene* s, DeviceState* d, const hrt_camera_desc* 
     if (s->any_bvh && (std::fmin(cam->time0, cam->time1) < s->time_min || std::fmax(cam->time0, cam->time1) > s->time_max))
         ref_boxes = true;
     L.reference_boxes = ref_boxes ? 1 : 0;
+    {
+        const char* env = getenv("HRT_KERNEL");  // diagnostic override: "interp" | "sched"
+        bool interp = (rd->flags & HRT_FLAG_INTERPRETER) != 0;
+        if (env && env[0] == 'i') interp = true;
+        if (env && env[0] == 's') interp = false;
+        L.interpreter = interp ? 1 : 0;
+    }
     L.counters = d->d_counters;
     L.accum = d_accum;
     L.chunk = 0;
-    HRT_CUDA(cudaMemsetAsync(d->d_counters, 0, 8 * sizeof(unsigned long long), stream));
+    HRT_CUDA(cudaMemsetAsync(d->d_counters, 0, 24 * sizeof(unsigned long long), stream));
     if (want_stats) HRT_CUDA(cudaEventRecord(d->ev[0], stream));
     cudaError_t e = (rd->flags & HRT_FLAG_EXACT_MATH) ? hrt_exact::launch_render(L, d->num_sms, stream)
                                                       : hrt_fast::launch_render(L, d->num_sms, stream);
@@ -291,9 +300,15 @@ static int32_t render_into(hrt_scene* s, DeviceState* d, const hrt_camera_desc* 
 
 static int32_t finish_stats(DeviceState* d, cudaStream_t stream, hrt_stats* stats) {
     if (!stats) return HRT_OK;
-    unsigned long long c[8];
+    unsigned long long c[24];
     HRT_CUDA(cudaMemcpyAsync(c, d->d_counters, sizeof(c), cudaMemcpyDeviceToHost, stream));
     HRT_CUDA(cudaStreamSynchronize(stream));
+    if (getenv("HRT_SCHED_STATS")) {
+        static const char* names[6] = {"box", "sphere", "rect", "misc", "done", "new"};
+        for (int i = 0; i < 6; ++i)
+            fprintf(stderr, "[sched] %-6s rounds %llu lanes %llu avg %.2f rounds/ray %.2f\n", names[i], c[8 + 2 * i], c[9 + 2 * i],
+                    c[8 + 2 * i] ? (double)c[9 + 2 * i] / (double)c[8 + 2 * i] : 0.0, c[1] ? 32.0 * (double)c[8 + 2 * i] / (double)c[1] : 0.0);
+    }
     stats->rays = c[1];
     stats->paths = c[2];
     float ms = 0.0f;
@@ -390,7 +405,7 @@ int32_t hrt_trace_hits(hrt_scene* s, int32_t device, const hrt_ray* rays, int32_
         HRT_CUDA(dx.alloc(n));
         HRT_CUDA(cudaMemcpy(dx.p, xi, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice));
     }
-    const int ref = (flags & HRT_FLAG_REFERENCE_TRAVERSAL) ? 1 : 0;
+    const int ref = ((flags & HRT_FLAG_REFERENCE_TRAVERSAL) ? 1 : 0) | ((flags & HRT_FLAG_WARP_SCHEDULER) ? 2 : 0);
     cudaError_t e = (flags & HRT_FLAG_EXACT_MATH) ? hrt_exact::launch_trace_hits(d->view, dr.p, n, dx.p, dh.p, ref, 0)
                                                   : hrt_fast::launch_trace_hits(d->view, dr.p, n, dx.p, dh.p, ref, 0);
     if (e != cudaSuccess) return cuda_fail(e, "trace_hits_kernel launch");

@@ -110,10 +110,26 @@ enum { RNG_BLOCK_SCATTER = 0, RNG_BLOCK_MEDIA0 = 1, RNG_BLOCK_CAMERA = 255 };
 struct RngKey {
     uint32_t k0, k1, pixel, sample;
 };
+#ifdef __CUDACC__
+// One out-of-line copy per kernel: the 10 unrolled rounds are ~100 instructions and there are four call sites; inlining
+// them all bloats the hot loop past the instruction cache (profiles/r01_v1_render_kernel.txt: stall_no_instruction).
+__device__ __noinline__ uint4 philox_call(uint32_t pixel, uint32_t sample, uint32_t z, uint32_t k0, uint32_t k1) {
+    U4 c;
+    c.x = pixel; c.y = sample; c.z = z; c.w = 0x68727421u;
+    U4 r = philox4x32_10(c, k0, k1);
+    return make_uint4(r.x, r.y, r.z, r.w);
+}
+#endif
 __host__ __device__ __forceinline__ void rng_block(const RngKey& k, uint32_t bounce, uint32_t block, float out[4]) {
+#ifdef __CUDA_ARCH__
+    const uint4 q = philox_call(k.pixel, k.sample, (bounce << 8) | block, k.k0, k.k1);
+    U4 r;
+    r.x = q.x; r.y = q.y; r.z = q.z; r.w = q.w;
+#else
     U4 c;
     c.x = k.pixel; c.y = k.sample; c.z = (bounce << 8) | block; c.w = 0x68727421u;
     U4 r = philox4x32_10(c, k.k0, k.k1);
+#endif
     out[0] = u32_to_unit(r.x); out[1] = u32_to_unit(r.y); out[2] = u32_to_unit(r.z); out[3] = u32_to_unit(r.w);
 }
 
@@ -172,41 +188,42 @@ __device__ __forceinline__ void load_op(const DeviceScene& S, int pc, float4& A,
 
 // translation.rs:25-29
 __device__ __forceinline__ void apply_translate(Ray& r, float4 A) { r.o = r.o - v3(A.x, A.y, A.z); }
-// rotation.rs:103-116
+// rotation.rs:103-116.  (r,a,b): X -> (0,1,2), Y -> (1,2,0), Z -> (2,0,1).  Branch-free component selection keeps each
+// inlined copy small (the three-way branchy version was 734 instructions of the render kernel).
+__device__ __forceinline__ float sel3(int i, float x, float y, float z) { return i == 0 ? x : (i == 1 ? y : z); }
+__device__ __forceinline__ V3 put2(V3 p, int ia, float va, int ib, float vb) {
+    p.x = ia == 0 ? va : (ib == 0 ? vb : p.x);
+    p.y = ia == 1 ? va : (ib == 1 ? vb : p.y);
+    p.z = ia == 2 ? va : (ib == 2 ? vb : p.z);
+    return p;
+}
 __device__ __forceinline__ void apply_rotate(Ray& r, float4 A) {
     const float sn = A.x, cs = A.y;
     const int axis = __float_as_int(A.z);
-    // (r,a,b): X -> (0,1,2), Y -> (1,2,0), Z -> (2,0,1)
-    float oa, ob, da, db;
-    if (axis == 1) { oa = r.o.z; ob = r.o.x; da = r.d.z; db = r.d.x; }
-    else if (axis == 0) { oa = r.o.y; ob = r.o.z; da = r.d.y; db = r.d.z; }
-    else { oa = r.o.x; ob = r.o.y; da = r.d.x; db = r.d.y; }
+    const int ia = axis == 2 ? 0 : axis + 1, ib = axis == 0 ? 2 : axis - 1;
+    const float oa = sel3(ia, r.o.x, r.o.y, r.o.z), ob = sel3(ib, r.o.x, r.o.y, r.o.z);
+    const float da = sel3(ia, r.d.x, r.d.y, r.d.z), db = sel3(ib, r.d.x, r.d.y, r.d.z);
     // individually rounded in both builds: with |o| ~ 1e3 an FMA-contracted rotation moves t by ~1e-4 relative
-    float noa = __fadd_rn(__fmul_rn(cs, oa), __fmul_rn(sn, ob)), nob = __fadd_rn(__fmul_rn(-sn, oa), __fmul_rn(cs, ob));
-    float nda = __fadd_rn(__fmul_rn(cs, da), __fmul_rn(sn, db)), ndb = __fadd_rn(__fmul_rn(-sn, da), __fmul_rn(cs, db));
-    if (axis == 1) { r.o.z = noa; r.o.x = nob; r.d.z = nda; r.d.x = ndb; }
-    else if (axis == 0) { r.o.y = noa; r.o.z = nob; r.d.y = nda; r.d.z = ndb; }
-    else { r.o.x = noa; r.o.y = nob; r.d.x = nda; r.d.y = ndb; }
+    const float noa = __fadd_rn(__fmul_rn(cs, oa), __fmul_rn(sn, ob)), nob = __fadd_rn(__fmul_rn(-sn, oa), __fmul_rn(cs, ob));
+    const float nda = __fadd_rn(__fmul_rn(cs, da), __fmul_rn(sn, db)), ndb = __fadd_rn(__fmul_rn(-sn, da), __fmul_rn(cs, db));
+    r.o = put2(r.o, ia, noa, ib, nob);
+    r.d = put2(r.d, ia, nda, ib, ndb);
 }
 // rotation.rs:119-131 (object -> parent space for a point or a normal)
 __device__ __forceinline__ V3 unrotate(V3 p, float4 A) {
     const float sn = A.x, cs = A.y;
     const int axis = __float_as_int(A.z);
-    float pa, pb;
-    if (axis == 1) { pa = p.z; pb = p.x; }
-    else if (axis == 0) { pa = p.y; pb = p.z; }
-    else { pa = p.x; pb = p.y; }
-    float na = __fsub_rn(__fmul_rn(cs, pa), __fmul_rn(sn, pb)), nb = __fadd_rn(__fmul_rn(sn, pa), __fmul_rn(cs, pb));
-    if (axis == 1) { p.z = na; p.x = nb; }
-    else if (axis == 0) { p.y = na; p.z = nb; }
-    else { p.x = na; p.y = nb; }
-    return p;
+    const int ia = axis == 2 ? 0 : axis + 1, ib = axis == 0 ? 2 : axis - 1;
+    const float pa = sel3(ia, p.x, p.y, p.z), pb = sel3(ib, p.x, p.y, p.z);
+    const float na = __fsub_rn(__fmul_rn(cs, pa), __fmul_rn(sn, pb)), nb = __fadd_rn(__fmul_rn(sn, pa), __fmul_rn(cs, pb));
+    return put2(p, ia, na, ib, nb);
 }
 // Map the world ray into context `ctx` by replaying its push records, outermost first.
 __device__ __noinline__ Ray ray_in_ctx(const DeviceScene& S, const Ray& world, int ctx) {
     Ray r = world;
     if (ctx == 0) return r;
     const Ctx c = S.ctxs[ctx];
+#pragma unroll 1
     for (int i = 0; i < c.depth; ++i) {
         float4 A, B;
         load_op(S, c.op_pc[i], A, B);
@@ -221,10 +238,29 @@ struct RayK {
     V3 inv;    // 1/d per component (aabb.rs:22)
     float dd;  // d·d (sphere.rs:42)
 };
+__device__ __forceinline__ float fast_rcp(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+// Out of line: three IEEE divisions (each with its slow path) were inlined at nine sites of the render kernel.
+__device__ __noinline__ float4 rayk_call(float dx, float dy, float dz) {
+    // __frcp_rn is the correctly rounded reciprocal == the IEEE quotient 1.0f / d (aabb.rs:22) without the generic
+    // division's slow path
+#if HRT_EXACT
+    return make_float4(__frcp_rn(dx), __frcp_rn(dy), __frcp_rn(dz),
+#else
+    // production build: MUFU.RCP (1 ulp).  The reciprocals only feed box culling and the rect plane distance, both of
+    // which already differ from the reference by an ulp through FMA contraction.
+    return make_float4(fast_rcp(dx), fast_rcp(dy), fast_rcp(dz),
+#endif
+                       __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+}
 __device__ __forceinline__ RayK make_rayk(const Ray& r) {
+    const float4 q = rayk_call(r.d.x, r.d.y, r.d.z);
     RayK k;
-    k.inv = v3(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z);
-    k.dd = dot_rn(r.d, r.d);
+    k.inv = v3(q.x, q.y, q.z);
+    k.dd = q.w;
     return k;
 }
 
@@ -481,6 +517,19 @@ __device__ __forceinline__ bool traverse(const DeviceScene& S, int pc, const int
     return any;
 }
 
+// ConstantMedium boundary query (constant_medium.rs:37-38): closest hit of the boundary sub-stream [pc, end) in
+// [tmin, +inf).  Out of line so that the hot loop carries ONE copy of the inner interpreter instead of two inlined ones.
+__device__ __noinline__ float boundary_hit(const DeviceScene& S, int pc, int end, Ray world, Ray cur, int ctx, float tmin,
+                                           bool reference_boxes) {
+    Best dummy;
+    MediumXi none;
+    none.key.k0 = 0; none.key.k1 = 0; none.key.pixel = 0; none.key.sample = 0;
+    none.bounce = 0; none.injected = 0.5f; none.inject = true;
+    float t = CUDART_INF_F;
+    const bool hit = traverse<true>(S, pc, end, world, cur, ctx, tmin, t, dummy, reference_boxes, none);
+    return hit ? t : CUDART_NAN_F;  // NaN = miss (a genuine NaN t cannot be told apart and is treated as a miss)
+}
+
 // ------------------------------------------------------------------------------------------------
 // Hit record
 // ------------------------------------------------------------------------------------------------
@@ -516,6 +565,7 @@ __device__ __noinline__ void make_hit_record(const DeviceScene& S, const Ray& wo
     bool is_translate[kMaxCtxDepth];
     if (best.ctx != 0) {
         c = S.ctxs[best.ctx];
+#pragma unroll 1
         for (int i = 0; i < c.depth; ++i) {
             float4 B;
             load_op(S, c.op_pc[i], PA[i], B);
@@ -590,10 +640,12 @@ __device__ __noinline__ void make_hit_record(const DeviceScene& S, const Ray& wo
     // the direction that entered it (translation.rs:25-34, Q4).
     if (c.depth > 0) {
         // directions entering each record: recompute by replaying (depth is tiny)
+#pragma unroll 1
         for (int i = c.depth - 1; i >= 0; --i) {
             if (is_translate[i]) {
                 // direction of moved_ray == direction entering record i
                 Ray rr = world;
+#pragma unroll 1
                 for (int j = 0; j < i; ++j) {
                     if (is_translate[j]) apply_translate(rr, PA[j]);
                     else apply_rotate(rr, PA[j]);
@@ -642,6 +694,7 @@ __device__ __forceinline__ float perlin_noise(const NoiseView& N, V3 p) {
 // perlin_noise.rs:66-78
 __device__ __forceinline__ float perlin_turbulence(const NoiseView& N, V3 p, int depth) {
     float acc = 0.0f, weight = 1.0f;
+#pragma unroll 1
     for (int d = 0; d < depth; ++d) {
         acc += weight * perlin_noise(N, p);
         weight *= 0.5f;
@@ -650,23 +703,32 @@ __device__ __forceinline__ float perlin_turbulence(const NoiseView& N, V3 p, int
     return fabsf(acc);
 }
 
-struct TexEnv {  // per-kernel texture environment
-    NoiseView noise[kMaxNoiseTablesShared];
+// Per-kernel texture environment.  The first kMaxNoiseTablesShared perlin tables are staged in shared memory by the
+// kernels that shade (stage_noise in hrt_kernels.cu); `n_shared_noise` says how many.
+struct TexEnv {
     int n_shared_noise;
 };
-__device__ __forceinline__ NoiseView noise_view(const DeviceScene& S, const TexEnv& E, int table) {
-    if (table < E.n_shared_noise) return E.noise[table];
+__shared__ NoiseTable g_sh_noise[kMaxNoiseTablesShared];
+__device__ __forceinline__ NoiseView noise_view(const DeviceScene& S, const TexEnv E, int table) {
     NoiseView nv;
-    nv.ranvec = reinterpret_cast<const float4*>(S.noise[table].ranvec);
-    nv.perm = &S.noise[table].perm[0][0];
+    if (table < E.n_shared_noise) {
+        nv.ranvec = reinterpret_cast<const float4*>(g_sh_noise[table].ranvec);
+        nv.perm = &g_sh_noise[table].perm[0][0];
+    } else {
+        nv.ranvec = reinterpret_cast<const float4*>(S.noise[table].ranvec);
+        nv.perm = &S.noise[table].perm[0][0];
+    }
     return nv;
 }
 
-__device__ __forceinline__ V3 texture_value(const DeviceScene& S, const TexEnv& E, int tex, float u, float v, V3 p) {
+// Out of line (one copy per kernel): perlin turbulence + image fetch + libm sinf slow paths are cold, bulky code.
+__device__ __noinline__ V3 texture_value(const DeviceScene& S, const TexEnv E, int tex, float u, float v, V3 p) {
     Texture T = S.texs[tex];
     // checker_texture.rs:22-30 — select and descend (checkers may nest)
     while (T.kind == TEX_CHECKER) {
-        float sines = sinf(10.0f * p.x) * sinf(10.0f * p.y) * sinf(10.0f * p.z);
+        float sines = 1.0f;  // (sin(10x) * sin(10y)) * sin(10z); 1.0f * s is exact
+#pragma unroll 1
+        for (int a = 0; a < 3; ++a) sines *= sinf(10.0f * comp(p, a));
         T = S.texs[sines < 0.0f ? T.i0 : T.i1];
     }
     if (T.kind == TEX_SOLID) return v3(T.v[0], T.v[1], T.v[2]);  // solid_color.rs:21-23
@@ -720,12 +782,12 @@ __device__ __forceinline__ float reflectance(float cosine, float ref_idx) {  // 
 }
 
 // Material::emitted (materials/mod.rs:18; only DiffuseLight is non-zero, diffuse_light.rs:25-27)
-__device__ __forceinline__ V3 material_emitted(const DeviceScene& S, const TexEnv& E, const Material& m, const HitRec& h) {
+__device__ __forceinline__ V3 material_emitted(const DeviceScene& S, const TexEnv E, const Material& m, const HitRec& h) {
     if (m.kind == MAT_DIFFUSE_LIGHT) return texture_value(S, E, m.tex, h.u, h.v, h.p);
     return v3(0.0f, 0.0f, 0.0f);
 }
 // Material::scatter with uniforms u[0..3].  Returns false for "None".
-__device__ __forceinline__ bool material_scatter(const DeviceScene& S, const TexEnv& E, const Material& m, const Ray& ray,
+__device__ __forceinline__ bool material_scatter(const DeviceScene& S, const TexEnv E, const Material& m, const Ray& ray,
                                                  const HitRec& h, const float u[4], V3& attenuation, Ray& scattered) {
     switch (m.kind) {
         case MAT_LAMBERTIAN: {  // lambertian.rs:27-38

@@ -11,7 +11,7 @@
 //   tex_value_kernel   Texture::value                          (parity entry)
 //   scatter_kernel     Material::scatter / emitted             (parity entry)
 //   camera_rays_kernel Camera::get_ray                         (parity entry)
-#include "hrt_device.cuh"
+#include "hrt_machine.cuh"
 #include "hrt_launch.h"
 
 namespace HRT_NS {
@@ -35,24 +35,197 @@ struct RenderParams {
     float4* accum;
 };
 
-__device__ __forceinline__ void stage_noise(const DeviceScene& S, NoiseTable* sh, TexEnv& E) {
+__device__ __forceinline__ void stage_noise(const DeviceScene& S, TexEnv& E) {
     E.n_shared_noise = S.n_noise < kMaxNoiseTablesShared ? S.n_noise : kMaxNoiseTablesShared;
     const int words = E.n_shared_noise * (int)(sizeof(NoiseTable) / 16);
     const uint4* src = reinterpret_cast<const uint4*>(S.noise);
-    uint4* dst = reinterpret_cast<uint4*>(sh);
+    uint4* dst = reinterpret_cast<uint4*>(g_sh_noise);
     for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = __ldg(src + i);
-    for (int i = 0; i < kMaxNoiseTablesShared; ++i) {
-        E.noise[i].ranvec = reinterpret_cast<const float4*>(sh[i].ranvec);
-        E.noise[i].perm = &sh[i].perm[0][0];
-    }
     __syncthreads();
 }
 
 __global__ void __launch_bounds__(kBlock, 2) render_kernel(const __grid_constant__ RenderParams P) {
-    __shared__ NoiseTable sh_noise[kMaxNoiseTablesShared];
     __shared__ float sh_acc[kWarpsPerBlock][32][3];
     TexEnv E;
-    stage_noise(P.S, sh_noise, E);
+    stage_noise(P.S, E);
+
+    const DeviceScene& S = P.S;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const bool ref_boxes = P.reference_boxes != 0;
+    const V3 bg = v3(P.bg[0], P.bg[1], P.bg[2]);
+    const float div_w = (float)P.width - 1.0f, div_h = (float)P.height - 1.0f;  // application.rs:444-445
+    const float kTmin = 0.001f;                                                 // application.rs:482
+    unsigned long long n_rays = 0, n_paths = 0;
+#ifdef HRT_SCHED_STATS
+    unsigned long long st_rounds = 0, st_lanes = 0;  // lane c of every warp counts class c
+#endif
+
+    for (;;) {
+        unsigned long long item = 0;
+        if (lane == 0) item = atomicAdd(P.counters, 1ULL);
+        item = __shfl_sync(kFull, item, 0);
+        if (item >= (unsigned long long)P.n_items) break;
+        const int tile = (int)(item % (unsigned long long)P.n_tiles);
+        const int chunk = (int)(item / (unsigned long long)P.n_tiles);
+        const int tx = tile % P.tiles_x, ty = tile / P.tiles_x;
+        const int s0 = P.sample_begin + chunk * P.chunk;
+        const int s_end = P.sample_begin + P.sample_count;
+        const int s_n = (s0 + P.chunk <= s_end) ? P.chunk : (s_end - s0);
+        const int pool_size = 32 * s_n;
+        int pool_next = 0;
+
+        sh_acc[warp][lane][0] = 0.0f;
+        sh_acc[warp][lane][1] = 0.0f;
+        sh_acc[warp][lane][2] = 0.0f;
+        __syncwarp();
+
+        // per-lane path state
+        Lane L;
+        int cls = CLS_NEW;
+        Ray world;  // the ray segment being traced, in world space
+        V3 T = v3(1.0f, 1.0f, 1.0f);
+        uint32_t bounce = 0;
+        RngKey key;
+        key.k0 = P.k0; key.k1 = P.k1; key.pixel = 0; key.sample = 0;
+        int my_pl = lane;
+
+        for (;;) {
+            const int run = warp_vote(cls);  // warp-uniform
+            if (run == CLS_IDLE) break;
+#ifdef HRT_SCHED_STATS
+            {
+                const int n = __popc(__ballot_sync(kFull, cls == run));
+                if (lane == run) { st_rounds++; st_lanes += n; }
+            }
+#endif
+            if (run == CLS_BOX) {
+                if (cls == CLS_BOX) { step_box(S, L, kTmin, ref_boxes); cls = lane_class(L); }
+            } else if (run == CLS_SPHERE) {
+                if (cls == CLS_SPHERE) { step_sphere(S, L, kTmin); cls = lane_class(L); }
+            } else if (run == CLS_RECT) {
+                if (cls == CLS_RECT) { step_rect(S, L, kTmin); cls = lane_class(L); }
+            } else if (run == CLS_MISC) {
+                if (cls == CLS_MISC) {
+                    MediumXi xi;
+                    xi.key = key; xi.bounce = bounce; xi.injected = 0.0f; xi.inject = false;
+                    step_misc(S, L, world, kTmin, ref_boxes, xi);
+                    cls = lane_class(L);
+                }
+            } else if (run == CLS_DONE) {
+                // ---- traversal finished: emitted + scatter (application.rs:482-494) ----
+                if (cls == CLS_DONE) {
+                    n_rays++;
+                    V3 add = v3(0.0f, 0.0f, 0.0f);
+                    bool alive = false;
+                    if (L.best_pc < 0) {
+                        add = T * bg;
+                    } else {
+                        Best best;
+                        best.t = L.closest; best.pc = L.best_pc; best.face = L.best_face; best.ctx = L.best_ctx;
+                        HitRec h;
+                        make_hit_record(S, world, best, false, h);
+                        const Material m = S.mats[h.mat];
+                        if (m.kind == MAT_DIFFUSE_LIGHT) {
+                            add = T * material_emitted(S, E, m, h);  // DiffuseLight::scatter -> None
+                        } else {
+                            float u4[4];
+                            rng_block(key, bounce, RNG_BLOCK_SCATTER, u4);
+                            V3 att;
+                            Ray sc;
+                            if (material_scatter(S, E, m, world, h, u4, att, sc)) {
+                                T = T * att;
+                                world = sc;
+                                bounce++;
+                                alive = bounce < (uint32_t)P.depth;  // ray_color(depth == 0) is black
+                            }
+                        }
+                    }
+                    if (add.x != 0.0f) atomicAdd(&sh_acc[warp][my_pl][0], add.x);
+                    if (add.y != 0.0f) atomicAdd(&sh_acc[warp][my_pl][1], add.y);
+                    if (add.z != 0.0f) atomicAdd(&sh_acc[warp][my_pl][2], add.z);
+                    if (alive) {
+                        lane_start(S, L, world, CUDART_INF_F);
+                        cls = lane_class(L);
+                    } else {
+                        cls = CLS_NEW;
+                    }
+                }
+            } else {
+                // ---- CLS_NEW: re-fill path-less lanes from the warp-local pool (ballot + popc compaction) ----
+                const unsigned need = __ballot_sync(kFull, cls == CLS_NEW);
+                const int idx = pool_next + __popc(need & lt_mask);
+                pool_next += __popc(need);
+                if (cls == CLS_NEW) {
+                    if (idx >= pool_size) {
+                        cls = CLS_IDLE;
+                    } else {
+                        const int pl = idx & 31;
+                        const int px = tx * 8 + (pl & 7), py = ty * 4 + (pl >> 3);
+                        if (px < P.width && py < P.height) {
+                            key.pixel = (uint32_t)(py * P.width + px);
+                            key.sample = (uint32_t)(s0 + (idx >> 5));
+                            n_paths++;
+                            if (P.depth > 0) {
+                                float c4[4];
+                                rng_block(key, 0, RNG_BLOCK_CAMERA, c4);  // jitter x, jitter y, shutter time, lens u1
+                                float lens_u2 = 0.0f;
+                                if (P.cam.lens_radius != 0.0f) {
+                                    float l4[4];
+                                    rng_block(key, 0, RNG_BLOCK_CAMERA - 1, l4);
+                                    lens_u2 = l4[0];
+                                }
+                                const float u = ((float)px + c4[0]) / div_w;
+                                const float v = ((float)py + c4[1]) / div_h;
+                                world = camera_get_ray(P.cam, u, v, c4[3], lens_u2, c4[2]);
+                                T = v3(1.0f, 1.0f, 1.0f);
+                                bounce = 0;
+                                my_pl = pl;
+                                lane_start(S, L, world, CUDART_INF_F);
+                                cls = lane_class(L);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        {
+            const int px = tx * 8 + (lane & 7), py = ty * 4 + (lane >> 3);
+            if (px < P.width && py < P.height) {
+                float* dst = reinterpret_cast<float*>(P.accum + (size_t)py * P.width + px);
+                atomicAdd(dst + 0, sh_acc[warp][lane][0]);
+                atomicAdd(dst + 1, sh_acc[warp][lane][1]);
+                atomicAdd(dst + 2, sh_acc[warp][lane][2]);
+                atomicAdd(dst + 3, (float)s_n);
+            }
+        }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        n_rays += __shfl_xor_sync(kFull, n_rays, o);
+        n_paths += __shfl_xor_sync(kFull, n_paths, o);
+    }
+    if (lane == 0) {
+        atomicAdd(P.counters + 1, n_rays);
+        atomicAdd(P.counters + 2, n_paths);
+    }
+#ifdef HRT_SCHED_STATS
+    if (lane < 6) {
+        atomicAdd(P.counters + 8 + 2 * lane, st_rounds);
+        atomicAdd(P.counters + 9 + 2 * lane, st_lanes);
+    }
+#endif
+}
+
+// The plain variant: every lane runs the per-lane interpreter (`traverse<>`) for one whole ray segment per iteration and
+// the warp re-converges for shading.  Kept selectable (HRT_FLAG_INTERPRETER) for A/B measurements against the scheduler.
+__global__ void __launch_bounds__(kBlock, 2) render_interp_kernel(const __grid_constant__ RenderParams P) {
+    __shared__ float sh_acc[kWarpsPerBlock][32][3];
+    TexEnv E;
+    stage_noise(P.S, E);
 
     const DeviceScene& S = P.S;
     const int lane = threadIdx.x & 31;
@@ -102,12 +275,17 @@ __global__ void __launch_bounds__(kBlock, 2) render_kernel(const __grid_constant
                     if (px < P.width && py < P.height) {
                         key.pixel = (uint32_t)(py * P.width + px);
                         key.sample = (uint32_t)(s0 + (idx >> 5));
-                        float c4[4], t4[4];
-                        rng_block(key, 0, RNG_BLOCK_CAMERA, c4);
-                        rng_block(key, 0, RNG_BLOCK_CAMERA - 1, t4);
+                        float c4[4];
+                        rng_block(key, 0, RNG_BLOCK_CAMERA, c4);  // jitter x, jitter y, shutter time, lens u1
+                        float lens_u2 = 0.0f;
+                        if (P.cam.lens_radius != 0.0f) {
+                            float l4[4];
+                            rng_block(key, 0, RNG_BLOCK_CAMERA - 1, l4);
+                            lens_u2 = l4[0];
+                        }
                         const float u = ((float)px + c4[0]) / div_w;
                         const float v = ((float)py + c4[1]) / div_h;
-                        ray = camera_get_ray(P.cam, u, v, c4[2], c4[3], t4[0]);
+                        ray = camera_get_ray(P.cam, u, v, c4[3], lens_u2, c4[2]);
                         T = v3(1.0f, 1.0f, 1.0f);
                         bounce = 0;
                         my_pl = pl;
@@ -233,11 +411,74 @@ __global__ void __launch_bounds__(128) trace_hits_kernel(const __grid_constant__
     out[i] = o;
 }
 
+// world.hit() through the warp scheduler (the control flow the render kernel uses): one ray per lane.
+__global__ void __launch_bounds__(128) trace_hits_sched_kernel(const __grid_constant__ DeviceScene S, const hrt_ray* __restrict__ rays,
+                                                               int n, const float* __restrict__ xi_in, hrt_hit* __restrict__ out,
+                                                               int reference_boxes) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    Lane L;
+    int cls = CLS_IDLE;
+    Ray world;
+    float tmin = 0.0f;
+    MediumXi xi;
+    xi.key.k0 = 0; xi.key.k1 = 0; xi.key.pixel = 0; xi.key.sample = 0;
+    xi.bounce = 0;
+    xi.inject = true;
+    xi.injected = 0.5f;
+    if (i < n) {
+        const hrt_ray r = rays[i];
+        world.o = v3(r.o[0], r.o[1], r.o[2]);
+        world.d = v3(r.d[0], r.d[1], r.d[2]);
+        world.time = r.time;
+        tmin = r.tmin;
+        if (xi_in) xi.injected = xi_in[i];
+        lane_start(S, L, world, r.tmax);
+        cls = lane_class(L);
+    }
+    const bool ref = reference_boxes != 0;
+    for (;;) {
+        const int run = warp_vote(cls);
+        if (run == CLS_IDLE) break;
+        if (run == CLS_BOX) { if (cls == CLS_BOX) { step_box(S, L, tmin, ref); cls = lane_class(L); } }
+        else if (run == CLS_SPHERE) { if (cls == CLS_SPHERE) { step_sphere(S, L, tmin); cls = lane_class(L); } }
+        else if (run == CLS_RECT) { if (cls == CLS_RECT) { step_rect(S, L, tmin); cls = lane_class(L); } }
+        else if (run == CLS_MISC) { if (cls == CLS_MISC) { step_misc(S, L, world, tmin, ref, xi); cls = lane_class(L); } }
+        else if (run == CLS_DONE) {
+            if (cls == CLS_DONE) {
+                hrt_hit o;
+                o.hit = 0; o.t = 0.0f;
+                o.p[0] = o.p[1] = o.p[2] = 0.0f;
+                o.n[0] = o.n[1] = o.n[2] = 0.0f;
+                o.u = 0.0f; o.v = 0.0f;
+                o.front_face = 0; o.material_id = -1; o.prim_id = -1; o.face = 0;
+                if (L.best_pc >= 0) {
+                    Best best;
+                    best.t = L.closest; best.pc = L.best_pc; best.face = L.best_face; best.ctx = L.best_ctx;
+                    HitRec h;
+                    make_hit_record(S, world, best, true, h);
+                    o.hit = 1;
+                    o.t = h.t;
+                    o.p[0] = h.p.x; o.p[1] = h.p.y; o.p[2] = h.p.z;
+                    o.n[0] = h.n.x; o.n[1] = h.n.y; o.n[2] = h.n.z;
+                    o.u = h.u; o.v = h.v;
+                    o.front_face = h.front_face ? 1 : 0;
+                    o.material_id = h.mat;
+                    o.prim_id = h.prim;
+                    o.face = h.face;
+                }
+                out[i] = o;
+                cls = CLS_IDLE;
+            }
+        } else {
+            if (cls == CLS_NEW) cls = CLS_IDLE;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kBlock) tex_value_kernel(const __grid_constant__ DeviceScene S, int tex,
                                                            const float* __restrict__ uvp, int n, float* __restrict__ out) {
-    __shared__ NoiseTable sh_noise[kMaxNoiseTablesShared];
     TexEnv E;
-    stage_noise(S, sh_noise, E);
+    stage_noise(S, E);
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float* q = uvp + 5 * (size_t)i;
@@ -250,9 +491,8 @@ __global__ void __launch_bounds__(kBlock) tex_value_kernel(const __grid_constant
 __global__ void __launch_bounds__(kBlock) scatter_kernel(const __grid_constant__ DeviceScene S, const hrt_ray* __restrict__ rays,
                                                          const hrt_hit* __restrict__ hits, const float* __restrict__ u4, int n,
                                                          hrt_scatter_out* __restrict__ out) {
-    __shared__ NoiseTable sh_noise[kMaxNoiseTablesShared];
     TexEnv E;
-    stage_noise(S, sh_noise, E);
+    stage_noise(S, E);
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     hrt_scatter_out o;
@@ -405,14 +645,18 @@ cudaError_t launch_render(hrt::RenderLaunch& L, int num_sms, cudaStream_t stream
     L.grid = grid;
     L.block = kBlock;
     L.chunk = chunk;
-    render_kernel<<<grid, kBlock, 0, stream>>>(P);
+    if (L.interpreter) render_interp_kernel<<<grid, kBlock, 0, stream>>>(P);
+    else render_kernel<<<grid, kBlock, 0, stream>>>(P);
     return cudaGetLastError();
 }
 
 cudaError_t launch_trace_hits(const hrt::DeviceSceneHost& S, const hrt_ray* d_rays, int n, const float* d_xi, hrt_hit* d_out,
                               int reference_boxes, cudaStream_t stream) {
     if (n <= 0) return cudaSuccess;
-    trace_hits_kernel<<<(n + 127) / 128, 128, 0, stream>>>(to_device_scene(S), d_rays, n, d_xi, d_out, reference_boxes);
+    if (reference_boxes & 2)  // bit 1: run through the warp scheduler (the render kernel's control flow)
+        trace_hits_sched_kernel<<<(n + 127) / 128, 128, 0, stream>>>(to_device_scene(S), d_rays, n, d_xi, d_out, reference_boxes & 1);
+    else
+        trace_hits_kernel<<<(n + 127) / 128, 128, 0, stream>>>(to_device_scene(S), d_rays, n, d_xi, d_out, reference_boxes & 1);
     return cudaGetLastError();
 }
 cudaError_t launch_tex_value(const hrt::DeviceSceneHost& S, int tex, const float* d_uvp, int n, float* d_out,

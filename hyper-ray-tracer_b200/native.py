@@ -9,10 +9,12 @@ from typing import Optional, Sequence
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libhrt.so")
+LIB_PATH = os.environ.get("HRT_LIB") or os.path.join(_HERE, "csrc", "libhrt.so")  # HRT_LIB: diagnostic builds
 
 HRT_FLAG_REFERENCE_TRAVERSAL = 1
 HRT_FLAG_EXACT_MATH = 2
+HRT_FLAG_WARP_SCHEDULER = 4
+HRT_FLAG_INTERPRETER = 8
 
 
 class HrtError(RuntimeError):

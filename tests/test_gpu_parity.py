@@ -104,6 +104,24 @@ def test_hit_records_tight_boxes_same_result(pkg, orc, built, name):
 
 
 @pytest.mark.parametrize("name", ALL_SCENES)
+def test_hit_records_through_warp_scheduler(pkg, orc, built, name):
+    """The render kernel does not run the plain per-lane interpreter but a warp-level op-class scheduler (hrt_machine.cuh).
+    HRT_FLAG_WARP_SCHEDULER pushes the same explicit rays through that control flow: results must be bit-identical."""
+    N = pkg.native
+    spec, gb, ob, _, _ = built(name)
+    rays = _ray_set(pkg, orc, spec, ob, seed=29)[:-7]  # ragged tail: not a multiple of the warp size
+    xi = np.random.default_rng(4).random(len(rays), dtype=np.float32)
+    want = ob.trace_hits(rays, xi)
+    got = gb.trace_hits(rays, xi, flags=N.HRT_FLAG_EXACT_MATH | N.HRT_FLAG_WARP_SCHEDULER)
+    _compare_hits(got, want, exact=True, what=f"{name}/exact+scheduler")
+    plain = gb.trace_hits(rays, xi, flags=N.HRT_FLAG_EXACT_MATH)
+    assert plain.tobytes() == got.tobytes()
+    fast_plain = gb.trace_hits(rays, xi, flags=0)
+    fast_sched = gb.trace_hits(rays, xi, flags=N.HRT_FLAG_WARP_SCHEDULER)
+    assert fast_plain.tobytes() == fast_sched.tobytes()
+
+
+@pytest.mark.parametrize("name", ALL_SCENES)
 def test_hit_records_production_build_within_tolerance(pkg, orc, built, name):
     """The production build (FMA contraction, reciprocal multiplies instead of divides).  On the well-conditioned part of
     the ray set — camera rays — hit records are within 1e-5 relative.  Secondary rays START ON a surface: there
