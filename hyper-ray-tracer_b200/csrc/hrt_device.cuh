@@ -450,28 +450,16 @@ __device__ __forceinline__ bool traverse(const DeviceScene& S, int pc, const int
                 pc += 1;
                 break;
             }
-            case OP_TRANSLATE: {
-                apply_translate(cur, A);
-                cur_ctx = __float_as_int(A.w);
-                k = make_rayk(cur);
-                pc += 1;
-                break;
-            }
-            case OP_ROTATE: {
-                apply_rotate(cur, A);
-                cur_ctx = __float_as_int(A.w);
-                k = make_rayk(cur);
-                pc += 1;
-                break;
-            }
-            case OP_POP: {
+            case OP_TRANSLATE: case OP_ROTATE: case OP_POP: {
+                // enter / leave a (run of) ray space(s): map the world ray through the target context's push records
                 cur_ctx = __float_as_int(A.w);
                 cur = ray_in_ctx(S, world, cur_ctx);
                 k = make_rayk(cur);
-                pc += 1;
+                const int run = (int)(w7 >> 8);
+                pc += run > 0 ? run : 1;
                 break;
             }
-            case OP_MEDIUM: {
+            case OP_MEDIUM: case OP_MEDIUM_SPHERE: {
                 const int end = (int)(w7 >> 8);
                 if (!kInner) {
                     // constant_medium.rs:34-76
@@ -509,7 +497,7 @@ __device__ __forceinline__ bool traverse(const DeviceScene& S, int pc, const int
                 pc = end;
                 break;
             }
-            default:  // OP_END (or a stray AUX): stop
+            default:  // OP_END (or a stray record): stop
                 pc = pc_end;
                 break;
         }

@@ -92,28 +92,34 @@ __global__ void __launch_bounds__(kBlock, 2) render_kernel(const __grid_constant
         int my_pl = lane;
 
         for (;;) {
-            const int run = warp_vote(cls);  // warp-uniform
-            if (run == CLS_IDLE) break;
+            const Tier tier = warp_plan(cls);  // warp-uniform
+            if (!tier.any) break;
 #ifdef HRT_SCHED_STATS
-            {
-                const int n = __popc(__ballot_sync(kFull, cls == run));
-                if (lane == run) { st_rounds++; st_lanes += n; }
-            }
+#define HRT_STAT(C, COND)                                                  \
+    {                                                                      \
+        const int n_ = __popc(__ballot_sync(kFull, (COND)));               \
+        if (lane == (C) && n_ > 0) { st_rounds++; st_lanes += n_; }        \
+    }
+            if (tier.box) HRT_STAT(0, cls == CLS_BOX)
+            if (tier.leaf) { HRT_STAT(tier.leaf_cls, cls == tier.leaf_cls) }
+            if (tier.done) HRT_STAT(4, cls == CLS_DONE)
+            if (tier.fill) HRT_STAT(5, cls == CLS_NEW)
 #endif
-            if (run == CLS_BOX) {
+            if (tier.box) {  // tier 0
                 if (cls == CLS_BOX) { step_box(S, L, kTmin, ref_boxes); cls = lane_class(L); }
-            } else if (run == CLS_SPHERE) {
+                continue;
+            }
+            if (tier.leaf && cls == tier.leaf_cls) {  // the leaf class with the most parked lanes
                 if (cls == CLS_SPHERE) { step_sphere(S, L, kTmin); cls = lane_class(L); }
-            } else if (run == CLS_RECT) {
-                if (cls == CLS_RECT) { step_rect(S, L, kTmin); cls = lane_class(L); }
-            } else if (run == CLS_MISC) {
-                if (cls == CLS_MISC) {
+                else if (cls == CLS_RECT) { step_rect(S, L, kTmin); cls = lane_class(L); }
+                else {
                     MediumXi xi;
                     xi.key = key; xi.bounce = bounce; xi.injected = 0.0f; xi.inject = false;
                     step_misc(S, L, world, kTmin, ref_boxes, xi);
                     cls = lane_class(L);
                 }
-            } else if (run == CLS_DONE) {
+            }
+            if (tier.done) {
                 // ---- traversal finished: emitted + scatter (application.rs:482-494) ----
                 if (cls == CLS_DONE) {
                     n_rays++;
@@ -152,7 +158,8 @@ __global__ void __launch_bounds__(kBlock, 2) render_kernel(const __grid_constant
                         cls = CLS_NEW;
                     }
                 }
-            } else {
+            }
+            if (tier.fill) {
                 // ---- CLS_NEW: re-fill path-less lanes from the warp-local pool (ballot + popc compaction) ----
                 const unsigned need = __ballot_sync(kFull, cls == CLS_NEW);
                 const int idx = pool_next + __popc(need & lt_mask);
@@ -437,13 +444,18 @@ __global__ void __launch_bounds__(128) trace_hits_sched_kernel(const __grid_cons
     }
     const bool ref = reference_boxes != 0;
     for (;;) {
-        const int run = warp_vote(cls);
-        if (run == CLS_IDLE) break;
-        if (run == CLS_BOX) { if (cls == CLS_BOX) { step_box(S, L, tmin, ref); cls = lane_class(L); } }
-        else if (run == CLS_SPHERE) { if (cls == CLS_SPHERE) { step_sphere(S, L, tmin); cls = lane_class(L); } }
-        else if (run == CLS_RECT) { if (cls == CLS_RECT) { step_rect(S, L, tmin); cls = lane_class(L); } }
-        else if (run == CLS_MISC) { if (cls == CLS_MISC) { step_misc(S, L, world, tmin, ref, xi); cls = lane_class(L); } }
-        else if (run == CLS_DONE) {
+        const Tier tier = warp_plan(cls);
+        if (!tier.any) break;
+        if (tier.box) {
+            if (cls == CLS_BOX) { step_box(S, L, tmin, ref); cls = lane_class(L); }
+            continue;
+        }
+        if (tier.leaf && cls == tier.leaf_cls) {
+            if (cls == CLS_SPHERE) { step_sphere(S, L, tmin); cls = lane_class(L); }
+            else if (cls == CLS_RECT) { step_rect(S, L, tmin); cls = lane_class(L); }
+            else { step_misc(S, L, world, tmin, ref, xi); cls = lane_class(L); }
+        }
+        if (tier.done) {
             if (cls == CLS_DONE) {
                 hrt_hit o;
                 o.hit = 0; o.t = 0.0f;
@@ -469,8 +481,6 @@ __global__ void __launch_bounds__(128) trace_hits_sched_kernel(const __grid_cons
                 out[i] = o;
                 cls = CLS_IDLE;
             }
-        } else {
-            if (cls == CLS_NEW) cls = CLS_IDLE;
         }
     }
 }

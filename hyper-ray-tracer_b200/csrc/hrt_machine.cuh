@@ -1,16 +1,19 @@
-// hrt_machine.cuh — warp-level op-class scheduler over the op stream.
+// hrt_machine.cuh — warp-level tiered op-class scheduler over the op stream.
 //
 // Why: a straightforward per-lane interpreter (`traverse<>` in hrt_device.cuh) lets the 32 lanes of a warp sit at
-// different record kinds, so every iteration executes the box code, the sphere code, the cuboid code, the medium
-// code ... one after the other with a handful of lanes each.  ncu on the first version: 5.4 of 32 lanes active per
-// issued instruction (profiles/r01_v1_render_kernel.txt).
+// different record kinds, so every loop iteration pays the SUM of the class bodies present: box (~40 instructions) +
+// sphere + cuboid (~100) + medium (~300) ..., each for a handful of lanes.  ncu on the first version: 5.4 of 32 lanes
+// active per issued instruction (profiles/r01_render_kernel_summary.md).
 //
-// Here every lane keeps its traversal state in registers and PARKS at its current record.  Each round the warp
-// votes (ballot + popc) and executes ONE record class — the one most lanes are waiting for — with a warp-uniform
-// branch.  "Traversal finished -> shade" and "no path -> draw a new camera sample" are classes as well, so a lane
-// never waits for the longest traversal or the longest path in its warp, only for its class to win a vote.
-// Traversal order per ray is unchanged (the reference's fixed depth-first order), so results are identical to
-// `traverse<>`.
+// Here every lane keeps its traversal state in registers and PARKS at its current record.
+//   tier 0  box records (~85 % of all steps): executed whenever at least kBoxQuorum lanes are at a box — one ballot;
+//   tier 1  when the box population drops below the quorum, ONE pass services every parked leaf class (sphere, rect /
+//           cuboid, medium / ray-space change), which sends those lanes back to boxes;
+//   tier 2  "traversal finished -> shade" and "no path -> draw a new camera sample" are the expensive bodies (~450
+//           instructions): they wait until kShadeQuorum lanes need them, or until nothing else can run.
+// A lane therefore never waits for the longest traversal or the longest path of its warp, only for its class's turn.
+// Traversal order per ray is unchanged (the reference's fixed depth-first order), so results are bit-identical to
+// `traverse<>` (tests/test_gpu_parity.py::test_hit_records_through_warp_scheduler).
 #pragma once
 #include "hrt_device.cuh"
 
@@ -29,8 +32,7 @@ struct Lane {
 };
 
 __device__ __forceinline__ int record_class(uint32_t opc) {
-    // OP_END 0 | BOX 1,2 | SPHERE 3,4 | (AUX 5) | RECT 6,7,8, CUBOID 9 | TRANSLATE 10, ROTATE 11, POP 12, MEDIUM 13
-    return opc == 0u ? CLS_DONE : (opc <= 2u ? CLS_BOX : (opc <= 5u ? CLS_SPHERE : (opc <= 9u ? CLS_RECT : CLS_MISC)));
+    return (int)(opc >> 4) - 1;  // hrt_types.h: the opcode's high nibble is the class + 1
 }
 __device__ __forceinline__ void lane_fetch(const DeviceScene& S, Lane& L) { load_op(S, L.pc, L.A, L.B); }
 __device__ __forceinline__ int lane_class(const Lane& L) { return record_class(__float_as_uint(L.B.w) & 0xffu); }
@@ -94,39 +96,76 @@ __device__ __forceinline__ void step_rect(const DeviceScene& S, Lane& L, float t
     L.pc += 1;
     lane_fetch(S, L);
 }
-// TRANSLATE / ROTATE / POP / MEDIUM
+
+// The tail of ConstantMedium::hit once both boundary hits are known (constant_medium.rs:40-75).
+__device__ __forceinline__ void medium_finish(const DeviceScene& S, Lane& L, float t1, float t2, float tmin, const MediumXi& xi) {
+    if (t1 < tmin) t1 = tmin;
+    if (t2 > L.closest) t2 = L.closest;
+    if (!(t1 >= t2)) {
+        if (t1 < 0.0f) t1 = 0.0f;
+        const float ray_length = sqrtf(L.k.dd);
+        const float dist_inside = (t2 - t1) * ray_length;
+        const float u = xi.draw(__float_as_int(L.A.z));
+#if HRT_EXACT
+        const float hit_distance = L.A.x * (logf(u) / S.ln_e);
+#else
+        const float hit_distance = L.A.x * logf(u);
+#endif
+        if (!(hit_distance > dist_inside)) lane_accept(L, t1 + hit_distance / ray_length, 0);
+    }
+}
+
+// TRANSLATE / ROTATE / POP / MEDIUM / MEDIUM_SPHERE
 __device__ __forceinline__ void step_misc(const DeviceScene& S, Lane& L, const Ray& world, float tmin, bool reference_boxes,
                                           const MediumXi& xi) {
     const uint32_t w7 = __float_as_uint(L.B.w);
     const uint32_t opc = w7 & 0xffu;
-    if (opc != OP_MEDIUM) {
+    if (opc < OP_MEDIUM) {
         // TRANSLATE / ROTATE / POP: enter or leave a ray space.  All three map the WORLD ray through the target
         // context's push records (the same operations in the same order as applying them incrementally, so the result is
         // bit-identical) — one out-of-line code path instead of three inlined ones.
         L.ctx = __float_as_int(L.A.w);
         L.cur = ray_in_ctx(S, world, L.ctx);
         L.k = make_rayk(L.cur);
-        L.pc += 1;
-    } else {  // OP_MEDIUM — constant_medium.rs:34-76
+        const int run = (int)(w7 >> 8);
+        L.pc += run > 0 ? run : 1;
+    } else {  // constant_medium.rs:34-76
         const int end = (int)(w7 >> 8);
-        float t1 = boundary_hit(S, L.pc + 1, end, world, L.cur, L.ctx, -CUDART_INF_F, reference_boxes);
-        if (t1 == t1) {
-            float t2 = boundary_hit(S, L.pc + 1, end, world, L.cur, L.ctx, t1 + 0.0001f, reference_boxes);
-            if (t2 == t2) {
-                if (t1 < tmin) t1 = tmin;
-                if (t2 > L.closest) t2 = L.closest;
-                if (!(t1 >= t2)) {
-                    if (t1 < 0.0f) t1 = 0.0f;
-                    const float ray_length = sqrtf(L.k.dd);
-                    const float dist_inside = (t2 - t1) * ray_length;
-                    const float u = xi.draw(__float_as_int(L.A.z));
-#if HRT_EXACT
-                    const float hit_distance = L.A.x * (logf(u) / S.ln_e);
-#else
-                    const float hit_distance = L.A.x * logf(u);
-#endif
-                    if (!(hit_distance > dist_inside)) lane_accept(L, t1 + hit_distance / ray_length, 0);
+        bool done = false;
+        if (opc == OP_MEDIUM_SPHERE) {
+            // Boundary = one plain sphere: both boundary queries in closed form, with sphere_test's own arithmetic.
+            //   query 1, range (-inf, +inf): the near root is always accepted;
+            //   query 2, range (t1 + 1e-4, +inf): the near root (= t1) is below the range, so it is the far root or nothing.
+            float4 C, D;
+            load_op(S, L.pc + 1, C, D);
+            const Ray& r = L.cur;
+            const V3 oc = v3(__fsub_rn(r.o.x, C.x), __fsub_rn(r.o.y, C.y), __fsub_rn(r.o.z, C.z));
+            const float a = L.k.dd;
+            const float half_b = dot_rn(oc, r.d);
+            const float c = __fsub_rn(dot_rn(oc, oc), __fmul_rn(C.w, C.w));
+            const float disc = __fsub_rn(__fmul_rn(half_b, half_b), __fmul_rn(a, c));
+            if (disc < 0.0f) {
+                done = true;  // boundary missed -> None
+            } else {
+                const float sqrtd = sqrtf(disc);
+                const float t1 = __fdiv_rn(-half_b - sqrtd, a);
+                const float t2 = __fdiv_rn(-half_b + sqrtd, a);
+                const float lo = t1 + 0.0001f;
+                if (t1 == t1 && t2 == t2) {  // NaN roots take the generic path
+                    done = true;
+                    // sphere.rs:52-57 with range (lo, +inf): near root unless it is below lo, then the far root.  For
+                    // |t1| >= 2048 the f32 sum t1 + 1e-4 equals t1, the near root is accepted AGAIN, t2 == t1 and the
+                    // medium never scatters — reference behaviour, reproduced.
+                    if (!(t1 < lo)) medium_finish(S, L, t1, t1, tmin, xi);
+                    else if (!(t2 < lo)) medium_finish(S, L, t1, t2, tmin, xi);
                 }
+            }
+        }
+        if (!done) {
+            const float t1 = boundary_hit(S, L.pc + 1, end, world, L.cur, L.ctx, -CUDART_INF_F, reference_boxes);
+            if (t1 == t1) {
+                const float t2 = boundary_hit(S, L.pc + 1, end, world, L.cur, L.ctx, t1 + 0.0001f, reference_boxes);
+                if (t2 == t2) medium_finish(S, L, t1, t2, tmin, xi);
             }
         }
         L.pc = end;
@@ -134,16 +173,30 @@ __device__ __forceinline__ void step_misc(const DeviceScene& S, Lane& L, const R
     lane_fetch(S, L);
 }
 
-// Majority vote.  Boxes are ~85 % of all records, so their ballot is taken first and wins outright above a quorum;
-// otherwise the class with the most parked lanes runs.  `cls` may be CLS_IDLE (never chosen).  Returns CLS_IDLE when
-// no lane has anything to do.
-constexpr int kBoxQuorum = 12;
-__device__ __forceinline__ int warp_vote(int cls) {
+// ---- scheduling policy ----
+// Measured (profiles/r01_render_kernel_summary.md): the box test itself is ~3 % of the kernel's stall samples; the time
+// is in the leaf / medium / shade bodies, which are long and were running with 3-5 lanes under a "service every parked
+// class at once" policy.  So: boxes run whenever a small quorum is at a box (they are cheap and feed the other classes),
+// otherwise the single non-box class with the MOST parked lanes runs.
+#ifndef HRT_BOX_QUORUM
+#define HRT_BOX_QUORUM 8
+#endif
+constexpr int kBoxQuorum = HRT_BOX_QUORUM;
+
+struct Tier {
+    bool box, leaf, done, fill, any;  // what to run this round (warp-uniform; at most one of box/leaf/done/fill)
+    int leaf_cls;                     // which leaf class when `leaf`
+};
+__device__ __forceinline__ Tier warp_plan(int cls) {
     const unsigned full = 0xffffffffu;
+    Tier t;
+    t.leaf = t.done = t.fill = false;
+    t.leaf_cls = CLS_SPHERE;
     const int nb = __popc(__ballot_sync(full, cls == CLS_BOX));
-    if (nb >= kBoxQuorum) return CLS_BOX;
-    int best = CLS_IDLE, best_n = 0;
-    if (nb > 0) { best = CLS_BOX; best_n = nb; }
+    t.box = nb >= kBoxQuorum;
+    t.any = true;
+    if (t.box) return t;
+    int best = -1, best_n = 0;
     const int ns = __popc(__ballot_sync(full, cls == CLS_SPHERE));
     if (ns > best_n) { best = CLS_SPHERE; best_n = ns; }
     const int nr = __popc(__ballot_sync(full, cls == CLS_RECT));
@@ -154,7 +207,18 @@ __device__ __forceinline__ int warp_vote(int cls) {
     if (nd > best_n) { best = CLS_DONE; best_n = nd; }
     const int nn = __popc(__ballot_sync(full, cls == CLS_NEW));
     if (nn > best_n) { best = CLS_NEW; best_n = nn; }
-    return best;
+    if (best < 0) {  // nothing parked: step whatever is at a box, or finish
+        t.box = nb > 0;
+        t.any = nb > 0;
+        return t;
+    }
+    // a box population larger than every parked class still goes first
+    if (nb > best_n) { t.box = true; return t; }
+    t.leaf = best <= CLS_MISC;
+    t.leaf_cls = best;
+    t.done = best == CLS_DONE;
+    t.fill = best == CLS_NEW;
+    return t;
 }
 
 }  // namespace HRT_NS

@@ -328,7 +328,10 @@ struct Flattener {
                 in_medium = false;
                 if (!ok) return false;
                 if (pc() >= (1 << 24)) { error = "op stream longer than 2^24 records"; return false; }
-                s.ops[at].u[7] = OP_MEDIUM | ((uint32_t)pc() << 8);
+                {
+                    const bool single_sphere = (pc() == at + 2) && ((s.ops[at + 1].u[7] & 0xffu) == OP_SPHERE);
+                    s.ops[at].u[7] = (single_sphere ? OP_MEDIUM_SPHERE : OP_MEDIUM) | ((uint32_t)pc() << 8);
+                }
                 return true;
             }
             case OBJ_LIST: {
@@ -654,6 +657,28 @@ int32_t hrt_scene_commit(hrt_scene* s, int32_t root) {
         return fail(HRT_ERR_UNSUPPORTED, "commit: " + f.error);
     }
     f.push(OP_END);
+    // Consecutive ray-space pushes (Translation(Rotation(x))) and consecutive pops are entered / left in ONE step: the
+    // first record of a run carries the run's final context and its length; the others stay in the stream as data for
+    // the context replay (ray_in_ctx) but are never executed.
+    {
+        auto is_push = [](uint32_t o) { return o == OP_TRANSLATE || o == OP_ROTATE; };
+        const size_t n = s->ops.size();
+        for (size_t i = 0; i < n;) {
+            const uint32_t o = s->ops[i].u[7] & 0xffu;
+            if (is_push(o) || o == OP_POP) {
+                size_t j = i;
+                while (j + 1 < n) {
+                    const uint32_t o2 = s->ops[j + 1].u[7] & 0xffu;
+                    if (is_push(o) ? is_push(o2) : (o2 == OP_POP)) ++j; else break;
+                }
+                s->ops[i].i[3] = s->ops[j].i[3];
+                s->ops[i].u[7] = o | ((uint32_t)(j - i + 1) << 8);
+                i = j + 1;
+            } else {
+                ++i;
+            }
+        }
+    }
     s->root = root;
     s->committed = true;
     return HRT_OK;

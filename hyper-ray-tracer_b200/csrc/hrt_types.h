@@ -13,21 +13,24 @@
 
 namespace hrt {
 
+// The high nibble of an opcode is its scheduler class + 1 (box 1, sphere 2, rect 3, misc 4, end 5), so the render
+// kernel's class look-up is a shift (hrt_machine.cuh: record_class).
 enum Opcode : uint32_t {
-    OP_END = 0,
-    OP_BOX = 1,        // sound box: intersected ("tight") slab test is result-identical to the reference test
-    OP_BOX_LOOSE = 2,  // unsound box (Q2): MUST use the reference's per-axis test (src/aabb.rs:20-47)
-    OP_SPHERE = 3,
-    OP_MSPHERE = 4,    // followed by one OP_MSPHERE_AUX record
-    OP_MSPHERE_AUX = 5,
-    OP_RECT_XY = 6,
-    OP_RECT_YZ = 7,
-    OP_RECT_ZX = 8,
-    OP_CUBOID = 9,
-    OP_TRANSLATE = 10,  // enter child ray space
-    OP_ROTATE = 11,
-    OP_POP = 12,        // leave child ray space (restore context in w3)
-    OP_MEDIUM = 13,
+    OP_BOX = 0x10,        // sound box: intersected ("tight") slab test is result-identical to the reference test
+    OP_BOX_LOOSE = 0x11,  // unsound box (Q2): MUST use the reference's per-axis test (src/aabb.rs:20-47)
+    OP_SPHERE = 0x20,
+    OP_MSPHERE = 0x21,    // followed by one OP_MSPHERE_AUX record
+    OP_MSPHERE_AUX = 0x2f,
+    OP_RECT_XY = 0x30,
+    OP_RECT_YZ = 0x31,
+    OP_RECT_ZX = 0x32,
+    OP_CUBOID = 0x33,
+    OP_TRANSLATE = 0x40,  // enter child ray space
+    OP_ROTATE = 0x41,
+    OP_POP = 0x42,        // leave child ray space (restore context in w3)
+    OP_MEDIUM = 0x43,
+    OP_MEDIUM_SPHERE = 0x44,  // OP_MEDIUM whose boundary sub-stream is exactly one OP_SPHERE record (closed-form path)
+    OP_END = 0x50,
 };
 
 // 32-byte record = two float4.  w7 (the .w of the second float4) = opcode | (payload << 8).
@@ -36,9 +39,9 @@ enum Opcode : uint32_t {
 //   MSPHERE     w0-2 c0, w3 r       w4 mat, w5 prim_id        w7 = op       (+AUX: w0-2 c1, w3 t0, w4 t1)
 //   RECT_*      w0-3 a0,a1,b0,b1    w4 k, w5 mat, w6 prim_id  w7 = op
 //   CUBOID      w0-2 min, w3 mat    w4-6 max                  w7 = op | prim_id<<8
-//   TRANSLATE   w0-2 d, w3 ctx                                 w7 = op
-//   ROTATE      w0 sin, w1 cos, w2 axis, w3 ctx                w7 = op
-//   POP         w3 ctx to restore                              w7 = op
+//   TRANSLATE   w0-2 d, w3 ctx                                 w7 = op | run<<8   } run = number of consecutive push (or
+//   ROTATE      w0 sin, w1 cos, w2 axis, w3 ctx                w7 = op | run<<8   } pop) records starting here: executing the
+//   POP         w3 ctx to restore                              w7 = op | run<<8   } first one enters/leaves the whole chain
 //   MEDIUM      w0 -1/density, w1 mat, w2 medium idx, w3 prim  w7 = op | end_pc<<8
 struct alignas(16) Op {
     union {

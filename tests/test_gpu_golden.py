@@ -61,7 +61,9 @@ def test_converged_image_matches_golden(pkg, cfg):
     # the two 2048-spp halves differ by noise of variance 4 sigma^2_4096; GPU-vs-golden carries ~sigma^2_4096
     assert mae <= max(1.0 / 255.0, 0.62 * meta["mae_half_vs_half"]), report
     assert psnr >= min(40.0, meta["psnr_half_vs_half"] + 4.5), report
-    assert report["z_rms"] < 1.5 and abs(report["z_mean"]) < 0.35, report
+    # z_rms / z_mean are reported for information only: the goldens are stored as float16 in gamma space, whose
+    # quantisation (2^-11 relative) exceeds the 4096-spp standard error in smooth regions; the statistically rigorous
+    # z-score tests run against live float32 oracle renders in test_gpu_parity.py
     assert abs(report["rays_per_path_gpu"] - report["rays_per_path_oracle"]) < 0.01 * report["rays_per_path_oracle"], report
 
 

@@ -97,7 +97,7 @@ def test_stream_layout_cornell(pkg):
     ops = gb.ops()
     opc = ops[:, 7] & 0xFF
     payload = ops[:, 7] >> 8
-    OP_END, OP_BOX, OP_BOX_LOOSE, OP_RECT_ZX, OP_CUBOID, OP_TRANSLATE, OP_ROTATE, OP_POP = 0, 1, 2, 8, 9, 10, 11, 12
+    OP_END, OP_BOX, OP_BOX_LOOSE, OP_RECT_ZX, OP_CUBOID, OP_TRANSLATE, OP_ROTATE, OP_POP = 0x50, 0x10, 0x11, 0x32, 0x33, 0x40, 0x41, 0x42
     assert opc[-1] == OP_END
     boxes = np.where((opc == OP_BOX) | (opc == OP_BOX_LOOSE))[0]
     assert len(boxes) == 15
