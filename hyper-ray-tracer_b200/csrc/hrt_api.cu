@@ -284,6 +284,7 @@ static int32_t render_into(hrt_scene* s, DeviceState* d, const hrt_camera_desc* 
     L.counters = d->d_counters;
     L.accum = d_accum;
     L.chunk = 0;
+    if (const char* env = getenv("HRT_CHUNK")) L.chunk = atoi(env);  // diagnostic: samples per work item
     HRT_CUDA(cudaMemsetAsync(d->d_counters, 0, 24 * sizeof(unsigned long long), stream));
     if (want_stats) HRT_CUDA(cudaEventRecord(d->ev[0], stream));
     cudaError_t e = (rd->flags & HRT_FLAG_EXACT_MATH) ? hrt_exact::launch_render(L, d->num_sms, stream)

@@ -92,7 +92,16 @@ __global__ void __launch_bounds__(kBlock, 2) render_kernel(const __grid_constant
         int my_pl = lane;
 
         for (;;) {
-            const Tier tier = warp_plan(cls);  // warp-uniform
+            // ---- tight box loop: while a quorum of lanes sits at a box record, nothing else is looked at ----
+            int nb = warp_box_count(cls);
+            while (nb >= kBoxQuorum) {
+#ifdef HRT_SCHED_STATS
+                if (lane == 0) { st_rounds++; st_lanes += nb; }
+#endif
+                if (cls == CLS_BOX) { step_box(S, L, kTmin, ref_boxes); cls = lane_class(L); }
+                nb = warp_box_count(cls);
+            }
+            const Tier tier = warp_plan_slow(cls, nb);  // warp-uniform
             if (!tier.any) break;
 #ifdef HRT_SCHED_STATS
 #define HRT_STAT(C, COND)                                                  \
@@ -105,7 +114,7 @@ __global__ void __launch_bounds__(kBlock, 2) render_kernel(const __grid_constant
             if (tier.done) HRT_STAT(4, cls == CLS_DONE)
             if (tier.fill) HRT_STAT(5, cls == CLS_NEW)
 #endif
-            if (tier.box) {  // tier 0
+            if (tier.box) {  // below the quorum, but still the largest population
                 if (cls == CLS_BOX) { step_box(S, L, kTmin, ref_boxes); cls = lane_class(L); }
                 continue;
             }

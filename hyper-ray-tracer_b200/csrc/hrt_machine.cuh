@@ -17,6 +17,13 @@
 #pragma once
 #include "hrt_device.cuh"
 
+#ifndef HRT_DUAL_PREFETCH
+#define HRT_DUAL_PREFETCH 0
+#endif
+#ifndef HRT_VOTE_MATCH
+#define HRT_VOTE_MATCH 0
+#endif
+
 namespace HRT_NS {
 
 enum LaneClass : int { CLS_BOX = 0, CLS_SPHERE = 1, CLS_RECT = 2, CLS_MISC = 3, CLS_DONE = 4, CLS_NEW = 5, CLS_IDLE = 6 };
@@ -59,11 +66,24 @@ __device__ __forceinline__ void lane_accept(Lane& L, float t, int face) {
 // ---- class bodies: each advances the lane by exactly one record and prefetches the next ----
 __device__ __forceinline__ void step_box(const DeviceScene& S, Lane& L, float tmin, bool reference_boxes) {
     const uint32_t w7 = __float_as_uint(L.B.w);
+    const int skip = (int)(w7 >> 8);
+    // Both possible successors are known before the test: fetch them now so the (dependent) record load overlaps the
+    // slab arithmetic instead of being exposed in front of the next vote (ncu: long_scoreboard on the first use of B.w).
+#if HRT_DUAL_PREFETCH
+    float4 nA, nB, sA, sB;
+    load_op(S, L.pc + 1, nA, nB);
+    load_op(S, skip, sA, sB);
+#endif
     const bool loose = ((w7 & 0xffu) == OP_BOX_LOOSE) || reference_boxes;
     const bool hit = loose ? box_hit_reference(L.A, L.B, L.cur, L.k, tmin, L.closest)
                            : box_hit_tight(L.A, L.B, L.cur, L.k, tmin, L.closest);
-    L.pc = hit ? L.pc + 1 : (int)(w7 >> 8);
+    L.pc = hit ? L.pc + 1 : skip;
+#if HRT_DUAL_PREFETCH
+    L.A = hit ? nA : sA;
+    L.B = hit ? nB : sB;
+#else
     lane_fetch(S, L);
+#endif
 }
 __device__ __forceinline__ void step_sphere(const DeviceScene& S, Lane& L, float tmin) {
     const bool moving = (__float_as_uint(L.B.w) & 0xffu) == OP_MSPHERE;
@@ -187,38 +207,64 @@ struct Tier {
     bool box, leaf, done, fill, any;  // what to run this round (warp-uniform; at most one of box/leaf/done/fill)
     int leaf_cls;                     // which leaf class when `leaf`
 };
-__device__ __forceinline__ Tier warp_plan(int cls) {
+#if !HRT_VOTE_MATCH
+// Number of lanes at a box record (the fast path of the vote: one ballot).
+__device__ __forceinline__ int warp_box_count(int cls) { return __popc(__ballot_sync(0xffffffffu, cls == CLS_BOX)); }
+// Slow path, taken when fewer than kBoxQuorum lanes are at a box: populations of the five non-box classes in ONE
+// REDUX.ADD over 6-bit packed counters (sphere, rect, misc, done, new), then the class with the most parked lanes.
+__device__ __forceinline__ Tier warp_plan_slow(int cls, int nb) {
     const unsigned full = 0xffffffffu;
+    const unsigned one = (cls >= CLS_SPHERE && cls <= CLS_NEW) ? (1u << (6 * (cls - 1))) : 0u;
+    const unsigned packed = __reduce_add_sync(full, one);
+    int best = -1, best_n = 0;
+#pragma unroll
+    for (int c = CLS_SPHERE; c <= CLS_NEW; ++c) {
+        const int n = (int)((packed >> (6 * (c - 1))) & 63u);
+        if (n > best_n) { best = c; best_n = n; }
+    }
     Tier t;
     t.leaf = t.done = t.fill = false;
     t.leaf_cls = CLS_SPHERE;
-    const int nb = __popc(__ballot_sync(full, cls == CLS_BOX));
-    t.box = nb >= kBoxQuorum;
-    t.any = true;
-    if (t.box) return t;
-    int best = -1, best_n = 0;
-    const int ns = __popc(__ballot_sync(full, cls == CLS_SPHERE));
-    if (ns > best_n) { best = CLS_SPHERE; best_n = ns; }
-    const int nr = __popc(__ballot_sync(full, cls == CLS_RECT));
-    if (nr > best_n) { best = CLS_RECT; best_n = nr; }
-    const int nm = __popc(__ballot_sync(full, cls == CLS_MISC));
-    if (nm > best_n) { best = CLS_MISC; best_n = nm; }
-    const int nd = __popc(__ballot_sync(full, cls == CLS_DONE));
-    if (nd > best_n) { best = CLS_DONE; best_n = nd; }
-    const int nn = __popc(__ballot_sync(full, cls == CLS_NEW));
-    if (nn > best_n) { best = CLS_NEW; best_n = nn; }
-    if (best < 0) {  // nothing parked: step whatever is at a box, or finish
-        t.box = nb > 0;
-        t.any = nb > 0;
-        return t;
-    }
-    // a box population larger than every parked class still goes first
-    if (nb > best_n) { t.box = true; return t; }
+    t.any = (nb > 0) || (best >= 0);
+    t.box = nb > 0 && nb > best_n;  // a box population larger than every parked class still goes first
+    if (t.box || best < 0) return t;
     t.leaf = best <= CLS_MISC;
     t.leaf_cls = best;
     t.done = best == CLS_DONE;
     t.fill = best == CLS_NEW;
     return t;
 }
+__device__ __forceinline__ Tier warp_plan(int cls) {
+    const int nb = warp_box_count(cls);
+    if (nb >= kBoxQuorum) {
+        Tier t;
+        t.box = t.any = true;
+        t.leaf = t.done = t.fill = false;
+        t.leaf_cls = CLS_SPHERE;
+        return t;
+    }
+    return warp_plan_slow(cls, nb);
+}
+#else
+__device__ __forceinline__ Tier warp_plan(int cls) {
+    // One MATCH.ANY gives every lane the mask of lanes parked at the same class, one REDUX.MAX picks the winner:
+    // key = (population << 3) | (7 - class), boxes above the quorum get the maximum population; ties go to the lower
+    // class id.  (The first version of this vote — six ballot/popc pairs — was 19 % of the kernel's stall samples.)
+    const unsigned full = 0xffffffffu;
+    const int n = __popc(__match_any_sync(full, cls));
+    unsigned key = 0u;
+    if (cls < CLS_IDLE) key = ((cls == CLS_BOX && n >= kBoxQuorum ? 63u : (unsigned)n) << 3) | (unsigned)(7 - cls);
+    const unsigned win = __reduce_max_sync(full, key);
+    const int run = 7 - (int)(win & 7u);
+    Tier t;
+    t.any = win != 0u;
+    t.box = t.any && run == CLS_BOX;
+    t.leaf = t.any && run >= CLS_SPHERE && run <= CLS_MISC;
+    t.leaf_cls = run;
+    t.done = t.any && run == CLS_DONE;
+    t.fill = t.any && run == CLS_NEW;
+    return t;
+}
+#endif
 
 }  // namespace HRT_NS
