@@ -275,11 +275,17 @@ static int32_t render_into(hrt_scene* s, DeviceState* d, const hrt_camera_desc* 
         ref_boxes = true;
     L.reference_boxes = ref_boxes ? 1 : 0;
     {
-        const char* env = getenv("HRT_KERNEL");  // diagnostic override: "interp" | "sched"
-        bool interp = (rd->flags & HRT_FLAG_INTERPRETER) != 0;
-        if (env && env[0] == 'i') interp = true;
-        if (env && env[0] == 's') interp = false;
-        L.interpreter = interp ? 1 : 0;
+        const char* env = getenv("HRT_KERNEL");  // diagnostic override: "interp" | "sched" | "pool"
+        // default: the shared-memory ray-pool kernel (best sustained throughput; its 96-ray pools need enough samples per
+        // launch to amortise), the in-register warp scheduler for short launches
+        int variant = L.sample_count >= 128 ? 2 : 0;
+        if (rd->flags & HRT_FLAG_SCHEDULER) variant = 0;
+        if (rd->flags & HRT_FLAG_INTERPRETER) variant = 1;
+        if (rd->flags & HRT_FLAG_POOL) variant = 2;
+        if (env && env[0] == 'i') variant = 1;
+        if (env && env[0] == 's') variant = 0;
+        if (env && env[0] == 'p') variant = 2;
+        L.interpreter = variant;
     }
     L.counters = d->d_counters;
     L.accum = d_accum;

@@ -11,7 +11,7 @@
 //   tex_value_kernel   Texture::value                          (parity entry)
 //   scatter_kernel     Material::scatter / emitted             (parity entry)
 //   camera_rays_kernel Camera::get_ray                         (parity entry)
-#include "hrt_machine.cuh"
+#include "hrt_pool.cuh"
 #include "hrt_launch.h"
 
 namespace HRT_NS {
@@ -22,6 +22,12 @@ constexpr int kBlock = 256;
 constexpr int kWarpsPerBlock = kBlock / 32;
 constexpr unsigned kFull = 0xffffffffu;
 
+constexpr int kMaxTailChunks = 12;
+
+// Sample range of chunk `c` (relative to sample_begin): big chunks first, the tail in shrinking chunks, so the last work
+// items handed out by the global cursor are short and the end-of-kernel tail stays small.
+struct RenderParams;
+
 struct RenderParams {
     DeviceScene S;
     CameraK cam;
@@ -30,6 +36,8 @@ struct RenderParams {
     uint32_t k0, k1;
     int sample_begin, sample_count;
     int chunk, n_chunks, tiles_x, tiles_y, n_tiles, n_items;
+    // guided schedule: n_big chunks of `chunk` samples, then up to kMaxTailChunks geometrically smaller ones
+    int n_big, tail_begin[kMaxTailChunks], tail_size[kMaxTailChunks];
     int reference_boxes;
     unsigned long long* counters;
     float4* accum;
@@ -70,9 +78,9 @@ __global__ void __launch_bounds__(kBlock, 2) render_kernel(const __grid_constant
         const int tile = (int)(item % (unsigned long long)P.n_tiles);
         const int chunk = (int)(item / (unsigned long long)P.n_tiles);
         const int tx = tile % P.tiles_x, ty = tile / P.tiles_x;
-        const int s0 = P.sample_begin + chunk * P.chunk;
-        const int s_end = P.sample_begin + P.sample_count;
-        const int s_n = (s0 + P.chunk <= s_end) ? P.chunk : (s_end - s0);
+        const int tc = chunk - P.n_big;  // >= 0: one of the shrinking tail chunks
+        const int s0 = P.sample_begin + (tc < 0 ? chunk * P.chunk : P.tail_begin[tc]);
+        const int s_n = tc < 0 ? P.chunk : P.tail_size[tc];
         const int pool_size = 32 * s_n;
         int pool_next = 0;
 
@@ -260,9 +268,9 @@ __global__ void __launch_bounds__(kBlock, 2) render_interp_kernel(const __grid_c
         const int tile = (int)(item % (unsigned long long)P.n_tiles);
         const int chunk = (int)(item / (unsigned long long)P.n_tiles);
         const int tx = tile % P.tiles_x, ty = tile / P.tiles_x;
-        const int s0 = P.sample_begin + chunk * P.chunk;
-        const int s_end = P.sample_begin + P.sample_count;
-        const int s_n = (s0 + P.chunk <= s_end) ? P.chunk : (s_end - s0);
+        const int tc = chunk - P.n_big;  // >= 0: one of the shrinking tail chunks
+        const int s0 = P.sample_begin + (tc < 0 ? chunk * P.chunk : P.tail_begin[tc]);
+        const int s_n = tc < 0 ? P.chunk : P.tail_size[tc];
         const int pool_size = 32 * s_n;
         int pool_next = 0;
 
@@ -376,6 +384,236 @@ __global__ void __launch_bounds__(kBlock, 2) render_interp_kernel(const __grid_c
         atomicAdd(P.counters + 1, n_rays);
         atomicAdd(P.counters + 2, n_paths);
     }
+}
+
+// ---- render kernel with a warp-private ray pool in shared memory (hrt_pool.cuh) ----
+__global__ void __launch_bounds__(kBlock, 2) render_pool_kernel(const __grid_constant__ RenderParams P) {
+    extern __shared__ __align__(16) float sh_pool[];
+    __shared__ float sh_acc[kWarpsPerBlock][32][3];
+    TexEnv E;
+    stage_noise(P.S, E);
+
+    const DeviceScene& S = P.S;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const bool ref_boxes = P.reference_boxes != 0;
+    const V3 bg = v3(P.bg[0], P.bg[1], P.bg[2]);
+    const float div_w = (float)P.width - 1.0f, div_h = (float)P.height - 1.0f;  // application.rs:444-445
+    const float kTmin = 0.001f;                                                 // application.rs:482
+    unsigned long long n_rays = 0, n_paths = 0;
+#ifdef HRT_SCHED_STATS
+    unsigned long long st_rounds = 0, st_lanes = 0;
+#endif
+    PoolWarp W;
+    W.f = sh_pool + warp * kPoolWarpWords;
+    W.cls_w = reinterpret_cast<uint32_t*>(W.f + PF_WORDS * kPoolSlots);
+    W.list = reinterpret_cast<int*>(W.cls_w + 32);
+    int first_cls;  // class of record 0: where every new ray segment starts
+    {
+        float4 A0, B0;
+        load_op(S, 0, A0, B0);
+        first_cls = record_class(__float_as_uint(B0.w) & 0xffu);
+    }
+
+    for (;;) {
+        unsigned long long item = 0;
+        if (lane == 0) item = atomicAdd(P.counters, 1ULL);
+        item = __shfl_sync(kFull, item, 0);
+        if (item >= (unsigned long long)P.n_items) break;
+        const int tile = (int)(item % (unsigned long long)P.n_tiles);
+        const int chunk = (int)(item / (unsigned long long)P.n_tiles);
+        const int tx = tile % P.tiles_x, ty = tile / P.tiles_x;
+        const int tc = chunk - P.n_big;  // >= 0: one of the shrinking tail chunks
+        const int s0 = P.sample_begin + (tc < 0 ? chunk * P.chunk : P.tail_begin[tc]);
+        const int s_n = tc < 0 ? P.chunk : P.tail_size[tc];
+        const int pool_size = 32 * s_n;
+        int pool_next = 0;
+
+        sh_acc[warp][lane][0] = 0.0f;
+        sh_acc[warp][lane][1] = 0.0f;
+        sh_acc[warp][lane][2] = 0.0f;
+        // every slot starts path-less (byte 3 of the class word is unused)
+        W.cls_w[lane] = (uint32_t)CLS_NEW * 0x00010101u | ((uint32_t)CLS_IDLE << 24);
+        __syncwarp();
+        int rot = 0;
+
+        for (;;) {
+            const uint32_t cw = W.cls_w[lane];
+            const PoolCounts cnt = pool_count(cw);
+            int run = CLS_BOX, best_n = cnt.n[CLS_BOX];
+#pragma unroll
+            for (int c = CLS_SPHERE; c <= CLS_NEW; ++c)
+                if (cnt.n[c] > best_n) { run = c; best_n = cnt.n[c]; }
+            if (best_n == 0) break;  // every slot idle: the item is finished
+            const int n = pool_gather(W, cw, run, lane, rot);
+            rot = rot + 1 == kPoolHomes ? 0 : rot + 1;
+            const int s = lane < n ? W.list[lane] : -1;
+#ifdef HRT_SCHED_STATS
+            if (lane == run) { st_rounds++; st_lanes += n; }
+#endif
+            if (run == CLS_BOX) {
+                Lane L;
+                int cls = CLS_IDLE;
+                if (s >= 0) {
+                    L.cur.o = v3(W.at(PF_COX, s), W.at(PF_COY, s), W.at(PF_COZ, s));
+                    L.cur.d = v3(W.at(PF_CDX, s), W.at(PF_CDY, s), W.at(PF_CDZ, s));
+                    L.closest = W.at(PF_CLOSEST, s);
+                    L.pc = __float_as_int(W.at(PF_PC, s));
+                    L.k = make_rayk(L.cur);
+                    lane_fetch(S, L);
+                    cls = lane_class(L);
+                }
+                // several box steps per gather, while most of the gathered rays are still at a box
+                for (int it = 0; it < kPoolMaxBoxSteps; ++it) {
+                    if (cls == CLS_BOX) { step_box(S, L, kTmin, ref_boxes); cls = lane_class(L); }
+                    if (__popc(__ballot_sync(kFull, cls == CLS_BOX)) < kPoolBoxKeep) break;
+                }
+                if (s >= 0) {
+                    W.at(PF_PC, s) = __int_as_float(L.pc);
+                    W.set_cls(s, cls);
+                }
+            } else if (run <= CLS_MISC) {
+                if (s >= 0) {
+                    Lane L;
+                    pool_load_traversal(W, s, L);
+                    L.k = make_rayk(L.cur);
+                    lane_fetch(S, L);
+                    if (run == CLS_SPHERE) step_sphere(S, L, kTmin);
+                    else if (run == CLS_RECT) step_rect(S, L, kTmin);
+                    else {
+                        const Ray world = pool_load_world(W, s);
+                        MediumXi xi;
+                        xi.key.k0 = P.k0; xi.key.k1 = P.k1;
+                        xi.key.pixel = __float_as_uint(W.at(PF_PIXEL, s));
+                        xi.key.sample = __float_as_uint(W.at(PF_SAMPLE, s));
+                        xi.bounce = __float_as_uint(W.at(PF_BOUNCE_PL, s)) & 0xffffu;
+                        xi.injected = 0.0f; xi.inject = false;
+                        step_misc(S, L, world, kTmin, ref_boxes, xi);
+                    }
+                    pool_store_traversal(W, s, L, run == CLS_MISC);
+                    W.set_cls(s, lane_class(L));
+                }
+            } else if (run == CLS_DONE) {
+                // ---- traversal finished: emitted + scatter (application.rs:482-494) ----
+                if (s >= 0) {
+                    n_rays++;
+                    Ray world = pool_load_world(W, s);
+                    V3 T = v3(W.at(PF_TX, s), W.at(PF_TY, s), W.at(PF_TZ, s));
+                    const uint32_t bpl = __float_as_uint(W.at(PF_BOUNCE_PL, s));
+                    uint32_t bounce = bpl & 0xffffu;
+                    const int my_pl = (int)(bpl >> 16);
+                    RngKey key;
+                    key.k0 = P.k0; key.k1 = P.k1;
+                    key.pixel = __float_as_uint(W.at(PF_PIXEL, s));
+                    key.sample = __float_as_uint(W.at(PF_SAMPLE, s));
+                    const int best_pc = __float_as_int(W.at(PF_BEST_PC, s));
+                    V3 add = v3(0.0f, 0.0f, 0.0f);
+                    bool alive = false;
+                    if (best_pc < 0) {
+                        add = T * bg;
+                    } else {
+                        const int fc = __float_as_int(W.at(PF_BEST_FC, s));
+                        Best best;
+                        best.t = W.at(PF_CLOSEST, s); best.pc = best_pc; best.face = fc & 0xff; best.ctx = fc >> 8;
+                        HitRec h;
+                        make_hit_record(S, world, best, false, h);
+                        const Material m = S.mats[h.mat];
+                        if (m.kind == MAT_DIFFUSE_LIGHT) {
+                            add = T * material_emitted(S, E, m, h);  // DiffuseLight::scatter -> None
+                        } else {
+                            float u4[4];
+                            rng_block(key, bounce, RNG_BLOCK_SCATTER, u4);
+                            V3 att;
+                            Ray sc;
+                            if (material_scatter(S, E, m, world, h, u4, att, sc)) {
+                                T = T * att;
+                                world = sc;
+                                bounce++;
+                                alive = bounce < (uint32_t)P.depth;  // ray_color(depth == 0) is black
+                            }
+                        }
+                    }
+                    if (add.x != 0.0f) atomicAdd(&sh_acc[warp][my_pl][0], add.x);
+                    if (add.y != 0.0f) atomicAdd(&sh_acc[warp][my_pl][1], add.y);
+                    if (add.z != 0.0f) atomicAdd(&sh_acc[warp][my_pl][2], add.z);
+                    if (alive) {
+                        pool_store_segment(W, s, world);
+                        W.at(PF_TX, s) = T.x; W.at(PF_TY, s) = T.y; W.at(PF_TZ, s) = T.z;
+                        W.at(PF_BOUNCE_PL, s) = __uint_as_float(bounce | ((uint32_t)my_pl << 16));
+                        W.set_cls(s, first_cls);
+                    } else {
+                        W.set_cls(s, CLS_NEW);
+                    }
+                }
+            } else {
+                // ---- CLS_NEW: the gathered path-less slots draw the next path indices of the item ----
+                const int idx = pool_next + lane;
+                pool_next += n;
+                if (s >= 0) {
+                    if (idx >= pool_size) {
+                        W.set_cls(s, CLS_IDLE);
+                    } else {
+                        const int pl = idx & 31;
+                        const int px = tx * 8 + (pl & 7), py = ty * 4 + (pl >> 3);
+                        if (px < P.width && py < P.height) {
+                            RngKey key;
+                            key.k0 = P.k0; key.k1 = P.k1;
+                            key.pixel = (uint32_t)(py * P.width + px);
+                            key.sample = (uint32_t)(s0 + (idx >> 5));
+                            n_paths++;
+                            if (P.depth > 0) {
+                                float c4[4];
+                                rng_block(key, 0, RNG_BLOCK_CAMERA, c4);  // jitter x, jitter y, shutter time, lens u1
+                                float lens_u2 = 0.0f;
+                                if (P.cam.lens_radius != 0.0f) {
+                                    float l4[4];
+                                    rng_block(key, 0, RNG_BLOCK_CAMERA - 1, l4);
+                                    lens_u2 = l4[0];
+                                }
+                                const float u = ((float)px + c4[0]) / div_w;
+                                const float v = ((float)py + c4[1]) / div_h;
+                                const Ray world = camera_get_ray(P.cam, u, v, c4[3], lens_u2, c4[2]);
+                                pool_store_segment(W, s, world);
+                                W.at(PF_TX, s) = 1.0f; W.at(PF_TY, s) = 1.0f; W.at(PF_TZ, s) = 1.0f;
+                                W.at(PF_PIXEL, s) = __uint_as_float(key.pixel);
+                                W.at(PF_SAMPLE, s) = __uint_as_float(key.sample);
+                                W.at(PF_BOUNCE_PL, s) = __uint_as_float((uint32_t)pl << 16);
+                                W.set_cls(s, first_cls);
+                            }
+                        }
+                    }
+                }
+            }
+            __syncwarp();  // slot state and class bytes written by this round are visible to the next round's readers
+        }
+        __syncwarp();
+        {
+            const int px = tx * 8 + (lane & 7), py = ty * 4 + (lane >> 3);
+            if (px < P.width && py < P.height) {
+                float* dst = reinterpret_cast<float*>(P.accum + (size_t)py * P.width + px);
+                atomicAdd(dst + 0, sh_acc[warp][lane][0]);
+                atomicAdd(dst + 1, sh_acc[warp][lane][1]);
+                atomicAdd(dst + 2, sh_acc[warp][lane][2]);
+                atomicAdd(dst + 3, (float)s_n);
+            }
+        }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        n_rays += __shfl_xor_sync(kFull, n_rays, o);
+        n_paths += __shfl_xor_sync(kFull, n_paths, o);
+    }
+    if (lane == 0) {
+        atomicAdd(P.counters + 1, n_rays);
+        atomicAdd(P.counters + 2, n_paths);
+    }
+#ifdef HRT_SCHED_STATS
+    if (lane < 6) {
+        atomicAdd(P.counters + 8 + 2 * lane, st_rounds);
+        atomicAdd(P.counters + 9 + 2 * lane, st_lanes);
+    }
+#endif
 }
 
 __global__ void __launch_bounds__(256) resolve_kernel(const float4* __restrict__ accum, int n_pixels, float scale,
@@ -641,7 +879,17 @@ cudaError_t launch_render(hrt::RenderLaunch& L, int num_sms, cudaStream_t stream
     P.tiles_y = (L.height + 3) / 4;
     P.n_tiles = P.tiles_x * P.tiles_y;
     int blocks_per_sm = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, render_kernel, kBlock, 0);
+    const size_t pool_smem = (size_t)kWarpsPerBlock * kPoolWarpWords * sizeof(float);
+    cudaError_t e;
+    if (L.interpreter == 2) {
+        e = cudaFuncSetAttribute(render_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pool_smem);
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, render_pool_kernel, kBlock, pool_smem);
+    } else if (L.interpreter == 1) {
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, render_interp_kernel, kBlock, 0);
+    } else {
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, render_kernel, kBlock, 0);
+    }
     if (e != cudaSuccess) return e;
     if (blocks_per_sm < 1) blocks_per_sm = 1;
     const int grid = num_sms * blocks_per_sm;
@@ -649,14 +897,31 @@ cudaError_t launch_render(hrt::RenderLaunch& L, int num_sms, cudaStream_t stream
     // enough that the dynamic cursor balances the last wave (>= ~8 items per resident warp when possible).
     int chunk = L.chunk;
     if (chunk <= 0) {
-        chunk = 64;
+        chunk = L.interpreter == 2 ? 256 : 64;  // the pool kernel keeps 96 rays in flight per warp: larger items
         const long long resident_warps = (long long)grid * kWarpsPerBlock;
         while (chunk > 4 && (long long)P.n_tiles * ((L.sample_count + chunk - 1) / chunk) < 8 * resident_warps) chunk /= 2;
     }
     if (chunk > L.sample_count) chunk = L.sample_count;
     if (chunk < 1) chunk = 1;
     P.chunk = chunk;
-    P.n_chunks = (L.sample_count + chunk - 1) / chunk;
+    {
+        // the last ~2 chunks' worth of samples is handed out in shrinking pieces: each a third of what is left (>= 16)
+        int remaining = L.sample_count;
+        P.n_big = 0;
+        while (remaining >= 3 * chunk) { remaining -= chunk; P.n_big++; }
+        int n_tail = 0, begin = P.n_big * chunk, piece = chunk;
+        while (remaining > 0) {
+            if (n_tail == kMaxTailChunks - 1) piece = remaining;
+            else { piece = (remaining + 2) / 3; if (piece < 16) piece = 16; if (piece > chunk) piece = chunk; if (piece > remaining) piece = remaining; }
+            P.tail_begin[n_tail] = begin;
+            P.tail_size[n_tail] = piece;
+            begin += piece;
+            remaining -= piece;
+            n_tail++;
+        }
+        for (int i = n_tail; i < kMaxTailChunks; ++i) { P.tail_begin[i] = begin; P.tail_size[i] = 0; }
+        P.n_chunks = P.n_big + n_tail;
+    }
     P.n_items = P.n_tiles * P.n_chunks;
     P.reference_boxes = L.reference_boxes;
     P.counters = L.counters;
@@ -664,7 +929,8 @@ cudaError_t launch_render(hrt::RenderLaunch& L, int num_sms, cudaStream_t stream
     L.grid = grid;
     L.block = kBlock;
     L.chunk = chunk;
-    if (L.interpreter) render_interp_kernel<<<grid, kBlock, 0, stream>>>(P);
+    if (L.interpreter == 2) render_pool_kernel<<<grid, kBlock, pool_smem, stream>>>(P);
+    else if (L.interpreter == 1) render_interp_kernel<<<grid, kBlock, 0, stream>>>(P);
     else render_kernel<<<grid, kBlock, 0, stream>>>(P);
     return cudaGetLastError();
 }

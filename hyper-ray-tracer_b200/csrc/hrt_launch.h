@@ -29,7 +29,7 @@ struct RenderLaunch {
     int32_t sample_begin, sample_count;
     int32_t chunk;        // samples per work item
     int32_t reference_boxes;
-    int32_t interpreter;  // 1: plain per-lane interpreter kernel, 0: warp-scheduler kernel
+    int32_t interpreter;  // render kernel variant: 0 warp scheduler, 1 plain per-lane interpreter, 2 shared-memory ray pool
     unsigned long long* counters;  // device: [0] work-item cursor, [1] rays, [2] paths
     float* accum;                  // device: width*height*4 f32, added into
     int32_t grid, block;           // out: launch configuration actually used

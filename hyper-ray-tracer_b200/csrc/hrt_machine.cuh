@@ -202,6 +202,10 @@ __device__ __forceinline__ void step_misc(const DeviceScene& S, Lane& L, const R
 #define HRT_BOX_QUORUM 8
 #endif
 constexpr int kBoxQuorum = HRT_BOX_QUORUM;
+#ifndef HRT_LEAF_QUORUM
+#define HRT_LEAF_QUORUM 1
+#endif
+constexpr int kLeafQuorum = HRT_LEAF_QUORUM;
 
 struct Tier {
     bool box, leaf, done, fill, any;  // what to run this round (warp-uniform; at most one of box/leaf/done/fill)
@@ -226,7 +230,9 @@ __device__ __forceinline__ Tier warp_plan_slow(int cls, int nb) {
     t.leaf = t.done = t.fill = false;
     t.leaf_cls = CLS_SPHERE;
     t.any = (nb > 0) || (best >= 0);
-    t.box = nb > 0 && nb > best_n;  // a box population larger than every parked class still goes first
+    // a box population larger than every parked class still goes first; so do boxes while no parked class has reached
+    // kLeafQuorum lanes (batching the expensive bodies)
+    t.box = nb > 0 && (nb > best_n || best_n < kLeafQuorum);
     if (t.box || best < 0) return t;
     t.leaf = best <= CLS_MISC;
     t.leaf_cls = best;

@@ -15,6 +15,8 @@ HRT_FLAG_REFERENCE_TRAVERSAL = 1
 HRT_FLAG_EXACT_MATH = 2
 HRT_FLAG_WARP_SCHEDULER = 4
 HRT_FLAG_INTERPRETER = 8
+HRT_FLAG_POOL = 16
+HRT_FLAG_SCHEDULER = 32
 
 
 class HrtError(RuntimeError):

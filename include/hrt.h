@@ -135,6 +135,8 @@ int32_t hrt_camera_init(const hrt_camera_desc*, hrt_camera_state* out);
 enum {
     HRT_FLAG_REFERENCE_TRAVERSAL = 1, /* per-axis (loose) box test on every node, as aabb.rs:20-47        */
     HRT_FLAG_EXACT_MATH = 2,          /* no FMA contraction, IEEE div/sqrt, accurate libm (parity build) */
+    HRT_FLAG_SCHEDULER = 32,          /* render: force the in-register warp-scheduler kernel                      */
+    HRT_FLAG_POOL = 16,               /* render: warp-private shared-memory ray pool kernel                       */
     HRT_FLAG_INTERPRETER = 8,         /* render: plain per-lane interpreter kernel instead of the warp scheduler  */
     HRT_FLAG_WARP_SCHEDULER = 4       /* hrt_trace_hits only: run through the render kernel's warp-level op-class
                                          scheduler instead of the plain per-lane interpreter                */

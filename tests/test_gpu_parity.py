@@ -375,6 +375,22 @@ def test_render_conventions_and_slices(pkg, orc, built):
     assert not np.allclose(other[..., :3], full[..., :3], rtol=2e-4, atol=1e-4)
 
 
+@pytest.mark.parametrize("name", ["random", "cornell-smoke", "final"])
+def test_render_kernel_variants_agree(pkg, orc, built, name):
+    """The three render kernels (shared-memory ray pool, in-register warp scheduler, plain interpreter) trace the SAME
+    paths — same Philox streams, same per-ray traversal order — so their accumulators agree up to f32 summation order and
+    their ray counts are identical."""
+    N = pkg.native
+    spec, gb, ob, _, _ = built(name)
+    outs = []
+    for flag in (N.HRT_FLAG_POOL, N.HRT_FLAG_SCHEDULER, N.HRT_FLAG_INTERPRETER):
+        acc, st = gb.render(spec.camera, 72, 48, 160, 50, spec.background, seed=31, resolve=False, flags=flag)
+        outs.append((np.nan_to_num(acc[..., :3]), st.rays, st.paths))
+    assert outs[0][1] == outs[1][1] == outs[2][1] and outs[0][2] == outs[1][2] == outs[2][2] == 72 * 48 * 160
+    for other in outs[1:]:
+        assert np.allclose(outs[0][0], other[0], rtol=2e-4, atol=2e-4)
+
+
 def test_exact_and_production_renders_agree(pkg, orc, built):
     """Same seed, same Philox streams: the parity build and the production build trace the same paths except where an
     ulp flips a decision; the images must agree far inside the noise."""
