@@ -251,7 +251,7 @@ def run_b200(args, scene_name, width, height, samples, depth):
             out = np.empty((height, width, 4), dtype=np.float32)
 
             def e2e_step(i):
-                dr.r.backend.evict(local_rank)  # next call uploads the scene tables again (H2D)
+                dr.r.backend.refresh(local_rank)  # H2D: re-copy the scene tables (op stream, materials, textures, texels)
                 dr.r.render(width, height, samples, depth, seed=2000 + i, out=out)  # blocking; D2H of the frame
             t0 = time.perf_counter()
             for i in range(args.steps):
@@ -259,14 +259,14 @@ def run_b200(args, scene_name, width, height, samples, depth):
             e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
         else:
             def e2e_step(i):
-                dr.r.backend.evict(local_rank)
+                dr.r.backend.refresh(local_rank)
                 dr.step(samples, depth, seed=2000 + i, to_host=True)
                 torch.cuda.current_stream().synchronize()
             e2e_ms = timed(e2e_step, args.steps) / args.steps
         e2e = {"value": total_paths / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms,
-               "api": "hrt_scene_upload + hrt_render (host RGBA-f32 out)" if world == 1 else
-                      "hrt_scene_upload + hrt_render_accum_device + NCCL all_reduce + hrt_resolve_device + D2H"}
+               "api": "hrt_scene_refresh (H2D tables) + hrt_render (host RGBA-f32 out)" if world == 1 else
+                      "hrt_scene_refresh + hrt_render_accum_device + NCCL all_reduce + hrt_resolve_device + D2H"}
 
     if rank != 0:
         if world > 1:

@@ -178,6 +178,28 @@ int32_t hrt_scene_evict(hrt_scene* s, int32_t device) {
     return HRT_OK;
 }
 
+int32_t hrt_scene_refresh(hrt_scene* s, int32_t device) {
+    if (!s) return fail(HRT_ERR_INVALID, "null scene");
+    if (!s->committed) return fail(HRT_ERR_STATE, "scene not committed");
+    DeviceState* d = find_state(s, device);
+    if (!d) return hrt_scene_upload(s, device);
+    HRT_CUDA(cudaSetDevice(device));
+    HRT_CUDA(cudaMemcpyAsync(d->d_ops, s->ops.data(), s->ops.size() * sizeof(Op), cudaMemcpyHostToDevice, 0));
+    HRT_CUDA(cudaMemcpyAsync(d->d_ctxs, s->ctxs.data(), s->ctxs.size() * sizeof(Ctx), cudaMemcpyHostToDevice, 0));
+    if (!s->materials.empty())
+        HRT_CUDA(cudaMemcpyAsync(d->d_mats, s->materials.data(), s->materials.size() * sizeof(Material), cudaMemcpyHostToDevice, 0));
+    if (!s->textures.empty())
+        HRT_CUDA(cudaMemcpyAsync(d->d_texs, s->textures.data(), s->textures.size() * sizeof(Texture), cudaMemcpyHostToDevice, 0));
+    if (!s->noise_tables.empty())
+        HRT_CUDA(cudaMemcpyAsync(d->d_noise, s->noise_tables.data(), s->noise_tables.size() * sizeof(NoiseTable), cudaMemcpyHostToDevice, 0));
+    for (size_t i = 0; i < s->images.size() && i < d->arrays.size(); ++i) {
+        const ImageData& img = s->images[i];
+        HRT_CUDA(cudaMemcpy2DToArrayAsync(d->arrays[i], 0, 0, img.rgba.data(), (size_t)img.width * 4, (size_t)img.width * 4, img.height,
+                                          cudaMemcpyHostToDevice, 0));
+    }
+    return HRT_OK;
+}
+
 int64_t hrt_scene_device_bytes(const hrt_scene* s) {
     if (!s || !s->committed) return fail(HRT_ERR_STATE, "scene not committed");
     int64_t b = (int64_t)(s->ops.size() * sizeof(Op) + s->ctxs.size() * sizeof(Ctx) + s->materials.size() * sizeof(Material) +

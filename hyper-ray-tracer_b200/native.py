@@ -79,7 +79,7 @@ EXPORTS = [
     "hrt_scene_get_ops", "hrt_bvh_leaf_order", "hrt_bounding_box", "hrt_camera_init", "hrt_scene_upload", "hrt_render",
     "hrt_render_accum", "hrt_render_accum_device", "hrt_resolve_device", "hrt_trace_hits", "hrt_tex_value",
     "hrt_scatter", "hrt_camera_rays", "hrt_philox_uniforms", "hrt_scene_evict", "hrt_scene_device_bytes",
-    "hrt_measure_peaks",
+    "hrt_measure_peaks", "hrt_scene_refresh",
 ]
 
 _lib = None
@@ -140,6 +140,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.hrt_camera_rays.argtypes = [i32, C.POINTER(CameraDesc), vp, i32, vp, C.c_uint32]
     lib.hrt_philox_uniforms.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, f3]
     lib.hrt_scene_evict.argtypes = [vp, i32]
+    lib.hrt_scene_refresh.argtypes = [vp, i32]
     lib.hrt_scene_device_bytes.argtypes = [vp]
     lib.hrt_measure_peaks.argtypes = [i32, C.POINTER(Peaks)]
     for name in EXPORTS:
@@ -294,6 +295,10 @@ class HrtBackend:
 
     def evict(self, device: int = 0):
         self._check(self.lib.hrt_scene_evict(self.handle, device))
+
+    def refresh(self, device: int = 0):
+        """Re-copy the scene tables host->device into the existing allocations."""
+        self._check(self.lib.hrt_scene_refresh(self.handle, device))
 
     def device_bytes(self) -> int:
         return int(self._check(self.lib.hrt_scene_device_bytes(self.handle)))

@@ -184,6 +184,10 @@ int32_t hrt_resolve_device(int32_t device, const void* d_accum, int32_t width, i
 
 /* Drop the device copy of the scene on `device` (next compute call uploads again). */
 int32_t hrt_scene_evict(hrt_scene*, int32_t device);
+/* Re-copy every scene table and image host->device into the EXISTING device allocations (uploads first if the scene
+ * is not resident).  bench.py's end-to-end leg calls it every step so that the H2D input copy sits inside the timed region
+ * without the allocator noise of evict + upload. */
+int32_t hrt_scene_refresh(hrt_scene*, int32_t device);
 /* Bytes hrt_scene_upload copies host->device (op stream + tables + image texels). */
 int64_t hrt_scene_device_bytes(const hrt_scene*);
 
