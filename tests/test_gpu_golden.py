@@ -79,3 +79,40 @@ def test_two_gpu_nccl_render_equals_single_gpu(pkg):
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
     assert json.loads(line)["ok"]
+
+
+@pytest.mark.parametrize("cfg", ["C3", "C4"])
+def test_deep_convergence_beyond_40db(pkg, cfg):
+    """The north-star bar — MAE <= 1/255, PSNR >= 40 dB — on the low-light scenes needs a reference far beyond 4096 spp
+    (two independent 2048-spp oracle halves are only ~28 dB apart).  tests/golden/<cfg>_deep.npz is the oracle's own
+    65 536-spp render at quarter resolution (tools/make_goldens.py with GOLDEN_SPP=65536 GOLDEN_DIV=4); the GPU renders
+    the same scene instance with 8x as many samples."""
+    path = os.path.join(ROOT, "tests", "golden", f"{cfg}_deep.npz")
+    if not os.path.exists(path):
+        pytest.skip(f"deep golden {cfg} not generated")
+    z = np.load(path)
+    img, meta = z["img"].astype(np.float64), json.loads(str(z["meta"]))
+    spec = pkg.make_scene(meta["scene"], meta["scene_seed"])
+    r = pkg.renderer.Renderer(spec, device=0)
+    w, h = meta["width"], meta["height"]
+    total = np.zeros((h, w, 3), dtype=np.float64)
+    spp_total = 0
+    for i in range(8):  # 8 launches of golden_spp samples each (distinct seeds = independent sample sets)
+        acc, st = r.render(w, h, meta["spp"], meta["depth"], seed=9000 + i, resolve=False)
+        total += np.nan_to_num(acc[..., :3].astype(np.float64), nan=0.0, posinf=0.0, neginf=0.0)
+        spp_total += meta["spp"]
+    gpu = np.sqrt(np.maximum(total / spp_total, 0.0))
+    mae = float(np.abs(gpu - img).mean())
+    mse = float(((np.clip(gpu, 0, 1) - np.clip(img, 0, 1)) ** 2).mean())
+    psnr = float(10 * np.log10(1.0 / max(mse, 1e-12)))
+    report = {"config": cfg + "_deep", "scene": meta["scene"], "width": w, "height": h, "golden_spp": meta["spp"],
+              "gpu_spp": spp_total, "mae": mae, "psnr_db": psnr, "oracle_half_vs_half_mae": meta["mae_half_vs_half"],
+              "oracle_half_vs_half_psnr_db": meta["psnr_half_vs_half"]}
+    rp = os.path.join(ROOT, "gpurun_out", "golden_report.json")
+    os.makedirs(os.path.dirname(rp), exist_ok=True)
+    allr = json.load(open(rp)) if os.path.exists(rp) else {}
+    allr[cfg + "_deep"] = report
+    json.dump(allr, open(rp, "w"), indent=1)
+    print(json.dumps(report))
+    assert psnr >= 40.0, report
+    assert mae <= 1.0 / 255.0, report
