@@ -391,6 +391,18 @@ def test_render_kernel_variants_agree(pkg, orc, built, name):
         assert np.allclose(outs[0][0], other[0], rtol=2e-4, atol=2e-4)
 
 
+def test_progressive_delivery_converges_to_the_full_render(pkg, orc, built):
+    """Sample-batch progressive delivery (the GPU analogue of the reference's per-tile delivery): batches are disjoint
+    slices of one render, so the last progressive frame equals the one-shot frame."""
+    spec, gb, ob, _, _ = built("cornell")
+    r = pkg.renderer.Renderer(spec, device=0)
+    full, _ = r.render(48, 48, 200, 50, seed=3)
+    frames = list(r.render_progressive(48, 48, 200, 50, batch=64, seed=3))
+    assert [d for d, _ in frames] == [64, 128, 192, 200]
+    assert np.allclose(np.nan_to_num(frames[-1][1]), np.nan_to_num(full), rtol=2e-4, atol=2e-4)
+    assert not np.allclose(np.nan_to_num(frames[0][1]), np.nan_to_num(full), rtol=2e-4, atol=2e-4)
+
+
 def test_exact_and_production_renders_agree(pkg, orc, built):
     """Same seed, same Philox streams: the parity build and the production build trace the same paths except where an
     ulp flips a decision; the images must agree far inside the noise."""
