@@ -388,6 +388,95 @@ int32_t hrt_render_accum(hrt_scene* s, int32_t device, const hrt_camera_desc* ca
     return render_host(s, device, cam, rd, out_sum, stats, false);
 }
 
+// Single-process multi-GPU render (the reference is ONE process): device k renders the k-th sample slice into its own
+// accumulator, all devices run concurrently, and the first device sums the others' accumulators over NVLink peer memory
+// inside the resolve kernel.
+static int32_t render_multi(hrt_scene* s, const int32_t* devices, int32_t n, const hrt_camera_desc* cam, const hrt_render_desc* rd,
+                            float* out, hrt_stats* stats, bool resolve) {
+    if (!devices || n < 1 || n > 8) return fail(HRT_ERR_INVALID, "render_multi: 1..8 devices");
+    if (!out) return fail(HRT_ERR_INVALID, "null output buffer");
+    int32_t rc = check_render_args(s, cam, rd);
+    if (rc != HRT_OK) return rc;
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < i; ++j)
+            if (devices[i] == devices[j]) return fail(HRT_ERR_INVALID, "render_multi: duplicate device");
+    const size_t pixels = (size_t)rd->width * rd->height;
+    DeviceState* st[8];
+    const float* accums[8];
+    for (int i = 0; i < n; ++i) {
+        if ((rc = get_state(s, devices[i], &st[i])) != HRT_OK) return rc;
+        if ((rc = ensure_scratch(st[i], pixels)) != HRT_OK) return rc;
+        accums[i] = st[i]->d_accum;
+    }
+    HRT_CUDA(cudaSetDevice(devices[0]));
+    for (int i = 1; i < n; ++i) {
+        int can = 0;
+        HRT_CUDA(cudaDeviceCanAccessPeer(&can, devices[0], devices[i]));
+        if (!can) return fail(HRT_ERR_CUDA, "render_multi: device " + std::to_string(devices[0]) + " cannot map peer memory of device " +
+                                                std::to_string(devices[i]));
+        cudaError_t pe = cudaDeviceEnablePeerAccess(devices[i], 0);
+        if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) return cuda_fail(pe, "cudaDeviceEnablePeerAccess");
+        cudaGetLastError();
+    }
+    hrt_stats local[8];
+    const int total = rd->sample_count > 0 ? rd->sample_count : rd->samples;
+    const int base = rd->sample_count > 0 ? rd->sample_begin : 0;
+    for (int i = 0; i < n; ++i) {  // launch everything first: the devices render concurrently
+        std::memset(&local[i], 0, sizeof(hrt_stats));
+        HRT_CUDA(cudaSetDevice(devices[i]));
+        HRT_CUDA(cudaMemsetAsync(st[i]->d_accum, 0, pixels * 16, 0));
+        hrt_render_desc slice = *rd;
+        const int q = total / n, r = total % n;
+        slice.sample_begin = base + i * q + (i < r ? i : r);
+        slice.sample_count = q + (i < r ? 1 : 0);
+        if (slice.sample_count > 0) {
+            if ((rc = render_into(s, st[i], cam, &slice, st[i]->d_accum, 0, true, &local[i])) != HRT_OK) return rc;
+        } else {
+            HRT_CUDA(cudaMemsetAsync(st[i]->d_counters, 0, 24 * sizeof(unsigned long long), 0));
+            HRT_CUDA(cudaEventRecord(st[i]->ev[0], 0));
+            HRT_CUDA(cudaEventRecord(st[i]->ev[1], 0));
+        }
+        HRT_CUDA(cudaEventRecord(st[i]->ev[2], 0));  // "my slice is in my accumulator"
+    }
+    HRT_CUDA(cudaSetDevice(devices[0]));
+    for (int i = 1; i < n; ++i) HRT_CUDA(cudaStreamWaitEvent(0, st[i]->ev[2], 0));
+    HRT_CUDA(cudaEventRecord(st[0]->ev[3], 0));
+    cudaError_t e = hrt_fast::launch_reduce_resolve(accums, n, (int)pixels, rd->samples, resolve ? st[0]->d_rgba : nullptr,
+                                                    resolve ? nullptr : st[0]->d_rgba, 0);
+    if (e != cudaSuccess) return cuda_fail(e, "reduce_resolve_kernel launch");
+    HRT_CUDA(cudaEventRecord(st[0]->ev[4], 0));
+    HRT_CUDA(cudaMemcpyAsync(out, st[0]->d_rgba, pixels * 16, cudaMemcpyDeviceToHost, 0));
+    HRT_CUDA(cudaEventRecord(st[0]->ev[5], 0));
+    hrt_stats agg;
+    std::memset(&agg, 0, sizeof(agg));
+    for (int i = 0; i < n; ++i) {
+        HRT_CUDA(cudaSetDevice(devices[i]));
+        if ((rc = finish_stats(st[i], 0, &local[i])) != HRT_OK) return rc;
+        agg.paths += local[i].paths;
+        agg.rays += local[i].rays;
+        agg.launches += local[i].launches;
+        if (local[i].kernel_ms > agg.kernel_ms) agg.kernel_ms = local[i].kernel_ms;
+        agg.grid = local[i].grid;
+        agg.block = local[i].block;
+    }
+    HRT_CUDA(cudaSetDevice(devices[0]));
+    HRT_CUDA(cudaStreamSynchronize(0));
+    HRT_CUDA(cudaEventElapsedTime(&agg.resolve_ms, st[0]->ev[3], st[0]->ev[4]));
+    HRT_CUDA(cudaEventElapsedTime(&agg.d2h_ms, st[0]->ev[4], st[0]->ev[5]));
+    agg.launches += 1;
+    if (stats) *stats = agg;
+    return HRT_OK;
+}
+
+int32_t hrt_render_multi(hrt_scene* s, const int32_t* devices, int32_t n_devices, const hrt_camera_desc* cam,
+                         const hrt_render_desc* rd, float* out_rgba, hrt_stats* stats) {
+    return render_multi(s, devices, n_devices, cam, rd, out_rgba, stats, true);
+}
+int32_t hrt_render_accum_multi(hrt_scene* s, const int32_t* devices, int32_t n_devices, const hrt_camera_desc* cam,
+                               const hrt_render_desc* rd, float* out_sum, hrt_stats* stats) {
+    return render_multi(s, devices, n_devices, cam, rd, out_sum, stats, false);
+}
+
 int32_t hrt_render_accum_device(hrt_scene* s, int32_t device, const hrt_camera_desc* cam, const hrt_render_desc* rd,
                                 void* d_accum, void* stream_ptr, hrt_stats* stats) {
     if (!d_accum) return fail(HRT_ERR_INVALID, "null device accumulator");

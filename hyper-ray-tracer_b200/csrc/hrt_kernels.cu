@@ -802,6 +802,37 @@ __global__ void __launch_bounds__(kBlock) camera_rays_kernel(const __grid_consta
 }
 
 #if !HRT_EXACT
+// Fused reduce + resolve for single-process multi-GPU renders (hrt_render_multi): every device rendered a disjoint sample
+// slice into its own accumulator; this kernel runs on the first device, loads the OTHER devices' accumulators directly
+// over NVLink peer mappings (plain ld.global on peer pointers), sums them in a fixed order and applies the reference's
+// gamma resolve (application.rs:451-456) in the same pass — no staging copies, no separate all-reduce.
+struct PeerAccums {
+    const float4* p[8];
+    int n;
+};
+__global__ void __launch_bounds__(256) reduce_resolve_kernel(const PeerAccums A, int n_pixels, float scale, float4* __restrict__ out,
+                                                             float4* __restrict__ sum_out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pixels) return;
+    float4 a = A.p[0][i];
+    for (int k = 1; k < A.n; ++k) {
+        const float4 b = A.p[k][i];  // peer memory over NVLink
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    if (sum_out) sum_out[i] = a;
+    if (out) out[i] = make_float4(sqrtf(a.x * scale), sqrtf(a.y * scale), sqrtf(a.z * scale), 1.0f);
+}
+cudaError_t launch_reduce_resolve(const float* const* d_accums, int n, int n_pixels, int samples, float* d_out, float* d_sum_out,
+                                  cudaStream_t stream) {
+    PeerAccums A;
+    A.n = n;
+    for (int k = 0; k < 8; ++k) A.p[k] = reinterpret_cast<const float4*>(k < n ? d_accums[k] : d_accums[0]);
+    const float scale = 1.0f / (float)samples;
+    reduce_resolve_kernel<<<(n_pixels + 255) / 256, 256, 0, stream>>>(A, n_pixels, scale, reinterpret_cast<float4*>(d_out),
+                                                                      reinterpret_cast<float4*>(d_sum_out));
+    return cudaGetLastError();
+}
+
 // Roofline microbenchmarks (hrt_measure_peaks): 8 independent FFMA chains per thread; L2-resident float4 reads.
 __global__ void __launch_bounds__(256) fma_peak_kernel(float* __restrict__ sink, int iters) {
     float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.0f, a2 = a0 + 2.0f, a3 = a0 + 3.0f, a4 = a0 + 4.0f, a5 = a0 + 5.0f,

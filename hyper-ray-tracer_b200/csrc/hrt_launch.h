@@ -54,6 +54,8 @@ struct RenderLaunch {
 
 namespace hrt_fast {
 cudaError_t launch_fma_peak(float* d_sink, int grid, int iters, cudaStream_t stream);
+cudaError_t launch_reduce_resolve(const float* const* d_accums, int n, int n_pixels, int samples, float* d_out, float* d_sum_out,
+                                  cudaStream_t stream);
 cudaError_t launch_l2_read(const float4* d_buf, size_t n_vec, int repeats, float* d_sink, int grid, cudaStream_t stream);
 }
 

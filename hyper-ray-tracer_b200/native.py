@@ -79,7 +79,7 @@ EXPORTS = [
     "hrt_scene_get_ops", "hrt_bvh_leaf_order", "hrt_bounding_box", "hrt_camera_init", "hrt_scene_upload", "hrt_render",
     "hrt_render_accum", "hrt_render_accum_device", "hrt_resolve_device", "hrt_trace_hits", "hrt_tex_value",
     "hrt_scatter", "hrt_camera_rays", "hrt_philox_uniforms", "hrt_scene_evict", "hrt_scene_device_bytes",
-    "hrt_measure_peaks", "hrt_scene_refresh",
+    "hrt_measure_peaks", "hrt_scene_refresh", "hrt_render_multi", "hrt_render_accum_multi",
 ]
 
 _lib = None
@@ -140,6 +140,8 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.hrt_camera_rays.argtypes = [i32, C.POINTER(CameraDesc), vp, i32, vp, C.c_uint32]
     lib.hrt_philox_uniforms.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, f3]
     lib.hrt_scene_evict.argtypes = [vp, i32]
+    lib.hrt_render_multi.argtypes = [vp, C.POINTER(i32), i32, C.POINTER(CameraDesc), C.POINTER(RenderDesc), vp, C.POINTER(Stats)]
+    lib.hrt_render_accum_multi.argtypes = [vp, C.POINTER(i32), i32, C.POINTER(CameraDesc), C.POINTER(RenderDesc), vp, C.POINTER(Stats)]
     lib.hrt_scene_refresh.argtypes = [vp, i32]
     lib.hrt_scene_device_bytes.argtypes = [vp]
     lib.hrt_measure_peaks.argtypes = [i32, C.POINTER(Peaks)]
@@ -316,6 +318,18 @@ class HrtBackend:
         st = Stats()
         fn = self.lib.hrt_render if resolve else self.lib.hrt_render_accum
         self._check(fn(self.handle, device, C.byref(cd), C.byref(rd), _ptr(out), C.byref(st)))
+        return out, st
+
+    def render_multi(self, devices, cam, width, height, samples, depth, background, seed=0, flags=0, resolve=True, out=None):
+        """Single-process multi-GPU render (hrt_render_multi): samples sharded over `devices`, fused peer reduce+resolve."""
+        cd = camera_desc(cam, width, height)
+        rd = self._render_desc(width, height, samples, depth, background, seed, 0, 0, flags)
+        if out is None:
+            out = np.empty((height, width, 4), dtype=np.float32)
+        devs = (C.c_int32 * len(devices))(*devices)
+        st = Stats()
+        fn = self.lib.hrt_render_multi if resolve else self.lib.hrt_render_accum_multi
+        self._check(fn(self.handle, devs, len(devices), C.byref(cd), C.byref(rd), _ptr(out), C.byref(st)))
         return out, st
 
     def render_accum_device(self, cam, width, height, samples, depth, background, seed, device, d_accum_ptr, stream_ptr=0,

@@ -173,6 +173,16 @@ int32_t hrt_render(hrt_scene*, int32_t device, const hrt_camera_desc*, const hrt
 int32_t hrt_render_accum(hrt_scene*, int32_t device, const hrt_camera_desc*, const hrt_render_desc*, float* out_sum,
                          hrt_stats* stats);
 
+/* Single-process multi-GPU render on `n_devices` (1..8) CUDA devices of one node — the shape the reference needs, being one
+ * process (src/main.rs:24-32): device k renders the k-th disjoint sample slice into its own accumulator, all devices run
+ * concurrently, and devices[0] sums the peers' accumulators over NVLink peer memory INSIDE the gamma-resolve kernel (no
+ * staging copy, no separate collective).  Output layout and blocking semantics as hrt_render / hrt_render_accum.
+ * stats: paths / rays / launches summed, kernel_ms = slowest device. */
+int32_t hrt_render_multi(hrt_scene*, const int32_t* devices, int32_t n_devices, const hrt_camera_desc*, const hrt_render_desc*,
+                         float* out_rgba, hrt_stats* stats);
+int32_t hrt_render_accum_multi(hrt_scene*, const int32_t* devices, int32_t n_devices, const hrt_camera_desc*,
+                               const hrt_render_desc*, float* out_sum, hrt_stats* stats);
+
 /* Device-resident variants for multi-GPU sample sharding: `d_accum` is a device pointer on `device` to
  * width*height*4 f32 that the call ADDS into (zero it first); `stream` is a cudaStream_t (0 = default).
  * Asynchronous w.r.t. the host except for the stats read-back when stats != NULL. */

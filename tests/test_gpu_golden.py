@@ -118,3 +118,25 @@ def test_deep_convergence_beyond_40db(pkg, cfg):
     print(json.dumps(report))
     assert psnr >= 40.0, report
     assert mae <= 1.0 / 255.0, report
+
+
+def test_single_process_multi_gpu_render(pkg):
+    """hrt_render_multi: one process, N devices, samples sharded, peers' accumulators summed over NVLink peer memory inside
+    the resolve kernel.  With one device it must equal hrt_render; with two (when present) it must equal the one-device
+    render of the same sample set up to f32 summation order."""
+    spec = pkg.make_scene("cornell-smoke", 1)
+    r = pkg.renderer.Renderer(spec, device=0)
+    w, h, spp = 80, 60, 131
+    one, st1 = r.render(w, h, spp, 50, seed=4)
+    m1, stm = r.backend.render_multi([0], spec.camera, w, h, spp, 50, spec.background, seed=4)
+    assert stm.paths == st1.paths == w * h * spp and stm.rays == st1.rays
+    assert np.allclose(np.nan_to_num(m1), np.nan_to_num(one), rtol=2e-4, atol=2e-4)
+    n = pkg.native.device_count()
+    if n < 2:
+        pytest.skip("needs 2 GPUs for the peer path")
+    devs = list(range(min(n, 8)))
+    mN, stN = r.backend.render_multi(devs, spec.camera, w, h, spp, 50, spec.background, seed=4)
+    assert stN.paths == st1.paths and stN.rays == st1.rays
+    assert np.allclose(np.nan_to_num(mN), np.nan_to_num(one), rtol=3e-4, atol=3e-4)
+    acc, _ = r.backend.render_multi(devs, spec.camera, w, h, spp, 50, spec.background, seed=4, resolve=False)
+    assert np.all(acc[..., 3] == spp)
