@@ -433,7 +433,12 @@ __global__ void __launch_bounds__(kBlock, 2) render_pool_kernel(const __grid_con
         sh_acc[warp][lane][1] = 0.0f;
         sh_acc[warp][lane][2] = 0.0f;
         // every slot starts path-less (byte 3 of the class word is unused)
-        W.cls_w[lane] = (uint32_t)CLS_NEW * 0x00010101u | ((uint32_t)CLS_IDLE << 24);
+        {
+            uint32_t w0 = 0u;  // home rows in use start path-less, the rest are idle
+#pragma unroll
+            for (int j = 0; j < 4; ++j) w0 |= (uint32_t)(j < kPoolHomes ? CLS_NEW : CLS_IDLE) << (8 * j);
+            W.cls_w[lane] = w0;
+        }
         __syncwarp();
         int rot = 0;
 

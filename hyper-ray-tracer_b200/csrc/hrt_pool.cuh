@@ -14,7 +14,10 @@
 
 namespace HRT_NS {
 
-constexpr int kPoolSlots = 96;   // rays per warp (3 home slots per lane)
+#ifndef HRT_POOL_SLOTS
+#define HRT_POOL_SLOTS 96
+#endif
+constexpr int kPoolSlots = HRT_POOL_SLOTS;   // rays per warp (32 x home slots per lane)
 constexpr int kPoolHomes = kPoolSlots / 32;
 enum PoolField {
     PF_WOX, PF_WOY, PF_WOZ, PF_WDX, PF_WDY, PF_WDZ, PF_TIME,  // world-space ray segment
