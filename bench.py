@@ -293,8 +293,16 @@ def run_b200(args, scene_name, width, height, samples, depth):
                 hbm_peak = json.load(f).get("hbm_gbs")
         except OSError:
             pass
+        traffic = None
+        try:  # DRAM bytes per launch of the dominant kernel, from a committed ncu metric pass of this very workload
+            with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+                t = json.load(f).get(f"{args.config}@{samples}")
+            if t and world == 1:
+                traffic = t["dram_bytes_per_launch"]
+        except OSError:
+            pass
         roofline = {"bound": "fp32_issue", "achieved": achieved, "peak": peaks.fp32_tflops, "unit": "TFLOP/s",
-                    "frac": achieved / peaks.fp32_tflops, "traffic": None,
+                    "frac": achieved / peaks.fp32_tflops, "traffic": traffic,
                     "peak_source": "measured live by hrt_measure_peaks (FFMA chains, CUDA events); MEASURED_PEAKS.json has "
                                    "no FP32 figure",
                     "kernel": "render_kernel", "kernel_ms": kernel_ms, "flops_per_path": wm["flops_per_path"],
