@@ -83,7 +83,7 @@ def test_two_gpu_nccl_render_equals_single_gpu(pkg):
     assert json.loads(line)["ok"]
 
 
-@pytest.mark.parametrize("cfg", ["C3", "C4"])
+@pytest.mark.parametrize("cfg", ["C3", "C4", "C5"])
 def test_deep_convergence_beyond_40db(pkg, cfg):
     """The north-star bar — MAE <= 1/255, PSNR >= 40 dB — on the low-light scenes needs a reference far beyond 4096 spp
     (two independent 2048-spp oracle halves are only ~28 dB apart).  tests/golden/<cfg>_deep.npz is the oracle's own
