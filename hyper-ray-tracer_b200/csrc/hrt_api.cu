@@ -270,6 +270,8 @@ static int32_t check_render_args(const hrt_scene* s, const hrt_camera_desc* cam,
     if (cam->width != rd->width || cam->height != rd->height)
         return fail(HRT_ERR_INVALID, "render: camera size differs from render size (Camera::resize uses the image size)");
     if ((long long)rd->width * rd->height > (1ll << 31) - 1) return fail(HRT_ERR_INVALID, "render: image too large");
+    // the ray pool keeps the bounce index in 16 bits next to the pixel lane (hrt_pool.cuh PF_BOUNCE_PL)
+    if (rd->depth > 65535) return fail(HRT_ERR_INVALID, "render: depth above 65535 is not supported");
     (void)s;
     return HRT_OK;
 }

@@ -17,13 +17,6 @@
 #pragma once
 #include "hrt_device.cuh"
 
-#ifndef HRT_DUAL_PREFETCH
-#define HRT_DUAL_PREFETCH 0
-#endif
-#ifndef HRT_VOTE_MATCH
-#define HRT_VOTE_MATCH 0
-#endif
-
 namespace HRT_NS {
 
 enum LaneClass : int { CLS_BOX = 0, CLS_SPHERE = 1, CLS_RECT = 2, CLS_MISC = 3, CLS_DONE = 4, CLS_NEW = 5, CLS_IDLE = 6 };
@@ -66,24 +59,11 @@ __device__ __forceinline__ void lane_accept(Lane& L, float t, int face) {
 // ---- class bodies: each advances the lane by exactly one record and prefetches the next ----
 __device__ __forceinline__ void step_box(const DeviceScene& S, Lane& L, float tmin, bool reference_boxes) {
     const uint32_t w7 = __float_as_uint(L.B.w);
-    const int skip = (int)(w7 >> 8);
-    // Both possible successors are known before the test: fetch them now so the (dependent) record load overlaps the
-    // slab arithmetic instead of being exposed in front of the next vote (ncu: long_scoreboard on the first use of B.w).
-#if HRT_DUAL_PREFETCH
-    float4 nA, nB, sA, sB;
-    load_op(S, L.pc + 1, nA, nB);
-    load_op(S, skip, sA, sB);
-#endif
     const bool loose = ((w7 & 0xffu) == OP_BOX_LOOSE) || reference_boxes;
     const bool hit = loose ? box_hit_reference(L.A, L.B, L.cur, L.k, tmin, L.closest)
                            : box_hit_tight(L.A, L.B, L.cur, L.k, tmin, L.closest);
-    L.pc = hit ? L.pc + 1 : skip;
-#if HRT_DUAL_PREFETCH
-    L.A = hit ? nA : sA;
-    L.B = hit ? nB : sB;
-#else
+    L.pc = hit ? L.pc + 1 : (int)(w7 >> 8);
     lane_fetch(S, L);
-#endif
 }
 __device__ __forceinline__ void step_sphere(const DeviceScene& S, Lane& L, float tmin) {
     const bool moving = (__float_as_uint(L.B.w) & 0xffu) == OP_MSPHERE;
@@ -197,21 +177,17 @@ __device__ __forceinline__ void step_misc(const DeviceScene& S, Lane& L, const R
 // Measured (profiles/r01_render_kernel_summary.md): the box test itself is ~3 % of the kernel's stall samples; the time
 // is in the leaf / medium / shade bodies, which are long and were running with 3-5 lanes under a "service every parked
 // class at once" policy.  So: boxes run whenever a small quorum is at a box (they are cheap and feed the other classes),
-// otherwise the single non-box class with the MOST parked lanes runs.
+// otherwise the single non-box class with the MOST parked lanes runs.  Alternatives measured and dropped: a MATCH.ANY +
+// REDUX.MAX vote (-9 %), prefetching both successors of a box (+-0), batching thresholds for the parked classes (+-0).
 #ifndef HRT_BOX_QUORUM
 #define HRT_BOX_QUORUM 8
 #endif
 constexpr int kBoxQuorum = HRT_BOX_QUORUM;
-#ifndef HRT_LEAF_QUORUM
-#define HRT_LEAF_QUORUM 1
-#endif
-constexpr int kLeafQuorum = HRT_LEAF_QUORUM;
 
 struct Tier {
     bool box, leaf, done, fill, any;  // what to run this round (warp-uniform; at most one of box/leaf/done/fill)
     int leaf_cls;                     // which leaf class when `leaf`
 };
-#if !HRT_VOTE_MATCH
 // Number of lanes at a box record (the fast path of the vote: one ballot).
 __device__ __forceinline__ int warp_box_count(int cls) { return __popc(__ballot_sync(0xffffffffu, cls == CLS_BOX)); }
 // Slow path, taken when fewer than kBoxQuorum lanes are at a box: populations of the five non-box classes in ONE
@@ -230,9 +206,7 @@ __device__ __forceinline__ Tier warp_plan_slow(int cls, int nb) {
     t.leaf = t.done = t.fill = false;
     t.leaf_cls = CLS_SPHERE;
     t.any = (nb > 0) || (best >= 0);
-    // a box population larger than every parked class still goes first; so do boxes while no parked class has reached
-    // kLeafQuorum lanes (batching the expensive bodies)
-    t.box = nb > 0 && (nb > best_n || best_n < kLeafQuorum);
+    t.box = nb > 0 && nb > best_n;  // a box population larger than every parked class still goes first
     if (t.box || best < 0) return t;
     t.leaf = best <= CLS_MISC;
     t.leaf_cls = best;
@@ -251,26 +225,5 @@ __device__ __forceinline__ Tier warp_plan(int cls) {
     }
     return warp_plan_slow(cls, nb);
 }
-#else
-__device__ __forceinline__ Tier warp_plan(int cls) {
-    // One MATCH.ANY gives every lane the mask of lanes parked at the same class, one REDUX.MAX picks the winner:
-    // key = (population << 3) | (7 - class), boxes above the quorum get the maximum population; ties go to the lower
-    // class id.  (The first version of this vote — six ballot/popc pairs — was 19 % of the kernel's stall samples.)
-    const unsigned full = 0xffffffffu;
-    const int n = __popc(__match_any_sync(full, cls));
-    unsigned key = 0u;
-    if (cls < CLS_IDLE) key = ((cls == CLS_BOX && n >= kBoxQuorum ? 63u : (unsigned)n) << 3) | (unsigned)(7 - cls);
-    const unsigned win = __reduce_max_sync(full, key);
-    const int run = 7 - (int)(win & 7u);
-    Tier t;
-    t.any = win != 0u;
-    t.box = t.any && run == CLS_BOX;
-    t.leaf = t.any && run >= CLS_SPHERE && run <= CLS_MISC;
-    t.leaf_cls = run;
-    t.done = t.any && run == CLS_DONE;
-    t.fill = t.any && run == CLS_NEW;
-    return t;
-}
-#endif
 
 }  // namespace HRT_NS

@@ -33,12 +33,8 @@ constexpr int kPoolWarpWords = PF_WORDS * kPoolSlots + 32 /* class bytes, 4 per 
 #ifndef HRT_POOL_BOX_KEEP
 #define HRT_POOL_BOX_KEEP 12
 #endif
-#ifndef HRT_POOL_BOX_QUORUM
-#define HRT_POOL_BOX_QUORUM 24
-#endif
 constexpr int kPoolMaxBoxSteps = HRT_POOL_BOX_STEPS;  // box steps per gather while enough lanes stay at a box
 constexpr int kPoolBoxKeep = HRT_POOL_BOX_KEEP;       // ... "enough" lanes
-constexpr int kPoolBoxQuorum = HRT_POOL_BOX_QUORUM;   // box population that wins a round without counting the other classes
 
 struct PoolWarp {  // views into this warp's slice of dynamic shared memory
     float* f;          // [PF_WORDS][kPoolSlots]
@@ -114,39 +110,6 @@ __device__ __forceinline__ PoolCounts pool_count(uint32_t my_cls_word) {
     p.n[3] = (int)(b & 1023u); p.n[4] = (int)((b >> 10) & 1023u); p.n[5] = (int)((b >> 20) & 1023u);
     return p;
 }
-// Box population only (the fast path of the vote): three ballots.
-__device__ __forceinline__ int pool_count_box(uint32_t my_cls_word) {
-    int n = 0;
-#pragma unroll
-    for (int j = 0; j < kPoolHomes; ++j)
-        n += __popc(__ballot_sync(0xffffffffu, ((my_cls_word >> (8 * j)) & 0xffu) == (uint32_t)CLS_BOX));
-    return n;
-}
-// Box step with both successors prefetched (hit -> pc + 1, miss -> skip) so the dependent record fetch overlaps the slab
-// arithmetic; with full rounds this latency was the top stall (profiles: long_scoreboard on the first use of B.w).
-__device__ __forceinline__ void step_box_prefetch(const DeviceScene& S, Lane& L, float tmin, bool reference_boxes) {
-    const uint32_t w7 = __float_as_uint(L.B.w);
-    const int skip = (int)(w7 >> 8);
-    float4 nA, nB, sA, sB;
-    load_op(S, L.pc + 1, nA, nB);
-    load_op(S, skip, sA, sB);
-    const bool loose = ((w7 & 0xffu) == OP_BOX_LOOSE) || reference_boxes;
-    const bool hit = loose ? box_hit_reference(L.A, L.B, L.cur, L.k, tmin, L.closest)
-                           : box_hit_tight(L.A, L.B, L.cur, L.k, tmin, L.closest);
-    L.pc = hit ? L.pc + 1 : skip;
-    L.A = hit ? nA : sA;
-    L.B = hit ? nB : sB;
-}
-// Reciprocals only (boxes do not need d.d); inline.
-__device__ __forceinline__ void make_rayk_box(Lane& L) {
-#if HRT_EXACT
-    L.k.inv = v3(__frcp_rn(L.cur.d.x), __frcp_rn(L.cur.d.y), __frcp_rn(L.cur.d.z));
-#else
-    L.k.inv = v3(fast_rcp(L.cur.d.x), fast_rcp(L.cur.d.y), fast_rcp(L.cur.d.z));
-#endif
-    L.k.dd = 0.0f;
-}
-
 // Compact up to 32 slots of class `c` into W.list; returns how many.  `start` rotates which home row is scanned first
 // so that no row is starved.
 __device__ __forceinline__ int pool_gather(const PoolWarp& W, uint32_t my_cls_word, int c, int lane, int start) {

@@ -144,7 +144,7 @@ enum {
 typedef struct hrt_render_desc {
     int32_t width, height;
     int32_t samples;     /* total samples per pixel of the whole job (--samples)                  */
-    int32_t depth;       /* --depth                                                               */
+    int32_t depth;       /* --depth; 0..65535 (0 renders black, as ray_color(depth == 0) does)     */
     float background[3];
     uint64_t seed;       /* Philox key                                                            */
     int32_t sample_begin, sample_count; /* slice [begin, begin+count) rendered by THIS call (multi-GPU
