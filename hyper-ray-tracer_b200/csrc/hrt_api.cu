@@ -16,10 +16,13 @@
 
 namespace hrt {
 
+constexpr int kCounterWords = 32;  // [0] work cursor, [1] rays, [2] paths, [8..27] diagnostic build's scheduler statistics
+
 struct DeviceState {
     int device = -1;
     int num_sms = 0;
     void* d_ops = nullptr;
+    void* d_box16 = nullptr;
     void* d_ctxs = nullptr;
     void* d_mats = nullptr;
     void* d_texs = nullptr;
@@ -41,7 +44,7 @@ void release_device_state(DeviceState* d) {
     if (cudaGetDevice(&prev) == cudaSuccess && cudaSetDevice(d->device) == cudaSuccess) {
         for (auto t : d->texobjs) cudaDestroyTextureObject(t);
         for (auto a : d->arrays) cudaFreeArray(a);
-        cudaFree(d->d_ops); cudaFree(d->d_ctxs); cudaFree(d->d_mats); cudaFree(d->d_texs); cudaFree(d->d_noise);
+        cudaFree(d->d_ops); cudaFree(d->d_box16); cudaFree(d->d_ctxs); cudaFree(d->d_mats); cudaFree(d->d_texs); cudaFree(d->d_noise);
         cudaFree(d->d_counters); cudaFree(d->d_accum); cudaFree(d->d_rgba);
         for (auto e : d->ev) if (e) cudaEventDestroy(e);
         cudaSetDevice(prev);
@@ -127,11 +130,12 @@ int32_t hrt_scene_upload(hrt_scene* s, int32_t device) {
     s->devices.push_back(d);
     int32_t rc;
     if ((rc = upload_table(&d->d_ops, s->ops.data(), s->ops.size() * sizeof(Op))) != HRT_OK) return rc;
+    if ((rc = upload_table(&d->d_box16, s->box16.data(), s->box16.size() * sizeof(Box16))) != HRT_OK) return rc;
     if ((rc = upload_table(&d->d_ctxs, s->ctxs.data(), s->ctxs.size() * sizeof(Ctx))) != HRT_OK) return rc;
     if ((rc = upload_table(&d->d_mats, s->materials.data(), s->materials.size() * sizeof(Material))) != HRT_OK) return rc;
     if ((rc = upload_table(&d->d_texs, s->textures.data(), s->textures.size() * sizeof(Texture))) != HRT_OK) return rc;
     if ((rc = upload_table(&d->d_noise, s->noise_tables.data(), s->noise_tables.size() * sizeof(NoiseTable))) != HRT_OK) return rc;
-    HRT_CUDA(cudaMalloc((void**)&d->d_counters, 24 * sizeof(unsigned long long)));
+    HRT_CUDA(cudaMalloc((void**)&d->d_counters, kCounterWords * sizeof(unsigned long long)));
     for (auto& ev : d->ev) HRT_CUDA(cudaEventCreate(&ev));
     std::memset(&d->view, 0, sizeof(d->view));
     // Image textures: RGBA8 CUDA arrays bound as point-sampled, unnormalised texture objects
@@ -157,7 +161,7 @@ int32_t hrt_scene_upload(hrt_scene* s, int32_t device) {
         HRT_CUDA(cudaCreateTextureObject(&tex, &rd, &td, nullptr));
         d->texobjs.push_back(tex);
     }
-    d->view.ops = d->d_ops; d->view.ctxs = d->d_ctxs; d->view.mats = d->d_mats; d->view.texs = d->d_texs;
+    d->view.ops = d->d_ops; d->view.box16 = d->d_box16; d->view.ctxs = d->d_ctxs; d->view.mats = d->d_mats; d->view.texs = d->d_texs;
     d->view.noise = d->d_noise;
     for (size_t i = 0; i < d->texobjs.size() && i < (size_t)kMaxImages; ++i) d->view.images[i] = d->texobjs[i];
     d->view.n_ops = (int32_t)s->ops.size();
@@ -185,6 +189,7 @@ int32_t hrt_scene_refresh(hrt_scene* s, int32_t device) {
     if (!d) return hrt_scene_upload(s, device);
     HRT_CUDA(cudaSetDevice(device));
     HRT_CUDA(cudaMemcpyAsync(d->d_ops, s->ops.data(), s->ops.size() * sizeof(Op), cudaMemcpyHostToDevice, 0));
+    HRT_CUDA(cudaMemcpyAsync(d->d_box16, s->box16.data(), s->box16.size() * sizeof(Box16), cudaMemcpyHostToDevice, 0));
     HRT_CUDA(cudaMemcpyAsync(d->d_ctxs, s->ctxs.data(), s->ctxs.size() * sizeof(Ctx), cudaMemcpyHostToDevice, 0));
     if (!s->materials.empty())
         HRT_CUDA(cudaMemcpyAsync(d->d_mats, s->materials.data(), s->materials.size() * sizeof(Material), cudaMemcpyHostToDevice, 0));
@@ -202,7 +207,7 @@ int32_t hrt_scene_refresh(hrt_scene* s, int32_t device) {
 
 int64_t hrt_scene_device_bytes(const hrt_scene* s) {
     if (!s || !s->committed) return fail(HRT_ERR_STATE, "scene not committed");
-    int64_t b = (int64_t)(s->ops.size() * sizeof(Op) + s->ctxs.size() * sizeof(Ctx) + s->materials.size() * sizeof(Material) +
+    int64_t b = (int64_t)(s->ops.size() * sizeof(Op) + s->box16.size() * sizeof(Box16) + s->ctxs.size() * sizeof(Ctx) + s->materials.size() * sizeof(Material) +
                           s->textures.size() * sizeof(Texture) + s->noise_tables.size() * sizeof(NoiseTable));
     for (const ImageData& img : s->images) b += (int64_t)img.rgba.size();
     return b;
@@ -315,7 +320,7 @@ static int32_t render_into(hrt_scene* s, DeviceState* d, const hrt_camera_desc* 
     L.accum = d_accum;
     L.chunk = 0;
     if (const char* env = getenv("HRT_CHUNK")) L.chunk = atoi(env);  // diagnostic: samples per work item
-    HRT_CUDA(cudaMemsetAsync(d->d_counters, 0, 24 * sizeof(unsigned long long), stream));
+    HRT_CUDA(cudaMemsetAsync(d->d_counters, 0, kCounterWords * sizeof(unsigned long long), stream));
     if (want_stats) HRT_CUDA(cudaEventRecord(d->ev[0], stream));
     cudaError_t e = (rd->flags & HRT_FLAG_EXACT_MATH) ? hrt_exact::launch_render(L, d->num_sms, stream)
                                                       : hrt_fast::launch_render(L, d->num_sms, stream);
@@ -331,7 +336,7 @@ static int32_t render_into(hrt_scene* s, DeviceState* d, const hrt_camera_desc* 
 
 static int32_t finish_stats(DeviceState* d, cudaStream_t stream, hrt_stats* stats) {
     if (!stats) return HRT_OK;
-    unsigned long long c[24];
+    unsigned long long c[kCounterWords];
     HRT_CUDA(cudaMemcpyAsync(c, d->d_counters, sizeof(c), cudaMemcpyDeviceToHost, stream));
     HRT_CUDA(cudaStreamSynchronize(stream));
     if (getenv("HRT_SCHED_STATS")) {
@@ -339,6 +344,12 @@ static int32_t finish_stats(DeviceState* d, cudaStream_t stream, hrt_stats* stat
         for (int i = 0; i < 6; ++i)
             fprintf(stderr, "[sched] %-6s rounds %llu lanes %llu avg %.2f rounds/ray %.2f\n", names[i], c[8 + 2 * i], c[9 + 2 * i],
                     c[8 + 2 * i] ? (double)c[9 + 2 * i] / (double)c[8 + 2 * i] : 0.0, c[1] ? 32.0 * (double)c[8 + 2 * i] / (double)c[1] : 0.0);
+        static const char* phases[8] = {"box", "sphere", "rect", "misc", "done", "new", "vote+gather", "item"};
+        double total = 0.0;
+        for (int i = 0; i < 8; ++i) total += (double)c[20 + i];
+        for (int i = 0; i < 8 && total > 0.0; ++i)
+            fprintf(stderr, "[sched] cycles %-12s %5.1f %%  (%.0f per round)\n", phases[i], 100.0 * (double)c[20 + i] / total,
+                    i < 6 && c[8 + 2 * i] ? (double)c[20 + i] / (double)c[8 + 2 * i] : 0.0);
     }
     stats->rays = c[1];
     stats->paths = c[2];
@@ -434,7 +445,7 @@ static int32_t render_multi(hrt_scene* s, const int32_t* devices, int32_t n, con
         if (slice.sample_count > 0) {
             if ((rc = render_into(s, st[i], cam, &slice, st[i]->d_accum, 0, true, &local[i])) != HRT_OK) return rc;
         } else {
-            HRT_CUDA(cudaMemsetAsync(st[i]->d_counters, 0, 24 * sizeof(unsigned long long), 0));
+            HRT_CUDA(cudaMemsetAsync(st[i]->d_counters, 0, kCounterWords * sizeof(unsigned long long), 0));
             HRT_CUDA(cudaEventRecord(st[i]->ev[0], 0));
             HRT_CUDA(cudaEventRecord(st[i]->ev[1], 0));
         }

@@ -9,6 +9,7 @@
 //
 // Reference citations are /root/reference paths.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include <stdint.h>
@@ -63,6 +64,7 @@ __device__ __forceinline__ V3 ray_at(const Ray& r, float t) { return r.o + t * r
 
 struct DeviceScene {
     const float4* ops;     // 2 x float4 per record
+    const uint4* box16;    // 16-byte companion per record (hrt_types.h Box16): fp16 outward-rounded box + w7
     const Ctx* ctxs;
     const Material* mats;
     const Texture* texs;
@@ -694,14 +696,14 @@ __device__ __forceinline__ float perlin_turbulence(const NoiseView& N, V3 p, int
 // Per-kernel texture environment.  The first kMaxNoiseTablesShared perlin tables are staged in shared memory by the
 // kernels that shade (stage_noise in hrt_kernels.cu); `n_shared_noise` says how many.
 struct TexEnv {
+    const NoiseTable* sh_noise;  // shared-memory copies of the first n_shared_noise tables
     int n_shared_noise;
 };
-__shared__ NoiseTable g_sh_noise[kMaxNoiseTablesShared];
 __device__ __forceinline__ NoiseView noise_view(const DeviceScene& S, const TexEnv E, int table) {
     NoiseView nv;
     if (table < E.n_shared_noise) {
-        nv.ranvec = reinterpret_cast<const float4*>(g_sh_noise[table].ranvec);
-        nv.perm = &g_sh_noise[table].perm[0][0];
+        nv.ranvec = reinterpret_cast<const float4*>(E.sh_noise[table].ranvec);
+        nv.perm = &E.sh_noise[table].perm[0][0];
     } else {
         nv.ranvec = reinterpret_cast<const float4*>(S.noise[table].ranvec);
         nv.perm = &S.noise[table].perm[0][0];

@@ -39,23 +39,28 @@ struct RenderParams {
     // guided schedule: n_big chunks of `chunk` samples, then up to kMaxTailChunks geometrically smaller ones
     int n_big, tail_begin[kMaxTailChunks], tail_size[kMaxTailChunks];
     int reference_boxes;
+    int n_tab;       // ray-pool kernel: Box16 records [0, n_tab) are staged in shared memory
+    int n_sh_noise;  // ray-pool kernel: noise tables staged behind them
     unsigned long long* counters;
     float4* accum;
 };
 
-__device__ __forceinline__ void stage_noise(const DeviceScene& S, TexEnv& E) {
-    E.n_shared_noise = S.n_noise < kMaxNoiseTablesShared ? S.n_noise : kMaxNoiseTablesShared;
+// Copies the first min(n_noise, cap) noise tables into the block's shared memory at `dst` (ends with a block barrier).
+__device__ __forceinline__ void stage_noise(const DeviceScene& S, TexEnv& E, NoiseTable* dst_tables, int cap) {
+    E.sh_noise = dst_tables;
+    E.n_shared_noise = S.n_noise < cap ? S.n_noise : cap;
     const int words = E.n_shared_noise * (int)(sizeof(NoiseTable) / 16);
     const uint4* src = reinterpret_cast<const uint4*>(S.noise);
-    uint4* dst = reinterpret_cast<uint4*>(g_sh_noise);
+    uint4* dst = reinterpret_cast<uint4*>(dst_tables);
     for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = __ldg(src + i);
     __syncthreads();
 }
 
 __global__ void __launch_bounds__(kBlock, 2) render_kernel(const __grid_constant__ RenderParams P) {
     __shared__ float sh_acc[kWarpsPerBlock][32][3];
+    __shared__ NoiseTable sh_noise[kMaxNoiseTablesShared];
     TexEnv E;
-    stage_noise(P.S, E);
+    stage_noise(P.S, E, sh_noise, kMaxNoiseTablesShared);
 
     const DeviceScene& S = P.S;
     const int lane = threadIdx.x & 31;
@@ -248,8 +253,9 @@ __global__ void __launch_bounds__(kBlock, 2) render_kernel(const __grid_constant
 // the warp re-converges for shading.  Kept selectable (HRT_FLAG_INTERPRETER) for A/B measurements against the scheduler.
 __global__ void __launch_bounds__(kBlock, 2) render_interp_kernel(const __grid_constant__ RenderParams P) {
     __shared__ float sh_acc[kWarpsPerBlock][32][3];
+    __shared__ NoiseTable sh_noise[kMaxNoiseTablesShared];
     TexEnv E;
-    stage_noise(P.S, E);
+    stage_noise(P.S, E, sh_noise, kMaxNoiseTablesShared);
 
     const DeviceScene& S = P.S;
     const int lane = threadIdx.x & 31;
@@ -387,13 +393,30 @@ __global__ void __launch_bounds__(kBlock, 2) render_interp_kernel(const __grid_c
 }
 
 // ---- render kernel with a warp-private ray pool in shared memory (hrt_pool.cuh) ----
-__global__ void __launch_bounds__(kBlock, 2) render_pool_kernel(const __grid_constant__ RenderParams P) {
-    extern __shared__ __align__(16) float sh_pool[];
-    __shared__ float sh_acc[kWarpsPerBlock][32][3];
-    TexEnv E;
-    stage_noise(P.S, E);
+// One 16-warp block per SM.  Dynamic shared memory: [16 warp pools][Box16 table, n_tab records][n_sh_noise noise tables].
+// The box loop — 85 % of all steps — then never leaves the SM: with the records in global memory a warp-wide fetch of
+// ~20 different records almost always contained at least one L1 miss (hit rate 82 %), so every box step paid an L2
+// round trip (profiles/r01_render_kernel_summary.md, "phase cycles").
+#ifndef HRT_POOL_BLOCK
+#define HRT_POOL_BLOCK 512
+#endif
+constexpr int kPoolBlock = HRT_POOL_BLOCK;
+constexpr int kPoolWarps = kPoolBlock / 32;
+constexpr size_t kPoolBytes = (size_t)kPoolWarps * kPoolWarpWords * sizeof(float);
+static_assert(kPoolBytes % 16 == 0, "the Box16 table behind the pools must stay 16-byte aligned");
 
+__global__ void __launch_bounds__(kPoolBlock, 1) render_pool_kernel(const __grid_constant__ RenderParams P) {
+    extern __shared__ __align__(16) float sh_pool[];
+    __shared__ float sh_acc[kPoolWarps][32][3];
     const DeviceScene& S = P.S;
+    uint4* const sh_tab = reinterpret_cast<uint4*>(sh_pool + kPoolWarps * kPoolWarpWords);
+    const int n_tab = P.n_tab;
+    for (int i = threadIdx.x; i < n_tab; i += kPoolBlock) sh_tab[i] = __ldg(S.box16 + i);
+    TexEnv E;
+    stage_noise(S, E, reinterpret_cast<NoiseTable*>(sh_tab + n_tab), P.n_sh_noise);  // ends with __syncthreads()
+    // Box16 of record pc: shared memory for the staged prefix, global memory behind it
+    auto box16_at = [&](int pc) -> uint4 { return pc < n_tab ? sh_tab[pc] : __ldg(S.box16 + pc); };
+
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const bool ref_boxes = P.reference_boxes != 0;
@@ -403,17 +426,22 @@ __global__ void __launch_bounds__(kBlock, 2) render_pool_kernel(const __grid_con
     unsigned long long n_rays = 0, n_paths = 0;
 #ifdef HRT_SCHED_STATS
     unsigned long long st_rounds = 0, st_lanes = 0;
+    // cycles per phase, kept by lane c for class c (lanes 0-5), lane 6: vote + gather, lane 7: item set-up and flush
+    long long st_cycles = 0, st_mark = clock64();
+#define HRT_STAT_PHASE(who)                                        \
+    {                                                              \
+        const long long now_ = clock64();                          \
+        if (lane == (who)) st_cycles += now_ - st_mark;            \
+        st_mark = now_;                                            \
+    }
+#else
+#define HRT_STAT_PHASE(who)
 #endif
     PoolWarp W;
     W.f = sh_pool + warp * kPoolWarpWords;
     W.cls_w = reinterpret_cast<uint32_t*>(W.f + PF_WORDS * kPoolSlots);
     W.list = reinterpret_cast<int*>(W.cls_w + 32);
-    int first_cls;  // class of record 0: where every new ray segment starts
-    {
-        float4 A0, B0;
-        load_op(S, 0, A0, B0);
-        first_cls = record_class(__float_as_uint(B0.w) & 0xffu);
-    }
+    const int first_cls = record_class(box16_at(0).w & 0xffu);  // class of record 0: where every new ray segment starts
 
     for (;;) {
         unsigned long long item = 0;
@@ -442,39 +470,82 @@ __global__ void __launch_bounds__(kBlock, 2) render_pool_kernel(const __grid_con
         __syncwarp();
         int rot = 0;
 
+        HRT_STAT_PHASE(7)
         for (;;) {
             const uint32_t cw = W.cls_w[lane];
             const PoolCounts cnt = pool_count(cw);
+#if HRT_POOL_POLICY == 0
             int run = CLS_BOX, best_n = cnt.n[CLS_BOX];
 #pragma unroll
             for (int c = CLS_SPHERE; c <= CLS_NEW; ++c)
                 if (cnt.n[c] > best_n) { run = c; best_n = cnt.n[c]; }
             if (best_n == 0) break;  // every slot idle: the item is finished
+#else
+            // Box steps are ~85 % of all steps, so the pool is steered to keep the BOX population large: a non-box class
+            // runs as soon as it has its quorum (cheap leaf bodies early, the long shading body later), which keeps the
+            // parked populations small and leaves the rest of the pool's rays at boxes.
+            int run, best_n;
+            {
+                const int nb = cnt.n[CLS_BOX];
+                int oc = CLS_SPHERE, on = cnt.n[CLS_SPHERE];
+#pragma unroll
+                for (int c = CLS_RECT; c <= CLS_NEW; ++c)
+                    if (cnt.n[c] > on) { oc = c; on = cnt.n[c]; }
+                if (nb == 0 && on == 0) break;  // every slot idle: the item is finished
+                const int thr = oc == CLS_DONE ? HRT_POOL_Q_DONE : (oc == CLS_MISC ? HRT_POOL_Q_MISC : (oc == CLS_NEW ? HRT_POOL_Q_NEW : HRT_POOL_Q_LEAF));
+                const bool box = nb >= HRT_POOL_Q_BOXFULL || (on < thr && nb >= on);
+                run = box ? CLS_BOX : oc;
+                best_n = box ? nb : on;
+                (void)best_n;
+            }
+#endif
             const int n = pool_gather(W, cw, run, lane, rot);
             rot = rot + 1 == kPoolHomes ? 0 : rot + 1;
             const int s = lane < n ? W.list[lane] : -1;
 #ifdef HRT_SCHED_STATS
             if (lane == run) { st_rounds++; st_lanes += n; }
 #endif
+            HRT_STAT_PHASE(6)
             if (run == CLS_BOX) {
-                Lane L;
-                int cls = CLS_IDLE;
+                Ray cur;
+                RayK k;
+                float closest = 0.0f;
+                int pc = 0, cls = CLS_IDLE;
+                uint4 Q = make_uint4(0u, 0u, 0u, 0u);
                 if (s >= 0) {
-                    L.cur.o = v3(W.at(PF_COX, s), W.at(PF_COY, s), W.at(PF_COZ, s));
-                    L.cur.d = v3(W.at(PF_CDX, s), W.at(PF_CDY, s), W.at(PF_CDZ, s));
-                    L.closest = W.at(PF_CLOSEST, s);
-                    L.pc = __float_as_int(W.at(PF_PC, s));
-                    L.k = make_rayk(L.cur);
-                    lane_fetch(S, L);
-                    cls = lane_class(L);
+                    cur.o = v3(W.at(PF_COX, s), W.at(PF_COY, s), W.at(PF_COZ, s));
+                    cur.d = v3(W.at(PF_CDX, s), W.at(PF_CDY, s), W.at(PF_CDZ, s));
+                    cur.time = 0.0f;  // boxes do not depend on the ray's time
+                    closest = W.at(PF_CLOSEST, s);
+                    pc = __float_as_int(W.at(PF_PC, s));
+                    k = make_rayk(cur);
+                    Q = box16_at(pc);
+                    cls = record_class(Q.w & 0xffu);
                 }
                 // several box steps per gather, while most of the gathered rays are still at a box
                 for (int it = 0; it < kPoolMaxBoxSteps; ++it) {
-                    if (cls == CLS_BOX) { step_box(S, L, kTmin, ref_boxes); cls = lane_class(L); }
+                    if (cls == CLS_BOX) {
+                        bool hit;
+                        if ((Q.w & 0xffu) == OP_BOX_LOOSE || ref_boxes) {
+                            // unsound box, fp16-unrepresentable box or reference traversal: the 32-byte record decides
+                            float4 A, B;
+                            load_op(S, pc, A, B);
+                            const bool loose = (__float_as_uint(B.w) & 0xffu) == OP_BOX_LOOSE || ref_boxes;
+                            hit = loose ? box_hit_reference(A, B, cur, k, kTmin, closest) : box_hit_tight(A, B, cur, k, kTmin, closest);
+                        } else {
+                            const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&Q.x));  // min.x, min.y
+                            const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&Q.y));  // min.z, max.x
+                            const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&Q.z));  // max.y, max.z
+                            hit = box_hit_tight(make_float4(a.x, a.y, b.x, 0.0f), make_float4(b.y, c.x, c.y, 0.0f), cur, k, kTmin, closest);
+                        }
+                        pc = hit ? pc + 1 : (int)(Q.w >> 8);
+                        Q = box16_at(pc);
+                        cls = record_class(Q.w & 0xffu);
+                    }
                     if (__popc(__ballot_sync(kFull, cls == CLS_BOX)) < kPoolBoxKeep) break;
                 }
                 if (s >= 0) {
-                    W.at(PF_PC, s) = __int_as_float(L.pc);
+                    W.at(PF_PC, s) = __int_as_float(pc);
                     W.set_cls(s, cls);
                 }
             } else if (run <= CLS_MISC) {
@@ -590,6 +661,7 @@ __global__ void __launch_bounds__(kBlock, 2) render_pool_kernel(const __grid_con
                 }
             }
             __syncwarp();  // slot state and class bytes written by this round are visible to the next round's readers
+            HRT_STAT_PHASE(run)
         }
         __syncwarp();
         {
@@ -614,10 +686,12 @@ __global__ void __launch_bounds__(kBlock, 2) render_pool_kernel(const __grid_con
         atomicAdd(P.counters + 2, n_paths);
     }
 #ifdef HRT_SCHED_STATS
+    HRT_STAT_PHASE(7)
     if (lane < 6) {
         atomicAdd(P.counters + 8 + 2 * lane, st_rounds);
         atomicAdd(P.counters + 9 + 2 * lane, st_lanes);
     }
+    if (lane < 8) atomicAdd(P.counters + 20 + lane, (unsigned long long)st_cycles);
 #endif
 }
 
@@ -739,8 +813,9 @@ __global__ void __launch_bounds__(128) trace_hits_sched_kernel(const __grid_cons
 
 __global__ void __launch_bounds__(kBlock) tex_value_kernel(const __grid_constant__ DeviceScene S, int tex,
                                                            const float* __restrict__ uvp, int n, float* __restrict__ out) {
+    __shared__ NoiseTable sh_noise[kMaxNoiseTablesShared];
     TexEnv E;
-    stage_noise(S, E);
+    stage_noise(S, E, sh_noise, kMaxNoiseTablesShared);
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float* q = uvp + 5 * (size_t)i;
@@ -753,8 +828,9 @@ __global__ void __launch_bounds__(kBlock) tex_value_kernel(const __grid_constant
 __global__ void __launch_bounds__(kBlock) scatter_kernel(const __grid_constant__ DeviceScene S, const hrt_ray* __restrict__ rays,
                                                          const hrt_hit* __restrict__ hits, const float* __restrict__ u4, int n,
                                                          hrt_scatter_out* __restrict__ out) {
+    __shared__ NoiseTable sh_noise[kMaxNoiseTablesShared];
     TexEnv E;
-    stage_noise(S, E);
+    stage_noise(S, E, sh_noise, kMaxNoiseTablesShared);
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     hrt_scatter_out o;
@@ -880,6 +956,7 @@ cudaError_t launch_l2_read(const float4* d_buf, size_t n_vec, int repeats, float
 static DeviceScene to_device_scene(const hrt::DeviceSceneHost& h) {
     DeviceScene S;
     S.ops = reinterpret_cast<const float4*>(h.ops);
+    S.box16 = reinterpret_cast<const uint4*>(h.box16);
     S.ctxs = reinterpret_cast<const Ctx*>(h.ctxs);
     S.mats = reinterpret_cast<const Material*>(h.mats);
     S.texs = reinterpret_cast<const Texture*>(h.texs);
@@ -915,12 +992,27 @@ cudaError_t launch_render(hrt::RenderLaunch& L, int num_sms, cudaStream_t stream
     P.tiles_y = (L.height + 3) / 4;
     P.n_tiles = P.tiles_x * P.tiles_y;
     int blocks_per_sm = 0;
-    const size_t pool_smem = (size_t)kWarpsPerBlock * kPoolWarpWords * sizeof(float);
+    size_t pool_smem = kPoolBytes;
+    P.n_tab = 0;
+    P.n_sh_noise = 0;
     cudaError_t e;
     if (L.interpreter == 2) {
+        // Shared-memory budget of the one resident block: the warp pools, then as much of the Box16 table as fits (all
+        // of it for the BASELINE scenes: 4236 records = 66 KB for `final`), then the noise tables.
+        int dev = 0, optin = 0;
+        cudaFuncAttributes fa;
+        if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+        if ((e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess) return e;
+        if ((e = cudaFuncGetAttributes(&fa, render_pool_kernel)) != cudaSuccess) return e;
+        long long avail = (long long)optin - (long long)fa.sharedSizeBytes - (long long)kPoolBytes;
+        if (avail < 0) return cudaErrorInvalidConfiguration;
+        P.n_tab = (int)std::min<long long>(P.S.n_ops, avail / 16);
+        avail -= 16ll * P.n_tab;
+        P.n_sh_noise = (int)std::min<long long>(std::min(P.S.n_noise, kMaxNoiseTablesShared), avail / (long long)sizeof(NoiseTable));
+        pool_smem = kPoolBytes + 16 * (size_t)P.n_tab + sizeof(NoiseTable) * (size_t)P.n_sh_noise;
         e = cudaFuncSetAttribute(render_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pool_smem);
         if (e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, render_pool_kernel, kBlock, pool_smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, render_pool_kernel, kPoolBlock, pool_smem);
     } else if (L.interpreter == 1) {
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, render_interp_kernel, kBlock, 0);
     } else {
@@ -934,7 +1026,7 @@ cudaError_t launch_render(hrt::RenderLaunch& L, int num_sms, cudaStream_t stream
     int chunk = L.chunk;
     if (chunk <= 0) {
         chunk = L.interpreter == 2 ? 256 : 64;  // the pool kernel keeps 96 rays in flight per warp: larger items
-        const long long resident_warps = (long long)grid * kWarpsPerBlock;
+        const long long resident_warps = (long long)grid * (L.interpreter == 2 ? kPoolWarps : kWarpsPerBlock);
         while (chunk > 4 && (long long)P.n_tiles * ((L.sample_count + chunk - 1) / chunk) < 8 * resident_warps) chunk /= 2;
     }
     if (chunk > L.sample_count) chunk = L.sample_count;
@@ -963,9 +1055,9 @@ cudaError_t launch_render(hrt::RenderLaunch& L, int num_sms, cudaStream_t stream
     P.counters = L.counters;
     P.accum = reinterpret_cast<float4*>(L.accum);
     L.grid = grid;
-    L.block = kBlock;
+    L.block = L.interpreter == 2 ? kPoolBlock : kBlock;
     L.chunk = chunk;
-    if (L.interpreter == 2) render_pool_kernel<<<grid, kBlock, pool_smem, stream>>>(P);
+    if (L.interpreter == 2) render_pool_kernel<<<grid, kPoolBlock, pool_smem, stream>>>(P);
     else if (L.interpreter == 1) render_interp_kernel<<<grid, kBlock, 0, stream>>>(P);
     else render_kernel<<<grid, kBlock, 0, stream>>>(P);
     return cudaGetLastError();

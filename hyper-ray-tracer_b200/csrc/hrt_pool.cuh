@@ -33,6 +33,24 @@ constexpr int kPoolWarpWords = PF_WORDS * kPoolSlots + 32 /* class bytes, 4 per 
 #ifndef HRT_POOL_BOX_KEEP
 #define HRT_POOL_BOX_KEEP 12
 #endif
+#ifndef HRT_POOL_POLICY
+#define HRT_POOL_POLICY 0
+#endif
+#ifndef HRT_POOL_Q_LEAF
+#define HRT_POOL_Q_LEAF 8
+#endif
+#ifndef HRT_POOL_Q_MISC
+#define HRT_POOL_Q_MISC 16
+#endif
+#ifndef HRT_POOL_Q_DONE
+#define HRT_POOL_Q_DONE 24
+#endif
+#ifndef HRT_POOL_Q_NEW
+#define HRT_POOL_Q_NEW 16
+#endif
+#ifndef HRT_POOL_Q_BOXFULL
+#define HRT_POOL_Q_BOXFULL 32
+#endif
 constexpr int kPoolMaxBoxSteps = HRT_POOL_BOX_STEPS;  // box steps per gather while enough lanes stay at a box
 constexpr int kPoolBoxKeep = HRT_POOL_BOX_KEEP;       // ... "enough" lanes
 

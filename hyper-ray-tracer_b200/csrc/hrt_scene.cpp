@@ -381,6 +381,54 @@ struct Flattener {
     }
 };
 
+// ---- fp16 with directed rounding (Box16, hrt_types.h) ----
+// Largest fp16 <= x (up == false) or smallest fp16 >= x (up == true); +-inf when x is outside the finite fp16 range on
+// the side that keeps the inequality.  x must not be NaN.
+static uint16_t float_to_half_directed(float x, bool up) {
+    if (x == 0.0f) return 0;
+    const bool neg = x < 0.0f;
+    const float a = std::fabs(x);
+    // the magnitude rounds towards zero when the direction points at zero, away from it otherwise
+    const bool away = neg ? !up : up;
+    uint16_t mag;
+    if (a > 65504.0f) {
+        mag = (away || std::isinf(a)) ? 0x7c00u : 0x7bffu;  // inf, or the largest finite
+    } else {
+        int e;
+        std::frexp(a, &e);    // a = f * 2^e, f in [0.5, 1)
+        int he = e - 1 + 15;  // biased fp16 exponent of a normal
+        float scaled;
+        if (he <= 0) { he = 0; scaled = std::ldexp(a, 24); }  // subnormal: units of 2^-24
+        else scaled = std::ldexp(a, 10 - (e - 1));            // in [1024, 2048)
+        const float fl = std::floor(scaled);
+        uint32_t q = (uint32_t)fl;
+        if (away && fl != scaled) q += 1;
+        // q may reach 2048 (or 1024 from the subnormal side): the bit-pattern sum carries into the exponent
+        mag = he == 0 ? (uint16_t)q : (uint16_t)(((uint32_t)he << 10) + (q - 1024u));
+    }
+    return (uint16_t)(mag | (neg ? 0x8000u : 0u));
+}
+
+static void build_box16(hrt_scene& s) {
+    s.box16.assign(s.ops.size(), Box16{});
+    for (size_t i = 0; i < s.ops.size(); ++i) {
+        const Op& op = s.ops[i];
+        Box16& b = s.box16[i];
+        b.w7 = op.u[7];
+        if ((op.u[7] & 0xffu) != OP_BOX) continue;
+        bool ok = true;
+        for (int a = 0; a < 3; ++a) ok = ok && !std::isnan(op.f[a]) && !std::isnan(op.f[4 + a]);
+        if (!ok) {
+            b.w7 = (op.u[7] & ~0xffu) | OP_BOX_LOOSE;  // "read the 32-byte record"
+            continue;
+        }
+        for (int a = 0; a < 3; ++a) {
+            b.h[a] = float_to_half_directed(op.f[a], false);
+            b.h[3 + a] = float_to_half_directed(op.f[4 + a], true);
+        }
+    }
+}
+
 }  // namespace hrt
 
 using namespace hrt;
@@ -679,6 +727,7 @@ int32_t hrt_scene_commit(hrt_scene* s, int32_t root) {
             }
         }
     }
+    build_box16(*s);
     s->root = root;
     s->committed = true;
     return HRT_OK;
@@ -706,6 +755,13 @@ int32_t hrt_scene_get_info(const hrt_scene* s, hrt_scene_info* out) {
     out->time_min = s->time_min;
     out->time_max = s->time_max;
     return HRT_OK;
+}
+int32_t hrt_scene_get_box16(const hrt_scene* s, void* out, int32_t cap_ops) {
+    if (!s) return fail(HRT_ERR_INVALID, "null scene");
+    if (!s->committed) return fail(HRT_ERR_STATE, "scene not committed");
+    int32_t n = (int32_t)s->box16.size();
+    if (out && cap_ops > 0) std::memcpy(out, s->box16.data(), sizeof(Box16) * (size_t)std::min(n, cap_ops));
+    return n;
 }
 int32_t hrt_scene_get_ops(const hrt_scene* s, void* out, int32_t cap_ops) {
     if (!s) return fail(HRT_ERR_INVALID, "null scene");

@@ -63,6 +63,7 @@ struct hrt_scene {
     bool committed = false;
     int32_t root = -1;
     std::vector<hrt::Op> ops;
+    std::vector<hrt::Box16> box16;  // derived from ops at commit (hrt_types.h)
     std::vector<hrt::Ctx> ctxs;
     int32_t n_box_ops = 0, n_loose_boxes = 0, n_prim_ops = 0, n_media = 0, max_ctx_depth = 0;
     float time_min = -3.402823466e38f, time_max = 3.402823466e38f;  // intersection of BVH build intervals

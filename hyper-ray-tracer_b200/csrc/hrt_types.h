@@ -52,6 +52,18 @@ struct alignas(16) Op {
 };
 static_assert(sizeof(Op) == 32, "op record must be 32 bytes");
 
+// 16-byte companion of every record (same index) — what the ray-pool kernel's box loop reads, from SHARED MEMORY, instead
+// of the 32-byte record: the box rounded OUTWARD to fp16 (any superset of a sound box is sound, so results do not
+// change) plus w7.
+//   h[0..2] = min rounded down, h[3..5] = max rounded up, w7 = the record's own w7
+// except that a box fp16 cannot carry (NaN bounds) and every OP_BOX_LOOSE record say OP_BOX_LOOSE here, which sends the
+// kernel to the 32-byte record.  Non-box records only carry w7 (their class).
+struct alignas(16) Box16 {
+    uint16_t h[6];
+    uint32_t w7;
+};
+static_assert(sizeof(Box16) == 16, "box16 record must be 16 bytes");
+
 constexpr int kMaxCtxDepth = 6;
 // A ray-space context = the chain of TRANSLATE/ROTATE records (outermost first) that maps the world ray
 // into it.  ctx 0 is world space.

@@ -79,7 +79,7 @@ EXPORTS = [
     "hrt_scene_get_ops", "hrt_bvh_leaf_order", "hrt_bounding_box", "hrt_camera_init", "hrt_scene_upload", "hrt_render",
     "hrt_render_accum", "hrt_render_accum_device", "hrt_resolve_device", "hrt_trace_hits", "hrt_tex_value",
     "hrt_scatter", "hrt_camera_rays", "hrt_philox_uniforms", "hrt_scene_evict", "hrt_scene_device_bytes",
-    "hrt_measure_peaks", "hrt_scene_refresh", "hrt_render_multi", "hrt_render_accum_multi",
+    "hrt_measure_peaks", "hrt_scene_refresh", "hrt_render_multi", "hrt_render_accum_multi", "hrt_scene_get_box16",
 ]
 
 _lib = None
@@ -126,6 +126,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.hrt_scene_count.argtypes = [vp]
     lib.hrt_scene_get_info.argtypes = [vp, C.POINTER(SceneInfo)]
     lib.hrt_scene_get_ops.argtypes = [vp, vp, i32]
+    lib.hrt_scene_get_box16.argtypes = [vp, vp, i32]
     lib.hrt_bvh_leaf_order.argtypes = [vp, i32, C.POINTER(i32), i32]
     lib.hrt_bounding_box.argtypes = [vp, i32, f3]
     lib.hrt_camera_init.argtypes = [C.POINTER(CameraDesc), C.POINTER(CameraState)]
@@ -273,6 +274,13 @@ class HrtBackend:
         n = self._check(self.lib.hrt_scene_get_ops(self.handle, None, 0))
         out = np.zeros((n, 8), dtype=np.uint32)
         self._check(self.lib.hrt_scene_get_ops(self.handle, _ptr(out), n))
+        return out
+
+    def box16(self) -> np.ndarray:
+        """(n_ops, 8) uint16: six fp16 bounds (min rounded down, max rounded up) + w7 as two halves (hrt_types.h Box16)."""
+        n = self._check(self.lib.hrt_scene_get_box16(self.handle, None, 0))
+        out = np.zeros((n, 8), dtype=np.uint16)
+        self._check(self.lib.hrt_scene_get_box16(self.handle, _ptr(out), n))
         return out
 
     def bvh_leaf_order(self, bvh: int):

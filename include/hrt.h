@@ -114,6 +114,9 @@ typedef struct hrt_scene_info {
 int32_t hrt_scene_get_info(const hrt_scene*, hrt_scene_info* out);
 /* Copies up to cap_ops 32-byte records; returns n_ops. */
 int32_t hrt_scene_get_ops(const hrt_scene*, void* out, int32_t cap_ops);
+/* Copies up to cap_ops 16-byte companions of the records (six fp16 bounds rounded outward + w7: what the render
+ * kernel's box loop reads from shared memory — hrt_types.h Box16); returns n_ops. */
+int32_t hrt_scene_get_box16(const hrt_scene*, void* out, int32_t cap_ops);
 /* DFS left->right leaf object ids of a hrt_bvh object; returns leaf count. */
 int32_t hrt_bvh_leaf_order(const hrt_scene*, int32_t bvh, int32_t* out, int32_t cap);
 /* Reference bounding box of any hittable over time [0,1] (what `bounding_box(0.0, 1.0)` returns). */
