@@ -33,8 +33,13 @@ import numpy as np  # noqa: E402
 
 import __graft_entry__ as graft  # noqa: E402
 
-METRIC = "Mpaths/s, book-2 final scene 800x800"
+METRIC = "Mpaths/s, book-2 final scene 800x800"  # BASELINE.json's metric (config C5)
 UNIT = "Mpaths/s"
+
+
+def metric_name(config, scene_name, width, height):
+    """BASELINE.json's metric for its headline config; the other configs are labelled with their own scene and size."""
+    return METRIC if config == "C5" else f"Mpaths/s, {scene_name} scene {width}x{height}"
 
 
 def parse_args():
@@ -174,7 +179,7 @@ def run_reference(args, scene_name, width, height, samples, depth):
             paths += c.paths
             last = res
     value = paths / sum(times) / 1e6
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+    line = {"impl": "reference", "metric": metric_name(args.config, scene_name, width, height), "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{scene_name} {width}x{height} depth {depth} (bounded sample of the {samples}-spp frame)",
@@ -305,14 +310,15 @@ def run_b200(args, scene_name, width, height, samples, depth):
                     "frac": achieved / peaks.fp32_tflops, "traffic": traffic,
                     "peak_source": "measured live by hrt_measure_peaks (FFMA chains, CUDA events); MEASURED_PEAKS.json has "
                                    "no FP32 figure",
-                    "kernel": "render_kernel", "kernel_ms": kernel_ms, "flops_per_path": wm["flops_per_path"],
+                    # hrt_api.cu render_into: the ray-pool kernel from 128 samples per launch, else the warp scheduler
+                    "kernel": "render_pool_kernel" if -(-samples // world) >= 128 else "render_kernel", "kernel_ms": kernel_ms, "flops_per_path": wm["flops_per_path"],
                     "work_model": wm["source"],
                     "l2": {"achieved_gbs": l2_ach, "peak_gbs": peaks.l2_read_gbs, "frac": l2_ach / peaks.l2_read_gbs,
                            "bytes_per_path": wm["bytes_per_path"]},
                     "hbm": {"achieved_gbs": (width * height * 16 * 2) / (kernel_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                             "note": "accumulator traffic only; the working set is L1/L2-resident"}}
 
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+    line = {"metric": metric_name(args.config, scene_name, width, height), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": f"{args.config}: {scene_name} {width}x{height}, {samples} spp, depth {depth}",

@@ -392,11 +392,7 @@ __global__ void __launch_bounds__(kBlock, 2) render_interp_kernel(const __grid_c
     }
 }
 
-// ---- render kernel with a warp-private ray pool in shared memory (hrt_pool.cuh) ----
-// One 16-warp block per SM.  Dynamic shared memory: [16 warp pools][Box16 table, n_tab records][n_sh_noise noise tables].
-// The box loop — 85 % of all steps — then never leaves the SM: with the records in global memory a warp-wide fetch of
-// ~20 different records almost always contained at least one L1 miss (hit rate 82 %), so every box step paid an L2
-// round trip (profiles/r01_render_kernel_summary.md, "phase cycles").
+// ---- render kernel with warp-private ray pools in shared memory (hrt_pool.cuh) ----
 #ifndef HRT_POOL_BLOCK
 #define HRT_POOL_BLOCK 512
 #endif
@@ -405,24 +401,221 @@ constexpr int kPoolWarps = kPoolBlock / 32;
 constexpr size_t kPoolBytes = (size_t)kPoolWarps * kPoolWarpWords * sizeof(float);
 static_assert(kPoolBytes % 16 == 0, "the Box16 table behind the pools must stay 16-byte aligned");
 
+// What a class body needs besides the pool: scene, staged tables, render constants and the current work item.
+struct RoundEnv {
+    const DeviceScene& S;
+    const RenderParams& P;
+    TexEnv E;
+    const uint4* sh_tab;  // Box16 records [0, n_tab) in shared memory
+    int n_tab;
+    int first_cls;        // class of record 0: where every new ray segment starts
+    bool ref_boxes;
+    V3 bg;
+    float div_w, div_h;   // application.rs:444-445
+    // current work item: 8x4-pixel tile, samples [s0, s0 + pool_size / 32)
+    int tx, ty, s0, pool_size;
+    float (*acc)[3];      // [32][3] shared-memory radiance sums of the item's pixels
+    __device__ __forceinline__ uint4 box16_at(int pc) const { return pc < n_tab ? sh_tab[pc] : __ldg(S.box16 + pc); }
+};
+
+// One round: every lane with a ray (slot s >= 0; all of class `run`, which is warp-uniform) advances it; returns the
+// ray's new class (CLS_IDLE for lanes without a ray).  `new_idx` is the path index a CLS_NEW slot draws.
+template <class PoolT>
+__device__ __forceinline__ int run_class(const RoundEnv& R, const PoolT& W, int run, int s, int new_idx,
+                                         unsigned long long& n_rays, unsigned long long& n_paths) {
+    const DeviceScene& S = R.S;
+    const RenderParams& P = R.P;
+    const float kTmin = 0.001f;  // application.rs:482
+    int cls = CLS_IDLE;
+    if (run == CLS_BOX) {
+        Ray cur;
+        RayK k;
+        float closest = 0.0f;
+        int pc = 0;
+        uint4 Q = make_uint4(0u, 0u, 0u, 0u);
+        if (s >= 0) {
+            cur.o = v3(W.at(PF_COX, s), W.at(PF_COY, s), W.at(PF_COZ, s));
+            cur.d = v3(W.at(PF_CDX, s), W.at(PF_CDY, s), W.at(PF_CDZ, s));
+            cur.time = 0.0f;  // boxes do not depend on the ray's time
+            closest = W.at(PF_CLOSEST, s);
+            pc = __float_as_int(W.at(PF_PC, s));
+            k = make_rayk(cur);
+            Q = R.box16_at(pc);
+            cls = record_class(Q.w & 0xffu);
+        }
+        // several box steps per gather, while most of the gathered rays are still at a box
+        for (int it = 0; it < kPoolMaxBoxSteps; ++it) {
+            if (cls == CLS_BOX) {
+                bool hit;
+                if ((Q.w & 0xffu) == OP_BOX_LOOSE || R.ref_boxes) {
+                    // unsound box, fp16-unrepresentable box or reference traversal: the 32-byte record decides
+                    float4 A, B;
+                    load_op(S, pc, A, B);
+                    const bool loose = (__float_as_uint(B.w) & 0xffu) == OP_BOX_LOOSE || R.ref_boxes;
+                    hit = loose ? box_hit_reference(A, B, cur, k, kTmin, closest) : box_hit_tight(A, B, cur, k, kTmin, closest);
+                } else {
+                    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&Q.x));  // min.x, min.y
+                    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&Q.y));  // min.z, max.x
+                    const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&Q.z));  // max.y, max.z
+                    hit = box_hit_tight(make_float4(a.x, a.y, b.x, 0.0f), make_float4(b.y, c.x, c.y, 0.0f), cur, k, kTmin, closest);
+                }
+                pc = hit ? pc + 1 : (int)(Q.w >> 8);
+                Q = R.box16_at(pc);
+                cls = record_class(Q.w & 0xffu);
+            }
+            if (__popc(__ballot_sync(kFull, cls == CLS_BOX)) < kPoolBoxKeep) break;
+        }
+        if (s >= 0) W.at(PF_PC, s) = __int_as_float(pc);
+    } else if (run <= CLS_MISC) {
+        if (s >= 0) {
+            Lane L;
+            pool_load_traversal(W, s, L);
+            L.k = make_rayk(L.cur);
+            lane_fetch(S, L);
+            if (run == CLS_SPHERE) step_sphere(S, L, kTmin);
+            else if (run == CLS_RECT) step_rect(S, L, kTmin);
+            else {
+                const Ray world = pool_load_world(W, s);
+                MediumXi xi;
+                xi.key.k0 = P.k0; xi.key.k1 = P.k1;
+                xi.key.pixel = __float_as_uint(W.at(PF_PIXEL, s));
+                xi.key.sample = __float_as_uint(W.at(PF_SAMPLE, s));
+                xi.bounce = __float_as_uint(W.at(PF_BOUNCE_PL, s)) & 0xffffu;
+                xi.injected = 0.0f; xi.inject = false;
+                step_misc(S, L, world, kTmin, R.ref_boxes, xi);
+            }
+            pool_store_traversal(W, s, L, run == CLS_MISC);
+            cls = lane_class(L);
+        }
+    } else if (run == CLS_DONE) {
+        // ---- traversal finished: emitted + scatter (application.rs:482-494) ----
+        if (s >= 0) {
+            n_rays++;
+            Ray world = pool_load_world(W, s);
+            V3 T = v3(W.at(PF_TX, s), W.at(PF_TY, s), W.at(PF_TZ, s));
+            const uint32_t bpl = __float_as_uint(W.at(PF_BOUNCE_PL, s));
+            uint32_t bounce = bpl & 0xffffu;
+            const int my_pl = (int)(bpl >> 16);
+            RngKey key;
+            key.k0 = P.k0; key.k1 = P.k1;
+            key.pixel = __float_as_uint(W.at(PF_PIXEL, s));
+            key.sample = __float_as_uint(W.at(PF_SAMPLE, s));
+            const int best_pc = __float_as_int(W.at(PF_BEST_PC, s));
+            V3 add = v3(0.0f, 0.0f, 0.0f);
+            bool alive = false;
+            if (best_pc < 0) {
+                add = T * R.bg;
+            } else {
+                const int fc = __float_as_int(W.at(PF_BEST_FC, s));
+                Best best;
+                best.t = W.at(PF_CLOSEST, s); best.pc = best_pc; best.face = fc & 0xff; best.ctx = fc >> 8;
+                HitRec h;
+                make_hit_record(S, world, best, false, h);
+                const Material m = S.mats[h.mat];
+                if (m.kind == MAT_DIFFUSE_LIGHT) {
+                    add = T * material_emitted(S, R.E, m, h);  // DiffuseLight::scatter -> None
+                } else {
+                    float u4[4];
+                    rng_block(key, bounce, RNG_BLOCK_SCATTER, u4);
+                    V3 att;
+                    Ray sc;
+                    if (material_scatter(S, R.E, m, world, h, u4, att, sc)) {
+                        T = T * att;
+                        world = sc;
+                        bounce++;
+                        alive = bounce < (uint32_t)P.depth;  // ray_color(depth == 0) is black
+                    }
+                }
+            }
+            if (add.x != 0.0f) atomicAdd(&R.acc[my_pl][0], add.x);
+            if (add.y != 0.0f) atomicAdd(&R.acc[my_pl][1], add.y);
+            if (add.z != 0.0f) atomicAdd(&R.acc[my_pl][2], add.z);
+            cls = CLS_NEW;
+            if (alive) {
+                pool_store_segment(W, s, world);
+                W.at(PF_TX, s) = T.x; W.at(PF_TY, s) = T.y; W.at(PF_TZ, s) = T.z;
+                W.at(PF_BOUNCE_PL, s) = __uint_as_float(bounce | ((uint32_t)my_pl << 16));
+                cls = R.first_cls;
+            }
+        }
+    } else {
+        // ---- CLS_NEW: the gathered path-less slots draw the next path indices of the item ----
+        if (s >= 0) {
+            cls = CLS_NEW;  // a slot whose index fell outside the image draws again
+            if (new_idx >= R.pool_size) {
+                cls = CLS_IDLE;
+            } else {
+                const int pl = new_idx & 31;
+                const int px = R.tx * 8 + (pl & 7), py = R.ty * 4 + (pl >> 3);
+                if (px < P.width && py < P.height) {
+                    RngKey key;
+                    key.k0 = P.k0; key.k1 = P.k1;
+                    key.pixel = (uint32_t)(py * P.width + px);
+                    key.sample = (uint32_t)(R.s0 + (new_idx >> 5));
+                    n_paths++;
+                    if (P.depth > 0) {
+                        float c4[4];
+                        rng_block(key, 0, RNG_BLOCK_CAMERA, c4);  // jitter x, jitter y, shutter time, lens u1
+                        float lens_u2 = 0.0f;
+                        if (P.cam.lens_radius != 0.0f) {
+                            float l4[4];
+                            rng_block(key, 0, RNG_BLOCK_CAMERA - 1, l4);
+                            lens_u2 = l4[0];
+                        }
+                        const float u = ((float)px + c4[0]) / R.div_w;
+                        const float v = ((float)py + c4[1]) / R.div_h;
+                        const Ray world = camera_get_ray(P.cam, u, v, c4[3], lens_u2, c4[2]);
+                        pool_store_segment(W, s, world);
+                        W.at(PF_TX, s) = 1.0f; W.at(PF_TY, s) = 1.0f; W.at(PF_TZ, s) = 1.0f;
+                        W.at(PF_PIXEL, s) = __uint_as_float(key.pixel);
+                        W.at(PF_SAMPLE, s) = __uint_as_float(key.sample);
+                        W.at(PF_BOUNCE_PL, s) = __uint_as_float((uint32_t)pl << 16);
+                        cls = R.first_cls;
+                    }
+                }
+            }
+        }
+    }
+    return cls;
+}
+
+// Sample range of work item `item` (tile-major inside a chunk; big chunks first, then the shrinking tail chunks).
+__device__ __forceinline__ void decode_item(const RenderParams& P, unsigned long long item, int& tx, int& ty, int& s0, int& s_n) {
+    const int tile = (int)(item % (unsigned long long)P.n_tiles);
+    const int chunk = (int)(item / (unsigned long long)P.n_tiles);
+    tx = tile % P.tiles_x;
+    ty = tile / P.tiles_x;
+    const int tc = chunk - P.n_big;  // >= 0: one of the shrinking tail chunks
+    s0 = P.sample_begin + (tc < 0 ? chunk * P.chunk : P.tail_begin[tc]);
+    s_n = tc < 0 ? P.chunk : P.tail_size[tc];
+}
+// Adds the item's radiance sums (lane = pixel of the 8x4 tile) into the frame accumulator.
+__device__ __forceinline__ void flush_item(const RenderParams& P, int tx, int ty, int s_n, float (*acc)[3], int lane) {
+    const int px = tx * 8 + (lane & 7), py = ty * 4 + (lane >> 3);
+    if (px < P.width && py < P.height) {
+        float* dst = reinterpret_cast<float*>(P.accum + (size_t)py * P.width + px);
+        atomicAdd(dst + 0, acc[lane][0]);
+        atomicAdd(dst + 1, acc[lane][1]);
+        atomicAdd(dst + 2, acc[lane][2]);
+        atomicAdd(dst + 3, (float)s_n);
+    }
+}
+
+// One 16-warp block per SM.  Dynamic shared memory: [16 warp pools][Box16 table, n_tab records][n_sh_noise noise tables].
+// The box loop — 85 % of all steps — then never leaves the SM: with the records in global memory a warp-wide fetch of
+// ~20 different records almost always contained at least one L1 miss (hit rate 82 %), so every box step paid an L2
+// round trip (profiles/r01_render_kernel_summary.md, "phase cycles").
 __global__ void __launch_bounds__(kPoolBlock, 1) render_pool_kernel(const __grid_constant__ RenderParams P) {
     extern __shared__ __align__(16) float sh_pool[];
     __shared__ float sh_acc[kPoolWarps][32][3];
     const DeviceScene& S = P.S;
     uint4* const sh_tab = reinterpret_cast<uint4*>(sh_pool + kPoolWarps * kPoolWarpWords);
-    const int n_tab = P.n_tab;
-    for (int i = threadIdx.x; i < n_tab; i += kPoolBlock) sh_tab[i] = __ldg(S.box16 + i);
+    for (int i = threadIdx.x; i < P.n_tab; i += kPoolBlock) sh_tab[i] = __ldg(S.box16 + i);
     TexEnv E;
-    stage_noise(S, E, reinterpret_cast<NoiseTable*>(sh_tab + n_tab), P.n_sh_noise);  // ends with __syncthreads()
-    // Box16 of record pc: shared memory for the staged prefix, global memory behind it
-    auto box16_at = [&](int pc) -> uint4 { return pc < n_tab ? sh_tab[pc] : __ldg(S.box16 + pc); };
+    stage_noise(S, E, reinterpret_cast<NoiseTable*>(sh_tab + P.n_tab), P.n_sh_noise);  // ends with __syncthreads()
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const bool ref_boxes = P.reference_boxes != 0;
-    const V3 bg = v3(P.bg[0], P.bg[1], P.bg[2]);
-    const float div_w = (float)P.width - 1.0f, div_h = (float)P.height - 1.0f;  // application.rs:444-445
-    const float kTmin = 0.001f;                                                 // application.rs:482
     unsigned long long n_rays = 0, n_paths = 0;
 #ifdef HRT_SCHED_STATS
     unsigned long long st_rounds = 0, st_lanes = 0;
@@ -441,20 +634,18 @@ __global__ void __launch_bounds__(kPoolBlock, 1) render_pool_kernel(const __grid
     W.f = sh_pool + warp * kPoolWarpWords;
     W.cls_w = reinterpret_cast<uint32_t*>(W.f + PF_WORDS * kPoolSlots);
     W.list = reinterpret_cast<int*>(W.cls_w + 32);
-    const int first_cls = record_class(box16_at(0).w & 0xffu);  // class of record 0: where every new ray segment starts
+    RoundEnv R{S, P, E, sh_tab, P.n_tab, 0, P.reference_boxes != 0, v3(P.bg[0], P.bg[1], P.bg[2]),
+               (float)P.width - 1.0f, (float)P.height - 1.0f, 0, 0, 0, 0, sh_acc[warp]};
+    R.first_cls = record_class(R.box16_at(0).w & 0xffu);
 
     for (;;) {
         unsigned long long item = 0;
         if (lane == 0) item = atomicAdd(P.counters, 1ULL);
         item = __shfl_sync(kFull, item, 0);
         if (item >= (unsigned long long)P.n_items) break;
-        const int tile = (int)(item % (unsigned long long)P.n_tiles);
-        const int chunk = (int)(item / (unsigned long long)P.n_tiles);
-        const int tx = tile % P.tiles_x, ty = tile / P.tiles_x;
-        const int tc = chunk - P.n_big;  // >= 0: one of the shrinking tail chunks
-        const int s0 = P.sample_begin + (tc < 0 ? chunk * P.chunk : P.tail_begin[tc]);
-        const int s_n = tc < 0 ? P.chunk : P.tail_size[tc];
-        const int pool_size = 32 * s_n;
+        int s_n;
+        decode_item(P, item, R.tx, R.ty, R.s0, s_n);
+        R.pool_size = 32 * s_n;
         int pool_next = 0;
 
         sh_acc[warp][lane][0] = 0.0f;
@@ -474,31 +665,11 @@ __global__ void __launch_bounds__(kPoolBlock, 1) render_pool_kernel(const __grid
         for (;;) {
             const uint32_t cw = W.cls_w[lane];
             const PoolCounts cnt = pool_count(cw);
-#if HRT_POOL_POLICY == 0
             int run = CLS_BOX, best_n = cnt.n[CLS_BOX];
 #pragma unroll
             for (int c = CLS_SPHERE; c <= CLS_NEW; ++c)
                 if (cnt.n[c] > best_n) { run = c; best_n = cnt.n[c]; }
             if (best_n == 0) break;  // every slot idle: the item is finished
-#else
-            // Box steps are ~85 % of all steps, so the pool is steered to keep the BOX population large: a non-box class
-            // runs as soon as it has its quorum (cheap leaf bodies early, the long shading body later), which keeps the
-            // parked populations small and leaves the rest of the pool's rays at boxes.
-            int run, best_n;
-            {
-                const int nb = cnt.n[CLS_BOX];
-                int oc = CLS_SPHERE, on = cnt.n[CLS_SPHERE];
-#pragma unroll
-                for (int c = CLS_RECT; c <= CLS_NEW; ++c)
-                    if (cnt.n[c] > on) { oc = c; on = cnt.n[c]; }
-                if (nb == 0 && on == 0) break;  // every slot idle: the item is finished
-                const int thr = oc == CLS_DONE ? HRT_POOL_Q_DONE : (oc == CLS_MISC ? HRT_POOL_Q_MISC : (oc == CLS_NEW ? HRT_POOL_Q_NEW : HRT_POOL_Q_LEAF));
-                const bool box = nb >= HRT_POOL_Q_BOXFULL || (on < thr && nb >= on);
-                run = box ? CLS_BOX : oc;
-                best_n = box ? nb : on;
-                (void)best_n;
-            }
-#endif
             const int n = pool_gather(W, cw, run, lane, rot);
             rot = rot + 1 == kPoolHomes ? 0 : rot + 1;
             const int s = lane < n ? W.list[lane] : -1;
@@ -506,174 +677,14 @@ __global__ void __launch_bounds__(kPoolBlock, 1) render_pool_kernel(const __grid
             if (lane == run) { st_rounds++; st_lanes += n; }
 #endif
             HRT_STAT_PHASE(6)
-            if (run == CLS_BOX) {
-                Ray cur;
-                RayK k;
-                float closest = 0.0f;
-                int pc = 0, cls = CLS_IDLE;
-                uint4 Q = make_uint4(0u, 0u, 0u, 0u);
-                if (s >= 0) {
-                    cur.o = v3(W.at(PF_COX, s), W.at(PF_COY, s), W.at(PF_COZ, s));
-                    cur.d = v3(W.at(PF_CDX, s), W.at(PF_CDY, s), W.at(PF_CDZ, s));
-                    cur.time = 0.0f;  // boxes do not depend on the ray's time
-                    closest = W.at(PF_CLOSEST, s);
-                    pc = __float_as_int(W.at(PF_PC, s));
-                    k = make_rayk(cur);
-                    Q = box16_at(pc);
-                    cls = record_class(Q.w & 0xffu);
-                }
-                // several box steps per gather, while most of the gathered rays are still at a box
-                for (int it = 0; it < kPoolMaxBoxSteps; ++it) {
-                    if (cls == CLS_BOX) {
-                        bool hit;
-                        if ((Q.w & 0xffu) == OP_BOX_LOOSE || ref_boxes) {
-                            // unsound box, fp16-unrepresentable box or reference traversal: the 32-byte record decides
-                            float4 A, B;
-                            load_op(S, pc, A, B);
-                            const bool loose = (__float_as_uint(B.w) & 0xffu) == OP_BOX_LOOSE || ref_boxes;
-                            hit = loose ? box_hit_reference(A, B, cur, k, kTmin, closest) : box_hit_tight(A, B, cur, k, kTmin, closest);
-                        } else {
-                            const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&Q.x));  // min.x, min.y
-                            const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&Q.y));  // min.z, max.x
-                            const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&Q.z));  // max.y, max.z
-                            hit = box_hit_tight(make_float4(a.x, a.y, b.x, 0.0f), make_float4(b.y, c.x, c.y, 0.0f), cur, k, kTmin, closest);
-                        }
-                        pc = hit ? pc + 1 : (int)(Q.w >> 8);
-                        Q = box16_at(pc);
-                        cls = record_class(Q.w & 0xffu);
-                    }
-                    if (__popc(__ballot_sync(kFull, cls == CLS_BOX)) < kPoolBoxKeep) break;
-                }
-                if (s >= 0) {
-                    W.at(PF_PC, s) = __int_as_float(pc);
-                    W.set_cls(s, cls);
-                }
-            } else if (run <= CLS_MISC) {
-                if (s >= 0) {
-                    Lane L;
-                    pool_load_traversal(W, s, L);
-                    L.k = make_rayk(L.cur);
-                    lane_fetch(S, L);
-                    if (run == CLS_SPHERE) step_sphere(S, L, kTmin);
-                    else if (run == CLS_RECT) step_rect(S, L, kTmin);
-                    else {
-                        const Ray world = pool_load_world(W, s);
-                        MediumXi xi;
-                        xi.key.k0 = P.k0; xi.key.k1 = P.k1;
-                        xi.key.pixel = __float_as_uint(W.at(PF_PIXEL, s));
-                        xi.key.sample = __float_as_uint(W.at(PF_SAMPLE, s));
-                        xi.bounce = __float_as_uint(W.at(PF_BOUNCE_PL, s)) & 0xffffu;
-                        xi.injected = 0.0f; xi.inject = false;
-                        step_misc(S, L, world, kTmin, ref_boxes, xi);
-                    }
-                    pool_store_traversal(W, s, L, run == CLS_MISC);
-                    W.set_cls(s, lane_class(L));
-                }
-            } else if (run == CLS_DONE) {
-                // ---- traversal finished: emitted + scatter (application.rs:482-494) ----
-                if (s >= 0) {
-                    n_rays++;
-                    Ray world = pool_load_world(W, s);
-                    V3 T = v3(W.at(PF_TX, s), W.at(PF_TY, s), W.at(PF_TZ, s));
-                    const uint32_t bpl = __float_as_uint(W.at(PF_BOUNCE_PL, s));
-                    uint32_t bounce = bpl & 0xffffu;
-                    const int my_pl = (int)(bpl >> 16);
-                    RngKey key;
-                    key.k0 = P.k0; key.k1 = P.k1;
-                    key.pixel = __float_as_uint(W.at(PF_PIXEL, s));
-                    key.sample = __float_as_uint(W.at(PF_SAMPLE, s));
-                    const int best_pc = __float_as_int(W.at(PF_BEST_PC, s));
-                    V3 add = v3(0.0f, 0.0f, 0.0f);
-                    bool alive = false;
-                    if (best_pc < 0) {
-                        add = T * bg;
-                    } else {
-                        const int fc = __float_as_int(W.at(PF_BEST_FC, s));
-                        Best best;
-                        best.t = W.at(PF_CLOSEST, s); best.pc = best_pc; best.face = fc & 0xff; best.ctx = fc >> 8;
-                        HitRec h;
-                        make_hit_record(S, world, best, false, h);
-                        const Material m = S.mats[h.mat];
-                        if (m.kind == MAT_DIFFUSE_LIGHT) {
-                            add = T * material_emitted(S, E, m, h);  // DiffuseLight::scatter -> None
-                        } else {
-                            float u4[4];
-                            rng_block(key, bounce, RNG_BLOCK_SCATTER, u4);
-                            V3 att;
-                            Ray sc;
-                            if (material_scatter(S, E, m, world, h, u4, att, sc)) {
-                                T = T * att;
-                                world = sc;
-                                bounce++;
-                                alive = bounce < (uint32_t)P.depth;  // ray_color(depth == 0) is black
-                            }
-                        }
-                    }
-                    if (add.x != 0.0f) atomicAdd(&sh_acc[warp][my_pl][0], add.x);
-                    if (add.y != 0.0f) atomicAdd(&sh_acc[warp][my_pl][1], add.y);
-                    if (add.z != 0.0f) atomicAdd(&sh_acc[warp][my_pl][2], add.z);
-                    if (alive) {
-                        pool_store_segment(W, s, world);
-                        W.at(PF_TX, s) = T.x; W.at(PF_TY, s) = T.y; W.at(PF_TZ, s) = T.z;
-                        W.at(PF_BOUNCE_PL, s) = __uint_as_float(bounce | ((uint32_t)my_pl << 16));
-                        W.set_cls(s, first_cls);
-                    } else {
-                        W.set_cls(s, CLS_NEW);
-                    }
-                }
-            } else {
-                // ---- CLS_NEW: the gathered path-less slots draw the next path indices of the item ----
-                const int idx = pool_next + lane;
-                pool_next += n;
-                if (s >= 0) {
-                    if (idx >= pool_size) {
-                        W.set_cls(s, CLS_IDLE);
-                    } else {
-                        const int pl = idx & 31;
-                        const int px = tx * 8 + (pl & 7), py = ty * 4 + (pl >> 3);
-                        if (px < P.width && py < P.height) {
-                            RngKey key;
-                            key.k0 = P.k0; key.k1 = P.k1;
-                            key.pixel = (uint32_t)(py * P.width + px);
-                            key.sample = (uint32_t)(s0 + (idx >> 5));
-                            n_paths++;
-                            if (P.depth > 0) {
-                                float c4[4];
-                                rng_block(key, 0, RNG_BLOCK_CAMERA, c4);  // jitter x, jitter y, shutter time, lens u1
-                                float lens_u2 = 0.0f;
-                                if (P.cam.lens_radius != 0.0f) {
-                                    float l4[4];
-                                    rng_block(key, 0, RNG_BLOCK_CAMERA - 1, l4);
-                                    lens_u2 = l4[0];
-                                }
-                                const float u = ((float)px + c4[0]) / div_w;
-                                const float v = ((float)py + c4[1]) / div_h;
-                                const Ray world = camera_get_ray(P.cam, u, v, c4[3], lens_u2, c4[2]);
-                                pool_store_segment(W, s, world);
-                                W.at(PF_TX, s) = 1.0f; W.at(PF_TY, s) = 1.0f; W.at(PF_TZ, s) = 1.0f;
-                                W.at(PF_PIXEL, s) = __uint_as_float(key.pixel);
-                                W.at(PF_SAMPLE, s) = __uint_as_float(key.sample);
-                                W.at(PF_BOUNCE_PL, s) = __uint_as_float((uint32_t)pl << 16);
-                                W.set_cls(s, first_cls);
-                            }
-                        }
-                    }
-                }
-            }
+            const int cls = run_class(R, W, run, s, pool_next + lane, n_rays, n_paths);
+            if (run == CLS_NEW) pool_next += n;
+            if (s >= 0) W.set_cls(s, cls);
             __syncwarp();  // slot state and class bytes written by this round are visible to the next round's readers
             HRT_STAT_PHASE(run)
         }
         __syncwarp();
-        {
-            const int px = tx * 8 + (lane & 7), py = ty * 4 + (lane >> 3);
-            if (px < P.width && py < P.height) {
-                float* dst = reinterpret_cast<float*>(P.accum + (size_t)py * P.width + px);
-                atomicAdd(dst + 0, sh_acc[warp][lane][0]);
-                atomicAdd(dst + 1, sh_acc[warp][lane][1]);
-                atomicAdd(dst + 2, sh_acc[warp][lane][2]);
-                atomicAdd(dst + 3, (float)s_n);
-            }
-        }
+        flush_item(P, R.tx, R.ty, s_n, sh_acc[warp], lane);
         __syncwarp();
     }
 #pragma unroll
@@ -996,23 +1007,26 @@ cudaError_t launch_render(hrt::RenderLaunch& L, int num_sms, cudaStream_t stream
     P.n_tab = 0;
     P.n_sh_noise = 0;
     cudaError_t e;
-    if (L.interpreter == 2) {
-        // Shared-memory budget of the one resident block: the warp pools, then as much of the Box16 table as fits (all
+    const bool pooled = L.interpreter == 2;
+    const void* pool_fn = (const void*)render_pool_kernel;
+    if (pooled) {
+        // Shared-memory budget of the one resident block: the ray pools, then as much of the Box16 table as fits (all
         // of it for the BASELINE scenes: 4236 records = 66 KB for `final`), then the noise tables.
+        const size_t pools = kPoolBytes;
         int dev = 0, optin = 0;
         cudaFuncAttributes fa;
         if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
         if ((e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess) return e;
-        if ((e = cudaFuncGetAttributes(&fa, render_pool_kernel)) != cudaSuccess) return e;
-        long long avail = (long long)optin - (long long)fa.sharedSizeBytes - (long long)kPoolBytes;
+        if ((e = cudaFuncGetAttributes(&fa, pool_fn)) != cudaSuccess) return e;
+        long long avail = (long long)optin - (long long)fa.sharedSizeBytes - (long long)pools;
         if (avail < 0) return cudaErrorInvalidConfiguration;
         P.n_tab = (int)std::min<long long>(P.S.n_ops, avail / 16);
         avail -= 16ll * P.n_tab;
         P.n_sh_noise = (int)std::min<long long>(std::min(P.S.n_noise, kMaxNoiseTablesShared), avail / (long long)sizeof(NoiseTable));
-        pool_smem = kPoolBytes + 16 * (size_t)P.n_tab + sizeof(NoiseTable) * (size_t)P.n_sh_noise;
-        e = cudaFuncSetAttribute(render_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pool_smem);
+        pool_smem = pools + 16 * (size_t)P.n_tab + sizeof(NoiseTable) * (size_t)P.n_sh_noise;
+        e = cudaFuncSetAttribute(pool_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pool_smem);
         if (e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, render_pool_kernel, kPoolBlock, pool_smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, pool_fn, kPoolBlock, pool_smem);
     } else if (L.interpreter == 1) {
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, render_interp_kernel, kBlock, 0);
     } else {
@@ -1025,8 +1039,8 @@ cudaError_t launch_render(hrt::RenderLaunch& L, int num_sms, cudaStream_t stream
     // enough that the dynamic cursor balances the last wave (>= ~8 items per resident warp when possible).
     int chunk = L.chunk;
     if (chunk <= 0) {
-        chunk = L.interpreter == 2 ? 256 : 64;  // the pool kernel keeps 96 rays in flight per warp: larger items
-        const long long resident_warps = (long long)grid * (L.interpreter == 2 ? kPoolWarps : kWarpsPerBlock);
+        chunk = pooled ? 256 : 64;  // the pool kernel keeps 96 rays in flight per warp: larger items
+        const long long resident_warps = (long long)grid * (pooled ? kPoolWarps : kWarpsPerBlock);
         while (chunk > 4 && (long long)P.n_tiles * ((L.sample_count + chunk - 1) / chunk) < 8 * resident_warps) chunk /= 2;
     }
     if (chunk > L.sample_count) chunk = L.sample_count;
@@ -1055,7 +1069,7 @@ cudaError_t launch_render(hrt::RenderLaunch& L, int num_sms, cudaStream_t stream
     P.counters = L.counters;
     P.accum = reinterpret_cast<float4*>(L.accum);
     L.grid = grid;
-    L.block = L.interpreter == 2 ? kPoolBlock : kBlock;
+    L.block = pooled ? kPoolBlock : kBlock;
     L.chunk = chunk;
     if (L.interpreter == 2) render_pool_kernel<<<grid, kPoolBlock, pool_smem, stream>>>(P);
     else if (L.interpreter == 1) render_interp_kernel<<<grid, kBlock, 0, stream>>>(P);

@@ -33,24 +33,6 @@ constexpr int kPoolWarpWords = PF_WORDS * kPoolSlots + 32 /* class bytes, 4 per 
 #ifndef HRT_POOL_BOX_KEEP
 #define HRT_POOL_BOX_KEEP 12
 #endif
-#ifndef HRT_POOL_POLICY
-#define HRT_POOL_POLICY 0
-#endif
-#ifndef HRT_POOL_Q_LEAF
-#define HRT_POOL_Q_LEAF 8
-#endif
-#ifndef HRT_POOL_Q_MISC
-#define HRT_POOL_Q_MISC 16
-#endif
-#ifndef HRT_POOL_Q_DONE
-#define HRT_POOL_Q_DONE 24
-#endif
-#ifndef HRT_POOL_Q_NEW
-#define HRT_POOL_Q_NEW 16
-#endif
-#ifndef HRT_POOL_Q_BOXFULL
-#define HRT_POOL_Q_BOXFULL 32
-#endif
 constexpr int kPoolMaxBoxSteps = HRT_POOL_BOX_STEPS;  // box steps per gather while enough lanes stay at a box
 constexpr int kPoolBoxKeep = HRT_POOL_BOX_KEEP;       // ... "enough" lanes
 
@@ -64,7 +46,8 @@ struct PoolWarp {  // views into this warp's slice of dynamic shared memory
     }
 };
 
-__device__ __forceinline__ void pool_load_traversal(const PoolWarp& W, int s, Lane& L) {
+template <class PoolT>
+__device__ __forceinline__ void pool_load_traversal(const PoolT& W, int s, Lane& L) {
     L.cur.o = v3(W.at(PF_COX, s), W.at(PF_COY, s), W.at(PF_COZ, s));
     L.cur.d = v3(W.at(PF_CDX, s), W.at(PF_CDY, s), W.at(PF_CDZ, s));
     L.cur.time = W.at(PF_TIME, s);
@@ -76,7 +59,8 @@ __device__ __forceinline__ void pool_load_traversal(const PoolWarp& W, int s, La
     L.best_ctx = fc >> 8;
     L.ctx = __float_as_int(W.at(PF_CTX, s));
 }
-__device__ __forceinline__ void pool_store_traversal(const PoolWarp& W, int s, const Lane& L, bool cur_changed) {
+template <class PoolT>
+__device__ __forceinline__ void pool_store_traversal(const PoolT& W, int s, const Lane& L, bool cur_changed) {
     W.at(PF_PC, s) = __int_as_float(L.pc);
     W.at(PF_CLOSEST, s) = L.closest;
     W.at(PF_BEST_PC, s) = __int_as_float(L.best_pc);
@@ -87,7 +71,8 @@ __device__ __forceinline__ void pool_store_traversal(const PoolWarp& W, int s, c
         W.at(PF_CTX, s) = __int_as_float(L.ctx);
     }
 }
-__device__ __forceinline__ Ray pool_load_world(const PoolWarp& W, int s) {
+template <class PoolT>
+__device__ __forceinline__ Ray pool_load_world(const PoolT& W, int s) {
     Ray w;
     w.o = v3(W.at(PF_WOX, s), W.at(PF_WOY, s), W.at(PF_WOZ, s));
     w.d = v3(W.at(PF_WDX, s), W.at(PF_WDY, s), W.at(PF_WDZ, s));
@@ -95,7 +80,8 @@ __device__ __forceinline__ Ray pool_load_world(const PoolWarp& W, int s) {
     return w;
 }
 // A new ray segment starts: world == current ray, traversal state reset (lane_start).
-__device__ __forceinline__ void pool_store_segment(const PoolWarp& W, int s, const Ray& w) {
+template <class PoolT>
+__device__ __forceinline__ void pool_store_segment(const PoolT& W, int s, const Ray& w) {
     W.at(PF_WOX, s) = w.o.x; W.at(PF_WOY, s) = w.o.y; W.at(PF_WOZ, s) = w.o.z;
     W.at(PF_WDX, s) = w.d.x; W.at(PF_WDY, s) = w.d.y; W.at(PF_WDZ, s) = w.d.z;
     W.at(PF_TIME, s) = w.time;
