@@ -16,7 +16,7 @@ import time
 
 import numpy as np
 
-from . import native, renderer, scenes
+from . import native, renderer, scene_io, scenes
 
 
 def parse(argv=None):
@@ -31,6 +31,8 @@ def parse(argv=None):
     ap.add_argument("--render-seed", type=int, default=0, help="Philox key of the sample streams")
     ap.add_argument("--device", type=int, default=0)
     ap.add_argument("--out", default="frame.png", help="output file: .png, .npy (float32 RGBA, bottom-up) or .pfm")
+    ap.add_argument("--save-scene", default=None, metavar="FILE", help="write the generated scene instance (.npz) before rendering")
+    ap.add_argument("--load-scene", default=None, metavar="FILE", help="render a stored scene instance instead of --scene/--seed")
     return ap.parse_args(argv)
 
 
@@ -55,7 +57,9 @@ def main(argv=None) -> int:
         print("error: no CUDA device — this renderer has no CPU fallback", file=sys.stderr)
         return 2
     print("Generating world...")                                    # application.rs:131
-    spec = scenes.make_scene(a.scene, a.seed)
+    spec = scene_io.load_scene(a.load_scene) if a.load_scene else scenes.make_scene(a.scene, a.seed)
+    if a.save_scene:
+        scene_io.save_scene(spec, a.save_scene)
     r = renderer.Renderer(spec, device=a.device)
     print("Generated world")                                        # application.rs:199
     print("Rendering image...")                                     # application.rs:387

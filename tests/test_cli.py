@@ -54,3 +54,14 @@ def test_cli_renders_a_frame(pkg, tmp_path):
     assert rc == 0
     f = np.load(out)
     assert f.shape == (64, 64, 4) and np.all(f[..., 3] == 1.0) and np.nanmax(f[..., :3]) > 0.5
+
+
+@pytest.mark.gpu
+def test_cli_stored_scene_renders_the_same_frame(pkg, tmp_path):
+    """--save-scene / --load-scene: the stored instance renders the same frame as the generated one (same render seed)."""
+    cli = _cli(pkg)
+    scene, a, b = str(tmp_path / "s.npz"), str(tmp_path / "a.npy"), str(tmp_path / "b.npy")
+    common = "--width 48 --height 32 --samples 16 --depth 20 --render-seed 5"
+    assert cli.main(f"--scene random --seed 9 {common} --save-scene {scene} --out {a}".split()) == 0
+    assert cli.main(f"--load-scene {scene} {common} --out {b}".split()) == 0
+    assert np.allclose(np.nan_to_num(np.load(a)), np.nan_to_num(np.load(b)), rtol=2e-4, atol=2e-4)
