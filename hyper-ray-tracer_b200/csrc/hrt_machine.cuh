@@ -1,16 +1,17 @@
-// hrt_machine.cuh — warp-level tiered op-class scheduler over the op stream.
+// hrt_machine.cuh — warp-level op-class scheduler over the op stream (render_kernel, trace_hits_sched_kernel), and the
+// step_* class bodies every render kernel shares.
 //
 // Why: a straightforward per-lane interpreter (`traverse<>` in hrt_device.cuh) lets the 32 lanes of a warp sit at
 // different record kinds, so every loop iteration pays the SUM of the class bodies present: box (~40 instructions) +
 // sphere + cuboid (~100) + medium (~300) ..., each for a handful of lanes.  ncu on the first version: 5.4 of 32 lanes
 // active per issued instruction (profiles/r01_render_kernel_summary.md).
 //
-// Here every lane keeps its traversal state in registers and PARKS at its current record.
-//   tier 0  box records (~85 % of all steps): executed whenever at least kBoxQuorum lanes are at a box — one ballot;
-//   tier 1  when the box population drops below the quorum, ONE pass services every parked leaf class (sphere, rect /
-//           cuboid, medium / ray-space change), which sends those lanes back to boxes;
-//   tier 2  "traversal finished -> shade" and "no path -> draw a new camera sample" are the expensive bodies (~450
-//           instructions): they wait until kShadeQuorum lanes need them, or until nothing else can run.
+// Here every lane keeps its traversal state in registers and PARKS at its current record; each round the warp votes and
+// runs ONE class with a warp-uniform branch:
+//   * box records (~85 % of all steps) whenever at least kBoxQuorum lanes are at a box (one ballot), or when the box
+//     population is larger than every parked class;
+//   * otherwise the non-box class with the most parked lanes: sphere, rect / cuboid, misc (ray-space change, medium),
+//     done ("traversal finished -> shade") or new ("no path -> draw a camera sample").
 // A lane therefore never waits for the longest traversal or the longest path of its warp, only for its class's turn.
 // Traversal order per ray is unchanged (the reference's fixed depth-first order), so results are bit-identical to
 // `traverse<>` (tests/test_gpu_parity.py::test_hit_records_through_warp_scheduler).
