@@ -347,6 +347,12 @@ def test_render_conventions_and_slices(pkg, orc, built):
     assert st.paths == 37 * 19 * 8 and st.rays == st.paths
     img0, st0 = gb.render(cam, 8, 8, 4, 0, (1, 1, 1))
     assert np.all(img0[..., :3] == 0) and st0.rays == 0
+    # the ray pool keeps the bounce index in 16 bits: deeper recursion is refused, not truncated
+    with pytest.raises(pkg.HrtError) as ei:
+        gb.render(cam, 8, 8, 4, 65536, (1, 1, 1))
+    assert ei.value.code == -1 and "65535" in str(ei.value)
+    img_d, _ = gb.render(cam, 8, 8, 4, 65535, (1, 1, 1))
+    assert np.allclose(img_d[..., :3], 1.0)
     # bottom-up rows: a light below the camera axis shows up in the LOW rows
     gb2 = pkg.HrtBackend()
     S.emit(S.BvhNode([S.Sphere((0, -3, -10), 1.0, S.DiffuseLight(S.SolidColor((5, 5, 5))))], 0.0, 1.0), gb2)
