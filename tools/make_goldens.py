@@ -30,6 +30,8 @@ SPP = int(os.environ.get("GOLDEN_SPP", "4096"))
 DIV = int(os.environ.get("GOLDEN_DIV", "2"))
 SUFFIX = os.environ.get("GOLDEN_SUFFIX", "")
 threads = int(os.environ.get("GOLDEN_THREADS", "7"))
+# the oracle hands out tiles dynamically: small frames need small tiles or most threads idle (80 is the reference's default)
+TILE = int(os.environ.get("GOLDEN_TILE", "80"))
 only = sys.argv[1:] or list(pkg.CONFIGS)
 for cfg in only:
     scene, W, H, _, depth = pkg.CONFIGS[cfg]
@@ -45,7 +47,7 @@ for cfg in only:
     halves = []
     counters = None
     for seed in (101, 202):
-        s, sq, c = ob.render(spec.camera, w, h, SPP // 2, depth, spec.background, seed=seed, threads=threads, want_sumsq=True)
+        s, sq, c = ob.render(spec.camera, w, h, SPP // 2, depth, spec.background, seed=seed, threads=threads, tile_size=TILE, want_sumsq=True)
         halves.append((np.nan_to_num(s.astype(np.float64)), np.nan_to_num(sq.astype(np.float64))))
         counters = c
         print(cfg, "half", seed, f"{time.time() - t0:.0f}s", flush=True)
