@@ -1026,17 +1026,6 @@ cudaError_t launch_render(hrt::RenderLaunch& L, int num_sms, cudaStream_t stream
         pool_smem = pools + 16 * (size_t)P.n_tab + sizeof(NoiseTable) * (size_t)P.n_sh_noise;
         e = cudaFuncSetAttribute(pool_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pool_smem);
         if (e != cudaSuccess) return e;
-        {
-            // Ask for no more shared memory than the one resident block uses, so that small scenes (whose table is tiny)
-            // leave the rest of the SM's 256 KB to L1 — shading spills and the 32-byte records live there.
-            int per_sm = 0;
-            if ((e = cudaDeviceGetAttribute(&per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev)) != cudaSuccess) return e;
-            const long long need = (long long)pool_smem + (long long)fa.sharedSizeBytes + 1024;  // + the per-block reservation
-            int carve = per_sm > 0 ? (int)((need * 100 + per_sm - 1) / per_sm) : 100;
-            if (const char* env = getenv("HRT_CARVEOUT")) carve = atoi(env);  // diagnostic override, percent
-            if (carve > 100) carve = 100;
-            if (carve >= 0 && (e = cudaFuncSetAttribute(pool_fn, cudaFuncAttributePreferredSharedMemoryCarveout, carve)) != cudaSuccess) return e;
-        }
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, pool_fn, kPoolBlock, pool_smem);
     } else if (L.interpreter == 1) {
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, render_interp_kernel, kBlock, 0);
