@@ -131,6 +131,18 @@ static thread_local Counters tls_cnt;
 // 0 = reference per-axis-independent slab test (src/aabb.rs:20-47); 1 = intersected ("tight") slab
 // test, used ONLY to count the traversal work a sound-box traversal needs.
 static int g_aabb_mode = 0;
+// WORK-MODEL STUDIES ONLY (tools/work_model.py --bvh-study): ORC_BVH_STUDY=sah builds every BvhNode with a full-sweep
+// surface-area heuristic instead of the reference's longest-axis median split, ORC_BVH_STUDY=sah+near additionally
+// visits the child whose box the ray enters first.  Neither is the reference's algorithm; they only answer "how many
+// box tests would a better tree / order save" (SURVEY.md §8f N4).  Unset (the default) = reference behaviour.
+static int bvh_study_mode() {
+    static const int mode = [] {
+        const char* e = std::getenv("ORC_BVH_STUDY");
+        if (!e) return 0;
+        return std::strcmp(e, "sah+near") == 0 ? 2 : (std::strcmp(e, "sah") == 0 ? 1 : (std::strcmp(e, "near") == 0 ? 3 : 0));
+    }();
+    return mode;
+}
 
 // ---------------------------------------------------------------------------------------------
 // src/math.rs
@@ -237,6 +249,23 @@ struct Aabb {
             if (t_max <= t_min) return false;
         }
         return true;
+    }
+    // entry distance of the ray into the box (study modes only; +inf when missed)
+    float entry_tight(const Ray& ray, float time_min, float time_max) const {
+        for (int a = 0; a < 3; ++a) {
+            float inverse_direction = 1.0f / ray.direction[a];
+            float time_start = (minimum[a] - ray.origin[a]) * inverse_direction;
+            float time_end = (maximum[a] - ray.origin[a]) * inverse_direction;
+            if (inverse_direction < 0.0f) std::swap(time_start, time_end);
+            time_min = time_start > time_min ? time_start : time_min;
+            time_max = time_end < time_max ? time_end : time_max;
+            if (time_max <= time_min) return std::numeric_limits<float>::infinity();
+        }
+        return time_min;
+    }
+    float half_area() const {
+        Vec3 d = maximum - minimum;
+        return d.x * d.y + d.y * d.z + d.z * d.x;
     }
     bool hit_tight(const Ray& ray, float time_min, float time_max) const {
         for (int a = 0; a < 3; ++a) {
@@ -819,6 +848,11 @@ struct BvhNode : Hittable {
     // a stable sort throughout ("parity unpinned" for tie order at n > 20; ties cannot change hit
     // results on sound boxes — SURVEY.md §8a a25).
     BvhNode(std::vector<const Hittable*> objects, float t0, float t1) {
+        const int study = bvh_study_mode();
+        if ((study == 1 || study == 2) && objects.size() > 2) {
+            build_sah(std::move(objects), t0, t1);
+            return;
+        }
         std::pair<int, float> ranges[3];
         for (int a = 0; a < 3; ++a) ranges[a] = {a, axis_range(objects, t0, t1, a)};
         std::stable_sort(ranges, ranges + 3, [](const std::pair<int, float>& a, const std::pair<int, float>& b) {
@@ -846,10 +880,60 @@ struct BvhNode : Hittable {
             bbox = Aabb::surrounding_box(left->bbox, right->bbox);
         }
     }
+    // study only (see bvh_study_mode): full-sweep SAH over the three centroid orders
+    void build_sah(std::vector<const Hittable*> objects, float t0, float t1) {
+        const size_t n = objects.size();
+        float best_cost = std::numeric_limits<float>::infinity();
+        int best_axis = 0;
+        size_t best_split = n / 2;
+        std::vector<Aabb> boxes(n);
+        std::vector<float> right_area(n + 1);
+        for (int axis = 0; axis < 3; ++axis) {
+            std::stable_sort(objects.begin(), objects.end(), [&](const Hittable* a, const Hittable* b) {
+                Aabb ba, bb;
+                a->bounding_box(t0, t1, ba);
+                b->bounding_box(t0, t1, bb);
+                return ba.minimum[axis] + ba.maximum[axis] < bb.minimum[axis] + bb.maximum[axis];
+            });
+            for (size_t i = 0; i < n; ++i) objects[i]->bounding_box(t0, t1, boxes[i]);
+            Aabb acc = boxes[n - 1];
+            right_area[n - 1] = acc.half_area();
+            for (size_t i = n - 1; i-- > 0;) { acc = Aabb::surrounding_box(acc, boxes[i]); right_area[i] = acc.half_area(); }
+            acc = boxes[0];
+            for (size_t i = 1; i < n; ++i) {  // left = [0, i), right = [i, n)
+                const float cost = acc.half_area() * (float)i + right_area[i] * (float)(n - i);
+                if (cost < best_cost) { best_cost = cost; best_axis = axis; best_split = i; }
+                acc = Aabb::surrounding_box(acc, boxes[i]);
+            }
+        }
+        std::stable_sort(objects.begin(), objects.end(), [&](const Hittable* a, const Hittable* b) {
+            Aabb ba, bb;
+            a->bounding_box(t0, t1, ba);
+            b->bounding_box(t0, t1, bb);
+            return ba.minimum[best_axis] + ba.maximum[best_axis] < bb.minimum[best_axis] + bb.maximum[best_axis];
+        });
+        std::vector<const Hittable*> r(objects.begin() + (long)best_split, objects.end());
+        std::vector<const Hittable*> l(objects.begin(), objects.begin() + (long)best_split);
+        right = std::make_unique<BvhNode>(std::move(r), t0, t1);
+        left = std::make_unique<BvhNode>(std::move(l), t0, t1);
+        bbox = Aabb::surrounding_box(left->bbox, right->bbox);
+    }
     // src/hittable/bvh_node.rs:104-127 — left first, narrow t_max, right wins if it hits (Q3).
     bool hit(const Ray& ray, float time_min, float time_max, HitRecord& rec) const override {
         if (!bbox.hit(ray, time_min, time_max)) return false;
         if (leaf) return leaf->hit(ray, time_min, time_max, rec);
+        if (bvh_study_mode() >= 2) {  // study only: nearer child first (not the reference's order)
+            const BvhNode* a = left.get();
+            const BvhNode* b = right.get();
+            if (b->bbox.entry_tight(ray, time_min, time_max) < a->bbox.entry_tight(ray, time_min, time_max)) std::swap(a, b);
+            HitRecord arec, brec;
+            const bool ahit = a->hit(ray, time_min, time_max, arec);
+            if (ahit) time_max = arec.t;
+            const bool bhit = b->hit(ray, time_min, time_max, brec);
+            if (bhit) { rec = brec; return true; }
+            if (ahit) { rec = arec; return true; }
+            return false;
+        }
         HitRecord lrec;
         bool lhit = left->hit(ray, time_min, time_max, lrec);
         if (lhit) time_max = lrec.t;
