@@ -13,6 +13,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 
@@ -215,6 +216,62 @@ static int32_t build_bvh(const hrt_scene& s, BvhTree& tree, std::vector<int32_t>
     return (int32_t)tree.nodes.size() - 1;
 }
 
+// Opt-in alternative to BvhNode::new's longest-axis median split (hrt_scene_set_bvh_builder): a full-sweep surface-area
+// heuristic over the three centroid orders.  The node boxes are still unions of the leaves' reference boxes; only the
+// topology — and with it the depth-first order of the leaves — changes.
+static float half_area(const Box3& b) {
+    const float dx = b.mx[0] - b.mn[0], dy = b.mx[1] - b.mn[1], dz = b.mx[2] - b.mn[2];
+    return dx * dy + dy * dz + dz * dx;
+}
+static int32_t build_bvh_sah(const hrt_scene& s, BvhTree& tree, std::vector<int32_t> objs, float ts, float te) {
+    const size_t n = objs.size();
+    BvhTreeNode node;
+    if (n == 1) {
+        node.leaf_obj = objs[0];
+        ref_box(s, node.leaf_obj, ts, te, false, node.box);
+        tree.nodes.push_back(node);
+        return (int32_t)tree.nodes.size() - 1;
+    }
+    struct Item { float key; int32_t id; Box3 box; };
+    std::vector<Item> items(n);
+    std::vector<float> right_area(n + 1);
+    float best_cost = std::numeric_limits<float>::infinity();
+    int best_axis = 0;
+    size_t best_split = n / 2;
+    auto sort_axis = [&](int axis) {
+        for (size_t i = 0; i < n; ++i) {
+            items[i].id = objs[i];
+            ref_box(s, objs[i], ts, te, false, items[i].box);
+            items[i].key = items[i].box.mn[axis] + items[i].box.mx[axis];
+        }
+        std::stable_sort(items.begin(), items.end(), [](const Item& a, const Item& b) { return a.key < b.key; });
+    };
+    for (int axis = 0; axis < 3; ++axis) {
+        sort_axis(axis);
+        Box3 acc = items[n - 1].box;
+        right_area[n - 1] = half_area(acc);
+        for (size_t i = n - 1; i-- > 0;) { acc = surrounding_box(acc, items[i].box); right_area[i] = half_area(acc); }
+        acc = items[0].box;
+        for (size_t i = 1; i < n; ++i) {  // left = [0, i), right = [i, n)
+            const float cost = half_area(acc) * (float)i + right_area[i] * (float)(n - i);
+            if (cost < best_cost) { best_cost = cost; best_axis = axis; best_split = i; }
+            acc = surrounding_box(acc, items[i].box);
+        }
+    }
+    sort_axis(best_axis);
+    std::vector<int32_t> l, r;
+    for (size_t i = 0; i < best_split; ++i) l.push_back(items[i].id);
+    for (size_t i = best_split; i < n; ++i) r.push_back(items[i].id);
+    items.clear();
+    const int32_t ri = build_bvh_sah(s, tree, std::move(r), ts, te);
+    const int32_t li = build_bvh_sah(s, tree, std::move(l), ts, te);
+    node.left = li;
+    node.right = ri;
+    node.box = surrounding_box(tree.nodes[li].box, tree.nodes[ri].box);
+    tree.nodes.push_back(node);
+    return (int32_t)tree.nodes.size() - 1;
+}
+
 static uint32_t count_of(const hrt_scene& s, int id) {
     const Obj& o = s.objects[id];
     switch (o.kind) {
@@ -341,17 +398,36 @@ struct Flattener {
                     if (!emit(c, ctx)) return false;
                 return true;
             }
-            case OBJ_BVH:
-                return emit_bvh(o, o.bvh.root, ctx);
+            case OBJ_BVH: {
+                if (s.bvh_builder == 1 && all_leaves_sound(o)) {
+                    // every leaf box contains its leaf, so every union of leaf boxes is sound in ANY topology and the
+                    // closest hit does not depend on it (only the winner of an exact tie between coincident surfaces
+                    // does: the leaf that comes later in the stream — documented in include/hrt.h)
+                    BvhTree alt;
+                    alt.root = build_bvh_sah(s, alt, o.children, o.t0, o.t1);
+                    s.n_bvh_rebuilt++;
+                    return emit_bvh(alt, o.t0, o.t1, alt.root, ctx);
+                }
+                return emit_bvh(o.bvh, o.t0, o.t1, o.bvh.root, ctx);
+            }
         }
         return false;
     }
 
-    bool emit_bvh(const Obj& bvh, int32_t node_index, int32_t ctx) {
-        const BvhTreeNode& n = bvh.bvh.nodes[node_index];
+    bool all_leaves_sound(const Obj& bvh) {
+        for (const BvhTreeNode& n : bvh.bvh.nodes) {
+            if (n.leaf_obj < 0) continue;
+            Box3 truth;
+            if (!ref_box(s, n.leaf_obj, bvh.t0, bvh.t1, true, truth) || !contains(n.box, truth)) return false;
+        }
+        return true;
+    }
+
+    bool emit_bvh(const BvhTree& tree, float t0, float t1, int32_t node_index, int32_t ctx) {
+        const BvhTreeNode& n = tree.nodes[node_index];
         // Soundness: does the reference box contain everything hit() can accept beneath this node?
         Box3 truth;
-        bool sound = true_extent(bvh, node_index, truth) && contains(n.box, truth);
+        bool sound = true_extent(tree, t0, t1, node_index, truth) && contains(n.box, truth);
         int32_t at = pc();
         {
             Op& op = push(sound ? OP_BOX : OP_BOX_LOOSE);
@@ -363,19 +439,19 @@ struct Flattener {
         if (n.leaf_obj >= 0) {
             if (!emit(n.leaf_obj, ctx)) return false;
         } else {
-            if (!emit_bvh(bvh, n.left, ctx)) return false;   // left first (bvh_node.rs:111)
-            if (!emit_bvh(bvh, n.right, ctx)) return false;
+            if (!emit_bvh(tree, t0, t1, n.left, ctx)) return false;   // left first (bvh_node.rs:111)
+            if (!emit_bvh(tree, t0, t1, n.right, ctx)) return false;
         }
         if (pc() >= (1 << 24)) { error = "op stream longer than 2^24 records"; return false; }
         s.ops[at].u[7] = (s.ops[at].u[7] & 0xffu) | ((uint32_t)pc() << 8);
         return true;
     }
 
-    bool true_extent(const Obj& bvh, int32_t node_index, Box3& out) {
-        const BvhTreeNode& n = bvh.bvh.nodes[node_index];
-        if (n.leaf_obj >= 0) return ref_box(s, n.leaf_obj, bvh.t0, bvh.t1, true, out);
+    bool true_extent(const BvhTree& tree, float t0, float t1, int32_t node_index, Box3& out) {
+        const BvhTreeNode& n = tree.nodes[node_index];
+        if (n.leaf_obj >= 0) return ref_box(s, n.leaf_obj, t0, t1, true, out);
         Box3 a, b;
-        if (!true_extent(bvh, n.left, a) || !true_extent(bvh, n.right, b)) return false;
+        if (!true_extent(tree, t0, t1, n.left, a) || !true_extent(tree, t0, t1, n.right, b)) return false;
         out = surrounding_box(a, b);
         return true;
     }
@@ -468,6 +544,8 @@ int32_t hrt_abi_version(void) { return HRT_ABI_VERSION; }
 int32_t hrt_scene_create(hrt_scene** out) {
     if (!out) return fail(HRT_ERR_INVALID, "null out pointer");
     *out = new hrt_scene();
+    if (const char* env = std::getenv("HRT_BVH_BUILDER"))  // diagnostic default for scenes the caller does not configure
+        (*out)->bvh_builder = std::strcmp(env, "sah") == 0 ? HRT_BVH_SAH : HRT_BVH_REFERENCE;
     Ctx root;
     std::memset(&root, 0, sizeof(root));
     root.parent = -1;
@@ -684,12 +762,20 @@ int32_t hrt_bvh(hrt_scene* s, const int32_t* children, int32_t n, float ts, floa
     return add_obj(s, std::move(o));
 }
 
+int32_t hrt_scene_set_bvh_builder(hrt_scene* s, int32_t builder) {
+    HRT_CHECK_SCENE(s);
+    if (builder != HRT_BVH_REFERENCE && builder != HRT_BVH_SAH) return fail(HRT_ERR_INVALID, "set_bvh_builder: unknown builder");
+    s->bvh_builder = builder;
+    return HRT_OK;
+}
+
 int32_t hrt_scene_commit(hrt_scene* s, int32_t root) {
     HRT_CHECK_SCENE(s);
     if (!obj_ok(s, root)) return fail(HRT_ERR_INVALID, "commit: unknown root id");
     s->ops.clear();
     s->ctxs.resize(1);
     s->n_box_ops = s->n_loose_boxes = s->n_prim_ops = s->n_media = s->max_ctx_depth = 0;
+    s->n_bvh_rebuilt = 0;
     s->any_bvh = false;
     s->time_min = -FMAX;
     s->time_max = FMAX;
@@ -754,6 +840,7 @@ int32_t hrt_scene_get_info(const hrt_scene* s, hrt_scene_info* out) {
     out->max_context_depth = s->max_ctx_depth;
     out->time_min = s->time_min;
     out->time_max = s->time_max;
+    out->n_bvh_rebuilt = s->n_bvh_rebuilt;
     return HRT_OK;
 }
 int32_t hrt_scene_get_box16(const hrt_scene* s, void* out, int32_t cap_ops) {

@@ -59,6 +59,9 @@ struct hrt_scene {
     std::vector<hrt::NoiseTable> noise_tables;
     std::vector<hrt::ImageData> images;
 
+    int32_t bvh_builder = 0;  // hrt_scene_set_bvh_builder: 0 reference trees, 1 SAH trees for BVHs whose leaves are all sound
+    int32_t n_bvh_rebuilt = 0;
+
     // committed (flattened) form
     bool committed = false;
     int32_t root = -1;

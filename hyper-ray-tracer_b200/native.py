@@ -17,6 +17,8 @@ HRT_FLAG_WARP_SCHEDULER = 4
 HRT_FLAG_INTERPRETER = 8
 HRT_FLAG_POOL = 16
 HRT_FLAG_SCHEDULER = 32
+HRT_BVH_REFERENCE = 0
+HRT_BVH_SAH = 1
 
 
 class HrtError(RuntimeError):
@@ -59,7 +61,8 @@ class SceneInfo(C.Structure):
     _fields_ = [("n_ops", C.c_int32), ("n_box_ops", C.c_int32), ("n_loose_boxes", C.c_int32), ("n_prim_ops", C.c_int32),
                 ("n_materials", C.c_int32), ("n_textures", C.c_int32), ("n_noise_tables", C.c_int32),
                 ("n_images", C.c_int32), ("n_media", C.c_int32), ("n_contexts", C.c_int32),
-                ("max_context_depth", C.c_int32), ("time_min", C.c_float), ("time_max", C.c_float)]
+                ("max_context_depth", C.c_int32), ("time_min", C.c_float), ("time_max", C.c_float),
+                ("n_bvh_rebuilt", C.c_int32)]
 
 
 RAY_DTYPE = np.dtype([("o", np.float32, 3), ("d", np.float32, 3), ("time", np.float32), ("tmin", np.float32),
@@ -80,6 +83,7 @@ EXPORTS = [
     "hrt_render_accum", "hrt_render_accum_device", "hrt_resolve_device", "hrt_trace_hits", "hrt_tex_value",
     "hrt_scatter", "hrt_camera_rays", "hrt_philox_uniforms", "hrt_scene_evict", "hrt_scene_device_bytes",
     "hrt_measure_peaks", "hrt_scene_refresh", "hrt_render_multi", "hrt_render_accum_multi", "hrt_scene_get_box16",
+    "hrt_scene_set_bvh_builder",
 ]
 
 _lib = None
@@ -127,6 +131,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.hrt_scene_get_info.argtypes = [vp, C.POINTER(SceneInfo)]
     lib.hrt_scene_get_ops.argtypes = [vp, vp, i32]
     lib.hrt_scene_get_box16.argtypes = [vp, vp, i32]
+    lib.hrt_scene_set_bvh_builder.argtypes = [vp, i32]
     lib.hrt_bvh_leaf_order.argtypes = [vp, i32, C.POINTER(i32), i32]
     lib.hrt_bounding_box.argtypes = [vp, i32, f3]
     lib.hrt_camera_init.argtypes = [C.POINTER(CameraDesc), C.POINTER(CameraState)]
@@ -257,6 +262,10 @@ class HrtBackend:
     def bvh(self, ids: Sequence[int], t0, t1):
         arr = (C.c_int32 * max(1, len(ids)))(*ids)
         return self._check(self.lib.hrt_bvh(self.handle, arr, len(ids), float(t0), float(t1)))
+
+    def set_bvh_builder(self, builder: int):
+        """HRT_BVH_REFERENCE (0, default) or HRT_BVH_SAH (1); before commit (include/hrt.h)."""
+        return self._check(self.lib.hrt_scene_set_bvh_builder(self.handle, int(builder)))
 
     def commit(self, root):
         return self._check(self.lib.hrt_scene_commit(self.handle, root))

@@ -29,10 +29,14 @@ def sample_slice(samples: int, world_size: int, rank: int) -> Tuple[int, int]:
 class Renderer:
     """Owns one committed scene on libhrt and renders it."""
 
-    def __init__(self, spec: SceneSpec, device: int = 0, upload: bool = True):
+    def __init__(self, spec: SceneSpec, device: int = 0, upload: bool = True, bvh_builder: Optional[int] = None):
+        """bvh_builder: native.HRT_BVH_REFERENCE / HRT_BVH_SAH (include/hrt.h hrt_scene_set_bvh_builder); None keeps the
+        library default (the reference's trees)."""
         self.spec = spec
         self.device = int(device)
         self.backend = native.HrtBackend()
+        if bvh_builder is not None:
+            self.backend.set_bvh_builder(bvh_builder)
         self.emitter = emit(spec.world, self.backend)
         if upload:
             self.backend.upload(self.device)

@@ -110,8 +110,21 @@ typedef struct hrt_scene_info {
     int32_t n_materials, n_textures, n_noise_tables, n_images, n_media, n_contexts;
     int32_t max_context_depth;
     float time_min, time_max; /* BVH build interval (intersection over all hrt_bvh calls)      */
+    int32_t n_bvh_rebuilt;    /* hrt_bvh objects flattened from an SAH tree (hrt_scene_set_bvh_builder) */
 } hrt_scene_info;
 int32_t hrt_scene_get_info(const hrt_scene*, hrt_scene_info* out);
+/* Which trees hrt_scene_commit flattens for the hrt_bvh objects.  Call before hrt_scene_commit.
+ *   HRT_BVH_REFERENCE (default)  BvhNode::new's own trees (longest axis, object median; bvh_node.rs:27-63).
+ *   HRT_BVH_SAH                  surface-area-heuristic trees for every hrt_bvh whose leaf boxes all contain their leaves
+ *                                (BVHs with an axis-swapped ZX rect beneath keep the reference tree, whose unsound boxes
+ *                                are part of the reference's behaviour).  Box tests only prune, so every closest hit is
+ *                                the same as with the reference trees; the one difference is the winner of an EXACT tie
+ *                                between two coincident surfaces of one BVH (the reference keeps the later leaf of ITS
+ *                                depth-first order, this stream the later leaf of the SAH order).  About half the box
+ *                                tests on the `random` scene, 0.9x on `final` (profiles/bvh_study.json).
+ * hrt_bvh_leaf_order / hrt_bounding_box keep describing the reference trees. */
+enum { HRT_BVH_REFERENCE = 0, HRT_BVH_SAH = 1 };
+int32_t hrt_scene_set_bvh_builder(hrt_scene*, int32_t builder);
 /* Copies up to cap_ops 32-byte records; returns n_ops. */
 int32_t hrt_scene_get_ops(const hrt_scene*, void* out, int32_t cap_ops);
 /* Copies up to cap_ops 16-byte companions of the records (six fp16 bounds rounded outward + w7: what the render

@@ -175,3 +175,77 @@ def test_stream_semantics_match_the_oracle(pkg, orc, name):
     assert m.sum() > len(rays) // 10
     assert np.array_equal(prim[m], want["prim_id"][m]), name
     assert np.allclose(t[m], want["t"][m], rtol=1e-5, atol=0), name
+
+
+@pytest.mark.parametrize("name", ["random", "cornell", "final"])
+def test_sah_trees_find_the_same_hits(pkg, orc, name):
+    """hrt_scene_set_bvh_builder(HRT_BVH_SAH): BVHs whose leaves are all sound are flattened from surface-area-heuristic
+    trees — same closest hits as the oracle's reference trees, fewer box visits; BVHs with an unsound (axis-swapped ZX
+    rect) leaf box keep the reference tree, clipping behaviour included (Cornell)."""
+    spec = pkg.make_scene(name, seed=4)
+    gb_ref, ob, _, _ = build_both(pkg, orc, spec.world)
+    gb = pkg.HrtBackend()
+    gb.set_bvh_builder(pkg.native.HRT_BVH_SAH)
+    pkg.scene.emit(spec.world, gb)
+    i_ref, i = gb_ref.info(), gb.info()
+    assert (i.n_ops, i.n_box_ops, i.n_prim_ops, i.n_loose_boxes) == (i_ref.n_ops, i_ref.n_box_ops, i_ref.n_prim_ops, i_ref.n_loose_boxes)
+    if name == "cornell":  # its one BVH holds the ZX light: untouched
+        assert i.n_bvh_rebuilt == 0 and np.array_equal(gb.ops(), gb_ref.ops())
+        return
+    assert i.n_bvh_rebuilt >= 1 and not np.array_equal(gb.ops(), gb_ref.ops())
+    rays = _rays(orc, ob, spec)
+    want = ob.trace_hits(rays, np.full(len(rays), 0.5, dtype=np.float32))
+    hit, t, prim = trace_stream(gb.ops(), rays)
+    medium = (want["hit"] == 1) & np.all(want["n"] == 0.0, axis=1)
+    keep = ~medium & np.isfinite(want["t"])
+    assert np.array_equal(hit[keep], want["hit"][keep] == 1)
+    m = keep & (want["hit"] == 1)
+    assert np.allclose(t[m], want["t"][m], rtol=1e-5, atol=0)
+    # Same primitive too, except on EXACT ties between coincident surfaces (include/hrt.h): `final`'s ground boxes share
+    # faces, and a ray that lands on a shared face gets the later leaf of the stream's order instead of the reference's.
+    other = m & (prim != want["prim_id"])
+    assert other.sum() <= 0.005 * m.sum() and np.array_equal(t[other], want["t"][other]), (name, int(other.sum()))
+    # skip links still point forward and stay inside the stream
+    ops = gb.ops()
+    boxes = np.where(((ops[:, 7] & 0xFF) == OP_BOX) | ((ops[:, 7] & 0xFF) == OP_BOX_LOOSE))[0]
+    assert np.all((ops[boxes, 7] >> 8) > boxes) and np.all((ops[boxes, 7] >> 8) <= len(ops) - 1)
+
+
+def test_sah_visits_fewer_boxes_on_the_random_scene(pkg, orc):
+    """The point of the option: count box records visited per ray by the interpreter on both streams."""
+    spec = pkg.make_scene("random", seed=4)
+    gb_ref, ob, _, _ = build_both(pkg, orc, spec.world)
+    gb = pkg.HrtBackend()
+    gb.set_bvh_builder(pkg.native.HRT_BVH_SAH)
+    pkg.scene.emit(spec.world, gb)
+    rays = _rays(orc, ob, spec, n=600)
+
+    def visits(ops):
+        f = ops.view(np.float32)
+        pc_of = np.zeros(len(rays), dtype=np.int64)
+        total = 0
+        o, d = rays["o"].astype(F), rays["d"].astype(F)
+        closest = rays["tmax"].astype(F).copy()
+        for pc in range(len(ops)):
+            idx = np.nonzero(pc_of == pc)[0]
+            w7 = int(ops[pc, 7]); op, payload = w7 & 0xFF, w7 >> 8
+            if op == OP_END or idx.size == 0:
+                continue
+            if op in (OP_BOX, OP_BOX_LOOSE):
+                total += idx.size
+                with np.errstate(all="ignore"):
+                    h = _box(o[idx], d[idx], f[pc, 0:3], f[pc, 4:7], rays["tmin"][idx].astype(F), closest[idx], False)
+                pc_of[idx] = np.where(h, pc + 1, payload)
+            elif op == OP_SPHERE:
+                with np.errstate(all="ignore"):
+                    ok, ts = _sphere(o[idx], d[idx], f[pc, 0:3][None, :], f[pc, 3], rays["tmin"][idx].astype(F), closest[idx])
+                closest[idx[ok]] = ts[ok]
+                pc_of[idx] = pc + 1
+            elif op == OP_MSPHERE:
+                pc_of[idx] = pc + 2  # moving spheres only shrink `closest`; leaving them out counts an upper bound on both
+            else:
+                pc_of[idx] = pc + 1
+        return total / len(rays)
+
+    v_ref, v_sah = visits(gb_ref.ops()), visits(gb.ops())
+    assert v_sah < 0.75 * v_ref, (v_ref, v_sah)

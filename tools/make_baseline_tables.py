@@ -27,6 +27,9 @@ out.append("\nThe roofline fractions are ALGORITHMIC work (oracle operation coun
            "`profiles/work_model.json`) over the peaks measured on the same GPU by `hrt_measure_peaks` (72.3 TFLOP/s FP32, 17.6 TB/s "
            "L2-resident reads); DRAM traffic of the C5 launch is 1.7 GB in 20.3 s (`profiles/r01_traffic.json`: 0.001 % of HBM "
            "bandwidth — the working set lives in shared memory / L1 / L2).\n")
+out.append("Opt-in SAH trees (`hrt_scene_set_bvh_builder(HRT_BVH_SAH)` / `HRT_BVH_BUILDER=sah`; same closest hits, exact ties between "
+           "coincident surfaces may name the other surface): C1 **933.9 Mpaths/s** (reference trees 543.5, same box and "
+           "session), C5 at 1024 spp 294.4 (reference trees 287–290).  The tables above use the reference's trees.\n")
 out.append("### Strong scaling on C5 (`final` 800×800, 10 000 spp): samples sharded over N ranks, one NCCL all-reduce, rank 0 resolves\n")
 out.append("| N GPUs | Mpaths/s | e2e Mpaths/s | ms / frame | efficiency vs N=1 |")
 out.append("|---:|---:|---:|---:|---:|")
