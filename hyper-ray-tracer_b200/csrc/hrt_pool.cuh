@@ -9,6 +9,8 @@
 //   4. SCATTERS the rays back and records their new class.
 // Parked rays cost no lanes, so rounds run nearly full.  Per-ray traversal order is unchanged (the reference's), and the
 // class bodies are the very same step_* functions as in hrt_machine.cuh, so each ray's result is identical.
+// The kernel (render_pool_kernel, hrt_kernels.cu) runs one 16-warp block per SM; behind the 16 pools the same dynamic
+// shared memory holds the fp16 box table (hrt_types.h Box16) the box rounds read, and the perlin tables.
 #pragma once
 #include "hrt_machine.cuh"
 
