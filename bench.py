@@ -299,11 +299,14 @@ def run_b200(args, scene_name, width, height, samples, depth):
         except OSError:
             pass
         traffic = None
+        issue = None
         try:  # DRAM bytes per launch of the dominant kernel, from a committed ncu metric pass of this very workload
             with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
                 t = json.load(f).get(f"{args.config}@{samples}")
             if t and world == 1:
                 traffic = t["dram_bytes_per_launch"]
+                if "issue_active_pct" in t:  # measured issue-slot utilisation of the same kernel (not algorithmic work)
+                    issue = {"issue_active_pct": t["issue_active_pct"], "source": t["issue_source"]}
         except OSError:
             pass
         roofline = {"bound": "fp32_issue", "achieved": achieved, "peak": peaks.fp32_tflops, "unit": "TFLOP/s",
@@ -312,7 +315,7 @@ def run_b200(args, scene_name, width, height, samples, depth):
                                    "no FP32 figure",
                     # hrt_api.cu render_into: the ray-pool kernel from 128 samples per launch, else the warp scheduler
                     "kernel": "render_pool_kernel" if -(-samples // world) >= 128 else "render_kernel", "kernel_ms": kernel_ms, "flops_per_path": wm["flops_per_path"],
-                    "work_model": wm["source"],
+                    "work_model": wm["source"], "issue": issue,
                     "l2": {"achieved_gbs": l2_ach, "peak_gbs": peaks.l2_read_gbs, "frac": l2_ach / peaks.l2_read_gbs,
                            "bytes_per_path": wm["bytes_per_path"]},
                     "hbm": {"achieved_gbs": (width * height * 16 * 2) / (kernel_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
