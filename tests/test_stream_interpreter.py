@@ -249,3 +249,34 @@ def test_sah_visits_fewer_boxes_on_the_random_scene(pkg, orc):
 
     v_ref, v_sah = visits(gb_ref.ops()), visits(gb.ops())
     assert v_sah < 0.75 * v_ref, (v_ref, v_sah)
+
+
+def test_sah_builder_edge_cases(pkg, orc):
+    """One- and two-leaf BVHs, nested BVHs, an unknown builder id, and the option after commit."""
+    S, N = pkg.scene, pkg.native
+    m = S.Lambertian(S.SolidColor((0.5, 0.5, 0.5)))
+    one = S.BvhNode([S.Sphere((0, 0, -5), 1.0, m)], 0.0, 1.0)
+    two = S.BvhNode([S.Sphere((3, 0, -5), 1.0, m), S.Sphere((-3, 0, -5), 1.0, m)], 0.0, 1.0)
+    moving = S.BvhNode([S.MovingSphere((0, 3, -5), (0, 4, -5), 0.0, 1.0, 0.5, m), S.Sphere((0, -3, -5), 0.5, m),
+                        S.Sphere((0, -6, -9), 0.5, m)], 0.0, 1.0)
+    world = S.BvhNode([one, two, moving, S.Sphere((0, -1000, 0), 990.0, m)], 0.0, 1.0)
+    gb_ref, ob, _, _ = build_both(pkg, orc, world)
+    gb = pkg.HrtBackend()
+    with pytest.raises(pkg.HrtError) as ei:
+        gb.set_bvh_builder(7)
+    assert ei.value.code == -1
+    gb.set_bvh_builder(N.HRT_BVH_SAH)
+    S.emit(world, gb)
+    assert gb.info().n_bvh_rebuilt == 4 and gb.info().n_ops == gb_ref.info().n_ops
+    with pytest.raises(pkg.HrtError):
+        gb.set_bvh_builder(N.HRT_BVH_REFERENCE)  # immutable after commit, like every builder call
+    rng = np.random.default_rng(1)
+    d = rng.normal(size=(800, 3)).astype(np.float32)
+    d[np.abs(d) < 1e-3] = 1e-3
+    rays = make_rays(orc, np.tile(np.float32([0, 0, 4]), (800, 1)), d, time=rng.random(800, dtype=np.float32))
+    want = ob.trace_hits(rays, np.full(800, 0.5, dtype=np.float32))
+    for ops in (gb_ref.ops(), gb.ops()):
+        hit, t, prim = trace_stream(ops, rays)
+        assert np.array_equal(hit, want["hit"] == 1) and (want["hit"] == 1).sum() > 100
+        k = want["hit"] == 1
+        assert np.array_equal(prim[k], want["prim_id"][k]) and np.allclose(t[k], want["t"][k], rtol=1e-5, atol=0)
