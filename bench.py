@@ -52,6 +52,9 @@ def parse_args():
     ap.add_argument("--samples", type=int, default=0, help="override spp of the config")
     ap.add_argument("--seed", type=int, default=1, help="scene-instance seed")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--bvh", default="reference", choices=["reference", "sah"],
+                    help="trees flattened for BvhNode objects (include/hrt.h hrt_scene_set_bvh_builder); the default and every "
+                         "committed number use the reference's trees")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -325,7 +328,7 @@ def run_b200(args, scene_name, width, height, samples, depth):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": f"{args.config}: {scene_name} {width}x{height}, {samples} spp, depth {depth}",
-                       "scene_seed": args.seed, "parallelism": f"spp-sharded x{world}" if world > 1 else "single GPU",
+                       "scene_seed": args.seed, "bvh": args.bvh, "parallelism": f"spp-sharded x{world}" if world > 1 else "single GPU",
                        "l2_policy": "working set (<3 MB scene tables + 10 MB accumulator) is cache-resident by design; the "
                                     "kernel is compute/latency-bound, not HBM-bound, so no L2 flush applies",
                        "grid": stats[0][3] if stats else None, "block": stats[0][4] if stats else None},
@@ -339,6 +342,8 @@ def run_b200(args, scene_name, width, height, samples, depth):
 
 def main():
     args = parse_args()
+    if args.bvh == "sah":
+        os.environ["HRT_BVH_BUILDER"] = "sah"  # read by hrt_scene_create (diagnostic default of the library)
     pkg = graft.load_package()
     scene_name, width, height, samples, depth = pkg.CONFIGS[args.config]
     if args.samples > 0:
