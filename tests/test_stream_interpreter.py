@@ -280,3 +280,20 @@ def test_sah_builder_edge_cases(pkg, orc):
         assert np.array_equal(hit, want["hit"] == 1) and (want["hit"] == 1).sum() > 100
         k = want["hit"] == 1
         assert np.array_equal(prim[k], want["prim_id"][k]) and np.allclose(t[k], want["t"][k], rtol=1e-5, atol=0)
+
+
+def test_builder_default_can_come_from_the_environment(pkg, monkeypatch):
+    """HRT_BVH_BUILDER=sah (what `bench.py --bvh sah` sets) is the default of scenes created afterwards; an explicit
+    hrt_scene_set_bvh_builder still wins."""
+    spec = pkg.make_scene("random", seed=2)
+    monkeypatch.setenv("HRT_BVH_BUILDER", "sah")
+    a = pkg.HrtBackend()
+    pkg.scene.emit(spec.world, a)
+    b = pkg.HrtBackend()
+    b.set_bvh_builder(pkg.native.HRT_BVH_REFERENCE)
+    pkg.scene.emit(spec.world, b)
+    monkeypatch.delenv("HRT_BVH_BUILDER")
+    c = pkg.HrtBackend()
+    pkg.scene.emit(spec.world, c)
+    assert a.info().n_bvh_rebuilt == 1 and b.info().n_bvh_rebuilt == 0 and c.info().n_bvh_rebuilt == 0
+    assert np.array_equal(b.ops(), c.ops()) and not np.array_equal(a.ops(), c.ops())
