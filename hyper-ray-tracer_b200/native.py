@@ -17,6 +17,7 @@ HRT_FLAG_WARP_SCHEDULER = 4
 HRT_FLAG_INTERPRETER = 8
 HRT_FLAG_POOL = 16
 HRT_FLAG_SCHEDULER = 32
+ABI_VERSION = 2  # include/hrt.h HRT_ABI_VERSION
 HRT_BVH_REFERENCE = 0
 HRT_BVH_SAH = 1
 
@@ -105,6 +106,8 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.hrt_last_error.restype = C.c_char_p
     lib.hrt_last_error.argtypes = []
     lib.hrt_abi_version.restype = i32
+    if lib.hrt_abi_version() != ABI_VERSION:  # the struct layouts below are those of this ABI version
+        raise OSError(f"{p} has ABI version {lib.hrt_abi_version()}, this binding needs {ABI_VERSION}: rebuild the extension")
     lib.hrt_device_count.restype = i32
     lib.hrt_scene_create.argtypes = [C.POINTER(vp)]
     lib.hrt_scene_destroy.argtypes = [vp]

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define HRT_ABI_VERSION 1
+#define HRT_ABI_VERSION 2 /* 2: hrt_scene_info grew (n_bvh_rebuilt); hrt_scene_set_bvh_builder, hrt_scene_get_box16 */
 
 typedef enum hrt_status {
     HRT_OK = 0,
