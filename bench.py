@@ -52,7 +52,7 @@ def parse_args():
     ap.add_argument("--samples", type=int, default=0, help="override spp of the config")
     ap.add_argument("--seed", type=int, default=1, help="scene-instance seed")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
-    ap.add_argument("--bvh", default="reference", choices=["reference", "sah"],
+    ap.add_argument("--bvh", default="reference", choices=["reference", "sah", "sah-spheres"],
                     help="trees flattened for BvhNode objects (include/hrt.h hrt_scene_set_bvh_builder); the default and every "
                          "committed number use the reference's trees")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -342,8 +342,8 @@ def run_b200(args, scene_name, width, height, samples, depth):
 
 def main():
     args = parse_args()
-    if args.bvh == "sah":
-        os.environ["HRT_BVH_BUILDER"] = "sah"  # read by hrt_scene_create (diagnostic default of the library)
+    if args.bvh != "reference":
+        os.environ["HRT_BVH_BUILDER"] = args.bvh  # read by hrt_scene_create (diagnostic default of the library)
     pkg = graft.load_package()
     scene_name, width, height, samples, depth = pkg.CONFIGS[args.config]
     if args.samples > 0:

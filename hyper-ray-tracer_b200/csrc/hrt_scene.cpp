@@ -12,6 +12,7 @@
 #include "hrt_scene.hpp"
 
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -399,7 +400,8 @@ struct Flattener {
                 return true;
             }
             case OBJ_BVH: {
-                if (s.bvh_builder == 1 && all_leaves_sound(o)) {
+                if ((s.bvh_builder == HRT_BVH_SAH && all_leaves_sound(o)) ||
+                    (s.bvh_builder == HRT_BVH_SAH_SPHERES && distinct_spheres_only(o))) {
                     // every leaf box contains its leaf, so every union of leaf boxes is sound in ANY topology and the
                     // closest hit does not depend on it (only the winner of an exact tie between coincident surfaces
                     // does: the leaf that comes later in the stream — documented in include/hrt.h)
@@ -412,6 +414,22 @@ struct Flattener {
             }
         }
         return false;
+    }
+
+    // HRT_BVH_SAH_SPHERES: every leaf is a plain sphere or moving sphere and no two are the same sphere, so no two
+    // surfaces of the BVH coincide and its depth-first order cannot decide a (systematic) tie.  Sphere boxes are sound.
+    bool distinct_spheres_only(const Obj& bvh) {
+        std::vector<std::array<float, 9>> keys;
+        for (int32_t id : bvh.children) {
+            const Obj& c = s.objects[id];
+            if (c.kind != OBJ_SPHERE && c.kind != OBJ_MSPHERE) return false;
+            // a "moving" sphere that does not move is the same surface as the static one
+            const bool moving = c.kind == OBJ_MSPHERE && (c.c0[0] != c.c1[0] || c.c0[1] != c.c1[1] || c.c0[2] != c.c1[2]);
+            keys.push_back({c.c0[0], c.c0[1], c.c0[2], moving ? c.c1[0] : c.c0[0], moving ? c.c1[1] : c.c0[1],
+                            moving ? c.c1[2] : c.c0[2], c.r, moving ? c.t0 : 0.0f, moving ? c.t1 : 0.0f});
+        }
+        std::sort(keys.begin(), keys.end());
+        return std::adjacent_find(keys.begin(), keys.end()) == keys.end();
     }
 
     bool all_leaves_sound(const Obj& bvh) {
@@ -545,7 +563,8 @@ int32_t hrt_scene_create(hrt_scene** out) {
     if (!out) return fail(HRT_ERR_INVALID, "null out pointer");
     *out = new hrt_scene();
     if (const char* env = std::getenv("HRT_BVH_BUILDER"))  // diagnostic default for scenes the caller does not configure
-        (*out)->bvh_builder = std::strcmp(env, "sah") == 0 ? HRT_BVH_SAH : HRT_BVH_REFERENCE;
+        (*out)->bvh_builder = std::strcmp(env, "sah") == 0 ? HRT_BVH_SAH
+                              : (std::strcmp(env, "sah-spheres") == 0 ? HRT_BVH_SAH_SPHERES : HRT_BVH_REFERENCE);
     Ctx root;
     std::memset(&root, 0, sizeof(root));
     root.parent = -1;
@@ -764,7 +783,7 @@ int32_t hrt_bvh(hrt_scene* s, const int32_t* children, int32_t n, float ts, floa
 
 int32_t hrt_scene_set_bvh_builder(hrt_scene* s, int32_t builder) {
     HRT_CHECK_SCENE(s);
-    if (builder != HRT_BVH_REFERENCE && builder != HRT_BVH_SAH) return fail(HRT_ERR_INVALID, "set_bvh_builder: unknown builder");
+    if (builder != HRT_BVH_REFERENCE && builder != HRT_BVH_SAH && builder != HRT_BVH_SAH_SPHERES) return fail(HRT_ERR_INVALID, "set_bvh_builder: unknown builder");
     s->bvh_builder = builder;
     return HRT_OK;
 }

@@ -20,6 +20,7 @@ HRT_FLAG_SCHEDULER = 32
 ABI_VERSION = 2  # include/hrt.h HRT_ABI_VERSION
 HRT_BVH_REFERENCE = 0
 HRT_BVH_SAH = 1
+HRT_BVH_SAH_SPHERES = 2
 
 
 class HrtError(RuntimeError):
@@ -267,7 +268,7 @@ class HrtBackend:
         return self._check(self.lib.hrt_bvh(self.handle, arr, len(ids), float(t0), float(t1)))
 
     def set_bvh_builder(self, builder: int):
-        """HRT_BVH_REFERENCE (0, default) or HRT_BVH_SAH (1); before commit (include/hrt.h)."""
+        """HRT_BVH_REFERENCE (0, default), HRT_BVH_SAH (1) or HRT_BVH_SAH_SPHERES (2); before commit (include/hrt.h)."""
         return self._check(self.lib.hrt_scene_set_bvh_builder(self.handle, int(builder)))
 
     def commit(self, root):

@@ -122,8 +122,11 @@ int32_t hrt_scene_get_info(const hrt_scene*, hrt_scene_info* out);
  *                                between two coincident surfaces of one BVH (the reference keeps the later leaf of ITS
  *                                depth-first order, this stream the later leaf of the SAH order).  About half the box
  *                                tests on the `random` scene, 0.9x on `final` (profiles/bvh_study.json).
+ *   HRT_BVH_SAH_SPHERES          the same, but only for hrt_bvh objects whose children are all (moving) spheres, no two of
+ *                                them identical: no two surfaces coincide, so there is no systematic tie to resolve
+ *                                differently (all of `random`; the 1000-sphere cube of `final`, not its ground boxes).
  * hrt_bvh_leaf_order / hrt_bounding_box keep describing the reference trees. */
-enum { HRT_BVH_REFERENCE = 0, HRT_BVH_SAH = 1 };
+enum { HRT_BVH_REFERENCE = 0, HRT_BVH_SAH = 1, HRT_BVH_SAH_SPHERES = 2 };
 int32_t hrt_scene_set_bvh_builder(hrt_scene*, int32_t builder);
 /* Copies up to cap_ops 32-byte records; returns n_ops. */
 int32_t hrt_scene_get_ops(const hrt_scene*, void* out, int32_t cap_ops);

@@ -297,3 +297,37 @@ def test_builder_default_can_come_from_the_environment(pkg, monkeypatch):
     pkg.scene.emit(spec.world, c)
     assert a.info().n_bvh_rebuilt == 1 and b.info().n_bvh_rebuilt == 0 and c.info().n_bvh_rebuilt == 0
     assert np.array_equal(b.ops(), c.ops()) and not np.array_equal(a.ops(), c.ops())
+
+
+def test_sah_for_sphere_only_bvhs_keeps_every_primitive(pkg, orc):
+    """HRT_BVH_SAH_SPHERES: only BVHs made of distinct (moving) spheres are rebuilt — `final` keeps the reference tree over
+    its face-sharing ground boxes, so every hit names the oracle's primitive, ties included; duplicates veto the rebuild."""
+    S, N = pkg.scene, pkg.native
+    spec = pkg.make_scene("final", seed=4)
+    gb_ref, ob, _, _ = build_both(pkg, orc, spec.world)
+    gb = pkg.HrtBackend()
+    gb.set_bvh_builder(N.HRT_BVH_SAH_SPHERES)
+    S.emit(spec.world, gb)
+    assert gb.info().n_bvh_rebuilt == 1  # the 1000-sphere cube; not the ground boxes, not the top-level BVH
+    rays = _rays(orc, ob, spec)
+    want = ob.trace_hits(rays, np.full(len(rays), 0.5, dtype=np.float32))
+    hit, t, prim = trace_stream(gb.ops(), rays)
+    medium = (want["hit"] == 1) & np.all(want["n"] == 0.0, axis=1)
+    keep = ~medium & np.isfinite(want["t"])
+    m = keep & (want["hit"] == 1)
+    assert np.array_equal(hit[keep], want["hit"][keep] == 1)
+    assert np.array_equal(prim[m], want["prim_id"][m]) and np.allclose(t[m], want["t"][m], rtol=1e-5, atol=0)
+
+    r = pkg.make_scene("random", seed=4)
+    g2 = pkg.HrtBackend()
+    g2.set_bvh_builder(N.HRT_BVH_SAH_SPHERES)
+    S.emit(r.world, g2)
+    assert g2.info().n_bvh_rebuilt == 1
+
+    mat = S.Lambertian(S.SolidColor((0.5, 0.5, 0.5)))
+    dup = S.BvhNode([S.Sphere((0, 0, 0), 1.0, mat), S.MovingSphere((0, 0, 0), (0, 0, 0), 0.0, 1.0, 1.0, mat),
+                     S.Sphere((3, 0, 0), 1.0, mat)], 0.0, 1.0)
+    g3 = pkg.HrtBackend()
+    g3.set_bvh_builder(N.HRT_BVH_SAH_SPHERES)
+    S.emit(dup, g3)
+    assert g3.info().n_bvh_rebuilt == 0
