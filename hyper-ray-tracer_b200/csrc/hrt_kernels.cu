@@ -1,12 +1,16 @@
 // hrt_kernels.cu — sm_100a kernels of the path-tracing hot path + their launchers.
 // Compiled twice (see hrt_device.cuh): -DHRT_EXACT=1 --fmad=false and -DHRT_EXACT=0.
 //
-//   render_kernel      replaces Application::render's sample loop + ray_color (src/application.rs:393-495):
-//                      persistent warps pull (8x4-pixel tile, sample-chunk) work items from a global cursor;
-//                      inside an item the 32 lanes draw path indices from a warp-local pool with
-//                      ballot/popc compaction, so a lane whose path ended is re-filled immediately and the
-//                      bounce "recursion" is one flat loop (one ray segment per lane per iteration).
+// Three render kernels replace Application::render's sample loop + ray_color (src/application.rs:393-495).  All are
+// persistent: warps pull (8x4-pixel tile, sample-chunk) work items from a global cursor, the bounce "recursion" is a
+// flat loop over ray segments, finished paths are replaced at once, and they trace identical paths (same Philox
+// streams, same per-ray record order):
+//   render_pool_kernel    default from 128 samples per launch: 96 rays per warp parked in shared memory, one record
+//                         class per round with gathered (nearly full) warps, fp16 box table in shared memory
+//   render_kernel         default below that: rays stay in their lanes, the warp votes on the class to run
+//   render_interp_kernel  every lane interprets its own ray's records (the simple form; diagnostic)
 //   resolve_kernel     the gamma resolve sqrt(sum * 1/spp), alpha 1 (src/application.rs:451-456).
+//   reduce_resolve_kernel  the same, summing the accumulators of several devices over peer memory (hrt_render_multi)
 //   trace_hits_kernel  world.hit() on explicit rays            (parity entry)
 //   tex_value_kernel   Texture::value                          (parity entry)
 //   scatter_kernel     Material::scatter / emitted             (parity entry)
