@@ -311,6 +311,8 @@ static int32_t render_into(hrt_scene* s, DeviceState* d, const hrt_camera_desc* 
         if (rd->flags & HRT_FLAG_SCHEDULER) variant = 0;
         if (rd->flags & HRT_FLAG_INTERPRETER) variant = 1;
         if (rd->flags & HRT_FLAG_POOL) variant = 2;
+        if (rd->flags & HRT_FLAG_UNIFORM) variant = 3;
+        if (env && env[0] == 'u') variant = 3;
         if (env && env[0] == 'i') variant = 1;
         if (env && env[0] == 's') variant = 0;
         if (env && env[0] == 'p') variant = 2;
@@ -536,7 +538,8 @@ int32_t hrt_trace_hits(hrt_scene* s, int32_t device, const hrt_ray* rays, int32_
         HRT_CUDA(dx.alloc(n));
         HRT_CUDA(cudaMemcpy(dx.p, xi, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice));
     }
-    const int ref = ((flags & HRT_FLAG_REFERENCE_TRAVERSAL) ? 1 : 0) | ((flags & HRT_FLAG_WARP_SCHEDULER) ? 2 : 0);
+    const int ref = ((flags & HRT_FLAG_REFERENCE_TRAVERSAL) ? 1 : 0) | ((flags & HRT_FLAG_WARP_SCHEDULER) ? 2 : 0) |
+                    ((flags & HRT_FLAG_UNIFORM) ? 4 : 0);
     cudaError_t e = (flags & HRT_FLAG_EXACT_MATH) ? hrt_exact::launch_trace_hits(d->view, dr.p, n, dx.p, dh.p, ref, 0)
                                                   : hrt_fast::launch_trace_hits(d->view, dr.p, n, dx.p, dh.p, ref, 0);
     if (e != cudaSuccess) return cuda_fail(e, "trace_hits_kernel launch");

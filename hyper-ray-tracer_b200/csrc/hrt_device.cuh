@@ -520,6 +520,207 @@ __device__ __noinline__ float boundary_hit(const DeviceScene& S, int pc, int end
     return hit ? t : CUDART_NAN_F;  // NaN = miss (a genuine NaN t cannot be told apart and is treated as a miss)
 }
 
+// The tail of ConstantMedium::hit once both boundary hits are known (constant_medium.rs:40-75): true and the
+// scattering distance `t_out` when the medium scatters inside [tmin, closest].  A = the medium record's first half.
+__device__ __forceinline__ bool medium_sample(const DeviceScene& S, float4 A, float dd, float t1, float t2, float tmin,
+                                              float closest, const MediumXi& xi, float& t_out) {
+    if (t1 < tmin) t1 = tmin;
+    if (t2 > closest) t2 = closest;
+    if (t1 >= t2) return false;
+    if (t1 < 0.0f) t1 = 0.0f;
+    const float ray_length = sqrtf(dd);
+    const float dist_inside = (t2 - t1) * ray_length;
+    const float u = xi.draw(__float_as_int(A.z));
+#if HRT_EXACT
+    const float hit_distance = A.x * (logf(u) / S.ln_e);
+#else
+    // accurate logf here too: __logf's absolute error near u = 1 is a relative error of up to ~1e-3 in the free-flight
+    // distance
+    const float hit_distance = A.x * logf(u);
+#endif
+    if (hit_distance > dist_inside) return false;
+    t_out = t1 + hit_distance / ray_length;
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Warp-uniform traversal of the op stream.
+//
+// The stream is forward-only (a missed box jumps FORWARD to its skip link, everything else falls through), so the 32
+// rays of a warp can walk it together: every step executes the record at the SMALLEST pc any lane still has to visit
+// (one REDUX.MIN), for exactly the lanes that are at it; lanes that are further ahead wait.  The record fetch is one
+// broadcast load, and the opcode — hence every branch of the interpreter — is warp-uniform: no divergence between
+// record kinds, no per-ray bookkeeping, no votes.  Per ray the visit order and the arithmetic are those of
+// `traverse<>`, so results are identical.  The price is that a warp walks the UNION of its rays' records; that is what
+// the short streams here want (Cornell: 34 records; `final`: a 21-node top level around two big BVHs).
+// Every lane of the warp must call it (`active` = this lane carries a ray).
+// ------------------------------------------------------------------------------------------------
+template <bool kInner>
+__device__ __forceinline__ bool traverse_uniform(const DeviceScene& S, const int pc_begin, const int pc_end, const bool active,
+                                                 const Ray& world, Ray cur, int cur_ctx, const float tmin, float& closest,
+                                                 Best& best, const bool reference_boxes, const MediumXi& xi);
+
+// Warp-uniform ConstantMedium boundary query (constant_medium.rs:37-38); NaN = miss.  Out of line: one copy of the inner
+// interpreter per kernel.
+__device__ __noinline__ float boundary_hit_uniform(const DeviceScene& S, int pc, int end, bool active, Ray world, Ray cur,
+                                                   int ctx, float tmin, bool reference_boxes) {
+    Best dummy;
+    MediumXi none;
+    none.key.k0 = 0; none.key.k1 = 0; none.key.pixel = 0; none.key.sample = 0;
+    none.bounce = 0; none.injected = 0.5f; none.inject = true;
+    float t = CUDART_INF_F;
+    const bool hit = traverse_uniform<true>(S, pc, end, active, world, cur, ctx, tmin, t, dummy, reference_boxes, none);
+    return hit ? t : CUDART_NAN_F;
+}
+
+template <bool kInner>
+__device__ __forceinline__ bool traverse_uniform(const DeviceScene& S, const int pc_begin, const int pc_end, const bool active,
+                                                 const Ray& world, Ray cur, int cur_ctx, const float tmin, float& closest,
+                                                 Best& best, const bool reference_boxes, const MediumXi& xi) {
+    const unsigned kAll = 0xffffffffu;
+    int pc = active ? pc_begin : pc_end;
+    RayK k = make_rayk(cur);
+    bool any = false;
+    for (;;) {
+        const int upc = __reduce_min_sync(kAll, pc);  // warp-uniform
+        if (upc >= pc_end) break;
+        float4 A, B;
+        load_op(S, upc, A, B);  // one address for the whole warp
+        const uint32_t w7 = __float_as_uint(B.w);
+        const uint32_t opc = w7 & 0xffu;
+        const bool me = pc == upc;
+        if (opc == OP_BOX || opc == OP_BOX_LOOSE) {
+            if (me) {
+                const bool hit = (opc == OP_BOX_LOOSE || reference_boxes) ? box_hit_reference(A, B, cur, k, tmin, closest)
+                                                                          : box_hit_tight(A, B, cur, k, tmin, closest);
+                pc = hit ? upc + 1 : (int)(w7 >> 8);
+            }
+            continue;
+        }
+        switch (opc) {
+            case OP_SPHERE: {
+                if (me) {
+                    float t;
+                    if (sphere_test(v3(A.x, A.y, A.z), A.w, cur, k, tmin, closest, t)) {
+                        closest = t; any = true;
+                        if (!kInner) { best.t = t; best.pc = upc; best.face = 0; best.ctx = cur_ctx; }
+                    }
+                    pc = upc + 1;
+                }
+                break;
+            }
+            case OP_MSPHERE: {
+                float4 C, D;
+                load_op(S, upc + 1, C, D);
+                if (me) {
+                    const V3 ctr = msphere_center(v3(A.x, A.y, A.z), v3(C.x, C.y, C.z), C.w, D.x, cur.time);
+                    float t;
+                    if (sphere_test(ctr, A.w, cur, k, tmin, closest, t)) {
+                        closest = t; any = true;
+                        if (!kInner) { best.t = t; best.pc = upc; best.face = 0; best.ctx = cur_ctx; }
+                    }
+                    pc = upc + 2;
+                }
+                break;
+            }
+            case OP_RECT_XY: case OP_RECT_YZ: case OP_RECT_ZX: {
+                if (me) {
+                    float t;
+                    bool h;
+                    if (opc == OP_RECT_XY) h = rect_test(cur.o.z, cur.d.z, k.inv.z, cur.o.x, cur.d.x, cur.o.y, cur.d.y, A.x, A.y, A.z, A.w, B.x, tmin, closest, t);
+                    else if (opc == OP_RECT_YZ) h = rect_test(cur.o.x, cur.d.x, k.inv.x, cur.o.y, cur.d.y, cur.o.z, cur.d.z, A.x, A.y, A.z, A.w, B.x, tmin, closest, t);
+                    else h = rect_test(cur.o.y, cur.d.y, k.inv.y, cur.o.z, cur.d.z, cur.o.x, cur.d.x, A.x, A.y, A.z, A.w, B.x, tmin, closest, t);
+                    if (h) {
+                        closest = t; any = true;
+                        if (!kInner) { best.t = t; best.pc = upc; best.face = 0; best.ctx = cur_ctx; }
+                    }
+                    pc = upc + 1;
+                }
+                break;
+            }
+            case OP_CUBOID: {
+                if (me) {
+                    float t;
+                    int face = 0;
+                    if (cuboid_test(v3(A.x, A.y, A.z), v3(B.x, B.y, B.z), cur, k, tmin, closest, t, face)) {
+                        closest = t; any = true;
+                        if (!kInner) { best.t = t; best.pc = upc; best.face = face; best.ctx = cur_ctx; }
+                    }
+                    pc = upc + 1;
+                }
+                break;
+            }
+            case OP_TRANSLATE: case OP_ROTATE: case OP_POP: {
+                if (me) {
+                    cur_ctx = __float_as_int(A.w);
+                    cur = ray_in_ctx(S, world, cur_ctx);
+                    k = make_rayk(cur);
+                    const int run = (int)(w7 >> 8);
+                    pc = upc + (run > 0 ? run : 1);
+                }
+                break;
+            }
+            case OP_MEDIUM: case OP_MEDIUM_SPHERE: {
+                const int end = (int)(w7 >> 8);
+                if (!kInner) {  // constant_medium.rs:34-76
+                    bool generic = me;
+                    if (opc == OP_MEDIUM_SPHERE) {
+                        // Boundary = one plain sphere: both boundary queries in closed form with sphere_test's arithmetic
+                        // (query 1 over (-inf, +inf) always takes the near root; query 2 over (t1 + 1e-4, +inf) takes the
+                        // near root again when the f32 sum t1 + 1e-4 == t1, else the far root).
+                        float4 C, D;
+                        load_op(S, upc + 1, C, D);
+                        generic = false;
+                        if (me) {
+                            const V3 oc = v3(__fsub_rn(cur.o.x, C.x), __fsub_rn(cur.o.y, C.y), __fsub_rn(cur.o.z, C.z));
+                            const float a = k.dd;
+                            const float half_b = dot_rn(oc, cur.d);
+                            const float c = __fsub_rn(dot_rn(oc, oc), __fmul_rn(C.w, C.w));
+                            const float disc = __fsub_rn(__fmul_rn(half_b, half_b), __fmul_rn(a, c));
+                            if (!(disc < 0.0f)) {
+                                const float sqrtd = sqrtf(disc);
+                                const float t1 = __fdiv_rn(-half_b - sqrtd, a);
+                                const float t2 = __fdiv_rn(-half_b + sqrtd, a);
+                                const float lo = t1 + 0.0001f;
+                                if (t1 == t1 && t2 == t2) {
+                                    float t;
+                                    bool h = false;
+                                    if (!(t1 < lo)) h = medium_sample(S, A, k.dd, t1, t1, tmin, closest, xi, t);
+                                    else if (!(t2 < lo)) h = medium_sample(S, A, k.dd, t1, t2, tmin, closest, xi, t);
+                                    if (h) {
+                                        closest = t; any = true;
+                                        best.t = t; best.pc = upc; best.face = 0; best.ctx = cur_ctx;
+                                    }
+                                } else {
+                                    generic = true;  // NaN roots take the generic path
+                                }
+                            }
+                        }
+                    }
+                    if (__any_sync(kAll, generic)) {
+                        const float t1 = boundary_hit_uniform(S, upc + 1, end, generic, world, cur, cur_ctx, -CUDART_INF_F, reference_boxes);
+                        const bool h1 = generic && t1 == t1;
+                        if (__any_sync(kAll, h1)) {
+                            const float t2 = boundary_hit_uniform(S, upc + 1, end, h1, world, cur, cur_ctx, t1 + 0.0001f, reference_boxes);
+                            float t;
+                            if (h1 && t2 == t2 && medium_sample(S, A, k.dd, t1, t2, tmin, closest, xi, t)) {
+                                closest = t; any = true;
+                                best.t = t; best.pc = upc; best.face = 0; best.ctx = cur_ctx;
+                            }
+                        }
+                    }
+                }
+                if (me) pc = end;
+                break;
+            }
+            default:  // OP_END (or a stray record): stop
+                if (me) pc = pc_end;
+                break;
+        }
+    }
+    return any;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Hit record
 // ------------------------------------------------------------------------------------------------

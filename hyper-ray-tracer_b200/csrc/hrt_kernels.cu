@@ -255,6 +255,8 @@ __global__ void __launch_bounds__(kBlock, 2) render_kernel(const __grid_constant
 
 // The plain variant: every lane runs the per-lane interpreter (`traverse<>`) for one whole ray segment per iteration and
 // the warp re-converges for shading.  Kept selectable (HRT_FLAG_INTERPRETER) for A/B measurements against the scheduler.
+// kUniform: the warp walks the stream together instead (traverse_uniform<>, hrt_device.cuh) — HRT_FLAG_UNIFORM.
+template <bool kUniform>
 __global__ void __launch_bounds__(kBlock, 2) render_interp_kernel(const __grid_constant__ RenderParams P) {
     __shared__ float sh_acc[kWarpsPerBlock][32][3];
     __shared__ NoiseTable sh_noise[kMaxNoiseTablesShared];
@@ -291,6 +293,7 @@ __global__ void __launch_bounds__(kBlock, 2) render_interp_kernel(const __grid_c
 
         bool active = false;
         Ray ray;
+        ray.o = v3(0.0f, 0.0f, 0.0f); ray.d = v3(1.0f, 1.0f, 1.0f); ray.time = 0.0f;
         V3 T = v3(1.0f, 1.0f, 1.0f);
         uint32_t bounce = 0;
         RngKey key;
@@ -333,13 +336,15 @@ __global__ void __launch_bounds__(kBlock, 2) render_interp_kernel(const __grid_c
                 continue;
             }
             // ---- one ray segment per live lane: world.hit + emitted + scatter (application.rs:477-495) ----
+            MediumXi xi;
+            xi.key = key; xi.bounce = bounce; xi.injected = 0.0f; xi.inject = false;
+            Best best;
+            best.pc = -1; best.t = 0.0f; best.face = 0; best.ctx = 0;
+            float closest = CUDART_INF_F;
+            bool hit = false;
+            if (kUniform) hit = traverse_uniform<false>(S, 0, S.n_ops, active, ray, ray, 0, 0.001f, closest, best, ref_boxes, xi);
+            else if (active) hit = traverse<false>(S, 0, S.n_ops, ray, ray, 0, 0.001f, closest, best, ref_boxes, xi);
             if (active) {
-                MediumXi xi;
-                xi.key = key; xi.bounce = bounce; xi.injected = 0.0f; xi.inject = false;
-                Best best;
-                best.pc = -1; best.t = 0.0f; best.face = 0; best.ctx = 0;
-                float closest = CUDART_INF_F;
-                const bool hit = traverse<false>(S, 0, S.n_ops, ray, ray, 0, 0.001f, closest, best, ref_boxes, xi);
                 n_rays++;
                 V3 add = v3(0.0f, 0.0f, 0.0f);
                 if (!hit) {
@@ -759,6 +764,55 @@ __global__ void __launch_bounds__(128) trace_hits_kernel(const __grid_constant__
     out[i] = o;
 }
 
+// world.hit() through the warp-uniform walk (traverse_uniform<>): one ray per lane, whole warps.
+__global__ void __launch_bounds__(128) trace_hits_uniform_kernel(const __grid_constant__ DeviceScene S, const hrt_ray* __restrict__ rays,
+                                                                 int n, const float* __restrict__ xi_in, hrt_hit* __restrict__ out,
+                                                                 int reference_boxes) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = i < n;
+    Ray ray;
+    ray.o = v3(0.0f, 0.0f, 0.0f); ray.d = v3(1.0f, 1.0f, 1.0f); ray.time = 0.0f;
+    float tmin = 0.0f, closest = 0.0f;
+    MediumXi xi;
+    xi.key.k0 = 0; xi.key.k1 = 0; xi.key.pixel = 0; xi.key.sample = 0;
+    xi.bounce = 0;
+    xi.inject = true;
+    xi.injected = 0.5f;
+    if (active) {
+        const hrt_ray r = rays[i];
+        ray.o = v3(r.o[0], r.o[1], r.o[2]);
+        ray.d = v3(r.d[0], r.d[1], r.d[2]);
+        ray.time = r.time;
+        tmin = r.tmin;
+        closest = r.tmax;
+        if (xi_in) xi.injected = xi_in[i];
+    }
+    Best best;
+    best.pc = -1; best.t = 0.0f; best.face = 0; best.ctx = 0;
+    const bool hit = traverse_uniform<false>(S, 0, S.n_ops, active, ray, ray, 0, tmin, closest, best, reference_boxes != 0, xi);
+    if (!active) return;
+    hrt_hit o;
+    o.hit = 0; o.t = 0.0f;
+    o.p[0] = o.p[1] = o.p[2] = 0.0f;
+    o.n[0] = o.n[1] = o.n[2] = 0.0f;
+    o.u = 0.0f; o.v = 0.0f;
+    o.front_face = 0; o.material_id = -1; o.prim_id = -1; o.face = 0;
+    if (hit) {
+        HitRec h;
+        make_hit_record(S, ray, best, true, h);
+        o.hit = 1;
+        o.t = h.t;
+        o.p[0] = h.p.x; o.p[1] = h.p.y; o.p[2] = h.p.z;
+        o.n[0] = h.n.x; o.n[1] = h.n.y; o.n[2] = h.n.z;
+        o.u = h.u; o.v = h.v;
+        o.front_face = h.front_face ? 1 : 0;
+        o.material_id = h.mat;
+        o.prim_id = h.prim;
+        o.face = h.face;
+    }
+    out[i] = o;
+}
+
 // world.hit() through the warp scheduler (the control flow the render kernel uses): one ray per lane.
 __global__ void __launch_bounds__(128) trace_hits_sched_kernel(const __grid_constant__ DeviceScene S, const hrt_ray* __restrict__ rays,
                                                                int n, const float* __restrict__ xi_in, hrt_hit* __restrict__ out,
@@ -1031,8 +1085,10 @@ cudaError_t launch_render(hrt::RenderLaunch& L, int num_sms, cudaStream_t stream
         e = cudaFuncSetAttribute(pool_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pool_smem);
         if (e != cudaSuccess) return e;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, pool_fn, kPoolBlock, pool_smem);
+    } else if (L.interpreter == 3) {
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, render_interp_kernel<true>, kBlock, 0);
     } else if (L.interpreter == 1) {
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, render_interp_kernel, kBlock, 0);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, render_interp_kernel<false>, kBlock, 0);
     } else {
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, render_kernel, kBlock, 0);
     }
@@ -1076,7 +1132,8 @@ cudaError_t launch_render(hrt::RenderLaunch& L, int num_sms, cudaStream_t stream
     L.block = pooled ? kPoolBlock : kBlock;
     L.chunk = chunk;
     if (L.interpreter == 2) render_pool_kernel<<<grid, kPoolBlock, pool_smem, stream>>>(P);
-    else if (L.interpreter == 1) render_interp_kernel<<<grid, kBlock, 0, stream>>>(P);
+    else if (L.interpreter == 3) render_interp_kernel<true><<<grid, kBlock, 0, stream>>>(P);
+    else if (L.interpreter == 1) render_interp_kernel<false><<<grid, kBlock, 0, stream>>>(P);
     else render_kernel<<<grid, kBlock, 0, stream>>>(P);
     return cudaGetLastError();
 }
@@ -1084,7 +1141,9 @@ cudaError_t launch_render(hrt::RenderLaunch& L, int num_sms, cudaStream_t stream
 cudaError_t launch_trace_hits(const hrt::DeviceSceneHost& S, const hrt_ray* d_rays, int n, const float* d_xi, hrt_hit* d_out,
                               int reference_boxes, cudaStream_t stream) {
     if (n <= 0) return cudaSuccess;
-    if (reference_boxes & 2)  // bit 1: run through the warp scheduler (the render kernel's control flow)
+    if (reference_boxes & 4)  // bit 2: the warp-uniform walk
+        trace_hits_uniform_kernel<<<(n + 127) / 128, 128, 0, stream>>>(to_device_scene(S), d_rays, n, d_xi, d_out, reference_boxes & 1);
+    else if (reference_boxes & 2)  // bit 1: run through the warp scheduler (the render kernel's control flow)
         trace_hits_sched_kernel<<<(n + 127) / 128, 128, 0, stream>>>(to_device_scene(S), d_rays, n, d_xi, d_out, reference_boxes & 1);
     else
         trace_hits_kernel<<<(n + 127) / 128, 128, 0, stream>>>(to_device_scene(S), d_rays, n, d_xi, d_out, reference_boxes & 1);

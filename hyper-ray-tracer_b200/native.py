@@ -17,6 +17,7 @@ HRT_FLAG_WARP_SCHEDULER = 4
 HRT_FLAG_INTERPRETER = 8
 HRT_FLAG_POOL = 16
 HRT_FLAG_SCHEDULER = 32
+HRT_FLAG_UNIFORM = 64
 ABI_VERSION = 2  # include/hrt.h HRT_ABI_VERSION
 HRT_BVH_REFERENCE = 0
 HRT_BVH_SAH = 1

@@ -157,6 +157,8 @@ enum {
     HRT_FLAG_SCHEDULER = 32,          /* render: force the in-register warp-scheduler kernel                      */
     HRT_FLAG_POOL = 16,               /* render: warp-private shared-memory ray pool kernel                       */
     HRT_FLAG_INTERPRETER = 8,         /* render: plain per-lane interpreter kernel instead of the warp scheduler  */
+    HRT_FLAG_UNIFORM = 64,            /* render / hrt_trace_hits: the warp walks the op stream together (one record per
+                                         step for the lanes that are at it; every branch warp-uniform)          */
     HRT_FLAG_WARP_SCHEDULER = 4       /* hrt_trace_hits only: run through the render kernel's warp-level op-class
                                          scheduler instead of the plain per-lane interpreter                */
 };

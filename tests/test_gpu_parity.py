@@ -122,6 +122,23 @@ def test_hit_records_through_warp_scheduler(pkg, orc, built, name):
 
 
 @pytest.mark.parametrize("name", ALL_SCENES)
+def test_hit_records_through_warp_uniform_walk(pkg, orc, built, name):
+    """HRT_FLAG_UNIFORM: the 32 rays of a warp walk the op stream together (traverse_uniform<>, hrt_device.cuh), every step
+    executing the record at the smallest pc for the lanes that are at it.  Per ray the visit order and the arithmetic are
+    unchanged, so the parity build must still be bit-identical to the oracle and to the per-lane interpreter."""
+    N = pkg.native
+    spec, gb, ob, _, _ = built(name)
+    rays = _ray_set(pkg, orc, spec, ob, seed=31)[:-5]  # ragged tail: the last warp is partly empty
+    xi = np.random.default_rng(8).random(len(rays), dtype=np.float32)
+    want = ob.trace_hits(rays, xi)
+    got = gb.trace_hits(rays, xi, flags=N.HRT_FLAG_EXACT_MATH | N.HRT_FLAG_UNIFORM)
+    _compare_hits(got, want, exact=True, what=f"{name}/exact+uniform")
+    got_ref = gb.trace_hits(rays, xi, flags=N.HRT_FLAG_EXACT_MATH | N.HRT_FLAG_UNIFORM | N.HRT_FLAG_REFERENCE_TRAVERSAL)
+    _compare_hits(got_ref, want, exact=True, what=f"{name}/exact+uniform+reference")
+    assert gb.trace_hits(rays, xi, flags=0).tobytes() == gb.trace_hits(rays, xi, flags=N.HRT_FLAG_UNIFORM).tobytes()
+
+
+@pytest.mark.parametrize("name", ALL_SCENES)
 def test_hit_records_production_build_within_tolerance(pkg, orc, built, name):
     """The production build (FMA contraction, reciprocal multiplies instead of divides).  On the well-conditioned part of
     the ray set — camera rays — hit records are within 1e-5 relative.  Secondary rays START ON a surface: there
@@ -391,7 +408,8 @@ def test_render_kernel_variants_agree(pkg, orc, built, name):
     outs = []
     # the last entry drives the pool kernel's box loop through the 32-byte records (reference test on every box) instead
     # of the fp16 table in shared memory: same hits, so the same paths
-    for flag in (N.HRT_FLAG_POOL, N.HRT_FLAG_SCHEDULER, N.HRT_FLAG_INTERPRETER, N.HRT_FLAG_POOL | N.HRT_FLAG_REFERENCE_TRAVERSAL):
+    for flag in (N.HRT_FLAG_POOL, N.HRT_FLAG_SCHEDULER, N.HRT_FLAG_INTERPRETER, N.HRT_FLAG_UNIFORM,
+                 N.HRT_FLAG_POOL | N.HRT_FLAG_REFERENCE_TRAVERSAL):
         acc, st = gb.render(spec.camera, 72, 48, 160, 50, spec.background, seed=31, resolve=False, flags=flag)
         outs.append((np.nan_to_num(acc[..., :3]), st.rays, st.paths))
     assert len({o[1] for o in outs}) == 1 and {o[2] for o in outs} == {72 * 48 * 160}
