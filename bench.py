@@ -52,9 +52,9 @@ def parse_args():
     ap.add_argument("--samples", type=int, default=0, help="override spp of the config")
     ap.add_argument("--seed", type=int, default=1, help="scene-instance seed")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
-    ap.add_argument("--bvh", default="reference", choices=["reference", "sah", "sah-spheres"],
-                    help="trees flattened for BvhNode objects (include/hrt.h hrt_scene_set_bvh_builder); the default and every "
-                         "committed number use the reference's trees")
+    ap.add_argument("--bvh", default="trees", choices=["trees", "reference"],
+                    help="flattened form that renders (include/hrt.h hrt_scene_set_bvh_builder): sound BVHs as OP_BVH trees "
+                         "(default), or every BvhNode as the reference built it")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="frames of the e2e leg (default max(2, steps // 8))")
@@ -346,7 +346,7 @@ def run_b200(args, scene_name, width, height, samples, depth):
 
 def main():
     args = parse_args()
-    if args.bvh != "reference":
+    if args.bvh != "trees":
         os.environ["HRT_BVH_BUILDER"] = args.bvh  # read by hrt_scene_create (diagnostic default of the library)
     pkg = graft.load_package()
     scene_name, width, height, samples, depth = pkg.CONFIGS[args.config]

@@ -31,9 +31,9 @@ def parse(argv=None):
     ap.add_argument("--render-seed", type=int, default=0, help="Philox key of the sample streams")
     ap.add_argument("--device", type=int, default=0)
     ap.add_argument("--out", default="frame.png", help="output file: .png, .npy (float32 RGBA, bottom-up) or .pfm")
-    ap.add_argument("--bvh", default="reference", choices=["reference", "sah", "sah-spheres"],
-                    help="trees flattened for BvhNode objects: the reference's (default) or surface-area-heuristic ones (same "
-                         "closest hits, fewer box tests; exact ties between coincident surfaces may pick the other surface)")
+    ap.add_argument("--bvh", default="trees", choices=["trees", "reference"],
+                    help="flattened form that renders: sound BVHs as stack-walked surface-area-heuristic trees (default; same "
+                         "hits, the reference's tie rule kept) or every BvhNode as the reference built it")
     ap.add_argument("--save-scene", default=None, metavar="FILE", help="write the generated scene instance (.npz) before rendering")
     ap.add_argument("--load-scene", default=None, metavar="FILE", help="render a stored scene instance instead of --scene/--seed")
     return ap.parse_args(argv)
@@ -63,7 +63,7 @@ def main(argv=None) -> int:
     spec = scene_io.load_scene(a.load_scene) if a.load_scene else scenes.make_scene(a.scene, a.seed)
     if a.save_scene:
         scene_io.save_scene(spec, a.save_scene)
-    r = renderer.Renderer(spec, device=a.device, bvh_builder={"sah": native.HRT_BVH_SAH, "sah-spheres": native.HRT_BVH_SAH_SPHERES}.get(a.bvh))
+    r = renderer.Renderer(spec, device=a.device, bvh_builder={"reference": native.HRT_BVH_REFERENCE, "trees": native.HRT_BVH_TREES}.get(a.bvh))
     print("Generated world")                                        # application.rs:199
     print("Rendering image...")                                     # application.rs:387
     t0 = time.time()

@@ -17,25 +17,40 @@
 namespace hrt {
 
 constexpr int kCounterWords = 32;  // [0] work cursor, [1] rays, [2] paths, [8..27] diagnostic build's scheduler statistics
+constexpr int kLaunchSlots = 8;
+
+// What one render launch owns on the device: its counter block (the kernel's work cursor lives there) and its timing
+// events.  hrt_render_accum_device returns before its kernel finishes, so two renders of one scene can be in flight on
+// one device (different streams): each takes the next slot of a ring, and re-using a slot first waits (on the new
+// launch's stream) for the slot's previous launch to finish.
+struct LaunchSlot {
+    unsigned long long* counters = nullptr;
+    cudaEvent_t t0 = nullptr, t1 = nullptr, done = nullptr;
+    bool used = false;
+};
 
 struct DeviceState {
     int device = -1;
     int num_sms = 0;
-    void* d_ops = nullptr;
-    void* d_box16 = nullptr;
-    void* d_ctxs = nullptr;
+    // [0] reference form, [1] fast form of the flattened scene (hrt_scene.hpp)
+    void* d_ops[2] = {nullptr, nullptr};
+    void* d_box16[2] = {nullptr, nullptr};
+    void* d_ctxs[2] = {nullptr, nullptr};
+    void* d_nodes = nullptr;
     void* d_mats = nullptr;
     void* d_texs = nullptr;
     void* d_noise = nullptr;
     std::vector<cudaArray_t> arrays;
     std::vector<cudaTextureObject_t> texobjs;
-    unsigned long long* d_counters = nullptr;
+    unsigned long long* d_counters = nullptr;  // kLaunchSlots blocks of kCounterWords
+    LaunchSlot slots[kLaunchSlots];
+    int next_slot = 0;
     // scratch for the host-buffer entry points
     float* d_accum = nullptr;
     float* d_rgba = nullptr;
     size_t accum_pixels = 0;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    DeviceSceneHost view;
+    DeviceSceneHost view[2];
 };
 
 void release_device_state(DeviceState* d) {
@@ -44,9 +59,15 @@ void release_device_state(DeviceState* d) {
     if (cudaGetDevice(&prev) == cudaSuccess && cudaSetDevice(d->device) == cudaSuccess) {
         for (auto t : d->texobjs) cudaDestroyTextureObject(t);
         for (auto a : d->arrays) cudaFreeArray(a);
-        cudaFree(d->d_ops); cudaFree(d->d_box16); cudaFree(d->d_ctxs); cudaFree(d->d_mats); cudaFree(d->d_texs); cudaFree(d->d_noise);
+        for (int k = 0; k < 2; ++k) { cudaFree(d->d_ops[k]); cudaFree(d->d_box16[k]); cudaFree(d->d_ctxs[k]); }
+        cudaFree(d->d_nodes); cudaFree(d->d_mats); cudaFree(d->d_texs); cudaFree(d->d_noise);
         cudaFree(d->d_counters); cudaFree(d->d_accum); cudaFree(d->d_rgba);
         for (auto e : d->ev) if (e) cudaEventDestroy(e);
+        for (auto& sl : d->slots) {
+            if (sl.t0) cudaEventDestroy(sl.t0);
+            if (sl.t1) cudaEventDestroy(sl.t1);
+            if (sl.done) cudaEventDestroy(sl.done);
+        }
         cudaSetDevice(prev);
     }
     delete d;
@@ -93,6 +114,68 @@ struct DevBuf {
     cudaError_t alloc(size_t n) { return cudaMalloc((void**)&p, (n ? n : 1) * sizeof(T)); }
 };
 
+static const FlatScene& flat_of(const hrt_scene* s, int k) { return k == 0 ? s->ref : s->fast; }
+
+static int32_t fill_device_state(hrt_scene* s, DeviceState* d) {
+    int32_t rc;
+    for (int k = 0; k < 2; ++k) {
+        const FlatScene& f = flat_of(s, k);
+        if ((rc = upload_table(&d->d_ops[k], f.ops.data(), f.ops.size() * sizeof(Op))) != HRT_OK) return rc;
+        if ((rc = upload_table(&d->d_box16[k], f.box16.data(), f.box16.size() * sizeof(Box16))) != HRT_OK) return rc;
+        if ((rc = upload_table(&d->d_ctxs[k], f.ctxs.data(), f.ctxs.size() * sizeof(Ctx))) != HRT_OK) return rc;
+    }
+    if ((rc = upload_table(&d->d_nodes, s->fast.nodes.data(), s->fast.nodes.size() * sizeof(Bvh2Node))) != HRT_OK) return rc;
+    if ((rc = upload_table(&d->d_mats, s->materials.data(), s->materials.size() * sizeof(Material))) != HRT_OK) return rc;
+    if ((rc = upload_table(&d->d_texs, s->textures.data(), s->textures.size() * sizeof(Texture))) != HRT_OK) return rc;
+    if ((rc = upload_table(&d->d_noise, s->noise_tables.data(), s->noise_tables.size() * sizeof(NoiseTable))) != HRT_OK) return rc;
+    HRT_CUDA(cudaMalloc((void**)&d->d_counters, kLaunchSlots * kCounterWords * sizeof(unsigned long long)));
+    for (auto& ev : d->ev) HRT_CUDA(cudaEventCreate(&ev));
+    for (int i = 0; i < kLaunchSlots; ++i) {
+        LaunchSlot& sl = d->slots[i];
+        sl.counters = d->d_counters + (size_t)i * kCounterWords;
+        HRT_CUDA(cudaEventCreate(&sl.t0));
+        HRT_CUDA(cudaEventCreate(&sl.t1));
+        HRT_CUDA(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+    }
+    // Image textures: RGBA8 CUDA arrays bound as point-sampled, unnormalised texture objects
+    // (nearest texel, no filtering — image_texture.rs:44-62).
+    for (const ImageData& img : s->images) {
+        cudaChannelFormatDesc desc = cudaCreateChannelDesc<uchar4>();
+        cudaArray_t arr = nullptr;
+        HRT_CUDA(cudaMallocArray(&arr, &desc, img.width, img.height));
+        d->arrays.push_back(arr);
+        HRT_CUDA(cudaMemcpy2DToArray(arr, 0, 0, img.rgba.data(), (size_t)img.width * 4, (size_t)img.width * 4, img.height,
+                                     cudaMemcpyHostToDevice));
+        cudaResourceDesc rd;
+        std::memset(&rd, 0, sizeof(rd));
+        rd.resType = cudaResourceTypeArray;
+        rd.res.array.array = arr;
+        cudaTextureDesc td;
+        std::memset(&td, 0, sizeof(td));
+        td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+        td.filterMode = cudaFilterModePoint;
+        td.readMode = cudaReadModeElementType;
+        td.normalizedCoords = 0;
+        cudaTextureObject_t tex = 0;
+        HRT_CUDA(cudaCreateTextureObject(&tex, &rd, &td, nullptr));
+        d->texobjs.push_back(tex);
+    }
+    for (int k = 0; k < 2; ++k) {
+        const FlatScene& f = flat_of(s, k);
+        DeviceSceneHost& v = d->view[k];
+        std::memset(&v, 0, sizeof(v));
+        v.ops = d->d_ops[k]; v.box16 = d->d_box16[k]; v.ctxs = d->d_ctxs[k];
+        v.nodes = d->d_nodes;  // only the fast form has OP_BVH records
+        v.mats = d->d_mats; v.texs = d->d_texs; v.noise = d->d_noise;
+        for (size_t i = 0; i < d->texobjs.size() && i < (size_t)kMaxImages; ++i) v.images[i] = d->texobjs[i];
+        v.n_ops = (int32_t)f.ops.size();
+        v.n_noise = (int32_t)s->noise_tables.size();
+        v.n_media = f.n_media;
+        v.ln_e = logf(2.71828182845904523536f);
+    }
+    return HRT_OK;
+}
+
 }  // namespace hrt
 
 using namespace hrt;
@@ -121,53 +204,20 @@ int32_t hrt_scene_upload(hrt_scene* s, int32_t device) {
     HRT_CUDA(cudaSetDevice(device));
     cudaDeviceProp prop;
     HRT_CUDA(cudaGetDeviceProperties(&prop, device));
-    if (prop.major != 10)
+    if (prop.major != 10 || prop.minor != 0)  // the library ships an sm_100a cubin and no PTX
         return fail(HRT_ERR_CUDA, std::string("device '") + prop.name + "' is sm_" + std::to_string(prop.major) +
                                       std::to_string(prop.minor) + "; this library ships sm_100a code only");
+    // Built locally and registered only when complete: a failure below must not leave a half-built state behind that a
+    // later call would find and launch kernels on.
     DeviceState* d = new DeviceState();
     d->device = device;
     d->num_sms = prop.multiProcessorCount;
-    s->devices.push_back(d);
-    int32_t rc;
-    if ((rc = upload_table(&d->d_ops, s->ops.data(), s->ops.size() * sizeof(Op))) != HRT_OK) return rc;
-    if ((rc = upload_table(&d->d_box16, s->box16.data(), s->box16.size() * sizeof(Box16))) != HRT_OK) return rc;
-    if ((rc = upload_table(&d->d_ctxs, s->ctxs.data(), s->ctxs.size() * sizeof(Ctx))) != HRT_OK) return rc;
-    if ((rc = upload_table(&d->d_mats, s->materials.data(), s->materials.size() * sizeof(Material))) != HRT_OK) return rc;
-    if ((rc = upload_table(&d->d_texs, s->textures.data(), s->textures.size() * sizeof(Texture))) != HRT_OK) return rc;
-    if ((rc = upload_table(&d->d_noise, s->noise_tables.data(), s->noise_tables.size() * sizeof(NoiseTable))) != HRT_OK) return rc;
-    HRT_CUDA(cudaMalloc((void**)&d->d_counters, kCounterWords * sizeof(unsigned long long)));
-    for (auto& ev : d->ev) HRT_CUDA(cudaEventCreate(&ev));
-    std::memset(&d->view, 0, sizeof(d->view));
-    // Image textures: RGBA8 CUDA arrays bound as point-sampled, unnormalised texture objects
-    // (nearest texel, no filtering — image_texture.rs:44-62).
-    for (const ImageData& img : s->images) {
-        cudaChannelFormatDesc desc = cudaCreateChannelDesc<uchar4>();
-        cudaArray_t arr = nullptr;
-        HRT_CUDA(cudaMallocArray(&arr, &desc, img.width, img.height));
-        d->arrays.push_back(arr);
-        HRT_CUDA(cudaMemcpy2DToArray(arr, 0, 0, img.rgba.data(), (size_t)img.width * 4, (size_t)img.width * 4, img.height,
-                                     cudaMemcpyHostToDevice));
-        cudaResourceDesc rd;
-        std::memset(&rd, 0, sizeof(rd));
-        rd.resType = cudaResourceTypeArray;
-        rd.res.array.array = arr;
-        cudaTextureDesc td;
-        std::memset(&td, 0, sizeof(td));
-        td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
-        td.filterMode = cudaFilterModePoint;
-        td.readMode = cudaReadModeElementType;
-        td.normalizedCoords = 0;
-        cudaTextureObject_t tex = 0;
-        HRT_CUDA(cudaCreateTextureObject(&tex, &rd, &td, nullptr));
-        d->texobjs.push_back(tex);
+    const int32_t rc = fill_device_state(s, d);
+    if (rc != HRT_OK) {
+        release_device_state(d);
+        return rc;
     }
-    d->view.ops = d->d_ops; d->view.box16 = d->d_box16; d->view.ctxs = d->d_ctxs; d->view.mats = d->d_mats; d->view.texs = d->d_texs;
-    d->view.noise = d->d_noise;
-    for (size_t i = 0; i < d->texobjs.size() && i < (size_t)kMaxImages; ++i) d->view.images[i] = d->texobjs[i];
-    d->view.n_ops = (int32_t)s->ops.size();
-    d->view.n_noise = (int32_t)s->noise_tables.size();
-    d->view.n_media = s->n_media;
-    d->view.ln_e = logf(2.71828182845904523536f);
+    s->devices.push_back(d);
     return HRT_OK;
 }
 
@@ -188,9 +238,14 @@ int32_t hrt_scene_refresh(hrt_scene* s, int32_t device) {
     DeviceState* d = find_state(s, device);
     if (!d) return hrt_scene_upload(s, device);
     HRT_CUDA(cudaSetDevice(device));
-    HRT_CUDA(cudaMemcpyAsync(d->d_ops, s->ops.data(), s->ops.size() * sizeof(Op), cudaMemcpyHostToDevice, 0));
-    HRT_CUDA(cudaMemcpyAsync(d->d_box16, s->box16.data(), s->box16.size() * sizeof(Box16), cudaMemcpyHostToDevice, 0));
-    HRT_CUDA(cudaMemcpyAsync(d->d_ctxs, s->ctxs.data(), s->ctxs.size() * sizeof(Ctx), cudaMemcpyHostToDevice, 0));
+    for (int k = 0; k < 2; ++k) {
+        const FlatScene& f = flat_of(s, k);
+        HRT_CUDA(cudaMemcpyAsync(d->d_ops[k], f.ops.data(), f.ops.size() * sizeof(Op), cudaMemcpyHostToDevice, 0));
+        HRT_CUDA(cudaMemcpyAsync(d->d_box16[k], f.box16.data(), f.box16.size() * sizeof(Box16), cudaMemcpyHostToDevice, 0));
+        HRT_CUDA(cudaMemcpyAsync(d->d_ctxs[k], f.ctxs.data(), f.ctxs.size() * sizeof(Ctx), cudaMemcpyHostToDevice, 0));
+    }
+    if (!s->fast.nodes.empty())
+        HRT_CUDA(cudaMemcpyAsync(d->d_nodes, s->fast.nodes.data(), s->fast.nodes.size() * sizeof(Bvh2Node), cudaMemcpyHostToDevice, 0));
     if (!s->materials.empty())
         HRT_CUDA(cudaMemcpyAsync(d->d_mats, s->materials.data(), s->materials.size() * sizeof(Material), cudaMemcpyHostToDevice, 0));
     if (!s->textures.empty())
@@ -207,8 +262,12 @@ int32_t hrt_scene_refresh(hrt_scene* s, int32_t device) {
 
 int64_t hrt_scene_device_bytes(const hrt_scene* s) {
     if (!s || !s->committed) return fail(HRT_ERR_STATE, "scene not committed");
-    int64_t b = (int64_t)(s->ops.size() * sizeof(Op) + s->box16.size() * sizeof(Box16) + s->ctxs.size() * sizeof(Ctx) + s->materials.size() * sizeof(Material) +
-                          s->textures.size() * sizeof(Texture) + s->noise_tables.size() * sizeof(NoiseTable));
+    int64_t b = (int64_t)(s->materials.size() * sizeof(Material) + s->textures.size() * sizeof(Texture) +
+                          s->noise_tables.size() * sizeof(NoiseTable) + s->fast.nodes.size() * sizeof(Bvh2Node));
+    for (int k = 0; k < 2; ++k) {
+        const FlatScene& f = flat_of(s, k);
+        b += (int64_t)(f.ops.size() * sizeof(Op) + f.box16.size() * sizeof(Box16) + f.ctxs.size() * sizeof(Ctx));
+    }
     for (const ImageData& img : s->images) b += (int64_t)img.rgba.size();
     return b;
 }
@@ -283,12 +342,11 @@ static int32_t check_render_args(const hrt_scene* s, const hrt_camera_desc* cam,
 
 // The part every render variant shares: launch the path-trace kernel for [sample_begin, +count) into d_accum.
 static int32_t render_into(hrt_scene* s, DeviceState* d, const hrt_camera_desc* cam, const hrt_render_desc* rd,
-                           float* d_accum, cudaStream_t stream, bool want_stats, hrt_stats* stats) {
+                           float* d_accum, cudaStream_t stream, hrt_stats* stats, LaunchSlot** slot_out) {
     int32_t rc = check_render_args(s, cam, rd);
     if (rc != HRT_OK) return rc;
     RenderLaunch L;
     std::memset(&L, 0, sizeof(L));
-    L.scene = d->view;
     if ((rc = hrt_camera_init(cam, &L.cam)) != HRT_OK) return rc;
     L.width = rd->width; L.height = rd->height; L.depth = rd->depth;
     std::memcpy(L.background, rd->background, 12);
@@ -303,6 +361,7 @@ static int32_t render_into(hrt_scene* s, DeviceState* d, const hrt_camera_desc* 
     if (s->any_bvh && (std::fmin(cam->time0, cam->time1) < s->time_min || std::fmax(cam->time0, cam->time1) > s->time_max))
         ref_boxes = true;
     L.reference_boxes = ref_boxes ? 1 : 0;
+    L.scene = d->view[ref_boxes ? 0 : 1];  // the reference form of the stream goes with the reference's box test
     {
         const char* env = getenv("HRT_KERNEL");  // diagnostic override: "interp" | "sched" | "pool"
         // default: the shared-memory ray-pool kernel (best sustained throughput; its 96-ray pools need enough samples per
@@ -318,16 +377,22 @@ static int32_t render_into(hrt_scene* s, DeviceState* d, const hrt_camera_desc* 
         if (env && env[0] == 'p') variant = 2;
         L.interpreter = variant;
     }
-    L.counters = d->d_counters;
+    LaunchSlot& slot = d->slots[d->next_slot];
+    d->next_slot = (d->next_slot + 1) % kLaunchSlots;
+    if (slot.used) HRT_CUDA(cudaStreamWaitEvent(stream, slot.done, 0));
+    slot.used = true;
+    if (slot_out) *slot_out = &slot;
+    L.counters = slot.counters;
     L.accum = d_accum;
     L.chunk = 0;
     if (const char* env = getenv("HRT_CHUNK")) L.chunk = atoi(env);  // diagnostic: samples per work item
-    HRT_CUDA(cudaMemsetAsync(d->d_counters, 0, kCounterWords * sizeof(unsigned long long), stream));
-    if (want_stats) HRT_CUDA(cudaEventRecord(d->ev[0], stream));
+    HRT_CUDA(cudaMemsetAsync(slot.counters, 0, kCounterWords * sizeof(unsigned long long), stream));
+    HRT_CUDA(cudaEventRecord(slot.t0, stream));
     cudaError_t e = (rd->flags & HRT_FLAG_EXACT_MATH) ? hrt_exact::launch_render(L, d->num_sms, stream)
                                                       : hrt_fast::launch_render(L, d->num_sms, stream);
     if (e != cudaSuccess) return cuda_fail(e, "render_kernel launch");
-    if (want_stats) HRT_CUDA(cudaEventRecord(d->ev[1], stream));
+    HRT_CUDA(cudaEventRecord(slot.t1, stream));
+    HRT_CUDA(cudaEventRecord(slot.done, stream));
     if (stats) {
         stats->launches += 1;
         stats->grid = L.grid;
@@ -336,10 +401,10 @@ static int32_t render_into(hrt_scene* s, DeviceState* d, const hrt_camera_desc* 
     return HRT_OK;
 }
 
-static int32_t finish_stats(DeviceState* d, cudaStream_t stream, hrt_stats* stats) {
-    if (!stats) return HRT_OK;
+static int32_t finish_stats(LaunchSlot* slot, cudaStream_t stream, hrt_stats* stats) {
+    if (!stats || !slot) return HRT_OK;
     unsigned long long c[kCounterWords];
-    HRT_CUDA(cudaMemcpyAsync(c, d->d_counters, sizeof(c), cudaMemcpyDeviceToHost, stream));
+    HRT_CUDA(cudaMemcpyAsync(c, slot->counters, sizeof(c), cudaMemcpyDeviceToHost, stream));
     HRT_CUDA(cudaStreamSynchronize(stream));
     if (getenv("HRT_SCHED_STATS")) {
         static const char* names[6] = {"box", "sphere", "rect", "misc", "done", "new"};
@@ -356,7 +421,7 @@ static int32_t finish_stats(DeviceState* d, cudaStream_t stream, hrt_stats* stat
     stats->rays = c[1];
     stats->paths = c[2];
     float ms = 0.0f;
-    HRT_CUDA(cudaEventElapsedTime(&ms, d->ev[0], d->ev[1]));
+    HRT_CUDA(cudaEventElapsedTime(&ms, slot->t0, slot->t1));
     stats->kernel_ms = ms;
     return HRT_OK;
 }
@@ -374,7 +439,8 @@ static int32_t render_host(hrt_scene* s, int32_t device, const hrt_camera_desc* 
     std::memset(&local, 0, sizeof(local));
     cudaStream_t stream = 0;
     HRT_CUDA(cudaMemsetAsync(d->d_accum, 0, pixels * 16, stream));
-    if ((rc = render_into(s, d, cam, rd, d->d_accum, stream, true, &local)) != HRT_OK) return rc;
+    LaunchSlot* slot = nullptr;
+    if ((rc = render_into(s, d, cam, rd, d->d_accum, stream, &local, &slot)) != HRT_OK) return rc;
     const float* src = d->d_accum;
     if (resolve) {
         HRT_CUDA(cudaEventRecord(d->ev[2], stream));
@@ -387,7 +453,7 @@ static int32_t render_host(hrt_scene* s, int32_t device, const hrt_camera_desc* 
     HRT_CUDA(cudaEventRecord(d->ev[4], stream));
     HRT_CUDA(cudaMemcpyAsync(out, src, pixels * 16, cudaMemcpyDeviceToHost, stream));
     HRT_CUDA(cudaEventRecord(d->ev[5], stream));
-    if ((rc = finish_stats(d, stream, &local)) != HRT_OK) return rc;
+    if ((rc = finish_stats(slot, stream, &local)) != HRT_OK) return rc;
     if (resolve) HRT_CUDA(cudaEventElapsedTime(&local.resolve_ms, d->ev[2], d->ev[3]));
     HRT_CUDA(cudaEventElapsedTime(&local.d2h_ms, d->ev[4], d->ev[5]));
     if (stats) *stats = local;
@@ -434,6 +500,7 @@ static int32_t render_multi(hrt_scene* s, const int32_t* devices, int32_t n, con
         cudaGetLastError();
     }
     hrt_stats local[8];
+    LaunchSlot* slots[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     const int total = rd->sample_count > 0 ? rd->sample_count : rd->samples;
     const int base = rd->sample_count > 0 ? rd->sample_begin : 0;
     for (int i = 0; i < n; ++i) {  // launch everything first: the devices render concurrently
@@ -444,13 +511,8 @@ static int32_t render_multi(hrt_scene* s, const int32_t* devices, int32_t n, con
         const int q = total / n, r = total % n;
         slice.sample_begin = base + i * q + (i < r ? i : r);
         slice.sample_count = q + (i < r ? 1 : 0);
-        if (slice.sample_count > 0) {
-            if ((rc = render_into(s, st[i], cam, &slice, st[i]->d_accum, 0, true, &local[i])) != HRT_OK) return rc;
-        } else {
-            HRT_CUDA(cudaMemsetAsync(st[i]->d_counters, 0, kCounterWords * sizeof(unsigned long long), 0));
-            HRT_CUDA(cudaEventRecord(st[i]->ev[0], 0));
-            HRT_CUDA(cudaEventRecord(st[i]->ev[1], 0));
-        }
+        if (slice.sample_count > 0 && (rc = render_into(s, st[i], cam, &slice, st[i]->d_accum, 0, &local[i], &slots[i])) != HRT_OK)
+            return rc;
         HRT_CUDA(cudaEventRecord(st[i]->ev[2], 0));  // "my slice is in my accumulator"
     }
     HRT_CUDA(cudaSetDevice(devices[0]));
@@ -466,7 +528,7 @@ static int32_t render_multi(hrt_scene* s, const int32_t* devices, int32_t n, con
     std::memset(&agg, 0, sizeof(agg));
     for (int i = 0; i < n; ++i) {
         HRT_CUDA(cudaSetDevice(devices[i]));
-        if ((rc = finish_stats(st[i], 0, &local[i])) != HRT_OK) return rc;
+        if ((rc = finish_stats(slots[i], 0, &local[i])) != HRT_OK) return rc;
         agg.paths += local[i].paths;
         agg.rays += local[i].rays;
         agg.launches += local[i].launches;
@@ -501,9 +563,10 @@ int32_t hrt_render_accum_device(hrt_scene* s, int32_t device, const hrt_camera_d
     cudaStream_t stream = (cudaStream_t)stream_ptr;
     hrt_stats local;
     std::memset(&local, 0, sizeof(local));
-    if ((rc = render_into(s, d, cam, rd, (float*)d_accum, stream, stats != nullptr, &local)) != HRT_OK) return rc;
+    LaunchSlot* slot = nullptr;
+    if ((rc = render_into(s, d, cam, rd, (float*)d_accum, stream, &local, &slot)) != HRT_OK) return rc;
     if (stats) {
-        if ((rc = finish_stats(d, stream, &local)) != HRT_OK) return rc;
+        if ((rc = finish_stats(slot, stream, &local)) != HRT_OK) return rc;
         *stats = local;
     }
     return HRT_OK;
@@ -538,10 +601,12 @@ int32_t hrt_trace_hits(hrt_scene* s, int32_t device, const hrt_ray* rays, int32_
         HRT_CUDA(dx.alloc(n));
         HRT_CUDA(cudaMemcpy(dx.p, xi, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice));
     }
+    // the reference form of the stream goes with the reference's box test (as in render_into)
+    const DeviceSceneHost& view = d->view[(flags & HRT_FLAG_REFERENCE_TRAVERSAL) ? 0 : 1];
     const int ref = ((flags & HRT_FLAG_REFERENCE_TRAVERSAL) ? 1 : 0) | ((flags & HRT_FLAG_WARP_SCHEDULER) ? 2 : 0) |
                     ((flags & HRT_FLAG_UNIFORM) ? 4 : 0);
-    cudaError_t e = (flags & HRT_FLAG_EXACT_MATH) ? hrt_exact::launch_trace_hits(d->view, dr.p, n, dx.p, dh.p, ref, 0)
-                                                  : hrt_fast::launch_trace_hits(d->view, dr.p, n, dx.p, dh.p, ref, 0);
+    cudaError_t e = (flags & HRT_FLAG_EXACT_MATH) ? hrt_exact::launch_trace_hits(view, dr.p, n, dx.p, dh.p, ref, 0)
+                                                  : hrt_fast::launch_trace_hits(view, dr.p, n, dx.p, dh.p, ref, 0);
     if (e != cudaSuccess) return cuda_fail(e, "trace_hits_kernel launch");
     HRT_CUDA(cudaMemcpy(out, dh.p, sizeof(hrt_hit) * (size_t)n, cudaMemcpyDeviceToHost));
     return HRT_OK;
@@ -558,8 +623,8 @@ int32_t hrt_tex_value(hrt_scene* s, int32_t device, int32_t tex, const float* uv
     HRT_CUDA(di.alloc((size_t)n * 5));
     HRT_CUDA(dout.alloc((size_t)n * 3));
     HRT_CUDA(cudaMemcpy(di.p, uvp, sizeof(float) * 5 * (size_t)n, cudaMemcpyHostToDevice));
-    cudaError_t e = (flags & HRT_FLAG_EXACT_MATH) ? hrt_exact::launch_tex_value(d->view, tex, di.p, n, dout.p, 0)
-                                                  : hrt_fast::launch_tex_value(d->view, tex, di.p, n, dout.p, 0);
+    cudaError_t e = (flags & HRT_FLAG_EXACT_MATH) ? hrt_exact::launch_tex_value(d->view[0], tex, di.p, n, dout.p, 0)
+                                                  : hrt_fast::launch_tex_value(d->view[0], tex, di.p, n, dout.p, 0);
     if (e != cudaSuccess) return cuda_fail(e, "tex_value_kernel launch");
     HRT_CUDA(cudaMemcpy(out, dout.p, sizeof(float) * 3 * (size_t)n, cudaMemcpyDeviceToHost));
     return HRT_OK;
@@ -583,8 +648,8 @@ int32_t hrt_scatter(hrt_scene* s, int32_t device, const hrt_ray* rays, const hrt
     HRT_CUDA(cudaMemcpy(dr.p, rays, sizeof(hrt_ray) * (size_t)n, cudaMemcpyHostToDevice));
     HRT_CUDA(cudaMemcpy(dh.p, hits, sizeof(hrt_hit) * (size_t)n, cudaMemcpyHostToDevice));
     HRT_CUDA(cudaMemcpy(du.p, u4, sizeof(float) * 4 * (size_t)n, cudaMemcpyHostToDevice));
-    cudaError_t e = (flags & HRT_FLAG_EXACT_MATH) ? hrt_exact::launch_scatter(d->view, dr.p, dh.p, du.p, n, dout.p, 0)
-                                                  : hrt_fast::launch_scatter(d->view, dr.p, dh.p, du.p, n, dout.p, 0);
+    cudaError_t e = (flags & HRT_FLAG_EXACT_MATH) ? hrt_exact::launch_scatter(d->view[0], dr.p, dh.p, du.p, n, dout.p, 0)
+                                                  : hrt_fast::launch_scatter(d->view[0], dr.p, dh.p, du.p, n, dout.p, 0);
     if (e != cudaSuccess) return cuda_fail(e, "scatter_kernel launch");
     HRT_CUDA(cudaMemcpy(out, dout.p, sizeof(hrt_scatter_out) * (size_t)n, cudaMemcpyDeviceToHost));
     return HRT_OK;

@@ -65,6 +65,7 @@ __device__ __forceinline__ V3 ray_at(const Ray& r, float t) { return r.o + t * r
 struct DeviceScene {
     const float4* ops;     // 2 x float4 per record
     const uint4* box16;    // 16-byte companion per record (hrt_types.h Box16): fp16 outward-rounded box + w7
+    const uint4* nodes;    // 2 x uint4 per OP_BVH tree node (hrt_types.h Bvh2Node)
     const Ctx* ctxs;
     const Material* mats;
     const Texture* texs;
@@ -378,6 +379,143 @@ __device__ __forceinline__ bool cuboid_test(V3 mn, V3 mx, const Ray& r, const Ra
 }
 
 // ------------------------------------------------------------------------------------------------
+// OP_BVH: a sound BvhNode as a two-child tree (hrt_types.h Bvh2Node), walked per ray with a stack, nearer child first.
+// ------------------------------------------------------------------------------------------------
+// Entry / exit distances of the ray against an fp16 box packed as three half2 words (min.x min.y | min.z max.x |
+// max.y max.z); same per-axis arithmetic and NaN behaviour as box_hit_tight.  The box is missed iff hi < lo: unlike
+// box_hit_tight (hi <= lo) a zero-width overlap still counts, so a primitive whose hit distance EQUALS the current
+// closest is always reached and the tie rule below decides, not the visit order.
+__device__ __forceinline__ void slab16(uint32_t w0, uint32_t w1, uint32_t w2, const Ray& r, const RayK& k, float tmin, float closest,
+                                       float& lo, float& hi) {
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&w0));  // min.x, min.y
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&w1));  // min.z, max.x
+    const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&w2));  // max.y, max.z
+    const float t0x = (a.x - r.o.x) * k.inv.x, t1x = (b.y - r.o.x) * k.inv.x;
+    const float t0y = (a.y - r.o.y) * k.inv.y, t1y = (c.x - r.o.y) * k.inv.y;
+    const float t0z = (b.x - r.o.z) * k.inv.z, t1z = (c.y - r.o.z) * k.inv.z;
+    const float lox = k.inv.x < 0.0f ? t1x : t0x, hix = k.inv.x < 0.0f ? t0x : t1x;
+    const float loy = k.inv.y < 0.0f ? t1y : t0y, hiy = k.inv.y < 0.0f ? t0y : t1y;
+    const float loz = k.inv.z < 0.0f ? t1z : t0z, hiz = k.inv.z < 0.0f ? t0z : t1z;
+    lo = fmaxf(fmaxf(lox, loy), fmaxf(loz, tmin));
+    hi = fminf(fminf(hix, hiy), fminf(hiz, closest));
+}
+
+struct TreeHit {
+    float t;   // closest so far (in: the running t_max; out: narrowed)
+    int pc;    // record of the closest hit so far (in: the caller's, -1 none; out: unchanged or a leaf of this tree)
+    int face;  // cuboid side when pc changed
+};
+
+// An EXACT tie between two surfaces (same t) inside an OP_BVH tree, decided as the reference decides it.  The reference
+// visits a BvhNode's leaves in ITS depth-first order with a running t_max (bvh_node.rs:110-124): the earlier leaf is hit
+// first, t_max becomes t, and the later leaf replaces it (`t <= t_max`) only if it is still REACHED — i.e. if its
+// bounding box passes Aabb::hit with t_max = t (aabb.rs:20-47: rejected when `min(t1, t_max) <= max(t0, t_min)` on an
+// axis, which is exactly what happens when the ray ENTERS that box at the tie point, as on the shared face of two
+// adjacent cuboids seen from inside one of them).  The leaf records keep the reference's order, so "later" is the larger
+// pc; this evaluates the reference's test on the later leaf's own reference box (sphere.rs:77-83,
+// moving_sphere.rs:98-110 over the BvhNode's time interval, rect.rs:88-103, cuboid.rs:104-106).  Cold: ties only.
+__device__ __noinline__ bool tie_goes_to_later(const DeviceScene& S, int later_pc, Ray cur, float tmin, float t, float ts, float te) {
+    const RayK k = make_rayk(cur);
+    float4 A, B;
+    load_op(S, later_pc, A, B);
+    const uint32_t opc = __float_as_uint(B.w) & 0xffu;
+    float4 mn, mx;
+    mn.w = mx.w = 0.0f;
+    if (opc == OP_SPHERE) {
+        mn.x = A.x - A.w; mn.y = A.y - A.w; mn.z = A.z - A.w;
+        mx.x = A.x + A.w; mx.y = A.y + A.w; mx.z = A.z + A.w;
+    } else if (opc == OP_MSPHERE) {
+        float4 C, D;
+        load_op(S, later_pc + 1, C, D);
+        const V3 ca = msphere_center(v3(A.x, A.y, A.z), v3(C.x, C.y, C.z), C.w, D.x, ts);
+        const V3 cb = msphere_center(v3(A.x, A.y, A.z), v3(C.x, C.y, C.z), C.w, D.x, te);
+        mn.x = fminf(ca.x - A.w, cb.x - A.w); mn.y = fminf(ca.y - A.w, cb.y - A.w); mn.z = fminf(ca.z - A.w, cb.z - A.w);
+        mx.x = fmaxf(ca.x + A.w, cb.x + A.w); mx.y = fmaxf(ca.y + A.w, cb.y + A.w); mx.z = fmaxf(ca.z + A.w, cb.z + A.w);
+    } else if (opc == OP_CUBOID) {
+        mn = A; mx = B;
+    } else {
+        const float lo = B.x - 0.0001f, hi = B.x + 0.0001f;
+        if (opc == OP_RECT_XY) { mn.x = A.x; mn.y = A.z; mn.z = lo; mx.x = A.y; mx.y = A.w; mx.z = hi; }
+        else if (opc == OP_RECT_YZ) { mn.x = lo; mn.y = A.x; mn.z = A.z; mx.x = hi; mx.y = A.y; mx.z = A.w; }
+        else { mn.x = A.x; mn.y = lo; mn.z = A.z; mx.x = A.y; mx.y = hi; mx.z = A.w; }  // rect.rs:98-101 as written
+    }
+    return box_hit_reference(mn, mx, cur, k, tmin, t);
+}
+
+// Closest hit of the tree whose first node is `base` for t in [tmin, closest]; leaves are primitive records of the op
+// stream.  Box tests only prune (every box is sound), so any visit order finds the same closest t; exact ties are
+// settled by tie_goes_to_later.  (ts, te): the BvhNode's time interval.  Out of line: one copy per kernel.
+__device__ __noinline__ TreeHit bvh2_walk(const DeviceScene& S, int base, Ray cur, float tmin, float closest, int best_pc,
+                                          float ts, float te) {
+    const RayK k = make_rayk(cur);
+    TreeHit h;
+    h.t = closest; h.pc = best_pc; h.face = 0;
+    int stack_ref[kBvh2Stack];
+    float stack_t[kBvh2Stack];
+    int sp = 0;
+    int ref = 0;  // the tree's first node is its root
+    const uint4* nodes = S.nodes + 2 * (size_t)base;
+    for (;;) {
+        if (ref >= 0) {
+            const uint4 L = __ldg(nodes + 2 * ref), R = __ldg(nodes + 2 * ref + 1);
+            float llo, lhi, rlo, rhi;
+            slab16(L.x, L.y, L.z, cur, k, tmin, h.t, llo, lhi);
+            slab16(R.x, R.y, R.z, cur, k, tmin, h.t, rlo, rhi);
+            const bool hl = !(lhi < llo), hr = !(rhi < rlo);
+            if (hl && hr) {
+                const bool right_first = rlo < llo;
+                stack_ref[sp] = right_first ? (int)L.w : (int)R.w;
+                stack_t[sp] = right_first ? llo : rlo;
+                sp++;
+                ref = right_first ? (int)R.w : (int)L.w;
+                continue;
+            }
+            if (hl || hr) {
+                ref = hl ? (int)L.w : (int)R.w;
+                continue;
+            }
+        } else {
+            const int pc = ~ref;
+            float4 A, B;
+            load_op(S, pc, A, B);
+            const uint32_t opc = __float_as_uint(B.w) & 0xffu;
+            float t = 0.0f;
+            int face = 0;
+            bool hit;
+            if (opc == OP_SPHERE) {
+                hit = sphere_test(v3(A.x, A.y, A.z), A.w, cur, k, tmin, h.t, t);
+            } else if (opc == OP_MSPHERE) {
+                float4 C, D;
+                load_op(S, pc + 1, C, D);
+                hit = sphere_test(msphere_center(v3(A.x, A.y, A.z), v3(C.x, C.y, C.z), C.w, D.x, cur.time), A.w, cur, k, tmin, h.t, t);
+            } else if (opc == OP_CUBOID) {
+                hit = cuboid_test(v3(A.x, A.y, A.z), v3(B.x, B.y, B.z), cur, k, tmin, h.t, t, face);
+            } else if (opc == OP_RECT_XY) {
+                hit = rect_test(cur.o.z, cur.d.z, k.inv.z, cur.o.x, cur.d.x, cur.o.y, cur.d.y, A.x, A.y, A.z, A.w, B.x, tmin, h.t, t);
+            } else if (opc == OP_RECT_YZ) {
+                hit = rect_test(cur.o.x, cur.d.x, k.inv.x, cur.o.y, cur.d.y, cur.o.z, cur.d.z, A.x, A.y, A.z, A.w, B.x, tmin, h.t, t);
+            } else {
+                hit = rect_test(cur.o.y, cur.d.y, k.inv.y, cur.o.z, cur.d.z, cur.o.x, cur.d.x, A.x, A.y, A.z, A.w, B.x, tmin, h.t, t);
+            }
+            if (hit) {  // the primitive tests accept t <= closest
+                bool take = t < h.t || h.pc < 0;
+                if (!take && !(t > h.t)) {  // exact tie (or a NaN, Q15) with the hit held so far
+                    const bool later_wins = tie_goes_to_later(S, pc > h.pc ? pc : h.pc, cur, tmin, t, ts, te);
+                    take = (pc > h.pc) == later_wins;
+                }
+                if (take) { h.t = t; h.pc = pc; h.face = face; }
+            }
+        }
+        // next: the nearest postponed child that can still hold a closer (or equal) hit
+        do {
+            if (sp == 0) return h;
+            --sp;
+            ref = stack_ref[sp];
+        } while (stack_t[sp] > h.t);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Traversal: a forward-only interpreter over the op stream.
 // ------------------------------------------------------------------------------------------------
 struct Best {
@@ -459,6 +597,15 @@ __device__ __forceinline__ bool traverse(const DeviceScene& S, int pc, const int
                 k = make_rayk(cur);
                 const int run = (int)(w7 >> 8);
                 pc += run > 0 ? run : 1;
+                break;
+            }
+            case OP_BVH: {
+                const TreeHit th = bvh2_walk(S, __float_as_int(A.x), cur, tmin, closest, kInner ? -1 : best.pc, B.x, B.y);
+                if (th.pc != (kInner ? -1 : best.pc)) {
+                    closest = th.t; any = true;
+                    if (!kInner) { best.t = th.t; best.pc = th.pc; best.face = th.face; best.ctx = cur_ctx; }
+                }
+                pc = (int)(w7 >> 8);
                 break;
             }
             case OP_MEDIUM: case OP_MEDIUM_SPHERE: {
@@ -657,6 +804,17 @@ __device__ __forceinline__ bool traverse_uniform(const DeviceScene& S, const int
                     k = make_rayk(cur);
                     const int run = (int)(w7 >> 8);
                     pc = upc + (run > 0 ? run : 1);
+                }
+                break;
+            }
+            case OP_BVH: {
+                if (me) {
+                    const TreeHit th = bvh2_walk(S, __float_as_int(A.x), cur, tmin, closest, kInner ? -1 : best.pc, B.x, B.y);
+                    if (th.pc != (kInner ? -1 : best.pc)) {
+                        closest = th.t; any = true;
+                        if (!kInner) { best.t = th.t; best.pc = th.pc; best.face = th.face; best.ctx = cur_ctx; }
+                    }
+                    pc = (int)(w7 >> 8);
                 }
                 break;
             }

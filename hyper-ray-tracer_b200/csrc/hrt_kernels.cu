@@ -1026,6 +1026,7 @@ static DeviceScene to_device_scene(const hrt::DeviceSceneHost& h) {
     DeviceScene S;
     S.ops = reinterpret_cast<const float4*>(h.ops);
     S.box16 = reinterpret_cast<const uint4*>(h.box16);
+    S.nodes = reinterpret_cast<const uint4*>(h.nodes);
     S.ctxs = reinterpret_cast<const Ctx*>(h.ctxs);
     S.mats = reinterpret_cast<const Material*>(h.mats);
     S.texs = reinterpret_cast<const Texture*>(h.texs);

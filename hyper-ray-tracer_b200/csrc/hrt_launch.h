@@ -12,6 +12,7 @@ namespace hrt {
 struct DeviceSceneHost {  // mirrors HRT_NS::DeviceScene field for field (checked by static_assert in the .cu)
     const void* ops;
     const void* box16;
+    const void* nodes;
     const void* ctxs;
     const void* mats;
     const void* texs;

@@ -116,7 +116,7 @@ __device__ __forceinline__ void medium_finish(const DeviceScene& S, Lane& L, flo
     }
 }
 
-// TRANSLATE / ROTATE / POP / MEDIUM / MEDIUM_SPHERE
+// TRANSLATE / ROTATE / POP / MEDIUM / MEDIUM_SPHERE / BVH
 __device__ __forceinline__ void step_misc(const DeviceScene& S, Lane& L, const Ray& world, float tmin, bool reference_boxes,
                                           const MediumXi& xi) {
     const uint32_t w7 = __float_as_uint(L.B.w);
@@ -130,6 +130,12 @@ __device__ __forceinline__ void step_misc(const DeviceScene& S, Lane& L, const R
         L.k = make_rayk(L.cur);
         const int run = (int)(w7 >> 8);
         L.pc += run > 0 ? run : 1;
+    } else if (opc == OP_BVH) {  // a sound BvhNode as a two-child tree: per-ray stack walk (hrt_device.cuh bvh2_walk)
+        const TreeHit th = bvh2_walk(S, __float_as_int(L.A.x), L.cur, tmin, L.closest, L.best_pc, L.B.x, L.B.y);
+        if (th.pc != L.best_pc) {
+            L.closest = th.t; L.best_pc = th.pc; L.best_face = th.face; L.best_ctx = L.ctx;
+        }
+        L.pc = (int)(w7 >> 8);
     } else {  // constant_medium.rs:34-76
         const int end = (int)(w7 >> 8);
         bool done = false;

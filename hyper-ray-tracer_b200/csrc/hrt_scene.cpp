@@ -171,8 +171,9 @@ static bool ref_box(const hrt_scene& s, int id, float ts, float te, bool truth, 
 }
 
 // BvhNode::new (bvh_node.rs:27-63).  sort_unstable_by is an insertion sort for n <= 20 in rustc's
-// implementation (stable order); for larger n the tie order is toolchain-defined.  A stable sort is used
-// throughout; ties cannot change hit results on sound boxes.
+// implementation (stable order); for larger n the order of EQUAL keys is toolchain-defined.  A stable sort is used
+// throughout, so the tree is the reference's up to the order of equal keys; ties cannot change hit results on sound
+// boxes.
 static int32_t build_bvh(const hrt_scene& s, BvhTree& tree, std::vector<int32_t> objs, float ts, float te) {
     std::pair<int, float> ranges[3];
     for (int axis = 0; axis < 3; ++axis) {  // axis_range, bvh_node.rs:83-100
@@ -217,14 +218,14 @@ static int32_t build_bvh(const hrt_scene& s, BvhTree& tree, std::vector<int32_t>
     return (int32_t)tree.nodes.size() - 1;
 }
 
-// Opt-in alternative to BvhNode::new's longest-axis median split (hrt_scene_set_bvh_builder): a full-sweep surface-area
-// heuristic over the three centroid orders.  The node boxes are still unions of the leaves' reference boxes; only the
-// topology — and with it the depth-first order of the leaves — changes.
+// Topology of the OP_BVH trees (hrt_types.h): a full-sweep surface-area heuristic over the three centroid orders down to
+// kBvh2SahDepth, balanced object-median splits below that (bounds the tree depth, hence the per-ray stack).  The node
+// boxes are unions of the leaves' reference boxes; only the topology differs from BvhNode::new's.
 static float half_area(const Box3& b) {
     const float dx = b.mx[0] - b.mn[0], dy = b.mx[1] - b.mn[1], dz = b.mx[2] - b.mn[2];
     return dx * dy + dy * dz + dz * dx;
 }
-static int32_t build_bvh_sah(const hrt_scene& s, BvhTree& tree, std::vector<int32_t> objs, float ts, float te) {
+static int32_t build_bvh_sah(const hrt_scene& s, BvhTree& tree, std::vector<int32_t> objs, float ts, float te, int depth) {
     const size_t n = objs.size();
     BvhTreeNode node;
     if (n == 1) {
@@ -247,25 +248,40 @@ static int32_t build_bvh_sah(const hrt_scene& s, BvhTree& tree, std::vector<int3
         }
         std::stable_sort(items.begin(), items.end(), [](const Item& a, const Item& b) { return a.key < b.key; });
     };
-    for (int axis = 0; axis < 3; ++axis) {
-        sort_axis(axis);
-        Box3 acc = items[n - 1].box;
-        right_area[n - 1] = half_area(acc);
-        for (size_t i = n - 1; i-- > 0;) { acc = surrounding_box(acc, items[i].box); right_area[i] = half_area(acc); }
-        acc = items[0].box;
-        for (size_t i = 1; i < n; ++i) {  // left = [0, i), right = [i, n)
-            const float cost = half_area(acc) * (float)i + right_area[i] * (float)(n - i);
-            if (cost < best_cost) { best_cost = cost; best_axis = axis; best_split = i; }
-            acc = surrounding_box(acc, items[i].box);
+    if (depth < kBvh2SahDepth) {
+        for (int axis = 0; axis < 3; ++axis) {
+            sort_axis(axis);
+            Box3 acc = items[n - 1].box;
+            right_area[n - 1] = half_area(acc);
+            for (size_t i = n - 1; i-- > 0;) { acc = surrounding_box(acc, items[i].box); right_area[i] = half_area(acc); }
+            acc = items[0].box;
+            for (size_t i = 1; i < n; ++i) {  // left = [0, i), right = [i, n)
+                const float cost = half_area(acc) * (float)i + right_area[i] * (float)(n - i);
+                if (cost < best_cost) { best_cost = cost; best_axis = axis; best_split = i; }
+                acc = surrounding_box(acc, items[i].box);
+            }
         }
+    } else {  // longest axis of the centroid range, object median
+        float ext[3];
+        for (int axis = 0; axis < 3; ++axis) {
+            float mn = FMAX, mx = -FMAX;
+            for (int32_t id : objs) {
+                Box3 b;
+                ref_box(s, id, ts, te, false, b);
+                mn = std::fmin(mn, b.mn[axis] + b.mx[axis]);
+                mx = std::fmax(mx, b.mn[axis] + b.mx[axis]);
+            }
+            ext[axis] = mx - mn;
+        }
+        best_axis = ext[0] >= ext[1] ? (ext[0] >= ext[2] ? 0 : 2) : (ext[1] >= ext[2] ? 1 : 2);
     }
     sort_axis(best_axis);
     std::vector<int32_t> l, r;
     for (size_t i = 0; i < best_split; ++i) l.push_back(items[i].id);
     for (size_t i = best_split; i < n; ++i) r.push_back(items[i].id);
     items.clear();
-    const int32_t ri = build_bvh_sah(s, tree, std::move(r), ts, te);
-    const int32_t li = build_bvh_sah(s, tree, std::move(l), ts, te);
+    const int32_t ri = build_bvh_sah(s, tree, std::move(r), ts, te, depth + 1);
+    const int32_t li = build_bvh_sah(s, tree, std::move(l), ts, te, depth + 1);
     node.left = li;
     node.right = ri;
     node.box = surrounding_box(tree.nodes[li].box, tree.nodes[ri].box);
@@ -290,29 +306,33 @@ static uint32_t count_of(const hrt_scene& s, int id) {
 // ------------------------------------------------------------------------------------------------
 // Flattener
 // ------------------------------------------------------------------------------------------------
+static uint16_t float_to_half_directed(float x, bool up);
+
 struct Flattener {
-    hrt_scene& s;
+    const hrt_scene& s;
+    FlatScene& f;
+    const bool trees;  // sound BVHs of plain primitives become OP_BVH trees
     std::string error;
     bool in_medium = false;
-    explicit Flattener(hrt_scene& sc) : s(sc) {}
+    Flattener(const hrt_scene& sc, FlatScene& out, bool bvh_trees) : s(sc), f(out), trees(bvh_trees) {}
 
-    int32_t pc() const { return (int32_t)s.ops.size(); }
+    int32_t pc() const { return (int32_t)f.ops.size(); }
     Op& push(uint32_t opcode) {
         Op op;
         std::memset(&op, 0, sizeof(op));
         op.u[7] = opcode;
-        s.ops.push_back(op);
-        return s.ops.back();
+        f.ops.push_back(op);
+        return f.ops.back();
     }
     int32_t new_ctx(int32_t parent, int32_t op_pc) {
-        Ctx c = s.ctxs[parent];
+        Ctx c = f.ctxs[parent];
         if (c.depth >= kMaxCtxDepth) { error = "Translation/Rotation nesting deeper than 6"; return -1; }
         c.op_pc[c.depth] = op_pc;
         c.depth += 1;
         c.parent = parent;
-        s.ctxs.push_back(c);
-        s.max_ctx_depth = std::max(s.max_ctx_depth, c.depth);
-        return (int32_t)s.ctxs.size() - 1;
+        f.ctxs.push_back(c);
+        f.max_ctx_depth = std::max(f.max_ctx_depth, c.depth);
+        return (int32_t)f.ctxs.size() - 1;
     }
 
     bool emit(int32_t id, int32_t ctx) {
@@ -322,7 +342,7 @@ struct Flattener {
                 Op& op = push(OP_SPHERE);
                 op.f[0] = o.c0[0]; op.f[1] = o.c0[1]; op.f[2] = o.c0[2]; op.f[3] = o.r;
                 op.i[4] = o.mat; op.i[5] = id;
-                s.n_prim_ops++;
+                f.n_prim_ops++;
                 return true;
             }
             case OBJ_MSPHERE: {
@@ -331,7 +351,7 @@ struct Flattener {
                 op.i[4] = o.mat; op.i[5] = id;
                 Op& aux = push(OP_MSPHERE_AUX);
                 aux.f[0] = o.c1[0]; aux.f[1] = o.c1[1]; aux.f[2] = o.c1[2]; aux.f[3] = o.t0; aux.f[4] = o.t1;
-                s.n_prim_ops++;
+                f.n_prim_ops++;
                 return true;
             }
             case OBJ_RECT: {
@@ -339,7 +359,7 @@ struct Flattener {
                 Op& op = push(opc);
                 op.f[0] = o.a0; op.f[1] = o.a1; op.f[2] = o.b0; op.f[3] = o.b1; op.f[4] = o.k;
                 op.i[5] = o.mat; op.i[6] = id;
-                s.n_prim_ops++;
+                f.n_prim_ops++;
                 return true;
             }
             case OBJ_CUBOID: {
@@ -348,7 +368,7 @@ struct Flattener {
                 op.f[0] = o.c0[0]; op.f[1] = o.c0[1]; op.f[2] = o.c0[2]; op.i[3] = o.mat;
                 op.f[4] = o.c1[0]; op.f[5] = o.c1[1]; op.f[6] = o.c1[2];
                 op.u[7] = OP_CUBOID | ((uint32_t)id << 8);
-                s.n_prim_ops++;
+                f.n_prim_ops++;
                 return true;
             }
             case OBJ_TRANSLATE: {
@@ -378,17 +398,17 @@ struct Flattener {
                 int32_t at = pc();
                 {
                     Op& op = push(OP_MEDIUM);
-                    op.f[0] = o.neg_inv_density; op.i[1] = o.mat; op.i[2] = s.n_media; op.i[3] = id;
+                    op.f[0] = o.neg_inv_density; op.i[1] = o.mat; op.i[2] = f.n_media; op.i[3] = id;
                 }
-                s.n_media++;
+                f.n_media++;
                 in_medium = true;
                 bool ok = emit(o.child, ctx);
                 in_medium = false;
                 if (!ok) return false;
                 if (pc() >= (1 << 24)) { error = "op stream longer than 2^24 records"; return false; }
                 {
-                    const bool single_sphere = (pc() == at + 2) && ((s.ops[at + 1].u[7] & 0xffu) == OP_SPHERE);
-                    s.ops[at].u[7] = (single_sphere ? OP_MEDIUM_SPHERE : OP_MEDIUM) | ((uint32_t)pc() << 8);
+                    const bool single_sphere = (pc() == at + 2) && ((f.ops[at + 1].u[7] & 0xffu) == OP_SPHERE);
+                    f.ops[at].u[7] = (single_sphere ? OP_MEDIUM_SPHERE : OP_MEDIUM) | ((uint32_t)pc() << 8);
                 }
                 return true;
             }
@@ -400,45 +420,101 @@ struct Flattener {
                 return true;
             }
             case OBJ_BVH: {
-                if ((s.bvh_builder == HRT_BVH_SAH && all_leaves_sound(o)) ||
-                    (s.bvh_builder == HRT_BVH_SAH_SPHERES && distinct_spheres_only(o))) {
-                    // every leaf box contains its leaf, so every union of leaf boxes is sound in ANY topology and the
-                    // closest hit does not depend on it (only the winner of an exact tie between coincident surfaces
-                    // does: the leaf that comes later in the stream — documented in include/hrt.h)
-                    BvhTree alt;
-                    alt.root = build_bvh_sah(s, alt, o.children, o.t0, o.t1);
-                    s.n_bvh_rebuilt++;
-                    return emit_bvh(alt, o.t0, o.t1, alt.root, ctx);
-                }
+                if (trees && tree_eligible(o)) return emit_tree(o, ctx);
                 return emit_bvh(o.bvh, o.t0, o.t1, o.bvh.root, ctx);
             }
         }
         return false;
     }
 
-    // HRT_BVH_SAH_SPHERES: every leaf is a plain sphere or moving sphere and no two are the same sphere, so no two
-    // surfaces of the BVH coincide and its depth-first order cannot decide a (systematic) tie.  Sphere boxes are sound.
-    bool distinct_spheres_only(const Obj& bvh) {
-        std::vector<std::array<float, 9>> keys;
-        for (int32_t id : bvh.children) {
-            const Obj& c = s.objects[id];
-            if (c.kind != OBJ_SPHERE && c.kind != OBJ_MSPHERE) return false;
-            // a "moving" sphere that does not move is the same surface as the static one
-            const bool moving = c.kind == OBJ_MSPHERE && (c.c0[0] != c.c1[0] || c.c0[1] != c.c1[1] || c.c0[2] != c.c1[2]);
-            keys.push_back({c.c0[0], c.c0[1], c.c0[2], moving ? c.c1[0] : c.c0[0], moving ? c.c1[1] : c.c0[1],
-                            moving ? c.c1[2] : c.c0[2], c.r, moving ? c.t0 : 0.0f, moving ? c.t1 : 0.0f});
+    // OP_BVH trees: every leaf is a plain primitive whose reference box contains it (so every union of leaf boxes is
+    // sound in ANY topology, and the closest hit does not depend on the visit order), and there are enough of them for a
+    // per-ray stack walk to pay.
+    bool tree_eligible(const Obj& bvh) {
+        if (bvh.children.size() < 4) return false;
+        {
+            std::vector<int32_t> ids = bvh.children;
+            std::sort(ids.begin(), ids.end());
+            if (std::adjacent_find(ids.begin(), ids.end()) != ids.end()) return false;  // the same object twice
         }
-        std::sort(keys.begin(), keys.end());
-        return std::adjacent_find(keys.begin(), keys.end()) == keys.end();
-    }
-
-    bool all_leaves_sound(const Obj& bvh) {
         for (const BvhTreeNode& n : bvh.bvh.nodes) {
             if (n.leaf_obj < 0) continue;
+            const ObjKind k = s.objects[n.leaf_obj].kind;
+            if (k != OBJ_SPHERE && k != OBJ_MSPHERE && k != OBJ_RECT && k != OBJ_CUBOID) return false;
             Box3 truth;
             if (!ref_box(s, n.leaf_obj, bvh.t0, bvh.t1, true, truth) || !contains(n.box, truth)) return false;
+            for (int a = 0; a < 3; ++a)
+                if (std::isnan(n.box.mn[a]) || std::isnan(n.box.mx[a])) return false;
         }
         return true;
+    }
+
+    static void box_to_half(const Box3& b, uint16_t h[6]) {
+        for (int a = 0; a < 3; ++a) {
+            h[a] = float_to_half_directed(b.mn[a], false);
+            h[3 + a] = float_to_half_directed(b.mx[a], true);
+        }
+    }
+    // Lay the inner nodes of `t` out depth-first from `node` (an inner node) and return its index relative to `base`.
+    int32_t emit_tree_nodes(const BvhTree& t, int32_t node, const std::vector<int32_t>& leaf_pc, int32_t base, int depth, int& max_depth) {
+        const BvhTreeNode& n = t.nodes[node];
+        const int32_t at = (int32_t)f.nodes.size();
+        f.nodes.push_back(Bvh2Node{});
+        max_depth = std::max(max_depth, depth);
+        const BvhTreeNode& l = t.nodes[n.left];
+        const BvhTreeNode& r = t.nodes[n.right];
+        const int32_t li = l.leaf_obj >= 0 ? ~leaf_pc[l.leaf_obj] : emit_tree_nodes(t, n.left, leaf_pc, base, depth + 1, max_depth);
+        const int32_t ri = r.leaf_obj >= 0 ? ~leaf_pc[r.leaf_obj] : emit_tree_nodes(t, n.right, leaf_pc, base, depth + 1, max_depth);
+        Bvh2Node& out = f.nodes[at];
+        box_to_half(l.box, out.lbox);
+        box_to_half(r.box, out.rbox);
+        out.left = li;
+        out.right = ri;
+        return at - base;
+    }
+    // [BOX root, skip = end] [BVH] [leaf primitive records in the REFERENCE's depth-first order] end:
+    bool emit_tree(const Obj& o, int32_t ctx) {
+        const BvhTreeNode& root = o.bvh.nodes[o.bvh.root];
+        const int32_t box_at = pc();
+        {
+            Op& op = push(OP_BOX);
+            op.f[0] = root.box.mn[0]; op.f[1] = root.box.mn[1]; op.f[2] = root.box.mn[2];
+            op.f[4] = root.box.mx[0]; op.f[5] = root.box.mx[1]; op.f[6] = root.box.mx[2];
+        }
+        f.n_box_ops++;
+        const int32_t at = pc();
+        push(OP_BVH);
+        // leaves in the reference's own visit order: a larger pc is "later in the reference's order" (the tie rule)
+        std::vector<int32_t> order;
+        leaf_order_of(o.bvh, o.bvh.root, order);
+        std::vector<int32_t> leaf_pc(s.objects.size(), -1);
+        for (int32_t id : order) {
+            leaf_pc[id] = pc();
+            if (!emit(id, ctx)) return false;
+        }
+        if (pc() >= (1 << 24)) { error = "op stream longer than 2^24 records"; return false; }
+        BvhTree alt;
+        alt.root = build_bvh_sah(s, alt, o.children, o.t0, o.t1, 0);
+        const int32_t base = (int32_t)f.nodes.size();
+        int max_depth = 0;
+        emit_tree_nodes(alt, alt.root, leaf_pc, base, 1, max_depth);
+        if (max_depth > kBvh2Stack) { error = "BVH tree deeper than the traversal stack"; return false; }
+        Op& op = f.ops[at];
+        op.i[0] = base;
+        op.i[1] = (int32_t)f.nodes.size() - base;
+        op.i[2] = (int32_t)order.size();
+        op.i[3] = max_depth;
+        op.f[4] = o.t0; op.f[5] = o.t1;  // the BvhNode's time interval: moving-sphere leaf boxes depend on it
+        op.u[7] = OP_BVH | ((uint32_t)pc() << 8);
+        f.ops[box_at].u[7] = OP_BOX | ((uint32_t)pc() << 8);
+        f.n_bvh_trees++;
+        f.max_tree_depth = std::max(f.max_tree_depth, max_depth);
+        return true;
+    }
+    static void leaf_order_of(const BvhTree& t, int32_t node, std::vector<int32_t>& out) {
+        const BvhTreeNode& n = t.nodes[node];
+        if (n.leaf_obj >= 0) out.push_back(n.leaf_obj);
+        else { leaf_order_of(t, n.left, out); leaf_order_of(t, n.right, out); }
     }
 
     bool emit_bvh(const BvhTree& tree, float t0, float t1, int32_t node_index, int32_t ctx) {
@@ -452,8 +528,8 @@ struct Flattener {
             op.f[0] = n.box.mn[0]; op.f[1] = n.box.mn[1]; op.f[2] = n.box.mn[2];
             op.f[4] = n.box.mx[0]; op.f[5] = n.box.mx[1]; op.f[6] = n.box.mx[2];
         }
-        s.n_box_ops++;
-        if (!sound) s.n_loose_boxes++;
+        f.n_box_ops++;
+        if (!sound) f.n_loose_boxes++;
         if (n.leaf_obj >= 0) {
             if (!emit(n.leaf_obj, ctx)) return false;
         } else {
@@ -461,7 +537,7 @@ struct Flattener {
             if (!emit_bvh(tree, t0, t1, n.right, ctx)) return false;
         }
         if (pc() >= (1 << 24)) { error = "op stream longer than 2^24 records"; return false; }
-        s.ops[at].u[7] = (s.ops[at].u[7] & 0xffu) | ((uint32_t)pc() << 8);
+        f.ops[at].u[7] = (f.ops[at].u[7] & 0xffu) | ((uint32_t)pc() << 8);
         return true;
     }
 
@@ -503,7 +579,7 @@ static uint16_t float_to_half_directed(float x, bool up) {
     return (uint16_t)(mag | (neg ? 0x8000u : 0u));
 }
 
-static void build_box16(hrt_scene& s) {
+static void build_box16(FlatScene& s) {
     s.box16.assign(s.ops.size(), Box16{});
     for (size_t i = 0; i < s.ops.size(); ++i) {
         const Op& op = s.ops[i];
@@ -563,12 +639,7 @@ int32_t hrt_scene_create(hrt_scene** out) {
     if (!out) return fail(HRT_ERR_INVALID, "null out pointer");
     *out = new hrt_scene();
     if (const char* env = std::getenv("HRT_BVH_BUILDER"))  // diagnostic default for scenes the caller does not configure
-        (*out)->bvh_builder = std::strcmp(env, "sah") == 0 ? HRT_BVH_SAH
-                              : (std::strcmp(env, "sah-spheres") == 0 ? HRT_BVH_SAH_SPHERES : HRT_BVH_REFERENCE);
-    Ctx root;
-    std::memset(&root, 0, sizeof(root));
-    root.parent = -1;
-    (*out)->ctxs.push_back(root);
+        (*out)->bvh_builder = std::strcmp(env, "reference") == 0 ? HRT_BVH_REFERENCE : HRT_BVH_TREES;
     return HRT_OK;
 }
 void hrt_scene_destroy(hrt_scene* scene) { delete scene; }
@@ -775,6 +846,8 @@ int32_t hrt_bvh(hrt_scene* s, const int32_t* children, int32_t n, float ts, floa
         Box3 b;
         if (!ref_box(*s, children[i], ts, te, false, b))
             return fail(HRT_ERR_INVALID, "bvh: object without a bounding box");  // bvh_node.rs:41-43,77-79 panic
+        for (int a = 0; a < 3; ++a)  // box_compare's partial_cmp().unwrap() panics on NaN keys (bvh_node.rs:70-76)
+            if (std::isnan(b.mn[a]) || std::isnan(b.mx[a])) return fail(HRT_ERR_INVALID, "bvh: NaN bounding box");
         o.children.push_back(children[i]);
     }
     o.bvh.root = build_bvh(*s, o.bvh, o.children, ts, te);
@@ -783,18 +856,51 @@ int32_t hrt_bvh(hrt_scene* s, const int32_t* children, int32_t n, float ts, floa
 
 int32_t hrt_scene_set_bvh_builder(hrt_scene* s, int32_t builder) {
     HRT_CHECK_SCENE(s);
-    if (builder != HRT_BVH_REFERENCE && builder != HRT_BVH_SAH && builder != HRT_BVH_SAH_SPHERES) return fail(HRT_ERR_INVALID, "set_bvh_builder: unknown builder");
+    if (builder != HRT_BVH_REFERENCE && builder != HRT_BVH_TREES) return fail(HRT_ERR_INVALID, "set_bvh_builder: unknown builder");
     s->bvh_builder = builder;
+    return HRT_OK;
+}
+
+// Flatten the tree under `root` into `f` (hrt_types.h).
+static int32_t flatten(const hrt_scene* s, int32_t root, FlatScene& f, bool trees) {
+    f = FlatScene{};
+    Ctx world;
+    std::memset(&world, 0, sizeof(world));
+    world.parent = -1;
+    f.ctxs.push_back(world);
+    Flattener fl(*s, f, trees);
+    if (!fl.emit(root, 0)) {
+        f = FlatScene{};
+        return fail(HRT_ERR_UNSUPPORTED, "commit: " + fl.error);
+    }
+    fl.push(OP_END);
+    // Consecutive ray-space pushes (Translation(Rotation(x))) and consecutive pops are entered / left in ONE step: the
+    // first record of a run carries the run's final context and its length; the others stay in the stream as data for
+    // the context replay (ray_in_ctx) but are never executed.
+    auto is_push = [](uint32_t o) { return o == OP_TRANSLATE || o == OP_ROTATE; };
+    const size_t n = f.ops.size();
+    for (size_t i = 0; i < n;) {
+        const uint32_t o = f.ops[i].u[7] & 0xffu;
+        if (is_push(o) || o == OP_POP) {
+            size_t j = i;
+            while (j + 1 < n) {
+                const uint32_t o2 = f.ops[j + 1].u[7] & 0xffu;
+                if (is_push(o) ? is_push(o2) : (o2 == OP_POP)) ++j; else break;
+            }
+            f.ops[i].i[3] = f.ops[j].i[3];
+            f.ops[i].u[7] = o | ((uint32_t)(j - i + 1) << 8);
+            i = j + 1;
+        } else {
+            ++i;
+        }
+    }
+    build_box16(f);
     return HRT_OK;
 }
 
 int32_t hrt_scene_commit(hrt_scene* s, int32_t root) {
     HRT_CHECK_SCENE(s);
     if (!obj_ok(s, root)) return fail(HRT_ERR_INVALID, "commit: unknown root id");
-    s->ops.clear();
-    s->ctxs.resize(1);
-    s->n_box_ops = s->n_loose_boxes = s->n_prim_ops = s->n_media = s->max_ctx_depth = 0;
-    s->n_bvh_rebuilt = 0;
     s->any_bvh = false;
     s->time_min = -FMAX;
     s->time_max = FMAX;
@@ -804,35 +910,11 @@ int32_t hrt_scene_commit(hrt_scene* s, int32_t root) {
             s->time_min = std::fmax(s->time_min, std::fmin(o.t0, o.t1));
             s->time_max = std::fmin(s->time_max, std::fmax(o.t0, o.t1));
         }
-    Flattener f(*s);
-    if (!f.emit(root, 0)) {
-        s->ops.clear();
-        return fail(HRT_ERR_UNSUPPORTED, "commit: " + f.error);
-    }
-    f.push(OP_END);
-    // Consecutive ray-space pushes (Translation(Rotation(x))) and consecutive pops are entered / left in ONE step: the
-    // first record of a run carries the run's final context and its length; the others stay in the stream as data for
-    // the context replay (ray_in_ctx) but are never executed.
-    {
-        auto is_push = [](uint32_t o) { return o == OP_TRANSLATE || o == OP_ROTATE; };
-        const size_t n = s->ops.size();
-        for (size_t i = 0; i < n;) {
-            const uint32_t o = s->ops[i].u[7] & 0xffu;
-            if (is_push(o) || o == OP_POP) {
-                size_t j = i;
-                while (j + 1 < n) {
-                    const uint32_t o2 = s->ops[j + 1].u[7] & 0xffu;
-                    if (is_push(o) ? is_push(o2) : (o2 == OP_POP)) ++j; else break;
-                }
-                s->ops[i].i[3] = s->ops[j].i[3];
-                s->ops[i].u[7] = o | ((uint32_t)(j - i + 1) << 8);
-                i = j + 1;
-            } else {
-                ++i;
-            }
-        }
-    }
-    build_box16(*s);
+    int32_t rc = flatten(s, root, s->ref, false);
+    if (rc == HRT_OK) rc = flatten(s, root, s->fast, s->bvh_builder == HRT_BVH_TREES);
+    if (rc != HRT_OK) return rc;
+    if (s->ref.n_media != s->fast.n_media || s->ref.n_prim_ops != s->fast.n_prim_ops)
+        return fail(HRT_ERR_UNSUPPORTED, "commit: the two flattened forms disagree (internal error)");
     s->root = root;
     s->committed = true;
     return HRT_OK;
@@ -846,34 +928,48 @@ int32_t hrt_scene_count(const hrt_scene* s) {
 int32_t hrt_scene_get_info(const hrt_scene* s, hrt_scene_info* out) {
     if (!s || !out) return fail(HRT_ERR_INVALID, "null argument");
     if (!s->committed) return fail(HRT_ERR_STATE, "scene not committed");
-    out->n_ops = (int32_t)s->ops.size();
-    out->n_box_ops = s->n_box_ops;
-    out->n_loose_boxes = s->n_loose_boxes;
-    out->n_prim_ops = s->n_prim_ops;
+    out->n_ops = (int32_t)s->ref.ops.size();
+    out->n_box_ops = s->ref.n_box_ops;
+    out->n_loose_boxes = s->ref.n_loose_boxes;
+    out->n_prim_ops = s->ref.n_prim_ops;
     out->n_materials = (int32_t)s->materials.size();
     out->n_textures = (int32_t)s->textures.size();
     out->n_noise_tables = (int32_t)s->noise_tables.size();
     out->n_images = (int32_t)s->images.size();
-    out->n_media = s->n_media;
-    out->n_contexts = (int32_t)s->ctxs.size();
-    out->max_context_depth = s->max_ctx_depth;
+    out->n_media = s->ref.n_media;
+    out->n_contexts = (int32_t)s->ref.ctxs.size();
+    out->max_context_depth = s->ref.max_ctx_depth;
     out->time_min = s->time_min;
     out->time_max = s->time_max;
-    out->n_bvh_rebuilt = s->n_bvh_rebuilt;
+    out->n_fast_ops = (int32_t)s->fast.ops.size();
+    out->n_fast_box_ops = s->fast.n_box_ops;
+    out->n_bvh_trees = s->fast.n_bvh_trees;
+    out->n_tree_nodes = (int32_t)s->fast.nodes.size();
+    out->max_tree_depth = s->fast.max_tree_depth;
     return HRT_OK;
 }
-int32_t hrt_scene_get_box16(const hrt_scene* s, void* out, int32_t cap_ops) {
+static const FlatScene* pick_flat(const hrt_scene* s, int32_t which) { return which == HRT_STREAM_FAST ? &s->fast : &s->ref; }
+int32_t hrt_scene_get_box16(const hrt_scene* s, int32_t which, void* out, int32_t cap_ops) {
     if (!s) return fail(HRT_ERR_INVALID, "null scene");
     if (!s->committed) return fail(HRT_ERR_STATE, "scene not committed");
-    int32_t n = (int32_t)s->box16.size();
-    if (out && cap_ops > 0) std::memcpy(out, s->box16.data(), sizeof(Box16) * (size_t)std::min(n, cap_ops));
+    const FlatScene* f = pick_flat(s, which);
+    int32_t n = (int32_t)f->box16.size();
+    if (out && cap_ops > 0) std::memcpy(out, f->box16.data(), sizeof(Box16) * (size_t)std::min(n, cap_ops));
     return n;
 }
-int32_t hrt_scene_get_ops(const hrt_scene* s, void* out, int32_t cap_ops) {
+int32_t hrt_scene_get_ops(const hrt_scene* s, int32_t which, void* out, int32_t cap_ops) {
     if (!s) return fail(HRT_ERR_INVALID, "null scene");
     if (!s->committed) return fail(HRT_ERR_STATE, "scene not committed");
-    int32_t n = (int32_t)s->ops.size();
-    if (out && cap_ops > 0) std::memcpy(out, s->ops.data(), sizeof(Op) * (size_t)std::min(n, cap_ops));
+    const FlatScene* f = pick_flat(s, which);
+    int32_t n = (int32_t)f->ops.size();
+    if (out && cap_ops > 0) std::memcpy(out, f->ops.data(), sizeof(Op) * (size_t)std::min(n, cap_ops));
+    return n;
+}
+int32_t hrt_scene_get_tree_nodes(const hrt_scene* s, void* out, int32_t cap_nodes) {
+    if (!s) return fail(HRT_ERR_INVALID, "null scene");
+    if (!s->committed) return fail(HRT_ERR_STATE, "scene not committed");
+    int32_t n = (int32_t)s->fast.nodes.size();
+    if (out && cap_nodes > 0) std::memcpy(out, s->fast.nodes.data(), sizeof(Bvh2Node) * (size_t)std::min(n, cap_nodes));
     return n;
 }
 

@@ -48,6 +48,17 @@ struct ImageData {
     uint32_t width = 0, height = 0;
 };
 
+// One flattened form of the scene (hrt_types.h): the op stream with its fp16 companions, the ray-space contexts whose
+// records it refers to, and the node table of its OP_BVH trees.
+struct FlatScene {
+    std::vector<Op> ops;
+    std::vector<Box16> box16;  // derived from ops at commit
+    std::vector<Ctx> ctxs;
+    std::vector<Bvh2Node> nodes;
+    int32_t n_box_ops = 0, n_loose_boxes = 0, n_prim_ops = 0, n_media = 0, max_ctx_depth = 0;
+    int32_t n_bvh_trees = 0, max_tree_depth = 0;
+};
+
 struct DeviceState;  // defined in hrt_api.cu
 
 }  // namespace hrt
@@ -59,16 +70,14 @@ struct hrt_scene {
     std::vector<hrt::NoiseTable> noise_tables;
     std::vector<hrt::ImageData> images;
 
-    int32_t bvh_builder = 0;  // hrt_scene_set_bvh_builder: 0 reference trees, 1 SAH trees for BVHs whose leaves are all sound
-    int32_t n_bvh_rebuilt = 0;
+    int32_t bvh_builder = 1;  // hrt_scene_set_bvh_builder: 0 reference trees only, 1 OP_BVH trees for sound BVHs
 
-    // committed (flattened) form
+    // committed (flattened) forms: `ref` keeps every BvhNode as the reference built it (left-first box records); `fast`
+    // is what renders by default — sound BVHs of plain primitives become OP_BVH trees.  Same primitives, materials,
+    // medium indices and hit results; `ref` is what HRT_FLAG_REFERENCE_TRAVERSAL and out-of-interval shutters use.
     bool committed = false;
     int32_t root = -1;
-    std::vector<hrt::Op> ops;
-    std::vector<hrt::Box16> box16;  // derived from ops at commit (hrt_types.h)
-    std::vector<hrt::Ctx> ctxs;
-    int32_t n_box_ops = 0, n_loose_boxes = 0, n_prim_ops = 0, n_media = 0, max_ctx_depth = 0;
+    hrt::FlatScene ref, fast;
     float time_min = -3.402823466e38f, time_max = 3.402823466e38f;  // intersection of BVH build intervals
     bool any_bvh = false;
 

@@ -30,6 +30,8 @@ enum Opcode : uint32_t {
     OP_POP = 0x42,        // leave child ray space (restore context in w3)
     OP_MEDIUM = 0x43,
     OP_MEDIUM_SPHERE = 0x44,  // OP_MEDIUM whose boundary sub-stream is exactly one OP_SPHERE record (closed-form path)
+    OP_BVH = 0x45,            // a whole sound BvhNode as a binary tree of Bvh2Node records walked with a per-ray stack,
+                              // nearer child first; its leaves are the primitive records [pc+1, end)
     OP_END = 0x50,
 };
 
@@ -43,6 +45,8 @@ enum Opcode : uint32_t {
 //   ROTATE      w0 sin, w1 cos, w2 axis, w3 ctx                w7 = op | run<<8   } pop) records starting here: executing the
 //   POP         w3 ctx to restore                              w7 = op | run<<8   } first one enters/leaves the whole chain
 //   MEDIUM      w0 -1/density, w1 mat, w2 medium idx, w3 prim  w7 = op | end_pc<<8
+//   BVH         w0 first node (index into the node table), w1 node count, w2 leaf count, w3 tree depth
+//               w4 time_start, w5 time_end of the BvhNode      w7 = op | end_pc<<8
 struct alignas(16) Op {
     union {
         float f[8];
@@ -63,6 +67,23 @@ struct alignas(16) Box16 {
     uint32_t w7;
 };
 static_assert(sizeof(Box16) == 16, "box16 record must be 16 bytes");
+
+// Node of an OP_BVH tree: the fp16 outward-rounded boxes of BOTH children (same layout and rounding as Box16) and the two
+// child links — >= 0: another node (index relative to the tree's first node), < 0: ~pc of the leaf's primitive record in
+// the op stream.  The reference visits a BvhNode's children left first with a running t_max and lets the later child win
+// an exact tie if it is still reached (bvh_node.rs:110-124); a sound tree can be walked in ANY order with the same
+// closest hit as long as exact ties are settled the reference's way.  The leaf records of a tree sit in the stream in
+// the reference's own depth-first order, so "later in the reference's order" is "larger pc" (hrt_device.cuh
+// tie_goes_to_later).
+struct alignas(16) Bvh2Node {
+    uint16_t lbox[6];  // left child: min xyz rounded down, max xyz rounded up
+    int32_t left;
+    uint16_t rbox[6];
+    int32_t right;
+};
+static_assert(sizeof(Bvh2Node) == 32, "bvh2 node must be 32 bytes");
+constexpr int kBvh2SahDepth = 24;  // SAH splits down to this depth, then balanced median splits: depth <= 24 + log2(n)
+constexpr int kBvh2Stack = 48;     // per-ray stack entries (one per tree level at most)
 
 constexpr int kMaxCtxDepth = 6;
 // A ray-space context = the chain of TRANSLATE/ROTATE records (outermost first) that maps the world ray

@@ -18,10 +18,11 @@ HRT_FLAG_INTERPRETER = 8
 HRT_FLAG_POOL = 16
 HRT_FLAG_SCHEDULER = 32
 HRT_FLAG_UNIFORM = 64
-ABI_VERSION = 2  # include/hrt.h HRT_ABI_VERSION
+ABI_VERSION = 3  # include/hrt.h HRT_ABI_VERSION
 HRT_BVH_REFERENCE = 0
-HRT_BVH_SAH = 1
-HRT_BVH_SAH_SPHERES = 2
+HRT_BVH_TREES = 1
+HRT_STREAM_REFERENCE = 0
+HRT_STREAM_FAST = 1
 
 
 class HrtError(RuntimeError):
@@ -65,7 +66,8 @@ class SceneInfo(C.Structure):
                 ("n_materials", C.c_int32), ("n_textures", C.c_int32), ("n_noise_tables", C.c_int32),
                 ("n_images", C.c_int32), ("n_media", C.c_int32), ("n_contexts", C.c_int32),
                 ("max_context_depth", C.c_int32), ("time_min", C.c_float), ("time_max", C.c_float),
-                ("n_bvh_rebuilt", C.c_int32)]
+                ("n_fast_ops", C.c_int32), ("n_fast_box_ops", C.c_int32), ("n_bvh_trees", C.c_int32),
+                ("n_tree_nodes", C.c_int32), ("max_tree_depth", C.c_int32)]
 
 
 RAY_DTYPE = np.dtype([("o", np.float32, 3), ("d", np.float32, 3), ("time", np.float32), ("tmin", np.float32),
@@ -86,7 +88,7 @@ EXPORTS = [
     "hrt_render_accum", "hrt_render_accum_device", "hrt_resolve_device", "hrt_trace_hits", "hrt_tex_value",
     "hrt_scatter", "hrt_camera_rays", "hrt_philox_uniforms", "hrt_scene_evict", "hrt_scene_device_bytes",
     "hrt_measure_peaks", "hrt_scene_refresh", "hrt_render_multi", "hrt_render_accum_multi", "hrt_scene_get_box16",
-    "hrt_scene_set_bvh_builder",
+    "hrt_scene_set_bvh_builder", "hrt_scene_get_tree_nodes",
 ]
 
 _lib = None
@@ -134,8 +136,9 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.hrt_scene_commit.argtypes = [vp, i32]
     lib.hrt_scene_count.argtypes = [vp]
     lib.hrt_scene_get_info.argtypes = [vp, C.POINTER(SceneInfo)]
-    lib.hrt_scene_get_ops.argtypes = [vp, vp, i32]
-    lib.hrt_scene_get_box16.argtypes = [vp, vp, i32]
+    lib.hrt_scene_get_ops.argtypes = [vp, i32, vp, i32]
+    lib.hrt_scene_get_box16.argtypes = [vp, i32, vp, i32]
+    lib.hrt_scene_get_tree_nodes.argtypes = [vp, vp, i32]
     lib.hrt_scene_set_bvh_builder.argtypes = [vp, i32]
     lib.hrt_bvh_leaf_order.argtypes = [vp, i32, C.POINTER(i32), i32]
     lib.hrt_bounding_box.argtypes = [vp, i32, f3]
@@ -269,7 +272,8 @@ class HrtBackend:
         return self._check(self.lib.hrt_bvh(self.handle, arr, len(ids), float(t0), float(t1)))
 
     def set_bvh_builder(self, builder: int):
-        """HRT_BVH_REFERENCE (0, default), HRT_BVH_SAH (1) or HRT_BVH_SAH_SPHERES (2); before commit (include/hrt.h)."""
+        """HRT_BVH_TREES (1, default: sound BVHs become OP_BVH trees in the fast form) or HRT_BVH_REFERENCE (0); before
+        commit (include/hrt.h)."""
         return self._check(self.lib.hrt_scene_set_bvh_builder(self.handle, int(builder)))
 
     def commit(self, root):
@@ -284,18 +288,27 @@ class HrtBackend:
         self._check(self.lib.hrt_scene_get_info(self.handle, C.byref(i)))
         return i
 
-    def ops(self) -> np.ndarray:
-        n = self._check(self.lib.hrt_scene_get_ops(self.handle, None, 0))
+    def ops(self, which: int = HRT_STREAM_REFERENCE) -> np.ndarray:
+        """(n, 8) uint32 records of the reference (default) or the fast form of the op stream (hrt_types.h)."""
+        n = self._check(self.lib.hrt_scene_get_ops(self.handle, which, None, 0))
         out = np.zeros((n, 8), dtype=np.uint32)
-        self._check(self.lib.hrt_scene_get_ops(self.handle, _ptr(out), n))
+        self._check(self.lib.hrt_scene_get_ops(self.handle, which, _ptr(out), n))
         return out
 
-    def box16(self) -> np.ndarray:
+    def box16(self, which: int = HRT_STREAM_REFERENCE) -> np.ndarray:
         """(n_ops, 8) uint16: six fp16 bounds (min rounded down, max rounded up) + w7 as two halves (hrt_types.h Box16)."""
-        n = self._check(self.lib.hrt_scene_get_box16(self.handle, None, 0))
+        n = self._check(self.lib.hrt_scene_get_box16(self.handle, which, None, 0))
         out = np.zeros((n, 8), dtype=np.uint16)
-        self._check(self.lib.hrt_scene_get_box16(self.handle, _ptr(out), n))
+        self._check(self.lib.hrt_scene_get_box16(self.handle, which, _ptr(out), n))
         return out
+
+    def tree_nodes(self) -> np.ndarray:
+        """(n, 16) uint16 view of the fast form's OP_BVH tree nodes (hrt_types.h Bvh2Node): halves 0-5 left box, 6-7 the
+        left link (int32), 8-13 right box, 14-15 the right link."""
+        n = self._check(self.lib.hrt_scene_get_tree_nodes(self.handle, None, 0))
+        out = np.zeros((max(n, 1), 16), dtype=np.uint16)
+        self._check(self.lib.hrt_scene_get_tree_nodes(self.handle, _ptr(out), n))
+        return out[:n]
 
     def bvh_leaf_order(self, bvh: int):
         n = self._check(self.lib.hrt_bvh_leaf_order(self.handle, bvh, None, 0))

@@ -30,7 +30,7 @@ class Renderer:
     """Owns one committed scene on libhrt and renders it."""
 
     def __init__(self, spec: SceneSpec, device: int = 0, upload: bool = True, bvh_builder: Optional[int] = None):
-        """bvh_builder: native.HRT_BVH_REFERENCE / HRT_BVH_SAH (include/hrt.h hrt_scene_set_bvh_builder); None keeps the
+        """bvh_builder: native.HRT_BVH_TREES / HRT_BVH_REFERENCE (include/hrt.h hrt_scene_set_bvh_builder); None keeps the
         library default (the reference's trees)."""
         self.spec = spec
         self.device = int(device)

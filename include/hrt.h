@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define HRT_ABI_VERSION 2 /* 2: hrt_scene_info grew (n_bvh_rebuilt); hrt_scene_set_bvh_builder, hrt_scene_get_box16 */
+#define HRT_ABI_VERSION 3 /* 3: two flattened forms (reference / fast), OP_BVH trees; hrt_scene_info, get_ops, get_box16 changed */
 
 typedef enum hrt_status {
     HRT_OK = 0,
@@ -92,7 +92,9 @@ int32_t hrt_rotate(hrt_scene*, int32_t axis, int32_t child, float angle_degrees)
 int32_t hrt_constant_medium(hrt_scene*, int32_t boundary, float density, int32_t albedo_tex);
 int32_t hrt_list(hrt_scene*, const int32_t* children, int32_t n);                                 /* list.rs:14 */
 /* BvhNode::new(objects, time_start, time_end)  — reproduces the reference's axis choice, centroid sort,
- * len/2 split and node boxes exactly (bvh_node.rs:27-100). */
+ * len/2 split and node boxes (bvh_node.rs:27-100); the tree is the reference's up to the order of objects with EQUAL
+ * sort keys (sort_unstable_by leaves it toolchain-defined; it cannot change a hit on sound boxes).  A NaN bounding box is
+ * refused (the reference panics in partial_cmp().unwrap()). */
 int32_t hrt_bvh(hrt_scene*, const int32_t* children, int32_t n, float time_start, float time_end);
 
 /* Flatten the tree under `root` into the device op stream + material/texture tables (host only). */
@@ -103,6 +105,7 @@ int32_t hrt_scene_count(const hrt_scene*);
 
 /* ---- flattened-table introspection (tests, tools) -------------------------------------------------- */
 typedef struct hrt_scene_info {
+    /* the REFERENCE form of the op stream (every BvhNode as the reference built it) */
     int32_t n_ops;          /* 32-byte records in the op stream                              */
     int32_t n_box_ops;      /* BVH node boxes                                                 */
     int32_t n_loose_boxes;  /* boxes that must use the reference's per-axis test (unsound)    */
@@ -110,29 +113,36 @@ typedef struct hrt_scene_info {
     int32_t n_materials, n_textures, n_noise_tables, n_images, n_media, n_contexts;
     int32_t max_context_depth;
     float time_min, time_max; /* BVH build interval (intersection over all hrt_bvh calls)      */
-    int32_t n_bvh_rebuilt;    /* hrt_bvh objects flattened from an SAH tree (hrt_scene_set_bvh_builder) */
+    /* the FAST form (what renders by default) */
+    int32_t n_fast_ops, n_fast_box_ops;
+    int32_t n_bvh_trees;      /* hrt_bvh objects flattened as OP_BVH trees                      */
+    int32_t n_tree_nodes;     /* 32-byte two-child nodes of those trees                         */
+    int32_t max_tree_depth;
 } hrt_scene_info;
 int32_t hrt_scene_get_info(const hrt_scene*, hrt_scene_info* out);
-/* Which trees hrt_scene_commit flattens for the hrt_bvh objects.  Call before hrt_scene_commit.
- *   HRT_BVH_REFERENCE (default)  BvhNode::new's own trees (longest axis, object median; bvh_node.rs:27-63).
- *   HRT_BVH_SAH                  surface-area-heuristic trees for every hrt_bvh whose leaf boxes all contain their leaves
- *                                (BVHs with an axis-swapped ZX rect beneath keep the reference tree, whose unsound boxes
- *                                are part of the reference's behaviour).  Box tests only prune, so every closest hit is
- *                                the same as with the reference trees; the one difference is the winner of an EXACT tie
- *                                between two coincident surfaces of one BVH (the reference keeps the later leaf of ITS
- *                                depth-first order, this stream the later leaf of the SAH order).  About half the box
- *                                tests on the `random` scene, 0.9x on `final` (profiles/bvh_study.json).
- *   HRT_BVH_SAH_SPHERES          the same, but only for hrt_bvh objects whose children are all (moving) spheres, no two of
- *                                them identical: no two surfaces coincide, so there is no systematic tie to resolve
- *                                differently (all of `random`; the 1000-sphere cube of `final`, not its ground boxes).
- * hrt_bvh_leaf_order / hrt_bounding_box keep describing the reference trees. */
-enum { HRT_BVH_REFERENCE = 0, HRT_BVH_SAH = 1, HRT_BVH_SAH_SPHERES = 2 };
+/* hrt_scene_commit flattens the scene twice.  The REFERENCE form keeps every BvhNode exactly as BvhNode::new built it
+ * (longest axis, object median, bvh_node.rs:27-63) as box records visited left first — what HRT_FLAG_REFERENCE_TRAVERSAL
+ * renders, and what a shutter outside the BVH build interval falls back to.  The FAST form (default for rendering) turns
+ * every hrt_bvh that is SOUND — at least four children, all plain spheres / moving spheres / rects / cuboids whose
+ * reference boxes contain them, i.e. no axis-swapped ZX rect — into a surface-area-heuristic binary tree walked with a
+ * per-ray stack, nearer child first.  Box tests only prune, so the closest hit is the same; on an EXACT tie between two
+ * surfaces the reference keeps the leaf that comes later in ITS depth-first order (bvh_node.rs:110-124: `t <= t_max`), and
+ * so does the tree walk: the leaf records stay in the stream in the reference's order and an equal-t hit only replaces
+ * an earlier record's.  BVHs that are not sound (the Cornell / final top levels, above the ceiling light) keep the
+ * reference form in both.
+ *   HRT_BVH_TREES (default)  as above
+ *   HRT_BVH_REFERENCE        the fast form is the reference form
+ * Call before hrt_scene_commit.  hrt_bvh_leaf_order / hrt_bounding_box always describe the reference trees. */
+enum { HRT_BVH_REFERENCE = 0, HRT_BVH_TREES = 1 };
 int32_t hrt_scene_set_bvh_builder(hrt_scene*, int32_t builder);
-/* Copies up to cap_ops 32-byte records; returns n_ops. */
-int32_t hrt_scene_get_ops(const hrt_scene*, void* out, int32_t cap_ops);
-/* Copies up to cap_ops 16-byte companions of the records (six fp16 bounds rounded outward + w7: what the render
- * kernel's box loop reads from shared memory — hrt_types.h Box16); returns n_ops. */
-int32_t hrt_scene_get_box16(const hrt_scene*, void* out, int32_t cap_ops);
+enum { HRT_STREAM_REFERENCE = 0, HRT_STREAM_FAST = 1 };
+/* Copies up to cap_ops 32-byte records of the chosen form; returns its record count. */
+int32_t hrt_scene_get_ops(const hrt_scene*, int32_t which, void* out, int32_t cap_ops);
+/* Copies up to cap_ops 16-byte companions of the records (six fp16 bounds rounded outward + w7, hrt_types.h Box16);
+ * returns the record count. */
+int32_t hrt_scene_get_box16(const hrt_scene*, int32_t which, void* out, int32_t cap_ops);
+/* Copies up to cap_nodes 32-byte tree nodes of the fast form (hrt_types.h Bvh2Node); returns the node count. */
+int32_t hrt_scene_get_tree_nodes(const hrt_scene*, void* out, int32_t cap_nodes);
 /* DFS left->right leaf object ids of a hrt_bvh object; returns leaf count. */
 int32_t hrt_bvh_leaf_order(const hrt_scene*, int32_t bvh, int32_t* out, int32_t cap);
 /* Reference bounding box of any hittable over time [0,1] (what `bounding_box(0.0, 1.0)` returns). */

@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol(pkg):
     for name in sorted(declared):
         assert hasattr(lib, name), f"libhrt.so does not export {name}"
     assert set(pkg.native.EXPORTS) == declared
-    assert lib.hrt_abi_version() == pkg.native.ABI_VERSION == 2
+    assert lib.hrt_abi_version() == pkg.native.ABI_VERSION == 3
 
 
 def test_no_cpu_fallback(pkg):

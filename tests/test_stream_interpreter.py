@@ -3,6 +3,8 @@ the 32-byte records — written from the record table in hrt_types.h, independen
 closest hit (t and primitive) as the CPU oracle's recursive `world.hit` on the same rays.  This pins, without a GPU, what
 the flattener emits: depth-first order, skip links, tight / loose box flags, ray-space push / pop runs, cuboid side order.
 Media are not interpreted (their boundary sub-streams are skipped); rays whose oracle hit is a medium hit are left out.
+The FAST form's OP_BVH trees (two-child nodes with fp16 boxes, walked with a stack, nearer child first, an exact tie
+going to the later record) are interpreted too, one ray at a time.
 """
 import numpy as np
 import pytest
@@ -11,8 +13,112 @@ from conftest import build_both, make_rays
 
 OP_BOX, OP_BOX_LOOSE, OP_SPHERE, OP_MSPHERE = 0x10, 0x11, 0x20, 0x21
 OP_RECT_XY, OP_RECT_YZ, OP_RECT_ZX, OP_CUBOID = 0x30, 0x31, 0x32, 0x33
-OP_TRANSLATE, OP_ROTATE, OP_POP, OP_MEDIUM, OP_MEDIUM_SPHERE, OP_END = 0x40, 0x41, 0x42, 0x43, 0x44, 0x50
+OP_TRANSLATE, OP_ROTATE, OP_POP, OP_MEDIUM, OP_MEDIUM_SPHERE, OP_BVH, OP_END = 0x40, 0x41, 0x42, 0x43, 0x44, 0x45, 0x50
 F = np.float32
+
+
+def _slab1(o, inv, box, tmin, closest):
+    """Entry / exit of ONE ray against a (6,) float32 box; missed iff hi < lo (hrt_device.cuh slab16)."""
+    t0 = (box[0:3] - o) * inv
+    t1 = (box[3:6] - o) * inv
+    lo = np.where(inv < 0, t1, t0)
+    hi = np.where(inv < 0, t0, t1)
+    return max(np.fmax.reduce(lo), tmin), min(np.fmin.reduce(hi), closest)
+
+
+def _leaf1(ops, f, pc, o, d, time, tmin, closest):
+    """One primitive record against ONE ray: (hit, t, prim id) with the reference's inclusive range checks."""
+    one = lambda x: np.asarray([x], dtype=F)
+    oo, dd = o[None, :], d[None, :]
+    op = int(ops[pc, 7]) & 0xFF
+    if op in (OP_SPHERE, OP_MSPHERE):
+        c = f[pc, 0:3][None, :]
+        if op == OP_MSPHERE:
+            c1, t0, t1 = f[pc + 1, 0:3], f[pc + 1, 3], f[pc + 1, 4]
+            c = c + ((one(time) - t0) / (t1 - t0))[:, None] * (c1 - f[pc, 0:3])[None, :]
+        ok, t = _sphere(oo, dd, c, f[pc, 3], one(tmin), one(closest))
+        return bool(ok[0]), t[0], int(ops[pc, 5])
+    if op in (OP_RECT_XY, OP_RECT_YZ, OP_RECT_ZX):
+        ik, ia, ib = {OP_RECT_XY: (2, 0, 1), OP_RECT_YZ: (0, 1, 2), OP_RECT_ZX: (1, 2, 0)}[op]
+        ok, t = _rect(oo, dd, ik, ia, ib, f[pc, 0], f[pc, 1], f[pc, 2], f[pc, 3], f[pc, 4], one(tmin), one(closest))
+        return bool(ok[0]), t[0], int(ops[pc, 6])
+    assert op == OP_CUBOID, hex(op)
+    mn, mx = f[pc, 0:3], f[pc, 4:7]
+    hit, t = False, one(closest)
+    for (ik, ia, ib), k in (((2, 0, 1), mx[2]), ((2, 0, 1), mn[2]), ((1, 2, 0), mx[1]), ((1, 2, 0), mn[1]),
+                            ((0, 1, 2), mx[0]), ((0, 1, 2), mn[0])):
+        h, ts = _rect(oo, dd, ik, ia, ib, mn[ia], mx[ia], mn[ib], mx[ib], k, one(tmin), t)
+        if h[0]:
+            hit, t = True, ts
+    return hit, t[0], int(ops[pc, 7]) >> 8
+
+
+def _ref_leaf_box(ops, f, pc, ts, te):
+    """The reference's bounding box of a leaf record (sphere.rs:77-83, moving_sphere.rs:98-110 over the BvhNode's time
+    interval, rect.rs:88-103 as written, cuboid.rs:104-106)."""
+    op = int(ops[pc, 7]) & 0xFF
+    if op == OP_SPHERE:
+        return f[pc, 0:3] - f[pc, 3], f[pc, 0:3] + f[pc, 3]
+    if op == OP_MSPHERE:
+        c0, c1, t0, t1, r = f[pc, 0:3], f[pc + 1, 0:3], f[pc + 1, 3], f[pc + 1, 4], f[pc, 3]
+        ca = c0 + ((F(ts) - t0) / (t1 - t0)) * (c1 - c0)
+        cb = c0 + ((F(te) - t0) / (t1 - t0)) * (c1 - c0)
+        return np.minimum(ca - r, cb - r), np.maximum(ca + r, cb + r)
+    if op == OP_CUBOID:
+        return f[pc, 0:3], f[pc, 4:7]
+    a0, a1, b0, b1, k = f[pc, 0:5]
+    lo, hi = k - F(0.0001), k + F(0.0001)
+    if op == OP_RECT_XY:
+        return np.array([a0, b0, lo], F), np.array([a1, b1, hi], F)
+    if op == OP_RECT_YZ:
+        return np.array([lo, a0, b0], F), np.array([hi, a1, b1], F)
+    return np.array([a0, lo, b0], F), np.array([a1, hi, b1], F)
+
+
+def walk_tree(ops, f, nodes, base, o, d, time, tmin, closest, best_pc, stats=None, ts=0.0, te=1.0):
+    """OP_BVH tree walk for ONE ray (hrt_types.h Bvh2Node): returns (closest, best_pc, prim id or None).  An exact tie
+    is settled as the reference settles it: the later leaf of the reference's order wins iff the reference would still
+    have reached it, i.e. iff its own bounding box passes Aabb::hit with t_max = t (hrt_device.cuh tie_goes_to_later)."""
+    boxes = nodes[:, [0, 1, 2, 3, 4, 5, 8, 9, 10, 11, 12, 13]].copy().view(np.float16).astype(F)  # (n, 12)
+    links = nodes.view(np.int32)[:, [3, 7]]
+    inv = F(1.0) / d
+    prim = None
+    stack = []
+    ref = 0
+    while True:
+        if ref >= 0:
+            n = base + ref
+            if stats is not None:
+                stats[0] += 2
+            llo, lhi = _slab1(o, inv, boxes[n, 0:6], tmin, closest)
+            rlo, rhi = _slab1(o, inv, boxes[n, 6:12], tmin, closest)
+            hl, hr = not (lhi < llo), not (rhi < rlo)
+            if hl and hr:
+                right_first = rlo < llo
+                stack.append((int(links[n, 0]) if right_first else int(links[n, 1]), llo if right_first else rlo))
+                ref = int(links[n, 1]) if right_first else int(links[n, 0])
+                continue
+            if hl or hr:
+                ref = int(links[n, 0]) if hl else int(links[n, 1])
+                continue
+        else:
+            pc = ~ref
+            hit, t, pid = _leaf1(ops, f, pc, o, d, time, tmin, closest)
+            if hit:
+                take = t < closest or best_pc < 0
+                if not take and not (t > closest):  # exact tie
+                    later = max(pc, best_pc)
+                    mn, mx = _ref_leaf_box(ops, f, later, ts, te)
+                    later_wins = bool(_box(o[None, :], d[None, :], mn, mx, np.asarray([[tmin]], F), np.asarray([t], F), True)[0])
+                    take = (pc > best_pc) == later_wins
+                if take:
+                    closest, best_pc, prim = t, pc, pid
+        while True:
+            if not stack:
+                return closest, best_pc, prim
+            ref, t_entry = stack.pop()
+            if not (t_entry > closest):
+                break
 
 
 def _box(o, d, mn, mx, tmin, closest, loose):
@@ -57,8 +163,9 @@ def _rect(o, d, ik, ia, ib, a0, a1, b0, b1, k, tmin, closest):
     return ok, t
 
 
-def trace_stream(ops, rays):
-    """Closest hit of every ray against the op stream; returns (hit mask, t, prim id)."""
+def trace_stream(ops, rays, nodes=None, stats=None):
+    """Closest hit of every ray against the op stream; returns (hit mask, t, prim id).  `nodes`: the tree-node table of
+    the fast form; `stats[0]` counts box tests."""
     f = ops.view(np.float32)
     n = len(rays)
     o = rays["o"].astype(F).copy()
@@ -67,6 +174,7 @@ def trace_stream(ops, rays):
     tmin = rays["tmin"].astype(F)
     closest = rays["tmax"].astype(F).copy()
     prim = np.full(n, -1, dtype=np.int64)
+    best_pc = np.full(n, -1, dtype=np.int64)
     pc_of = np.zeros(n, dtype=np.int64)
     saved = []  # ray-space stack: (ray indices, their o, their d) per pushed level
     pc = 0
@@ -81,8 +189,19 @@ def trace_stream(ops, rays):
             if idx.size:
                 oo, dd, cl, tm = o[idx], d[idx], closest[idx], tmin[idx]
                 if op in (OP_BOX, OP_BOX_LOOSE):
+                    if stats is not None:
+                        stats[0] += idx.size
                     hit = _box(oo, dd, f[pc, 0:3], f[pc, 4:7], tm[:, None] if op == OP_BOX_LOOSE else tm, cl, op == OP_BOX_LOOSE)
                     pc_of[idx] = np.where(hit, pc + 1, payload)
+                    pc += 1
+                    continue
+                if op == OP_BVH:
+                    for i in idx:
+                        closest[i], best_pc[i], pid = walk_tree(ops, f, nodes, int(ops[pc, 0]), o[i], d[i], time[i], tmin[i],
+                                                                closest[i], best_pc[i], stats, f[pc, 4], f[pc, 5])
+                        if pid is not None:
+                            prim[i] = pid
+                    pc_of[idx] = payload
                     pc += 1
                     continue
                 if op == OP_SPHERE or op == OP_MSPHERE:
@@ -141,6 +260,7 @@ def trace_stream(ops, rays):
                 sel = idx[ok]
                 closest[sel] = t[ok]
                 prim[sel] = pid
+                best_pc[sel] = pc
                 pc_of[idx] = nxt
             pc += 1
     return prim >= 0, closest, prim
@@ -177,157 +297,164 @@ def test_stream_semantics_match_the_oracle(pkg, orc, name):
     assert np.allclose(t[m], want["t"][m], rtol=1e-5, atol=0), name
 
 
+def _both_forms(pkg, orc, world):
+    gb, ob, _, _ = build_both(pkg, orc, world)
+    N = pkg.native
+    return gb, ob, gb.ops(N.HRT_STREAM_REFERENCE), gb.ops(N.HRT_STREAM_FAST), gb.tree_nodes()
+
+
 @pytest.mark.parametrize("name", ["random", "cornell", "final"])
-def test_sah_trees_find_the_same_hits(pkg, orc, name):
-    """hrt_scene_set_bvh_builder(HRT_BVH_SAH): BVHs whose leaves are all sound are flattened from surface-area-heuristic
-    trees — same closest hits as the oracle's reference trees, fewer box visits; BVHs with an unsound (axis-swapped ZX
-    rect) leaf box keep the reference tree, clipping behaviour included (Cornell)."""
+def test_fast_form_finds_the_same_hits(pkg, orc, name):
+    """The FAST form (include/hrt.h): sound BVHs of plain primitives become OP_BVH trees — surface-area-heuristic
+    topology, nearer child first — and must return the oracle's hits INCLUDING the primitive named on an exact tie
+    between coincident surfaces (`final`'s ground boxes share faces): the leaf records stay in the reference's order
+    and an equal-t hit only replaces an earlier record's.  BVHs with an unsound (axis-swapped ZX rect) leaf box keep the
+    reference form, clipping behaviour included (Cornell)."""
     spec = pkg.make_scene(name, seed=4)
-    gb_ref, ob, _, _ = build_both(pkg, orc, spec.world)
-    gb = pkg.HrtBackend()
-    gb.set_bvh_builder(pkg.native.HRT_BVH_SAH)
-    pkg.scene.emit(spec.world, gb)
-    i_ref, i = gb_ref.info(), gb.info()
-    assert (i.n_ops, i.n_box_ops, i.n_prim_ops, i.n_loose_boxes) == (i_ref.n_ops, i_ref.n_box_ops, i_ref.n_prim_ops, i_ref.n_loose_boxes)
+    gb, ob, ref_ops, fast_ops, nodes = _both_forms(pkg, orc, spec.world)
+    i = gb.info()
     if name == "cornell":  # its one BVH holds the ZX light: untouched
-        assert i.n_bvh_rebuilt == 0 and np.array_equal(gb.ops(), gb_ref.ops())
+        assert i.n_bvh_trees == 0 and i.n_tree_nodes == 0 and np.array_equal(ref_ops, fast_ops)
         return
-    assert i.n_bvh_rebuilt >= 1 and not np.array_equal(gb.ops(), gb_ref.ops())
-    rays = _rays(orc, ob, spec)
+    assert i.n_bvh_trees == {"random": 1, "final": 2}[name]
+    assert i.n_fast_ops == len(fast_ops) and i.n_tree_nodes == len(nodes) and 0 < i.max_tree_depth <= 48
+    # the trees replace the box records of those BVHs: one root box + one OP_BVH record per tree instead of 2n-1 boxes
+    kinds = fast_ops[:, 7] & 0xFF
+    assert (kinds == OP_BVH).sum() == i.n_bvh_trees and i.n_fast_box_ops < i.n_box_ops // 10
+    for k in (OP_SPHERE, OP_MSPHERE, OP_CUBOID, OP_RECT_XY, OP_RECT_YZ, OP_RECT_ZX, OP_MEDIUM, OP_MEDIUM_SPHERE):
+        assert (kinds == k).sum() == ((ref_ops[:, 7] & 0xFF) == k).sum()
+    rays = _rays(orc, ob, spec, n=700)
     want = ob.trace_hits(rays, np.full(len(rays), 0.5, dtype=np.float32))
-    hit, t, prim = trace_stream(gb.ops(), rays)
+    hit, t, prim = trace_stream(fast_ops, rays, nodes)
     medium = (want["hit"] == 1) & np.all(want["n"] == 0.0, axis=1)
     keep = ~medium & np.isfinite(want["t"])
     assert np.array_equal(hit[keep], want["hit"][keep] == 1)
     m = keep & (want["hit"] == 1)
+    assert m.sum() > len(rays) // 10
+    assert np.array_equal(prim[m], want["prim_id"][m]), (name, int((prim[m] != want["prim_id"][m]).sum()))
     assert np.allclose(t[m], want["t"][m], rtol=1e-5, atol=0)
-    # Same primitive too, except on EXACT ties between coincident surfaces (include/hrt.h): `final`'s ground boxes share
-    # faces, and a ray that lands on a shared face gets the later leaf of the stream's order instead of the reference's.
-    other = m & (prim != want["prim_id"])
-    assert other.sum() <= 0.005 * m.sum() and np.array_equal(t[other], want["t"][other]), (name, int(other.sum()))
-    # skip links still point forward and stay inside the stream
-    ops = gb.ops()
-    boxes = np.where(((ops[:, 7] & 0xFF) == OP_BOX) | ((ops[:, 7] & 0xFF) == OP_BOX_LOOSE))[0]
-    assert np.all((ops[boxes, 7] >> 8) > boxes) and np.all((ops[boxes, 7] >> 8) <= len(ops) - 1)
 
 
-def test_sah_visits_fewer_boxes_on_the_random_scene(pkg, orc):
-    """The point of the option: count box records visited per ray by the interpreter on both streams."""
+def test_tree_structure_is_well_formed(pkg, orc):
+    """Every leaf record of a tree is referenced exactly once, links stay inside the tree, the leaf records sit between the
+    OP_BVH record and its end, and every child box (fp16, rounded outward) contains the boxes beneath it."""
+    spec = pkg.make_scene("final", seed=4)
+    gb, ob, ref_ops, ops, nodes = _both_forms(pkg, orc, spec.world)
+    f = ops.view(np.float32)
+    boxes = nodes[:, [0, 1, 2, 3, 4, 5, 8, 9, 10, 11, 12, 13]].copy().view(np.float16).astype(F)
+    links = nodes.view(np.int32)[:, [3, 7]]
+    for pc in np.where((ops[:, 7] & 0xFF) == OP_BVH)[0]:
+        base, n_nodes, n_leaves, depth = (int(x) for x in ops[pc, 0:4].view(np.int32))
+        end = int(ops[pc, 7]) >> 8
+        assert (int(ops[pc - 1, 7]) & 0xFF) == OP_BOX and (int(ops[pc - 1, 7]) >> 8) == end  # root box skips the tree
+        assert n_nodes == n_leaves - 1
+        seen_leaf, seen_node = [], []
+
+        def extent(pcl):
+            op = int(ops[pcl, 7]) & 0xFF
+            if op == OP_SPHERE:
+                return np.concatenate([f[pcl, 0:3] - f[pcl, 3], f[pcl, 0:3] + f[pcl, 3]])
+            assert op == OP_CUBOID
+            return np.concatenate([f[pcl, 0:3], f[pcl, 4:7]])
+
+        def visit(ref, d):
+            if ref < 0:
+                assert pc < ~ref < end
+                seen_leaf.append(~ref)
+                return extent(~ref), d
+            assert 0 <= ref < n_nodes
+            seen_node.append(ref)
+            n = base + ref
+            out, dmax = None, d
+            for side in (0, 1):
+                e, dd = visit(int(links[n, side]), d + 1)
+                b = boxes[n, 6 * side:6 * side + 6]
+                assert np.all(b[0:3] <= e[0:3]) and np.all(b[3:6] >= e[3:6])
+                # ... and not by more than fp16 rounding
+                assert np.all(np.abs(b - e) <= np.maximum(np.abs(e) * 2.0 ** -10, 2.0 ** -14))
+                out = e if out is None else np.concatenate([np.minimum(out[0:3], e[0:3]), np.maximum(out[3:6], e[3:6])])
+                dmax = max(dmax, dd)
+            return out, dmax
+
+        _, dmax = visit(0, 1)
+        assert sorted(seen_node) == list(range(n_nodes)) and len(set(seen_leaf)) == len(seen_leaf) == n_leaves
+        assert dmax - 1 == depth
+        # leaf records = every primitive record between the OP_BVH record and its end
+        prim_pcs = [q for q in range(pc + 1, end) if (int(ops[q, 7]) & 0xFF) in (OP_SPHERE, OP_MSPHERE, OP_CUBOID, OP_RECT_XY, OP_RECT_YZ, OP_RECT_ZX)]
+        assert sorted(seen_leaf) == prim_pcs
+
+
+def test_trees_visit_fewer_boxes(pkg, orc):
+    """The point of the fast form: box tests per ray, reference form (tight tests) vs trees, by the interpreter."""
     spec = pkg.make_scene("random", seed=4)
-    gb_ref, ob, _, _ = build_both(pkg, orc, spec.world)
-    gb = pkg.HrtBackend()
-    gb.set_bvh_builder(pkg.native.HRT_BVH_SAH)
-    pkg.scene.emit(spec.world, gb)
-    rays = _rays(orc, ob, spec, n=600)
-
-    def visits(ops):
-        f = ops.view(np.float32)
-        pc_of = np.zeros(len(rays), dtype=np.int64)
-        total = 0
-        o, d = rays["o"].astype(F), rays["d"].astype(F)
-        closest = rays["tmax"].astype(F).copy()
-        for pc in range(len(ops)):
-            idx = np.nonzero(pc_of == pc)[0]
-            w7 = int(ops[pc, 7]); op, payload = w7 & 0xFF, w7 >> 8
-            if op == OP_END or idx.size == 0:
-                continue
-            if op in (OP_BOX, OP_BOX_LOOSE):
-                total += idx.size
-                with np.errstate(all="ignore"):
-                    h = _box(o[idx], d[idx], f[pc, 0:3], f[pc, 4:7], rays["tmin"][idx].astype(F), closest[idx], False)
-                pc_of[idx] = np.where(h, pc + 1, payload)
-            elif op == OP_SPHERE:
-                with np.errstate(all="ignore"):
-                    ok, ts = _sphere(o[idx], d[idx], f[pc, 0:3][None, :], f[pc, 3], rays["tmin"][idx].astype(F), closest[idx])
-                closest[idx[ok]] = ts[ok]
-                pc_of[idx] = pc + 1
-            elif op == OP_MSPHERE:
-                pc_of[idx] = pc + 2  # moving spheres only shrink `closest`; leaving them out counts an upper bound on both
-            else:
-                pc_of[idx] = pc + 1
-        return total / len(rays)
-
-    v_ref, v_sah = visits(gb_ref.ops()), visits(gb.ops())
-    assert v_sah < 0.75 * v_ref, (v_ref, v_sah)
+    gb, ob, ref_ops, fast_ops, nodes = _both_forms(pkg, orc, spec.world)
+    rays = _rays(orc, ob, spec, n=150)
+    a, b = [0], [0]
+    h1 = trace_stream(ref_ops, rays, None, a)
+    h2 = trace_stream(fast_ops, rays, nodes, b)
+    assert np.array_equal(h1[2], h2[2]) and np.array_equal(h1[1], h2[1])
+    assert b[0] < 0.5 * a[0], (a, b)
 
 
-def test_sah_builder_edge_cases(pkg, orc):
-    """One- and two-leaf BVHs, nested BVHs, an unknown builder id, and the option after commit."""
+def test_tree_edge_cases(pkg, orc):
+    """Small and nested BVHs, moving spheres, coincident surfaces (the tie rule), an unknown builder id, the option after
+    commit."""
     S, N = pkg.scene, pkg.native
     m = S.Lambertian(S.SolidColor((0.5, 0.5, 0.5)))
+    m2 = S.Metal((0.5, 0.5, 0.5), 0.0)
     one = S.BvhNode([S.Sphere((0, 0, -5), 1.0, m)], 0.0, 1.0)
-    two = S.BvhNode([S.Sphere((3, 0, -5), 1.0, m), S.Sphere((-3, 0, -5), 1.0, m)], 0.0, 1.0)
-    moving = S.BvhNode([S.MovingSphere((0, 3, -5), (0, 4, -5), 0.0, 1.0, 0.5, m), S.Sphere((0, -3, -5), 0.5, m),
-                        S.Sphere((0, -6, -9), 0.5, m)], 0.0, 1.0)
-    world = S.BvhNode([one, two, moving, S.Sphere((0, -1000, 0), 990.0, m)], 0.0, 1.0)
-    gb_ref, ob, _, _ = build_both(pkg, orc, world)
-    gb = pkg.HrtBackend()
+    three = S.BvhNode([S.Sphere((3, 0, -5), 1.0, m), S.Sphere((-3, 0, -5), 1.0, m), S.Sphere((-3, 3, -5), 1.0, m)], 0.0, 1.0)
+    # six leaves, two pairs of COINCIDENT surfaces: identical spheres, and cuboids sharing the face x = 1
+    tied = S.BvhNode([S.MovingSphere((0, 3, -5), (0, 4, -5), 0.0, 1.0, 0.5, m), S.Sphere((0, -3, -5), 0.5, m),
+                      S.Sphere((0, -3, -5), 0.5, m2), S.Sphere((0, -6, -9), 0.5, m),
+                      S.Cuboid((0, 0, -9), (1, 1, -8), m), S.Cuboid((1, 0, -9), (2, 1, -8), m2)], 0.0, 1.0)
+    world = S.BvhNode([one, three, tied, S.Sphere((0, -1000, 0), 990.0, m)], 0.0, 1.0)
+    gb, ob, ref_ops, fast_ops, nodes = _both_forms(pkg, orc, world)
+    i = gb.info()
+    assert i.n_bvh_trees == 1 and i.n_tree_nodes == 5  # `tied` only: the others have fewer than four children / BVH leaves
+    bad = pkg.HrtBackend()
     with pytest.raises(pkg.HrtError) as ei:
-        gb.set_bvh_builder(7)
+        bad.set_bvh_builder(7)
     assert ei.value.code == -1
-    gb.set_bvh_builder(N.HRT_BVH_SAH)
-    S.emit(world, gb)
-    assert gb.info().n_bvh_rebuilt == 4 and gb.info().n_ops == gb_ref.info().n_ops
     with pytest.raises(pkg.HrtError):
         gb.set_bvh_builder(N.HRT_BVH_REFERENCE)  # immutable after commit, like every builder call
     rng = np.random.default_rng(1)
     d = rng.normal(size=(800, 3)).astype(np.float32)
     d[np.abs(d) < 1e-3] = 1e-3
     rays = make_rays(orc, np.tile(np.float32([0, 0, 4]), (800, 1)), d, time=rng.random(800, dtype=np.float32))
-    want = ob.trace_hits(rays, np.full(800, 0.5, dtype=np.float32))
-    for ops in (gb_ref.ops(), gb.ops()):
-        hit, t, prim = trace_stream(ops, rays)
+    # rays aimed at the coincident surfaces: the identical spheres, and points ON the shared cuboid face seen from inside
+    aim = np.float32([[0, -3, -5]]) + 0.3 * rng.normal(size=(200, 3)).astype(np.float32) - np.float32([[0, 0, 4]])
+    face = np.stack([np.full(100, 1.0), rng.uniform(0.05, 0.95, 100), rng.uniform(-8.95, -8.05, 100)], axis=1).astype(np.float32)
+    inside = np.float32([[0.5, 0.5, -8.5]])
+    rays = np.concatenate([rays, make_rays(orc, np.tile(np.float32([0, 0, 4]), (200, 1)), aim),
+                           make_rays(orc, np.tile(inside, (100, 1)), face - inside)])
+    want = ob.trace_hits(rays, np.full(len(rays), 0.5, dtype=np.float32))
+    for ops, nd in ((ref_ops, None), (fast_ops, nodes)):
+        hit, t, prim = trace_stream(ops, rays, nd)
         assert np.array_equal(hit, want["hit"] == 1) and (want["hit"] == 1).sum() > 100
         k = want["hit"] == 1
         assert np.array_equal(prim[k], want["prim_id"][k]) and np.allclose(t[k], want["t"][k], rtol=1e-5, atol=0)
+    # the tie cases were really exercised: both identical spheres' later twin and the later cuboid win
+    ids = set(want["prim_id"][want["hit"] == 1].tolist())
+    sph_ids = [int(x) for x in fast_ops[(fast_ops[:, 7] & 0xFF) == OP_SPHERE][:, 5]]
+    assert len(ids & set(sph_ids)) >= 3
 
 
 def test_builder_default_can_come_from_the_environment(pkg, monkeypatch):
-    """HRT_BVH_BUILDER=sah (what `bench.py --bvh sah` sets) is the default of scenes created afterwards; an explicit
-    hrt_scene_set_bvh_builder still wins."""
+    """HRT_BVH_BUILDER=reference (what `bench.py --bvh reference` sets) is the default of scenes created afterwards; an
+    explicit hrt_scene_set_bvh_builder still wins."""
+    N = pkg.native
     spec = pkg.make_scene("random", seed=2)
-    monkeypatch.setenv("HRT_BVH_BUILDER", "sah")
+    monkeypatch.setenv("HRT_BVH_BUILDER", "reference")
     a = pkg.HrtBackend()
     pkg.scene.emit(spec.world, a)
     b = pkg.HrtBackend()
-    b.set_bvh_builder(pkg.native.HRT_BVH_REFERENCE)
+    b.set_bvh_builder(N.HRT_BVH_TREES)
     pkg.scene.emit(spec.world, b)
     monkeypatch.delenv("HRT_BVH_BUILDER")
     c = pkg.HrtBackend()
     pkg.scene.emit(spec.world, c)
-    assert a.info().n_bvh_rebuilt == 1 and b.info().n_bvh_rebuilt == 0 and c.info().n_bvh_rebuilt == 0
-    assert np.array_equal(b.ops(), c.ops()) and not np.array_equal(a.ops(), c.ops())
-
-
-def test_sah_for_sphere_only_bvhs_keeps_every_primitive(pkg, orc):
-    """HRT_BVH_SAH_SPHERES: only BVHs made of distinct (moving) spheres are rebuilt — `final` keeps the reference tree over
-    its face-sharing ground boxes, so every hit names the oracle's primitive, ties included; duplicates veto the rebuild."""
-    S, N = pkg.scene, pkg.native
-    spec = pkg.make_scene("final", seed=4)
-    gb_ref, ob, _, _ = build_both(pkg, orc, spec.world)
-    gb = pkg.HrtBackend()
-    gb.set_bvh_builder(N.HRT_BVH_SAH_SPHERES)
-    S.emit(spec.world, gb)
-    assert gb.info().n_bvh_rebuilt == 1  # the 1000-sphere cube; not the ground boxes, not the top-level BVH
-    rays = _rays(orc, ob, spec)
-    want = ob.trace_hits(rays, np.full(len(rays), 0.5, dtype=np.float32))
-    hit, t, prim = trace_stream(gb.ops(), rays)
-    medium = (want["hit"] == 1) & np.all(want["n"] == 0.0, axis=1)
-    keep = ~medium & np.isfinite(want["t"])
-    m = keep & (want["hit"] == 1)
-    assert np.array_equal(hit[keep], want["hit"][keep] == 1)
-    assert np.array_equal(prim[m], want["prim_id"][m]) and np.allclose(t[m], want["t"][m], rtol=1e-5, atol=0)
-
-    r = pkg.make_scene("random", seed=4)
-    g2 = pkg.HrtBackend()
-    g2.set_bvh_builder(N.HRT_BVH_SAH_SPHERES)
-    S.emit(r.world, g2)
-    assert g2.info().n_bvh_rebuilt == 1
-
-    mat = S.Lambertian(S.SolidColor((0.5, 0.5, 0.5)))
-    dup = S.BvhNode([S.Sphere((0, 0, 0), 1.0, mat), S.MovingSphere((0, 0, 0), (0, 0, 0), 0.0, 1.0, 1.0, mat),
-                     S.Sphere((3, 0, 0), 1.0, mat)], 0.0, 1.0)
-    g3 = pkg.HrtBackend()
-    g3.set_bvh_builder(N.HRT_BVH_SAH_SPHERES)
-    S.emit(dup, g3)
-    assert g3.info().n_bvh_rebuilt == 0
+    assert a.info().n_bvh_trees == 0 and b.info().n_bvh_trees == 1 and c.info().n_bvh_trees == 1
+    assert np.array_equal(a.ops(N.HRT_STREAM_FAST), a.ops(N.HRT_STREAM_REFERENCE))
+    assert np.array_equal(b.ops(N.HRT_STREAM_FAST), c.ops(N.HRT_STREAM_FAST))
+    assert np.array_equal(a.ops(), c.ops())  # the reference form does not depend on the option
