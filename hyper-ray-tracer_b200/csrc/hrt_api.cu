@@ -364,9 +364,8 @@ static int32_t render_into(hrt_scene* s, DeviceState* d, const hrt_camera_desc* 
     L.scene = d->view[ref_boxes ? 0 : 1];  // the reference form of the stream goes with the reference's box test
     {
         const char* env = getenv("HRT_KERNEL");  // diagnostic override: "interp" | "sched" | "pool"
-        // default: the shared-memory ray-pool kernel (best sustained throughput; its 96-ray pools need enough samples per
-        // launch to amortise), the in-register warp scheduler for short launches
-        int variant = L.sample_count >= 128 ? 2 : 0;
+        // default: the warp-uniform walk
+        int variant = 3;
         if (rd->flags & HRT_FLAG_SCHEDULER) variant = 0;
         if (rd->flags & HRT_FLAG_INTERPRETER) variant = 1;
         if (rd->flags & HRT_FLAG_POOL) variant = 2;

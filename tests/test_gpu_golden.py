@@ -24,12 +24,16 @@ def _load(cfg):
     if not os.path.exists(path):
         pytest.skip(f"golden {cfg} not generated")
     z = np.load(path)
-    return z["img"].astype(np.float64), z["sigma"].astype(np.float64), json.loads(str(z["meta"]))
+    if "lin" in z.files:  # float32 LINEAR mean + its standard error (tools/make_goldens.py)
+        lin = z["lin"].astype(np.float64)
+        return np.sqrt(np.maximum(lin, 0.0)), lin, z["sigma"].astype(np.float64), json.loads(str(z["meta"])), True
+    img = z["img"].astype(np.float64)  # first-version files: gamma-space float16
+    return img, img ** 2, z["sigma"].astype(np.float64), json.loads(str(z["meta"])), False
 
 
 @pytest.mark.parametrize("cfg", ["C1", "C2a", "C2b", "C3", "C4", "C5"])
 def test_converged_image_matches_golden(pkg, cfg):
-    img, sigma, meta = _load(cfg)
+    img, gold_lin, sigma, meta, f32_golden = _load(cfg)
     spec = pkg.make_scene(meta["scene"], meta["scene_seed"])
     r = pkg.renderer.Renderer(spec, device=0)
     w, h, spp = meta["width"], meta["height"], GPU_SPP[cfg]
@@ -43,7 +47,6 @@ def test_converged_image_matches_golden(pkg, cfg):
     k = 8
     hh, ww = h // k * k, w // k * k
     pool = lambda a: a[:hh, :ww].reshape(hh // k, k, ww // k, k, 3).sum(axis=(1, 3))  # noqa: E731
-    gold_lin = img ** 2
     var_blk = pool(sigma ** 2) * (1.0 + meta["spp"] / spp)
     ok = var_blk > 0
     z = (pool(mean) - pool(gold_lin))[ok] / np.sqrt(var_blk[ok])
@@ -63,9 +66,12 @@ def test_converged_image_matches_golden(pkg, cfg):
     gain_db = 10.0 * np.log10(4.0 / (1.0 + meta["spp"] / spp))
     assert mae <= max(1.0 / 255.0, 1.08 * meta["mae_half_vs_half"] * 10 ** (-gain_db / 20.0)), report
     assert psnr >= min(40.0, meta["psnr_half_vs_half"] + gain_db - 0.6), report
-    # z_rms / z_mean are reported for information only: the goldens are stored as float16 in gamma space, whose
-    # quantisation (2^-11 relative) exceeds the 4096-spp standard error in smooth regions; the statistically rigorous
-    # z-score tests run against live float32 oracle renders in test_gpu_parity.py
+    # Pooled z-scores against the golden's own standard error: unbiased (|mean| small) and of unit scale.  The float16
+    # gamma-space files of the first generator version (C3 / C4 / C5: black background, every pixel noisy) pass as they
+    # are; on C1 / C2a / C2b that storage put a 5.6e-4 relative error on the constant (0.7, 0.8, 1.0) background — many
+    # sigmas of a nearly noise-free block, the +2 .. +22 z-means of round 1 — hence their float32 linear goldens.
+    assert abs(report["z_mean"]) < 0.5, report
+    assert report["z_rms"] < 1.6, report
     assert abs(report["rays_per_path_gpu"] - report["rays_per_path_oracle"]) < 0.01 * report["rays_per_path_oracle"], report
 
 
