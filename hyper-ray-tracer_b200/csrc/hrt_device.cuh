@@ -73,6 +73,10 @@ struct DeviceScene {
     cudaTextureObject_t images[kMaxImages];
     int32_t n_ops, n_noise, n_media;
     float ln_e;            // logf(E_f32) as computed by the host libm (f32::log(self, E) = ln(x)/ln(E))
+    // Kernel-local (0 as uploaded): records [0, n_sh_ops) and tree nodes [0, n_sh_nodes) staged in the block's shared
+    // memory at these shared-space addresses (render_phase_kernel); everything beyond comes from global memory.
+    uint32_t sh_ops, sh_nodes;
+    int32_t n_sh_ops, n_sh_nodes;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -184,9 +188,29 @@ __device__ __forceinline__ V3 sample_in_unit_disk(float u1, float u2) {
 // ------------------------------------------------------------------------------------------------
 // Ray-space contexts
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
 __device__ __forceinline__ void load_op(const DeviceScene& S, int pc, float4& A, float4& B) {
-    A = __ldg(S.ops + 2 * pc);
-    B = __ldg(S.ops + 2 * pc + 1);
+    if (pc < S.n_sh_ops) {
+        A = lds128(S.sh_ops + 32u * (uint32_t)pc);
+        B = lds128(S.sh_ops + 32u * (uint32_t)pc + 16u);
+    } else {
+        A = __ldg(S.ops + 2 * pc);
+        B = __ldg(S.ops + 2 * pc + 1);
+    }
+}
+__device__ __forceinline__ void load_node(const DeviceScene& S, int node, uint4& L, uint4& R) {
+    if (node < S.n_sh_nodes) {
+        const float4 a = lds128(S.sh_nodes + 32u * (uint32_t)node), b = lds128(S.sh_nodes + 32u * (uint32_t)node + 16u);
+        L = make_uint4(__float_as_uint(a.x), __float_as_uint(a.y), __float_as_uint(a.z), __float_as_uint(a.w));
+        R = make_uint4(__float_as_uint(b.x), __float_as_uint(b.y), __float_as_uint(b.z), __float_as_uint(b.w));
+    } else {
+        L = __ldg(S.nodes + 2 * (size_t)node);
+        R = __ldg(S.nodes + 2 * (size_t)node + 1);
+    }
 }
 
 // translation.rs:25-29
@@ -454,10 +478,10 @@ __device__ __noinline__ TreeHit bvh2_walk(const DeviceScene& S, int base, Ray cu
     float stack_t[kBvh2Stack];
     int sp = 0;
     int ref = 0;  // the tree's first node is its root
-    const uint4* nodes = S.nodes + 2 * (size_t)base;
     for (;;) {
         if (ref >= 0) {
-            const uint4 L = __ldg(nodes + 2 * ref), R = __ldg(nodes + 2 * ref + 1);
+            uint4 L, R;
+            load_node(S, base + ref, L, R);
             float llo, lhi, rlo, rhi;
             slab16(L.x, L.y, L.z, cur, k, tmin, h.t, llo, lhi);
             slab16(R.x, R.y, R.z, cur, k, tmin, h.t, rlo, rhi);
@@ -720,14 +744,46 @@ __device__ __noinline__ float boundary_hit_uniform(const DeviceScene& S, int pc,
     return hit ? t : CUDART_NAN_F;
 }
 
+// Per-lane state of a warp-uniform walk.  walk_uniform<.., kStopAtTree = true> returns at every OP_BVH record some lane
+// has to enter (its pc, warp-uniform, or -1 when the walk is over) and can be called again to go on.
+struct Walk {
+    int pc;       // next record of this lane (pc_end: done / no ray)
+    Ray cur;      // ray in the current context
+    RayK k;
+    int ctx;
+    float closest;
+    Best best;
+    bool any;
+};
+__device__ __forceinline__ void walk_begin(Walk& W, int pc_begin, int pc_end, bool active, const Ray& cur, int ctx, float closest) {
+    W.pc = active ? pc_begin : pc_end;
+    W.cur = cur;
+    W.k = make_rayk(cur);
+    W.ctx = ctx;
+    W.closest = closest;
+    W.best.pc = -1; W.best.t = 0.0f; W.best.face = 0; W.best.ctx = 0;
+    W.any = false;
+}
+// What a lane standing at the OP_BVH record (A, B) does with the result of its tree walk.
 template <bool kInner>
-__device__ __forceinline__ bool traverse_uniform(const DeviceScene& S, const int pc_begin, const int pc_end, const bool active,
-                                                 const Ray& world, Ray cur, int cur_ctx, const float tmin, float& closest,
-                                                 Best& best, const bool reference_boxes, const MediumXi& xi) {
+__device__ __forceinline__ void walk_take_tree(Walk& W, const TreeHit& th, int end_pc) {
+    if (th.pc != (kInner ? -1 : W.best.pc)) {
+        W.closest = th.t; W.any = true;
+        if (!kInner) { W.best.t = th.t; W.best.pc = th.pc; W.best.face = th.face; W.best.ctx = W.ctx; }
+    }
+    W.pc = end_pc;
+}
+template <bool kInner, bool kStopAtTree>
+__device__ __forceinline__ int walk_uniform(const DeviceScene& S, const int pc_end, Walk& W, const Ray& world, const float tmin,
+                                            const bool reference_boxes, const MediumXi& xi) {
     const unsigned kAll = 0xffffffffu;
-    int pc = active ? pc_begin : pc_end;
-    RayK k = make_rayk(cur);
-    bool any = false;
+    int& pc = W.pc;
+    Ray& cur = W.cur;
+    RayK& k = W.k;
+    int& cur_ctx = W.ctx;
+    float& closest = W.closest;
+    Best& best = W.best;
+    bool& any = W.any;
     for (;;) {
         const int upc = __reduce_min_sync(kAll, pc);  // warp-uniform
         if (upc >= pc_end) break;
@@ -808,14 +864,9 @@ __device__ __forceinline__ bool traverse_uniform(const DeviceScene& S, const int
                 break;
             }
             case OP_BVH: {
-                if (me) {
-                    const TreeHit th = bvh2_walk(S, __float_as_int(A.x), cur, tmin, closest, kInner ? -1 : best.pc, B.x, B.y);
-                    if (th.pc != (kInner ? -1 : best.pc)) {
-                        closest = th.t; any = true;
-                        if (!kInner) { best.t = th.t; best.pc = th.pc; best.face = th.face; best.ctx = cur_ctx; }
-                    }
-                    pc = (int)(w7 >> 8);
-                }
+                if (kStopAtTree) return upc;  // the caller walks the tree for the lanes with W.pc == upc (walk_take_tree)
+                if (me) walk_take_tree<kInner>(W, bvh2_walk(S, __float_as_int(A.x), cur, tmin, closest, kInner ? -1 : best.pc, B.x, B.y),
+                                               (int)(w7 >> 8));
                 break;
             }
             case OP_MEDIUM: case OP_MEDIUM_SPHERE: {
@@ -876,7 +927,21 @@ __device__ __forceinline__ bool traverse_uniform(const DeviceScene& S, const int
                 break;
         }
     }
-    return any;
+    return -1;
+}
+
+template <bool kInner>
+__device__ __forceinline__ bool traverse_uniform(const DeviceScene& S, const int pc_begin, const int pc_end, const bool active,
+                                                 const Ray& world, Ray cur, int cur_ctx, const float tmin, float& closest,
+                                                 Best& best, const bool reference_boxes, const MediumXi& xi) {
+    Walk W;
+    walk_begin(W, pc_begin, pc_end, active, cur, cur_ctx, closest);
+    walk_uniform<kInner, false>(S, pc_end, W, world, tmin, reference_boxes, xi);
+    if (W.any) {
+        closest = W.closest;
+        if (!kInner) best = W.best;
+    }
+    return W.any;
 }
 
 // ------------------------------------------------------------------------------------------------
