@@ -365,15 +365,13 @@ static int32_t render_into(hrt_scene* s, DeviceState* d, const hrt_camera_desc* 
     L.n_nodes = ref_boxes ? 0 : (int32_t)s->fast.nodes.size();
     {
         const char* env = getenv("HRT_KERNEL");  // diagnostic override: "interp" | "sched" | "pool"
-        // default: the phase kernel (warp-uniform walks, block-wide tree rounds)
-        int variant = 4;
-        if (rd->flags & HRT_FLAG_PHASE) variant = 4;
+        // default: the warp-uniform walk
+        int variant = 3;
         if (rd->flags & HRT_FLAG_SCHEDULER) variant = 0;
         if (rd->flags & HRT_FLAG_INTERPRETER) variant = 1;
         if (rd->flags & HRT_FLAG_POOL) variant = 2;
         if (rd->flags & HRT_FLAG_UNIFORM) variant = 3;
         if (env && env[0] == 'u') variant = 3;
-        if (env && env[0] == 'f') variant = 4;  // "fazed" (p is the pool)
         if (env && env[0] == 'i') variant = 1;
         if (env && env[0] == 's') variant = 0;
         if (env && env[0] == 'p') variant = 2;

@@ -73,10 +73,6 @@ struct DeviceScene {
     cudaTextureObject_t images[kMaxImages];
     int32_t n_ops, n_noise, n_media;
     float ln_e;            // logf(E_f32) as computed by the host libm (f32::log(self, E) = ln(x)/ln(E))
-    // Kernel-local (0 as uploaded): records [0, n_sh_ops) and tree nodes [0, n_sh_nodes) staged in the block's shared
-    // memory at these shared-space addresses (render_phase_kernel); everything beyond comes from global memory.
-    uint32_t sh_ops, sh_nodes;
-    int32_t n_sh_ops, n_sh_nodes;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -188,29 +184,13 @@ __device__ __forceinline__ V3 sample_in_unit_disk(float u1, float u2) {
 // ------------------------------------------------------------------------------------------------
 // Ray-space contexts
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float4 lds128(uint32_t addr) {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-    return v;
-}
 __device__ __forceinline__ void load_op(const DeviceScene& S, int pc, float4& A, float4& B) {
-    if (pc < S.n_sh_ops) {
-        A = lds128(S.sh_ops + 32u * (uint32_t)pc);
-        B = lds128(S.sh_ops + 32u * (uint32_t)pc + 16u);
-    } else {
-        A = __ldg(S.ops + 2 * pc);
-        B = __ldg(S.ops + 2 * pc + 1);
-    }
+    A = __ldg(S.ops + 2 * pc);
+    B = __ldg(S.ops + 2 * pc + 1);
 }
 __device__ __forceinline__ void load_node(const DeviceScene& S, int node, uint4& L, uint4& R) {
-    if (node < S.n_sh_nodes) {
-        const float4 a = lds128(S.sh_nodes + 32u * (uint32_t)node), b = lds128(S.sh_nodes + 32u * (uint32_t)node + 16u);
-        L = make_uint4(__float_as_uint(a.x), __float_as_uint(a.y), __float_as_uint(a.z), __float_as_uint(a.w));
-        R = make_uint4(__float_as_uint(b.x), __float_as_uint(b.y), __float_as_uint(b.z), __float_as_uint(b.w));
-    } else {
-        L = __ldg(S.nodes + 2 * (size_t)node);
-        R = __ldg(S.nodes + 2 * (size_t)node + 1);
-    }
+    L = __ldg(S.nodes + 2 * (size_t)node);
+    R = __ldg(S.nodes + 2 * (size_t)node + 1);
 }
 
 // translation.rs:25-29
@@ -384,20 +364,39 @@ __device__ __forceinline__ bool rect_test(float ok, float dk, float invk, float 
     t_out = t;
     return true;
 }
-// cuboid.rs:30-96 + list.rs:20-31: six rects in construction order with closest-so-far narrowing.
+// rect.rs:54-69 for any plane: (k, a, b) = XY (z, x, y), YZ (x, y, z), ZX (y, z, x)
+__device__ __forceinline__ bool rect_any(uint32_t opc, float4 A, float kk, const Ray& c, const RayK& k, float tmin, float closest,
+                                         float& t) {
+    const int ik = opc == OP_RECT_XY ? 2 : (opc == OP_RECT_YZ ? 0 : 1);
+    const int ia = ik == 2 ? 0 : ik + 1, ib = ik == 0 ? 2 : ik - 1;
+    return rect_test(sel3(ik, c.o.x, c.o.y, c.o.z), sel3(ik, c.d.x, c.d.y, c.d.z), sel3(ik, k.inv.x, k.inv.y, k.inv.z),
+                     sel3(ia, c.o.x, c.o.y, c.o.z), sel3(ia, c.d.x, c.d.y, c.d.z), sel3(ib, c.o.x, c.o.y, c.o.z),
+                     sel3(ib, c.d.x, c.d.y, c.d.z), A.x, A.y, A.z, A.w, kk, tmin, closest, t);
+}
+
+// cuboid.rs:30-96 + list.rs:20-31: six rects in construction order with closest-so-far narrowing:
+//   0: XY @ max.z   1: XY @ min.z   2: ZX @ max.y   3: ZX @ min.y   4: YZ @ max.x   5: YZ @ min.x
+// i.e. (k, a, b) = (z, x, y), (y, z, x), (x, y, z): each axis step rotates the components by one.  A rolled loop: the
+// unrolled form is 6 inlined rect tests per call site, and code size is what bounds the render kernel.
 __device__ __forceinline__ bool cuboid_test(V3 mn, V3 mx, const Ray& r, const RayK& k, float tmin, float closest,
                                             float& t_out, int& face_out) {
+    float ok = r.o.z, dk = r.d.z, ik = k.inv.z, oa = r.o.x, da = r.d.x, ob = r.o.y, db = r.d.y;
+    float k0 = mn.z, k1 = mx.z, a0 = mn.x, a1 = mx.x, b0 = mn.y, b1 = mx.y;
+    float ia = k.inv.x, ib = k.inv.y;
     bool any = false;
-    float t;
-    // 0: XY @ max.z   1: XY @ min.z
-    if (rect_test(r.o.z, r.d.z, k.inv.z, r.o.x, r.d.x, r.o.y, r.d.y, mn.x, mx.x, mn.y, mx.y, mx.z, tmin, closest, t)) { closest = t; face_out = 0; any = true; }
-    if (rect_test(r.o.z, r.d.z, k.inv.z, r.o.x, r.d.x, r.o.y, r.d.y, mn.x, mx.x, mn.y, mx.y, mn.z, tmin, closest, t)) { closest = t; face_out = 1; any = true; }
-    // 2: ZX @ max.y   3: ZX @ min.y   (a = z, b = x)
-    if (rect_test(r.o.y, r.d.y, k.inv.y, r.o.z, r.d.z, r.o.x, r.d.x, mn.z, mx.z, mn.x, mx.x, mx.y, tmin, closest, t)) { closest = t; face_out = 2; any = true; }
-    if (rect_test(r.o.y, r.d.y, k.inv.y, r.o.z, r.d.z, r.o.x, r.d.x, mn.z, mx.z, mn.x, mx.x, mn.y, tmin, closest, t)) { closest = t; face_out = 3; any = true; }
-    // 4: YZ @ max.x   5: YZ @ min.x   (a = y, b = z)
-    if (rect_test(r.o.x, r.d.x, k.inv.x, r.o.y, r.d.y, r.o.z, r.d.z, mn.y, mx.y, mn.z, mx.z, mx.x, tmin, closest, t)) { closest = t; face_out = 4; any = true; }
-    if (rect_test(r.o.x, r.d.x, k.inv.x, r.o.y, r.d.y, r.o.z, r.d.z, mn.y, mx.y, mn.z, mx.z, mn.x, tmin, closest, t)) { closest = t; face_out = 5; any = true; }
+#pragma unroll 1
+    for (int axis = 0; axis < 3; ++axis) {
+        float t;
+        if (rect_test(ok, dk, ik, oa, da, ob, db, a0, a1, b0, b1, k1, tmin, closest, t)) { closest = t; face_out = 2 * axis; any = true; }
+        if (rect_test(ok, dk, ik, oa, da, ob, db, a0, a1, b0, b1, k0, tmin, closest, t)) { closest = t; face_out = 2 * axis + 1; any = true; }
+        // next axis: k <- b, a <- k, b <- a
+        float x;
+        x = ob; ob = oa; oa = ok; ok = x;
+        x = db; db = da; da = dk; dk = x;
+        x = ib; ib = ia; ia = ik; ik = x;
+        x = b0; b0 = a0; a0 = k0; k0 = x;
+        x = b1; b1 = a1; a1 = k1; k1 = x;
+    }
     t_out = closest;
     return any;
 }
@@ -506,20 +505,18 @@ __device__ __noinline__ TreeHit bvh2_walk(const DeviceScene& S, int base, Ray cu
             float t = 0.0f;
             int face = 0;
             bool hit;
-            if (opc == OP_SPHERE) {
-                hit = sphere_test(v3(A.x, A.y, A.z), A.w, cur, k, tmin, h.t, t);
-            } else if (opc == OP_MSPHERE) {
-                float4 C, D;
-                load_op(S, pc + 1, C, D);
-                hit = sphere_test(msphere_center(v3(A.x, A.y, A.z), v3(C.x, C.y, C.z), C.w, D.x, cur.time), A.w, cur, k, tmin, h.t, t);
+            if (opc == OP_SPHERE || opc == OP_MSPHERE) {
+                V3 ctr = v3(A.x, A.y, A.z);
+                if (opc == OP_MSPHERE) {
+                    float4 C, D;
+                    load_op(S, pc + 1, C, D);
+                    ctr = msphere_center(ctr, v3(C.x, C.y, C.z), C.w, D.x, cur.time);
+                }
+                hit = sphere_test(ctr, A.w, cur, k, tmin, h.t, t);
             } else if (opc == OP_CUBOID) {
                 hit = cuboid_test(v3(A.x, A.y, A.z), v3(B.x, B.y, B.z), cur, k, tmin, h.t, t, face);
-            } else if (opc == OP_RECT_XY) {
-                hit = rect_test(cur.o.z, cur.d.z, k.inv.z, cur.o.x, cur.d.x, cur.o.y, cur.d.y, A.x, A.y, A.z, A.w, B.x, tmin, h.t, t);
-            } else if (opc == OP_RECT_YZ) {
-                hit = rect_test(cur.o.x, cur.d.x, k.inv.x, cur.o.y, cur.d.y, cur.o.z, cur.d.z, A.x, A.y, A.z, A.w, B.x, tmin, h.t, t);
             } else {
-                hit = rect_test(cur.o.y, cur.d.y, k.inv.y, cur.o.z, cur.d.z, cur.o.x, cur.d.x, A.x, A.y, A.z, A.w, B.x, tmin, h.t, t);
+                hit = rect_any(opc, A, B.x, cur, k, tmin, h.t, t);
             }
             if (hit) {  // the primitive tests accept t <= closest
                 bool take = t < h.t || h.pc < 0;
@@ -693,7 +690,7 @@ __device__ __noinline__ float boundary_hit(const DeviceScene& S, int pc, int end
 
 // The tail of ConstantMedium::hit once both boundary hits are known (constant_medium.rs:40-75): true and the
 // scattering distance `t_out` when the medium scatters inside [tmin, closest].  A = the medium record's first half.
-__device__ __forceinline__ bool medium_sample(const DeviceScene& S, float4 A, float dd, float t1, float t2, float tmin,
+__device__ __noinline__ bool medium_sample(const DeviceScene& S, float4 A, float dd, float t1, float t2, float tmin,
                                               float closest, const MediumXi& xi, float& t_out) {
     if (t1 < tmin) t1 = tmin;
     if (t2 > closest) t2 = closest;
@@ -719,74 +716,64 @@ __device__ __forceinline__ bool medium_sample(const DeviceScene& S, float4 A, fl
 //
 // The stream is forward-only (a missed box jumps FORWARD to its skip link, everything else falls through), so the 32
 // rays of a warp can walk it together: every step executes the record at the SMALLEST pc any lane still has to visit
-// (one REDUX.MIN), for exactly the lanes that are at it; lanes that are further ahead wait.  The record fetch is one
-// broadcast load, and the opcode — hence every branch of the interpreter — is warp-uniform: no divergence between
-// record kinds, no per-ray bookkeeping, no votes.  Per ray the visit order and the arithmetic are those of
-// `traverse<>`, so results are identical.  The price is that a warp walks the UNION of its rays' records; that is what
-// the short streams here want (Cornell: 34 records; `final`: a 21-node top level around two big BVHs).
+// (one REDUX.MIN into a uniform register), for exactly the lanes that are at it; lanes that are further ahead wait.
+// The record fetch is one broadcast load, and the opcode — hence every branch of the interpreter — is warp-uniform: no
+// divergence between record kinds, no per-ray bookkeeping, no votes.  Per ray the visit order and the arithmetic are
+// those of `traverse<>`, so results are identical.  The price is that a warp walks the UNION of its rays' records;
+// that is what the short streams of the fast form want (Cornell: 34 records; `final`: a 21-node top level around two
+// OP_BVH trees, which each ray walks on its own with a stack).
+//
+// ONE copy of the interpreter serves the world ray and the two boundary queries of a ConstantMedium
+// (constant_medium.rs:37-38): a medium whose boundary is not a plain sphere switches the walk — warp-uniformly — into
+// query mode over its sub-stream [pc+1, end): the medium's lanes restart there with the query's own range, (-inf, +inf)
+// and then (t1 + 1e-4, +inf), and afterwards go on behind the sub-stream with the world ray's state restored.  Code
+// size is what bounds this kernel (instruction fetch was the top stall of its first version, profiles/r02_u1_*), hence
+// also the compact forms of the rect / cuboid tests.
 // Every lane of the warp must call it (`active` = this lane carries a ray).
 // ------------------------------------------------------------------------------------------------
-template <bool kInner>
 __device__ __forceinline__ bool traverse_uniform(const DeviceScene& S, const int pc_begin, const int pc_end, const bool active,
-                                                 const Ray& world, Ray cur, int cur_ctx, const float tmin, float& closest,
-                                                 Best& best, const bool reference_boxes, const MediumXi& xi);
-
-// Warp-uniform ConstantMedium boundary query (constant_medium.rs:37-38); NaN = miss.  Out of line: one copy of the inner
-// interpreter per kernel.
-__device__ __noinline__ float boundary_hit_uniform(const DeviceScene& S, int pc, int end, bool active, Ray world, Ray cur,
-                                                   int ctx, float tmin, bool reference_boxes) {
-    Best dummy;
-    MediumXi none;
-    none.key.k0 = 0; none.key.k1 = 0; none.key.pixel = 0; none.key.sample = 0;
-    none.bounce = 0; none.injected = 0.5f; none.inject = true;
-    float t = CUDART_INF_F;
-    const bool hit = traverse_uniform<true>(S, pc, end, active, world, cur, ctx, tmin, t, dummy, reference_boxes, none);
-    return hit ? t : CUDART_NAN_F;
-}
-
-// Per-lane state of a warp-uniform walk.  walk_uniform<.., kStopAtTree = true> returns at every OP_BVH record some lane
-// has to enter (its pc, warp-uniform, or -1 when the walk is over) and can be called again to go on.
-struct Walk {
-    int pc;       // next record of this lane (pc_end: done / no ray)
-    Ray cur;      // ray in the current context
-    RayK k;
-    int ctx;
-    float closest;
-    Best best;
-    bool any;
-};
-__device__ __forceinline__ void walk_begin(Walk& W, int pc_begin, int pc_end, bool active, const Ray& cur, int ctx, float closest) {
-    W.pc = active ? pc_begin : pc_end;
-    W.cur = cur;
-    W.k = make_rayk(cur);
-    W.ctx = ctx;
-    W.closest = closest;
-    W.best.pc = -1; W.best.t = 0.0f; W.best.face = 0; W.best.ctx = 0;
-    W.any = false;
-}
-// What a lane standing at the OP_BVH record (A, B) does with the result of its tree walk.
-template <bool kInner>
-__device__ __forceinline__ void walk_take_tree(Walk& W, const TreeHit& th, int end_pc) {
-    if (th.pc != (kInner ? -1 : W.best.pc)) {
-        W.closest = th.t; W.any = true;
-        if (!kInner) { W.best.t = th.t; W.best.pc = th.pc; W.best.face = th.face; W.best.ctx = W.ctx; }
-    }
-    W.pc = end_pc;
-}
-template <bool kInner, bool kStopAtTree>
-__device__ __forceinline__ int walk_uniform(const DeviceScene& S, const int pc_end, Walk& W, const Ray& world, const float tmin,
-                                            const bool reference_boxes, const MediumXi& xi) {
+                                                 const Ray& world, Ray cur, int cur_ctx, const float tmin_world, float& closest_io,
+                                                 Best& best, const bool reference_boxes, const MediumXi& xi) {
     const unsigned kAll = 0xffffffffu;
-    int& pc = W.pc;
-    Ray& cur = W.cur;
-    RayK& k = W.k;
-    int& cur_ctx = W.ctx;
-    float& closest = W.closest;
-    Best& best = W.best;
-    bool& any = W.any;
+    int pc = active ? pc_begin : pc_end;
+    RayK k = make_rayk(cur);
+    float closest = closest_io;
+    float tmin = tmin_world;  // t_min of the query this lane is in
+    bool hitf = false;        // the query this lane is in has hit something
+    // query mode (warp-uniform): 0 = world ray; 1 / 2 = first / second boundary query of the medium record at m_pc
+    int mode = 0, m_pc = 0, range_end = pc_end;
+    bool in_q = false;        // this lane takes part in the medium's queries
+    bool saved_hitf = false;
+    float saved_closest = 0.0f, q_t1 = 0.0f;
     for (;;) {
         const int upc = __reduce_min_sync(kAll, pc);  // warp-uniform
-        if (upc >= pc_end) break;
+        if (upc >= range_end) {
+            if (mode == 0) break;
+            // ---- a boundary query of the medium at m_pc is over for every lane that took part ----
+            float4 A, B;
+            load_op(S, m_pc, A, B);
+            if (in_q) {
+                const bool q_hit = hitf && closest == closest;  // a NaN boundary t counts as a miss
+                if (mode == 1 && q_hit) {  // second query: (t1 + 1e-4, +inf)
+                    q_t1 = closest;
+                    pc = m_pc + 1; tmin = q_t1 + 0.0001f; closest = CUDART_INF_F; hitf = false;
+                } else {  // the medium is decided: back to the world ray, behind the boundary sub-stream
+                    const float t2 = closest;
+                    closest = saved_closest; tmin = tmin_world; hitf = saved_hitf;
+                    float t;
+                    if (mode == 2 && q_hit && medium_sample(S, A, k.dd, q_t1, t2, tmin_world, closest, xi, t)) {
+                        closest = t; hitf = true;
+                        best.t = t; best.pc = m_pc; best.face = 0; best.ctx = cur_ctx;
+                    }
+                    pc = (int)(__float_as_uint(B.w) >> 8);
+                    in_q = false;
+                }
+            }
+            if (mode == 1 && __any_sync(kAll, in_q)) { mode = 2; continue; }
+            mode = 0;
+            range_end = pc_end;
+            continue;
+        }
         float4 A, B;
         load_op(S, upc, A, B);  // one address for the whole warp
         const uint32_t w7 = __float_as_uint(B.w);
@@ -800,56 +787,40 @@ __device__ __forceinline__ int walk_uniform(const DeviceScene& S, const int pc_e
             }
             continue;
         }
+        // primitive records share one acceptance tail
+        bool prim = false, hit = false;
+        float t = 0.0f;
+        int face = 0, next = upc + 1;
         switch (opc) {
-            case OP_SPHERE: {
-                if (me) {
-                    float t;
-                    if (sphere_test(v3(A.x, A.y, A.z), A.w, cur, k, tmin, closest, t)) {
-                        closest = t; any = true;
-                        if (!kInner) { best.t = t; best.pc = upc; best.face = 0; best.ctx = cur_ctx; }
-                    }
-                    pc = upc + 1;
+            case OP_SPHERE: case OP_MSPHERE: {
+                prim = true;
+                V3 ctr = v3(A.x, A.y, A.z);
+                if (opc == OP_MSPHERE) {
+                    float4 C, D;
+                    load_op(S, upc + 1, C, D);
+                    ctr = msphere_center(ctr, v3(C.x, C.y, C.z), C.w, D.x, cur.time);
+                    next = upc + 2;
                 }
+                if (me) hit = sphere_test(ctr, A.w, cur, k, tmin, closest, t);
                 break;
             }
-            case OP_MSPHERE: {
-                float4 C, D;
-                load_op(S, upc + 1, C, D);
-                if (me) {
-                    const V3 ctr = msphere_center(v3(A.x, A.y, A.z), v3(C.x, C.y, C.z), C.w, D.x, cur.time);
-                    float t;
-                    if (sphere_test(ctr, A.w, cur, k, tmin, closest, t)) {
-                        closest = t; any = true;
-                        if (!kInner) { best.t = t; best.pc = upc; best.face = 0; best.ctx = cur_ctx; }
-                    }
-                    pc = upc + 2;
-                }
+            case OP_RECT_XY: case OP_RECT_YZ: case OP_RECT_ZX:
+                prim = true;
+                if (me) hit = rect_any(opc, A, B.x, cur, k, tmin, closest, t);
                 break;
-            }
-            case OP_RECT_XY: case OP_RECT_YZ: case OP_RECT_ZX: {
-                if (me) {
-                    float t;
-                    bool h;
-                    if (opc == OP_RECT_XY) h = rect_test(cur.o.z, cur.d.z, k.inv.z, cur.o.x, cur.d.x, cur.o.y, cur.d.y, A.x, A.y, A.z, A.w, B.x, tmin, closest, t);
-                    else if (opc == OP_RECT_YZ) h = rect_test(cur.o.x, cur.d.x, k.inv.x, cur.o.y, cur.d.y, cur.o.z, cur.d.z, A.x, A.y, A.z, A.w, B.x, tmin, closest, t);
-                    else h = rect_test(cur.o.y, cur.d.y, k.inv.y, cur.o.z, cur.d.z, cur.o.x, cur.d.x, A.x, A.y, A.z, A.w, B.x, tmin, closest, t);
-                    if (h) {
-                        closest = t; any = true;
-                        if (!kInner) { best.t = t; best.pc = upc; best.face = 0; best.ctx = cur_ctx; }
-                    }
-                    pc = upc + 1;
-                }
+            case OP_CUBOID:
+                prim = true;
+                if (me) hit = cuboid_test(v3(A.x, A.y, A.z), v3(B.x, B.y, B.z), cur, k, tmin, closest, t, face);
                 break;
-            }
-            case OP_CUBOID: {
+            case OP_BVH: {  // a sound BvhNode as a two-child tree: every ray walks it on its own (bvh2_walk)
                 if (me) {
-                    float t;
-                    int face = 0;
-                    if (cuboid_test(v3(A.x, A.y, A.z), v3(B.x, B.y, B.z), cur, k, tmin, closest, t, face)) {
-                        closest = t; any = true;
-                        if (!kInner) { best.t = t; best.pc = upc; best.face = face; best.ctx = cur_ctx; }
+                    const int held = mode == 0 ? best.pc : -1;
+                    const TreeHit th = bvh2_walk(S, __float_as_int(A.x), cur, tmin, closest, held, B.x, B.y);
+                    if (th.pc != held) {
+                        closest = th.t; hitf = true;
+                        if (mode == 0) { best.t = th.t; best.pc = th.pc; best.face = th.face; best.ctx = cur_ctx; }
                     }
-                    pc = upc + 1;
+                    pc = (int)(w7 >> 8);
                 }
                 break;
             }
@@ -863,85 +834,67 @@ __device__ __forceinline__ int walk_uniform(const DeviceScene& S, const int pc_e
                 }
                 break;
             }
-            case OP_BVH: {
-                if (kStopAtTree) return upc;  // the caller walks the tree for the lanes with W.pc == upc (walk_take_tree)
-                if (me) walk_take_tree<kInner>(W, bvh2_walk(S, __float_as_int(A.x), cur, tmin, closest, kInner ? -1 : best.pc, B.x, B.y),
-                                               (int)(w7 >> 8));
-                break;
-            }
-            case OP_MEDIUM: case OP_MEDIUM_SPHERE: {
+            case OP_MEDIUM: case OP_MEDIUM_SPHERE: {  // constant_medium.rs:34-76; media do not nest, so mode == 0 here
                 const int end = (int)(w7 >> 8);
-                if (!kInner) {  // constant_medium.rs:34-76
-                    bool generic = me;
-                    if (opc == OP_MEDIUM_SPHERE) {
-                        // Boundary = one plain sphere: both boundary queries in closed form with sphere_test's arithmetic
-                        // (query 1 over (-inf, +inf) always takes the near root; query 2 over (t1 + 1e-4, +inf) takes the
-                        // near root again when the f32 sum t1 + 1e-4 == t1, else the far root).
-                        float4 C, D;
-                        load_op(S, upc + 1, C, D);
-                        generic = false;
-                        if (me) {
-                            const V3 oc = v3(__fsub_rn(cur.o.x, C.x), __fsub_rn(cur.o.y, C.y), __fsub_rn(cur.o.z, C.z));
-                            const float a = k.dd;
-                            const float half_b = dot_rn(oc, cur.d);
-                            const float c = __fsub_rn(dot_rn(oc, oc), __fmul_rn(C.w, C.w));
-                            const float disc = __fsub_rn(__fmul_rn(half_b, half_b), __fmul_rn(a, c));
-                            if (!(disc < 0.0f)) {
-                                const float sqrtd = sqrtf(disc);
-                                const float t1 = __fdiv_rn(-half_b - sqrtd, a);
-                                const float t2 = __fdiv_rn(-half_b + sqrtd, a);
-                                const float lo = t1 + 0.0001f;
-                                if (t1 == t1 && t2 == t2) {
-                                    float t;
-                                    bool h = false;
-                                    if (!(t1 < lo)) h = medium_sample(S, A, k.dd, t1, t1, tmin, closest, xi, t);
-                                    else if (!(t2 < lo)) h = medium_sample(S, A, k.dd, t1, t2, tmin, closest, xi, t);
-                                    if (h) {
-                                        closest = t; any = true;
-                                        best.t = t; best.pc = upc; best.face = 0; best.ctx = cur_ctx;
-                                    }
-                                } else {
-                                    generic = true;  // NaN roots take the generic path
+                bool generic = me;
+                if (opc == OP_MEDIUM_SPHERE) {
+                    // Boundary = one plain sphere: both boundary queries in closed form with sphere_test's arithmetic
+                    // (query 1 over (-inf, +inf) always takes the near root; query 2 over (t1 + 1e-4, +inf) takes the
+                    // near root again when the f32 sum t1 + 1e-4 == t1, else the far root).
+                    float4 C, D;
+                    load_op(S, upc + 1, C, D);
+                    generic = false;
+                    if (me) {
+                        const V3 oc = v3(__fsub_rn(cur.o.x, C.x), __fsub_rn(cur.o.y, C.y), __fsub_rn(cur.o.z, C.z));
+                        const float a = k.dd;
+                        const float half_b = dot_rn(oc, cur.d);
+                        const float c = __fsub_rn(dot_rn(oc, oc), __fmul_rn(C.w, C.w));
+                        const float disc = __fsub_rn(__fmul_rn(half_b, half_b), __fmul_rn(a, c));
+                        if (!(disc < 0.0f)) {
+                            const float sqrtd = sqrtf(disc);
+                            const float t1 = __fdiv_rn(-half_b - sqrtd, a);
+                            const float t2 = __fdiv_rn(-half_b + sqrtd, a);
+                            const float lo = t1 + 0.0001f;
+                            if (t1 == t1 && t2 == t2) {
+                                float tm;
+                                bool h = false;
+                                if (!(t1 < lo)) h = medium_sample(S, A, k.dd, t1, t1, tmin, closest, xi, tm);
+                                else if (!(t2 < lo)) h = medium_sample(S, A, k.dd, t1, t2, tmin, closest, xi, tm);
+                                if (h) {
+                                    closest = tm; hitf = true;
+                                    best.t = tm; best.pc = upc; best.face = 0; best.ctx = cur_ctx;
                                 }
-                            }
-                        }
-                    }
-                    if (__any_sync(kAll, generic)) {
-                        const float t1 = boundary_hit_uniform(S, upc + 1, end, generic, world, cur, cur_ctx, -CUDART_INF_F, reference_boxes);
-                        const bool h1 = generic && t1 == t1;
-                        if (__any_sync(kAll, h1)) {
-                            const float t2 = boundary_hit_uniform(S, upc + 1, end, h1, world, cur, cur_ctx, t1 + 0.0001f, reference_boxes);
-                            float t;
-                            if (h1 && t2 == t2 && medium_sample(S, A, k.dd, t1, t2, tmin, closest, xi, t)) {
-                                closest = t; any = true;
-                                best.t = t; best.pc = upc; best.face = 0; best.ctx = cur_ctx;
+                            } else {
+                                generic = true;  // NaN roots take the generic path
                             }
                         }
                     }
                 }
-                if (me) pc = end;
+                if (me && !generic) pc = end;
+                if (__any_sync(kAll, generic)) {  // query mode over [upc + 1, end): first query (-inf, +inf)
+                    in_q = generic;
+                    if (generic) {
+                        saved_closest = closest; saved_hitf = hitf;
+                        pc = upc + 1; tmin = -CUDART_INF_F; closest = CUDART_INF_F; hitf = false;
+                    }
+                    mode = 1; m_pc = upc; range_end = end;
+                }
                 break;
             }
             default:  // OP_END (or a stray record): stop
-                if (me) pc = pc_end;
+                if (me) pc = range_end;
                 break;
         }
+        if (prim && me) {
+            if (hit) {
+                closest = t; hitf = true;
+                if (mode == 0) { best.t = t; best.pc = upc; best.face = face; best.ctx = cur_ctx; }
+            }
+            pc = next;
+        }
     }
-    return -1;
-}
-
-template <bool kInner>
-__device__ __forceinline__ bool traverse_uniform(const DeviceScene& S, const int pc_begin, const int pc_end, const bool active,
-                                                 const Ray& world, Ray cur, int cur_ctx, const float tmin, float& closest,
-                                                 Best& best, const bool reference_boxes, const MediumXi& xi) {
-    Walk W;
-    walk_begin(W, pc_begin, pc_end, active, cur, cur_ctx, closest);
-    walk_uniform<kInner, false>(S, pc_end, W, world, tmin, reference_boxes, xi);
-    if (W.any) {
-        closest = W.closest;
-        if (!kInner) best = W.best;
-    }
-    return W.any;
+    if (hitf) closest_io = closest;
+    return hitf;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -971,23 +924,9 @@ __device__ __forceinline__ void sphere_uv(V3 p, float& u, float& v) {
 // at best.t, then undo the enclosing Rotation/Translation records innermost-first
 // (rotation.rs:119-131, translation.rs:33-34).
 __device__ __noinline__ void make_hit_record(const DeviceScene& S, const Ray& world, const Best& best, bool want_uv, HitRec& h) {
-    // forward: world -> local, remembering the direction seen by each push record
-    Ray r = world;
-    Ctx c;
-    c.depth = 0;
-    float4 PA[kMaxCtxDepth];
-    bool is_translate[kMaxCtxDepth];
-    if (best.ctx != 0) {
-        c = S.ctxs[best.ctx];
-#pragma unroll 1
-        for (int i = 0; i < c.depth; ++i) {
-            float4 B;
-            load_op(S, c.op_pc[i], PA[i], B);
-            is_translate[i] = (__float_as_uint(B.w) & 0xffu) == OP_TRANSLATE;
-            if (is_translate[i]) apply_translate(r, PA[i]);
-            else apply_rotate(r, PA[i]);
-        }
-    }
+    // forward: world -> the record's ray space
+    const int depth = best.ctx != 0 ? S.ctxs[best.ctx].depth : 0;
+    const Ray r = depth > 0 ? ray_in_ctx(S, world, best.ctx) : world;
     float4 A, B;
     load_op(S, best.pc, A, B);
     const uint32_t w7 = __float_as_uint(B.w);
@@ -996,80 +935,70 @@ __device__ __noinline__ void make_hit_record(const DeviceScene& S, const Ray& wo
     h.u = 0.0f; h.v = 0.0f;
     h.face = 0;
     h.p = ray_at(r, best.t);
-    switch (opc) {
-        case OP_SPHERE: case OP_MSPHERE: {
-            V3 ctr = v3(A.x, A.y, A.z);
-            if (opc == OP_MSPHERE) {
-                float4 C, D;
-                load_op(S, best.pc + 1, C, D);
-                ctr = msphere_center(ctr, v3(C.x, C.y, C.z), C.w, D.x, r.time);
-            }
-            V3 outward = (h.p - ctr) / A.w;
-            h.mat = __float_as_int(B.x);
-            // sphere.rs:61 computes (u,v) on every hit; only image-textured materials ever read them
-            if (want_uv || (S.mats[h.mat].flags & MATF_NEEDS_UV)) sphere_uv(outward, h.u, h.v);
-            set_face_normal(h, r.d, outward);
-            h.prim = __float_as_int(B.y);
-            break;
+    if (opc == OP_SPHERE || opc == OP_MSPHERE) {
+        V3 ctr = v3(A.x, A.y, A.z);
+        if (opc == OP_MSPHERE) {
+            float4 C, D;
+            load_op(S, best.pc + 1, C, D);
+            ctr = msphere_center(ctr, v3(C.x, C.y, C.z), C.w, D.x, r.time);
         }
-        case OP_RECT_XY: case OP_RECT_YZ: case OP_RECT_ZX: {
-            float a, b;
-            V3 outward;
-            if (opc == OP_RECT_XY) { a = h.p.x; b = h.p.y; outward = v3(0, 0, 1); }
-            else if (opc == OP_RECT_YZ) { a = h.p.y; b = h.p.z; outward = v3(1, 0, 0); }
-            else { a = h.p.z; b = h.p.x; outward = v3(0, 1, 0); }
-            h.u = (a - A.x) / (A.y - A.x);  // rect.rs:75-76
-            h.v = (b - A.z) / (A.w - A.z);
-            set_face_normal(h, r.d, outward);
-            h.mat = __float_as_int(B.y);
-            h.prim = __float_as_int(B.z);
-            break;
-        }
-        case OP_CUBOID: {
-            const V3 mn = v3(A.x, A.y, A.z), mx = v3(B.x, B.y, B.z);
+        const V3 outward = (h.p - ctr) / A.w;
+        h.mat = __float_as_int(B.x);
+        // sphere.rs:61 computes (u,v) on every hit; only image-textured materials ever read them
+        if (want_uv || (S.mats[h.mat].flags & MATF_NEEDS_UV)) sphere_uv(outward, h.u, h.v);
+        set_face_normal(h, r.d, outward);
+        h.prim = __float_as_int(B.y);
+    } else if (opc == OP_MEDIUM || opc == OP_MEDIUM_SPHERE) {  // constant_medium.rs:67-75
+        h.n = v3(0.0f, 0.0f, 0.0f);
+        h.front_face = false;
+        h.mat = __float_as_int(A.y);
+        h.prim = __float_as_int(A.w);
+    } else {
+        // rect.rs:71-84 / the cuboid's side `face` (cuboid.rs:30-96): plane axis k, in-plane axes (a, b)
+        int ik;
+        float a0, a1, b0, b1;
+        if (opc == OP_CUBOID) {
             const int f = best.face;
-            float a, b, a0, a1, b0, b1;
-            V3 outward;
-            if (f < 2) { a = h.p.x; b = h.p.y; a0 = mn.x; a1 = mx.x; b0 = mn.y; b1 = mx.y; outward = v3(0, 0, 1); }
-            else if (f < 4) { a = h.p.z; b = h.p.x; a0 = mn.z; a1 = mx.z; b0 = mn.x; b1 = mx.x; outward = v3(0, 1, 0); }
-            else { a = h.p.y; b = h.p.z; a0 = mn.y; a1 = mx.y; b0 = mn.z; b1 = mx.z; outward = v3(1, 0, 0); }
-            h.u = (a - a0) / (a1 - a0);
-            h.v = (b - b0) / (b1 - b0);
-            set_face_normal(h, r.d, outward);
+            ik = f < 2 ? 2 : (f < 4 ? 1 : 0);
+            const int ia = ik == 2 ? 0 : ik + 1, ib = ik == 0 ? 2 : ik - 1;
+            a0 = sel3(ia, A.x, A.y, A.z); a1 = sel3(ia, B.x, B.y, B.z);
+            b0 = sel3(ib, A.x, A.y, A.z); b1 = sel3(ib, B.x, B.y, B.z);
             h.mat = __float_as_int(A.w);
             h.prim = (int)(w7 >> 8);
             h.face = f;
-            break;
+        } else {
+            ik = opc == OP_RECT_XY ? 2 : (opc == OP_RECT_YZ ? 0 : 1);
+            a0 = A.x; a1 = A.y; b0 = A.z; b1 = A.w;
+            h.mat = __float_as_int(B.y);
+            h.prim = __float_as_int(B.z);
         }
-        default: {  // OP_MEDIUM — constant_medium.rs:67-75
-            h.n = v3(0.0f, 0.0f, 0.0f);
-            h.front_face = false;
-            h.mat = __float_as_int(A.y);
-            h.prim = __float_as_int(A.w);
-            break;
-        }
+        const int ia = ik == 2 ? 0 : ik + 1, ib = ik == 0 ? 2 : ik - 1;
+        h.u = (sel3(ia, h.p.x, h.p.y, h.p.z) - a0) / (a1 - a0);  // rect.rs:75-76
+        h.v = (sel3(ib, h.p.x, h.p.y, h.p.z) - b0) / (b1 - b0);
+        set_face_normal(h, r.d, v3(ik == 0 ? 1.0f : 0.0f, ik == 1 ? 1.0f : 0.0f, ik == 2 ? 1.0f : 0.0f));
     }
-    // backward: local -> world.  After undoing record i the ray seen by the enclosing space has the
-    // direction that entered record i; Translation re-faces against ITS moved ray, whose direction equals
-    // the direction that entered it (translation.rs:25-34, Q4).
-    if (c.depth > 0) {
-        // directions entering each record: recompute by replaying (depth is tiny)
+    // backward: the record's space -> world, innermost Rotation / Translation first (rotation.rs:119-131,
+    // translation.rs:33-34).  Translation re-faces the normal against ITS moved ray (Q4), whose direction is the world
+    // direction mapped through the records outside it.
 #pragma unroll 1
-        for (int i = c.depth - 1; i >= 0; --i) {
-            if (is_translate[i]) {
-                // direction of moved_ray == direction entering record i
-                Ray rr = world;
+    for (int i = depth - 1; i >= 0; --i) {
+        const int op_pc = S.ctxs[best.ctx].op_pc[i];
+        float4 PA, PB;
+        load_op(S, op_pc, PA, PB);
+        if ((__float_as_uint(PB.w) & 0xffu) == OP_TRANSLATE) {
+            Ray rr = world;
 #pragma unroll 1
-                for (int j = 0; j < i; ++j) {
-                    if (is_translate[j]) apply_translate(rr, PA[j]);
-                    else apply_rotate(rr, PA[j]);
-                }
-                h.p = h.p + v3(PA[i].x, PA[i].y, PA[i].z);
-                set_face_normal(h, rr.d, h.n);
-            } else {
-                h.p = unrotate(h.p, PA[i]);
-                h.n = unrotate(h.n, PA[i]);
+            for (int j = 0; j < i; ++j) {
+                float4 QA, QB;
+                load_op(S, S.ctxs[best.ctx].op_pc[j], QA, QB);
+                if ((__float_as_uint(QB.w) & 0xffu) == OP_TRANSLATE) apply_translate(rr, QA);
+                else apply_rotate(rr, QA);
             }
+            h.p = h.p + v3(PA.x, PA.y, PA.z);
+            set_face_normal(h, rr.d, h.n);
+        } else {
+            h.p = unrotate(h.p, PA);
+            h.n = unrotate(h.n, PA);
         }
     }
 }

@@ -44,8 +44,8 @@ struct RenderParams {
     int n_big, tail_begin[kMaxTailChunks], tail_size[kMaxTailChunks];
     int reference_boxes;
     int n_tab;       // ray-pool kernel: Box16 records [0, n_tab) are staged in shared memory
-    int n_sh_noise;  // ray-pool / phase kernel: noise tables staged in shared memory
-    int n_sh_ops, n_sh_nodes;  // phase kernel: records / tree nodes staged in shared memory
+    int n_sh_noise;  // ray-pool kernel: noise tables staged behind them
+
     unsigned long long* counters;
     float4* accum;
 };
@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(kBlock, 2) render_interp_kernel(const __grid_c
             best.pc = -1; best.t = 0.0f; best.face = 0; best.ctx = 0;
             float closest = CUDART_INF_F;
             bool hit = false;
-            if (kUniform) hit = traverse_uniform<false>(S, 0, S.n_ops, active, ray, ray, 0, 0.001f, closest, best, ref_boxes, xi);
+            if (kUniform) hit = traverse_uniform(S, 0, S.n_ops, active, ray, ray, 0, 0.001f, closest, best, ref_boxes, xi);
             else if (active) hit = traverse<false>(S, 0, S.n_ops, ray, ray, 0, 0.001f, closest, best, ref_boxes, xi);
             if (active) {
                 n_rays++;
@@ -421,223 +421,6 @@ __device__ __forceinline__ void flush_item(const RenderParams& P, int tx, int ty
         atomicAdd(dst + 1, acc[lane][1]);
         atomicAdd(dst + 2, acc[lane][2]);
         atomicAdd(dst + 3, (float)s_n);
-    }
-}
-
-// ---- the phase kernel: warp-uniform walks + block-wide tree rounds ----
-// The production kernel.  One 16-warp block per SM; every thread owns one path (its state stays in registers) and every
-// ray segment goes through block-synchronous phases:
-//   1. walk    each warp walks the op stream together (walk_uniform) until one of its rays has to enter an OP_BVH tree;
-//              those rays post a REQUEST (ray in the tree's space, running t_max, current best record) to a block-wide
-//              queue in shared memory;
-//   2. trees   the requests of the whole block — compacted, so they fill whole warps even though each warp only
-//              contributes a few — are walked one per thread (bvh2_walk); results go back through shared memory and
-//              the walks resume.  (ncu on the per-warp version: the tree walk was half of all issued instructions at
-//              4.7 of 32 lanes.)  Rounds repeat until every warp has finished its stream;
-//   3. shade   emitted + scatter for every live path, finished paths are replaced from the warp's work item.
-// All warps of the SM are in the same phase at the same time, so they share one phase's worth of instruction cache.
-// The op stream, the tree nodes and the perlin tables are staged in shared memory as far as they fit.
-constexpr int kPhaseBlock = 512;
-constexpr int kPhaseWarps = kPhaseBlock / 32;
-struct alignas(16) TreeReq {
-    float4 a;  // o.xyz (in the tree's ray space), t_min
-    float4 b;  // d.xyz, time
-    float4 c;  // running t_max, best record so far (int), pc of the OP_BVH record (int), -
-};
-constexpr size_t kPhaseQueueBytes = (size_t)kPhaseBlock * (sizeof(TreeReq) + sizeof(float4));
-
-__global__ void __launch_bounds__(kPhaseBlock, 1) render_phase_kernel(const __grid_constant__ RenderParams P) {
-    extern __shared__ __align__(16) unsigned char sh_dyn[];
-    __shared__ float sh_acc[kPhaseWarps][32][3];
-    __shared__ int sh_qcount[2];
-    // dynamic shared memory: [requests][results][records][tree nodes][noise tables]
-    TreeReq* const sh_req = reinterpret_cast<TreeReq*>(sh_dyn);
-    float4* const sh_res = reinterpret_cast<float4*>(sh_dyn + kPhaseBlock * sizeof(TreeReq));
-    float4* const sh_ops = reinterpret_cast<float4*>(sh_dyn + kPhaseQueueBytes);
-    float4* const sh_nodes = sh_ops + 2 * (size_t)P.n_sh_ops;
-    NoiseTable* const sh_noise = reinterpret_cast<NoiseTable*>(sh_nodes + 2 * (size_t)P.n_sh_nodes);
-    DeviceScene S = P.S;
-    for (int i = threadIdx.x; i < 2 * P.n_sh_ops; i += kPhaseBlock) sh_ops[i] = __ldg(P.S.ops + i);
-    for (int i = threadIdx.x; i < 2 * P.n_sh_nodes; i += kPhaseBlock) {
-        const uint4 q = __ldg(P.S.nodes + i);
-        sh_nodes[i] = make_float4(__uint_as_float(q.x), __uint_as_float(q.y), __uint_as_float(q.z), __uint_as_float(q.w));
-    }
-    if (threadIdx.x < 2) sh_qcount[threadIdx.x] = 0;
-    S.sh_ops = (uint32_t)__cvta_generic_to_shared(sh_ops);
-    S.sh_nodes = (uint32_t)__cvta_generic_to_shared(sh_nodes);
-    S.n_sh_ops = P.n_sh_ops;
-    S.n_sh_nodes = P.n_sh_nodes;
-    TexEnv E;
-    stage_noise(S, E, sh_noise, P.n_sh_noise);  // ends with __syncthreads()
-
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    const bool ref_boxes = P.reference_boxes != 0;
-    const V3 bg = v3(P.bg[0], P.bg[1], P.bg[2]);
-    const float div_w = (float)P.width - 1.0f, div_h = (float)P.height - 1.0f;  // application.rs:444-445
-    const float kTmin = 0.001f;                                                 // application.rs:482
-    unsigned long long n_rays = 0, n_paths = 0;
-
-    // the warp's current work item: 8x4-pixel tile, samples [s0, s0 + s_n)
-    bool have_item = false, more_items = true;
-    int tx = 0, ty = 0, s0 = 0, s_n = 0, pool_size = 0, pool_next = 0;
-    // this thread's path
-    bool active = false;
-    Ray ray;
-    ray.o = v3(0.0f, 0.0f, 0.0f); ray.d = v3(1.0f, 1.0f, 1.0f); ray.time = 0.0f;
-    V3 T = v3(1.0f, 1.0f, 1.0f);
-    uint32_t bounce = 0;
-    RngKey key;
-    key.k0 = P.k0; key.k1 = P.k1; key.pixel = 0; key.sample = 0;
-    int my_pl = lane;
-    int round = 0;
-
-    for (;;) {
-        // ---- refill: replace finished paths from the warp's work item; fetch the next item when this one is done ----
-        while (more_items) {
-            if (!have_item) {
-                unsigned long long item = 0;
-                if (lane == 0) item = atomicAdd(P.counters, 1ULL);
-                item = __shfl_sync(kFull, item, 0);
-                if (item >= (unsigned long long)P.n_items) { more_items = false; break; }
-                decode_item(P, item, tx, ty, s0, s_n);
-                pool_size = 32 * s_n;
-                pool_next = 0;
-                sh_acc[warp][lane][0] = 0.0f;
-                sh_acc[warp][lane][1] = 0.0f;
-                sh_acc[warp][lane][2] = 0.0f;
-                __syncwarp();
-                have_item = true;
-            }
-            const unsigned need = __ballot_sync(kFull, !active);
-            if (need && pool_next < pool_size) {
-                const int idx = pool_next + __popc(need & lt_mask);
-                pool_next += __popc(need);
-                if (!active && idx < pool_size) {
-                    const int pl = idx & 31;
-                    const int px = tx * 8 + (pl & 7), py = ty * 4 + (pl >> 3);
-                    if (px < P.width && py < P.height) {
-                        key.pixel = (uint32_t)(py * P.width + px);
-                        key.sample = (uint32_t)(s0 + (idx >> 5));
-                        float c4[4];
-                        rng_block(key, 0, RNG_BLOCK_CAMERA, c4);  // jitter x, jitter y, shutter time, lens u1
-                        float lens_u2 = 0.0f;
-                        if (P.cam.lens_radius != 0.0f) {
-                            float l4[4];
-                            rng_block(key, 0, RNG_BLOCK_CAMERA - 1, l4);
-                            lens_u2 = l4[0];
-                        }
-                        const float u = ((float)px + c4[0]) / div_w;
-                        const float v = ((float)py + c4[1]) / div_h;
-                        ray = camera_get_ray(P.cam, u, v, c4[3], lens_u2, c4[2]);
-                        T = v3(1.0f, 1.0f, 1.0f);
-                        bounce = 0;
-                        my_pl = pl;
-                        active = P.depth > 0;  // ray_color(depth == 0) is black (application.rs:478-480)
-                        n_paths++;
-                    }
-                }
-            }
-            if (__any_sync(kFull, active)) break;
-            if (pool_next < pool_size) continue;  // only out-of-image pixels (or depth 0) were drawn: draw again
-            __syncwarp();
-            flush_item(P, tx, ty, s_n, sh_acc[warp], lane);
-            __syncwarp();
-            have_item = false;
-        }
-        if (!__syncthreads_or(active ? 1 : 0)) break;  // no live path left in the block and no work item either
-
-        // ---- one ray segment per live path: world.hit (application.rs:482) ----
-        MediumXi xi;
-        xi.key = key; xi.bounce = bounce; xi.injected = 0.0f; xi.inject = false;
-        Walk W;
-        walk_begin(W, 0, S.n_ops, active, ray, 0, CUDART_INF_F);
-        for (;;) {
-            const int tree_pc = walk_uniform<false, true>(S, S.n_ops, W, ray, kTmin, ref_boxes, xi);  // warp-uniform; -1: done
-            const bool mine = tree_pc >= 0 && W.pc == tree_pc;
-            int slot = 0;
-            if (tree_pc >= 0) {
-                const unsigned m = __ballot_sync(kFull, mine);
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&sh_qcount[round & 1], __popc(m));
-                base = __shfl_sync(kFull, base, 0);
-                slot = base + __popc(m & lt_mask);
-                if (mine) {
-                    TreeReq q;
-                    q.a = make_float4(W.cur.o.x, W.cur.o.y, W.cur.o.z, kTmin);
-                    q.b = make_float4(W.cur.d.x, W.cur.d.y, W.cur.d.z, W.cur.time);
-                    q.c = make_float4(W.closest, __int_as_float(W.best.pc), __int_as_float(tree_pc), 0.0f);
-                    sh_req[slot] = q;
-                }
-            }
-            if (!__syncthreads_or(tree_pc >= 0 ? 1 : 0)) break;  // every warp of the block has finished its stream
-            const int n_req = sh_qcount[round & 1];
-            if (threadIdx.x == 0) sh_qcount[(round + 1) & 1] = 0;
-            if ((int)threadIdx.x < n_req) {  // the block's requests, one per thread: whole warps
-                const TreeReq q = sh_req[threadIdx.x];
-                float4 A, B;
-                load_op(S, __float_as_int(q.c.z), A, B);
-                Ray r;
-                r.o = v3(q.a.x, q.a.y, q.a.z); r.d = v3(q.b.x, q.b.y, q.b.z); r.time = q.b.w;
-                const TreeHit th = bvh2_walk(S, __float_as_int(A.x), r, q.a.w, q.c.x, __float_as_int(q.c.y), B.x, B.y);
-                sh_res[threadIdx.x] = make_float4(th.t, __int_as_float(th.pc), __int_as_float(th.face), 0.0f);
-            }
-            __syncthreads();
-            if (mine) {
-                const float4 r = sh_res[slot];
-                float4 A, B;
-                load_op(S, tree_pc, A, B);
-                TreeHit th;
-                th.t = r.x; th.pc = __float_as_int(r.y); th.face = __float_as_int(r.z);
-                walk_take_tree<false>(W, th, (int)(__float_as_uint(B.w) >> 8));
-            }
-            round++;
-        }
-
-        // ---- emitted + scatter (application.rs:486-494) ----
-        if (active) {
-            n_rays++;
-            V3 add = v3(0.0f, 0.0f, 0.0f);
-            if (!W.any) {
-                add = T * bg;
-                active = false;
-            } else {
-                HitRec h;
-                make_hit_record(S, ray, W.best, false, h);
-                const Material m = S.mats[h.mat];
-                if (m.kind == MAT_DIFFUSE_LIGHT) {
-                    add = T * material_emitted(S, E, m, h);
-                    active = false;  // DiffuseLight::scatter -> None
-                } else {
-                    float u4[4];
-                    rng_block(key, bounce, RNG_BLOCK_SCATTER, u4);
-                    V3 att;
-                    Ray sc;
-                    if (material_scatter(S, E, m, ray, h, u4, att, sc)) {
-                        T = T * att;
-                        ray = sc;
-                        bounce++;
-                        if (bounce >= (uint32_t)P.depth) active = false;  // ray_color(depth == 0) is black
-                    } else {
-                        active = false;
-                    }
-                }
-            }
-            if (add.x != 0.0f) atomicAdd(&sh_acc[warp][my_pl][0], add.x);
-            if (add.y != 0.0f) atomicAdd(&sh_acc[warp][my_pl][1], add.y);
-            if (add.z != 0.0f) atomicAdd(&sh_acc[warp][my_pl][2], add.z);
-        }
-        // (a finished item is flushed by the refill step of the next iteration)
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        n_rays += __shfl_xor_sync(kFull, n_rays, o);
-        n_paths += __shfl_xor_sync(kFull, n_paths, o);
-    }
-    if (lane == 0) {
-        atomicAdd(P.counters + 1, n_rays);
-        atomicAdd(P.counters + 2, n_paths);
     }
 }
 
@@ -1007,7 +790,7 @@ __global__ void __launch_bounds__(128) trace_hits_uniform_kernel(const __grid_co
     }
     Best best;
     best.pc = -1; best.t = 0.0f; best.face = 0; best.ctx = 0;
-    const bool hit = traverse_uniform<false>(S, 0, S.n_ops, active, ray, ray, 0, tmin, closest, best, reference_boxes != 0, xi);
+    const bool hit = traverse_uniform(S, 0, S.n_ops, active, ray, ray, 0, tmin, closest, best, reference_boxes != 0, xi);
     if (!active) return;
     hrt_hit o;
     o.hit = 0; o.t = 0.0f;
@@ -1252,8 +1035,7 @@ static DeviceScene to_device_scene(const hrt::DeviceSceneHost& h) {
     for (int i = 0; i < kMaxImages; ++i) S.images[i] = h.images[i];
     S.n_ops = h.n_ops; S.n_noise = h.n_noise; S.n_media = h.n_media;
     S.ln_e = h.ln_e;
-    S.sh_ops = S.sh_nodes = 0u;
-    S.n_sh_ops = S.n_sh_nodes = 0;
+
     return S;
 }
 static CameraK to_camera(const hrt_camera_state& c) {
@@ -1287,9 +1069,6 @@ cudaError_t launch_render(hrt::RenderLaunch& L, int num_sms, cudaStream_t stream
     P.n_sh_noise = 0;
     cudaError_t e;
     const bool pooled = L.interpreter == 2;
-    const bool phased = L.interpreter == 4;
-    size_t phase_smem = 0;
-    P.n_sh_ops = P.n_sh_nodes = 0;
     const void* pool_fn = (const void*)render_pool_kernel;
     if (pooled) {
         // Shared-memory budget of the one resident block: the ray pools, then as much of the Box16 table as fits (all
@@ -1309,27 +1088,6 @@ cudaError_t launch_render(hrt::RenderLaunch& L, int num_sms, cudaStream_t stream
         e = cudaFuncSetAttribute(pool_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pool_smem);
         if (e != cudaSuccess) return e;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, pool_fn, kPoolBlock, pool_smem);
-    } else if (phased) {
-        // Shared-memory budget of the one resident block: the request queue, then the op stream, the tree nodes and the
-        // noise tables, each as far as it fits (all of them for the BASELINE scenes: `final` = 47 + 45 + 5 KB).
-        const void* fn = (const void*)render_phase_kernel;
-        int dev = 0, optin = 0;
-        cudaFuncAttributes fa;
-        if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
-        if ((e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess) return e;
-        if ((e = cudaFuncGetAttributes(&fa, fn)) != cudaSuccess) return e;
-        long long avail = (long long)optin - (long long)fa.sharedSizeBytes - (long long)kPhaseQueueBytes;
-        if (avail < 0) return cudaErrorInvalidConfiguration;
-        P.n_sh_ops = (int)std::min<long long>(P.S.n_ops, avail / 32);
-        avail -= 32ll * P.n_sh_ops;
-        P.n_sh_nodes = (int)std::min<long long>(L.n_nodes, avail / 32);
-        avail -= 32ll * P.n_sh_nodes;
-        P.n_sh_noise = (int)std::min<long long>(std::min(P.S.n_noise, kMaxNoiseTablesShared), avail / (long long)sizeof(NoiseTable));
-        phase_smem = kPhaseQueueBytes + 32 * (size_t)P.n_sh_ops + 32 * (size_t)P.n_sh_nodes + sizeof(NoiseTable) * (size_t)P.n_sh_noise;
-        // the opt-in maximum, always: the attribute is per function and device, not per launch
-        e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
-        if (e != cudaSuccess) return e;
-        blocks_per_sm = 1;
     } else if (L.interpreter == 3) {
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, render_interp_kernel<true>, kBlock, 0);
     } else if (L.interpreter == 1) {
@@ -1345,7 +1103,7 @@ cudaError_t launch_render(hrt::RenderLaunch& L, int num_sms, cudaStream_t stream
     int chunk = L.chunk;
     if (chunk <= 0) {
         chunk = pooled ? 256 : 64;  // the pool kernel keeps 96 rays in flight per warp: larger items
-        const long long resident_warps = (long long)grid * (pooled ? kPoolWarps : (phased ? kPhaseWarps : kWarpsPerBlock));
+        const long long resident_warps = (long long)grid * (pooled ? kPoolWarps : kWarpsPerBlock);
         while (chunk > 4 && (long long)P.n_tiles * ((L.sample_count + chunk - 1) / chunk) < 8 * resident_warps) chunk /= 2;
     }
     if (chunk > L.sample_count) chunk = L.sample_count;
@@ -1374,10 +1132,9 @@ cudaError_t launch_render(hrt::RenderLaunch& L, int num_sms, cudaStream_t stream
     P.counters = L.counters;
     P.accum = reinterpret_cast<float4*>(L.accum);
     L.grid = grid;
-    L.block = pooled ? kPoolBlock : (phased ? kPhaseBlock : kBlock);
+    L.block = pooled ? kPoolBlock : kBlock;
     L.chunk = chunk;
-    if (phased) render_phase_kernel<<<grid, kPhaseBlock, phase_smem, stream>>>(P);
-    else if (L.interpreter == 2) render_pool_kernel<<<grid, kPoolBlock, pool_smem, stream>>>(P);
+    if (L.interpreter == 2) render_pool_kernel<<<grid, kPoolBlock, pool_smem, stream>>>(P);
     else if (L.interpreter == 3) render_interp_kernel<true><<<grid, kBlock, 0, stream>>>(P);
     else if (L.interpreter == 1) render_interp_kernel<false><<<grid, kBlock, 0, stream>>>(P);
     else render_kernel<<<grid, kBlock, 0, stream>>>(P);

@@ -20,8 +20,6 @@ struct DeviceSceneHost {  // mirrors HRT_NS::DeviceScene field for field (checke
     cudaTextureObject_t images[kMaxImages];
     int32_t n_ops, n_noise, n_media;
     float ln_e;
-    uint32_t sh_ops, sh_nodes;      // kernel-local staging info (0 on the host side)
-    int32_t n_sh_ops, n_sh_nodes;
 };
 
 struct RenderLaunch {
@@ -35,7 +33,7 @@ struct RenderLaunch {
     int32_t reference_boxes;
     int32_t n_nodes;      // tree nodes of the scene form being rendered
     int32_t interpreter;  // render kernel variant: 0 warp scheduler, 1 per-lane interpreter, 2 shared-memory ray pool,
-                          // 3 warp-uniform walk, 4 phase kernel (uniform walks + block-wide tree rounds; production)
+                          // 3 warp-uniform walk (production)
     unsigned long long* counters;  // device: [0] work-item cursor, [1] rays, [2] paths
     float* accum;                  // device: width*height*4 f32, added into
     int32_t grid, block;           // out: launch configuration actually used

@@ -169,8 +169,6 @@ enum {
     HRT_FLAG_INTERPRETER = 8,         /* render: plain per-lane interpreter kernel instead of the warp scheduler  */
     HRT_FLAG_UNIFORM = 64,            /* render / hrt_trace_hits: the warp walks the op stream together (one record per
                                          step for the lanes that are at it; every branch warp-uniform)          */
-    HRT_FLAG_PHASE = 128,             /* render: the production kernel (default): warp-uniform walks with block-wide
-                                         rounds for the OP_BVH trees                                              */
     HRT_FLAG_WARP_SCHEDULER = 4       /* hrt_trace_hits only: run through the render kernel's warp-level op-class
                                          scheduler instead of the plain per-lane interpreter                */
 };
