@@ -363,6 +363,10 @@ static int32_t render_into(hrt_scene* s, DeviceState* d, const hrt_camera_desc* 
     L.reference_boxes = ref_boxes ? 1 : 0;
     L.scene = d->view[ref_boxes ? 0 : 1];  // the reference form of the stream goes with the reference's box test
     L.n_nodes = ref_boxes ? 0 : (int32_t)s->fast.nodes.size();
+    L.n_pre = 0;
+    if (!ref_boxes)
+        for (const PreTree& t : s->fast.trees)
+            if (L.n_pre < kMaxPreTrees) L.pre[L.n_pre++] = t;
     {
         const char* env = getenv("HRT_KERNEL");  // diagnostic override: "interp" | "sched" | "pool"
         // default: the warp-uniform walk
@@ -385,6 +389,8 @@ static int32_t render_into(hrt_scene* s, DeviceState* d, const hrt_camera_desc* 
     L.counters = slot.counters;
     L.accum = d_accum;
     L.chunk = 0;
+    L.shape = 1;
+    if (const char* env = getenv("HRT_SHAPE")) L.shape = atoi(env);  // diagnostic: block shape of the uniform-walk kernel
     if (const char* env = getenv("HRT_CHUNK")) L.chunk = atoi(env);  // diagnostic: samples per work item
     HRT_CUDA(cudaMemsetAsync(slot.counters, 0, kCounterWords * sizeof(unsigned long long), stream));
     HRT_CUDA(cudaEventRecord(slot.t0, stream));

@@ -32,6 +32,9 @@ struct RenderLaunch {
     int32_t chunk;        // samples per work item
     int32_t reference_boxes;
     int32_t n_nodes;      // tree nodes of the scene form being rendered
+    int32_t n_pre;        // OP_BVH trees walked ahead of the stream walk (<= kMaxPreTrees)
+    hrt::PreTree pre[hrt::kMaxPreTrees];
+    int32_t shape;        // uniform-walk kernel: block shape / synchronisation variant (diagnostic)
     int32_t interpreter;  // render kernel variant: 0 warp scheduler, 1 per-lane interpreter, 2 shared-memory ray pool,
                           // 3 warp-uniform walk (production)
     unsigned long long* counters;  // device: [0] work-item cursor, [1] rays, [2] paths
