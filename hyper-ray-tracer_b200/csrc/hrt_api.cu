@@ -45,6 +45,7 @@ struct DeviceState {
     unsigned long long* d_counters = nullptr;  // kLaunchSlots blocks of kCounterWords
     LaunchSlot slots[kLaunchSlots];
     int next_slot = 0;
+    WaveBuffers wave;  // path slots of the wavefront render, allocated on first use
     // scratch for the host-buffer entry points
     float* d_accum = nullptr;
     float* d_rgba = nullptr;
@@ -63,6 +64,9 @@ void release_device_state(DeviceState* d) {
         cudaFree(d->d_nodes); cudaFree(d->d_mats); cudaFree(d->d_texs); cudaFree(d->d_noise);
         cudaFree(d->d_counters); cudaFree(d->d_accum); cudaFree(d->d_rgba);
         for (auto e : d->ev) if (e) cudaEventDestroy(e);
+        cudaFree(d->wave.state); cudaFree(d->wave.d_live);
+        if (d->wave.h_live) cudaFreeHost(d->wave.h_live);
+        for (auto e : d->wave.ev) if (e) cudaEventDestroy(e);
         for (auto& sl : d->slots) {
             if (sl.t0) cudaEventDestroy(sl.t0);
             if (sl.t1) cudaEventDestroy(sl.t1);
@@ -94,6 +98,20 @@ static DeviceState* find_state(hrt_scene* s, int device) {
     for (DeviceState* d : s->devices)
         if (d && d->device == device) return d;
     return nullptr;
+}
+
+static int32_t ensure_wave(DeviceState* d) {
+    if (d->wave.state) return HRT_OK;
+    int n = 1 << 20;  // path slots in flight (64 MB of state)
+    if (const char* env = getenv("HRT_WAVE_SLOTS")) n = atoi(env);
+    if (n < 256) n = 256;
+    n = (n + 255) / 256 * 256;
+    HRT_CUDA(cudaMalloc((void**)&d->wave.state, sizeof(float) * (size_t)kWaveStateWords * (size_t)n));
+    HRT_CUDA(cudaMalloc((void**)&d->wave.d_live, 2 * sizeof(int)));
+    HRT_CUDA(cudaMallocHost((void**)&d->wave.h_live, 2 * sizeof(int)));
+    for (auto& e : d->wave.ev) HRT_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    d->wave.n_slots = n;
+    return HRT_OK;
 }
 
 static int32_t ensure_scratch(DeviceState* d, size_t pixels) {
@@ -363,19 +381,17 @@ static int32_t render_into(hrt_scene* s, DeviceState* d, const hrt_camera_desc* 
     L.reference_boxes = ref_boxes ? 1 : 0;
     L.scene = d->view[ref_boxes ? 0 : 1];  // the reference form of the stream goes with the reference's box test
     L.n_nodes = ref_boxes ? 0 : (int32_t)s->fast.nodes.size();
-    L.n_pre = 0;
-    if (!ref_boxes)
-        for (const PreTree& t : s->fast.trees)
-            if (L.n_pre < kMaxPreTrees) L.pre[L.n_pre++] = t;
     {
         const char* env = getenv("HRT_KERNEL");  // diagnostic override: "interp" | "sched" | "pool"
-        // default: the warp-uniform walk
-        int variant = 3;
+        // default: the wavefront render (two small kernels per ray segment)
+        int variant = 5;
+        if (rd->flags & HRT_FLAG_WAVEFRONT) variant = 5;
         if (rd->flags & HRT_FLAG_SCHEDULER) variant = 0;
         if (rd->flags & HRT_FLAG_INTERPRETER) variant = 1;
         if (rd->flags & HRT_FLAG_POOL) variant = 2;
         if (rd->flags & HRT_FLAG_UNIFORM) variant = 3;
         if (env && env[0] == 'u') variant = 3;
+        if (env && env[0] == 'w') variant = 5;
         if (env && env[0] == 'i') variant = 1;
         if (env && env[0] == 's') variant = 0;
         if (env && env[0] == 'p') variant = 2;
@@ -389,18 +405,24 @@ static int32_t render_into(hrt_scene* s, DeviceState* d, const hrt_camera_desc* 
     L.counters = slot.counters;
     L.accum = d_accum;
     L.chunk = 0;
-    L.shape = 1;
-    if (const char* env = getenv("HRT_SHAPE")) L.shape = atoi(env);  // diagnostic: block shape of the uniform-walk kernel
     if (const char* env = getenv("HRT_CHUNK")) L.chunk = atoi(env);  // diagnostic: samples per work item
     HRT_CUDA(cudaMemsetAsync(slot.counters, 0, kCounterWords * sizeof(unsigned long long), stream));
     HRT_CUDA(cudaEventRecord(slot.t0, stream));
-    cudaError_t e = (rd->flags & HRT_FLAG_EXACT_MATH) ? hrt_exact::launch_render(L, d->num_sms, stream)
-                                                      : hrt_fast::launch_render(L, d->num_sms, stream);
+    cudaError_t e;
+    if (L.interpreter == 5) {
+        if ((rc = ensure_wave(d)) != HRT_OK) return rc;
+        e = (rd->flags & HRT_FLAG_EXACT_MATH) ? hrt_exact::launch_render_wave(L, d->wave, d->num_sms, stream)
+                                              : hrt_fast::launch_render_wave(L, d->wave, d->num_sms, stream);
+    } else {
+        L.launches = 1;
+        e = (rd->flags & HRT_FLAG_EXACT_MATH) ? hrt_exact::launch_render(L, d->num_sms, stream)
+                                              : hrt_fast::launch_render(L, d->num_sms, stream);
+    }
     if (e != cudaSuccess) return cuda_fail(e, "render_kernel launch");
     HRT_CUDA(cudaEventRecord(slot.t1, stream));
     HRT_CUDA(cudaEventRecord(slot.done, stream));
     if (stats) {
-        stats->launches += 1;
+        stats->launches += L.launches;
         stats->grid = L.grid;
         stats->block = L.block;
     }

@@ -45,8 +45,6 @@ struct RenderParams {
     int reference_boxes;
     int n_tab;       // ray-pool kernel: Box16 records [0, n_tab) are staged in shared memory
     int n_sh_noise;  // ray-pool kernel: noise tables staged behind them
-    int n_pre;       // uniform-walk kernel: OP_BVH trees walked ahead of the stream walk
-    PreTree pre[kMaxPreTrees];
 
     unsigned long long* counters;
     float4* accum;
@@ -256,311 +254,6 @@ __global__ void __launch_bounds__(kBlock, 2) render_kernel(const __grid_constant
 #endif
 }
 
-// Sample range of work item `item` (tile-major inside a chunk; big chunks first, then the shrinking tail chunks).
-__device__ __forceinline__ void decode_item(const RenderParams& P, unsigned long long item, int& tx, int& ty, int& s0, int& s_n) {
-    const int tile = (int)(item % (unsigned long long)P.n_tiles);
-    const int chunk = (int)(item / (unsigned long long)P.n_tiles);
-    tx = tile % P.tiles_x;
-    ty = tile / P.tiles_x;
-    const int tc = chunk - P.n_big;  // >= 0: one of the shrinking tail chunks
-    s0 = P.sample_begin + (tc < 0 ? chunk * P.chunk : P.tail_begin[tc]);
-    s_n = tc < 0 ? P.chunk : P.tail_size[tc];
-}
-// Adds the item's radiance sums (lane = pixel of the 8x4 tile) into the frame accumulator.
-__device__ __forceinline__ void flush_item(const RenderParams& P, int tx, int ty, int s_n, float (*acc)[3], int lane) {
-    const int px = tx * 8 + (lane & 7), py = ty * 4 + (lane >> 3);
-    if (px < P.width && py < P.height) {
-        float* dst = reinterpret_cast<float*>(P.accum + (size_t)py * P.width + px);
-        atomicAdd(dst + 0, acc[lane][0]);
-        atomicAdd(dst + 1, acc[lane][1]);
-        atomicAdd(dst + 2, acc[lane][2]);
-        atomicAdd(dst + 3, (float)s_n);
-    }
-}
-
-// ---- the production kernel: warp-uniform walks, tree walks pooled over several batches of paths ----
-// A warp owns kBatches x 32 paths whose state lives in its slice of shared memory; one iteration of the main loop
-// advances every live path by one ray segment (world.hit + emitted + scatter, application.rs:477-495) in three phases:
-//   R  per batch: finished paths are replaced from the batch's work item (camera rays, camera.rs:85-95);
-//   T  the first kMaxPreTrees OP_BVH trees of the stream are walked AHEAD, for all batches together: every (path, tree)
-//      pair whose root box the ray hits becomes an entry of a warp-local list, and the lanes pull entries from that list
-//      as they finish (persistent lanes).  A sound tree's closest hit over [t_min, +inf) is all the stream walk needs
-//      (traverse_uniform merges it at the OP_BVH record), so the walks do not depend on the stream walk, and pooling
-//      them over 64-128 paths keeps the lanes of the tree loop filled: walked inline, only the few rays of ONE batch
-//      that reach ONE tree walk together (4.7 of 32 lanes for half of all issued instructions, profiles/r02_u1_*);
-//   W  per batch: the warp-uniform walk of the op stream (traverse_uniform, hrt_device.cuh), then emitted + scatter.
-template <int kThreads, int kBlocksPerSm, int kBatches>
-struct PooledShape {
-    static constexpr int kWarps = kThreads / 32;
-    static constexpr int kSlots = 32 * kBatches;                // paths per warp
-    enum Field { F_OX, F_OY, F_OZ, F_DX, F_DY, F_DZ, F_TIME, F_TX, F_TY, F_TZ, F_PIXEL, F_SAMPLE, F_BOUNCE_PL, F_WORDS };
-    static constexpr int kListCap = kSlots;                     // tree-walk entries per iteration (more: walked inline)
-    // per warp, in 4-byte words: path state, pre-walk results, walk list, per-batch radiance sums, per-batch item variables
-    static constexpr int kStateWords = F_WORDS * kSlots;
-    static constexpr int kPreWords = 2 * kMaxPreTrees * kSlots;
-    static constexpr int kListWords = 8 * kListCap;
-    static constexpr int kAccWords = 3 * kSlots;
-    static constexpr int kWarpWords = kStateWords + kPreWords + kListWords + kAccWords;
-    static constexpr size_t kBytes = (size_t)kWarps * kWarpWords * 4;
-};
-
-template <int kThreads, int kBlocksPerSm, int kBatches>
-__global__ void __launch_bounds__(kThreads, kBlocksPerSm) render_uniform_kernel(const __grid_constant__ RenderParams P) {
-    using Sh = PooledShape<kThreads, kBlocksPerSm, kBatches>;
-    constexpr int kSlots = Sh::kSlots;
-    extern __shared__ __align__(16) float sh_dyn[];
-    __shared__ NoiseTable sh_noise[kMaxNoiseTablesShared];
-    TexEnv E;
-    stage_noise(P.S, E, sh_noise, kMaxNoiseTablesShared);
-
-    const DeviceScene& S = P.S;
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    const bool ref_boxes = P.reference_boxes != 0;
-    const V3 bg = v3(P.bg[0], P.bg[1], P.bg[2]);
-    const float div_w = (float)P.width - 1.0f, div_h = (float)P.height - 1.0f;  // application.rs:444-445
-    const float kTmin = 0.001f;                                                 // application.rs:482
-    unsigned long long n_rays = 0, n_paths = 0;
-
-    float* const st = sh_dyn + (size_t)warp * Sh::kWarpWords;          // [F_WORDS][kSlots]
-    float2* const pre = reinterpret_cast<float2*>(st + Sh::kStateWords);   // [kSlots][kMaxPreTrees]
-    float4* const list = reinterpret_cast<float4*>(st + Sh::kStateWords + Sh::kPreWords);  // [kListCap][2]
-    float* const acc = st + Sh::kStateWords + Sh::kPreWords + Sh::kListWords;              // [kBatches][32][3]
-#define ST(f, slot) st[(Sh::f) * kSlots + (slot)]
-
-    // per batch: the work item (8x4-pixel tile, samples [s0, s0 + s_n)) and which lanes carry a live path
-    bool have_item[kBatches], more_items = true;
-    int tx[kBatches], ty[kBatches], s0[kBatches], s_n[kBatches], pool_next[kBatches];
-    unsigned live[kBatches];  // warp-uniform masks
-#pragma unroll
-    for (int b = 0; b < kBatches; ++b) { have_item[b] = false; tx[b] = ty[b] = s0[b] = s_n[b] = pool_next[b] = 0; live[b] = 0u; }
-
-    for (;;) {
-        // ---- R: refill ----
-        unsigned any_live = 0u;
-#pragma unroll
-        for (int b = 0; b < kBatches; ++b) {
-            const int slot = b * 32 + lane;
-            float (*bacc)[3] = reinterpret_cast<float (*)[3]>(acc + b * 96);
-            while (more_items || have_item[b]) {
-                if (!have_item[b]) {
-                    unsigned long long item = 0;
-                    if (lane == 0) item = atomicAdd(P.counters, 1ULL);
-                    item = __shfl_sync(kFull, item, 0);
-                    if (item >= (unsigned long long)P.n_items) { more_items = false; break; }
-                    decode_item(P, item, tx[b], ty[b], s0[b], s_n[b]);
-                    pool_next[b] = 0;
-                    bacc[lane][0] = 0.0f; bacc[lane][1] = 0.0f; bacc[lane][2] = 0.0f;
-                    __syncwarp();
-                    have_item[b] = true;
-                }
-                const int pool_size = 32 * s_n[b];
-                const unsigned need = ~live[b];
-                if (need && pool_next[b] < pool_size) {
-                    const bool dead = (need >> lane) & 1u;
-                    const int idx = pool_next[b] + __popc(need & lt_mask);
-                    pool_next[b] += __popc(need);
-                    bool started = false;
-                    if (dead && idx < pool_size) {
-                        const int pl = idx & 31;
-                        const int px = tx[b] * 8 + (pl & 7), py = ty[b] * 4 + (pl >> 3);
-                        if (px < P.width && py < P.height) {
-                            RngKey key;
-                            key.k0 = P.k0; key.k1 = P.k1;
-                            key.pixel = (uint32_t)(py * P.width + px);
-                            key.sample = (uint32_t)(s0[b] + (idx >> 5));
-                            n_paths++;
-                            if (P.depth > 0) {  // ray_color(depth == 0) is black (application.rs:478-480)
-                                float c4[4];
-                                rng_block(key, 0, RNG_BLOCK_CAMERA, c4);  // jitter x, jitter y, shutter time, lens u1
-                                float lens_u2 = 0.0f;
-                                if (P.cam.lens_radius != 0.0f) {
-                                    float l4[4];
-                                    rng_block(key, 0, RNG_BLOCK_CAMERA - 1, l4);
-                                    lens_u2 = l4[0];
-                                }
-                                const float u = ((float)px + c4[0]) / div_w;
-                                const float v = ((float)py + c4[1]) / div_h;
-                                const Ray r = camera_get_ray(P.cam, u, v, c4[3], lens_u2, c4[2]);
-                                ST(F_OX, slot) = r.o.x; ST(F_OY, slot) = r.o.y; ST(F_OZ, slot) = r.o.z;
-                                ST(F_DX, slot) = r.d.x; ST(F_DY, slot) = r.d.y; ST(F_DZ, slot) = r.d.z;
-                                ST(F_TIME, slot) = r.time;
-                                ST(F_TX, slot) = 1.0f; ST(F_TY, slot) = 1.0f; ST(F_TZ, slot) = 1.0f;
-                                ST(F_PIXEL, slot) = __uint_as_float(key.pixel);
-                                ST(F_SAMPLE, slot) = __uint_as_float(key.sample);
-                                ST(F_BOUNCE_PL, slot) = __uint_as_float((uint32_t)pl << 16);
-                                started = true;
-                            }
-                        }
-                    }
-                    live[b] |= __ballot_sync(kFull, started);
-                }
-                if (live[b]) break;
-                if (pool_next[b] < pool_size) continue;  // only out-of-image pixels (or depth 0) were drawn: draw again
-                __syncwarp();
-                flush_item(P, tx[b], ty[b], s_n[b], bacc, lane);
-                __syncwarp();
-                have_item[b] = false;
-            }
-            any_live |= live[b];
-        }
-        if (!any_live) break;  // no live path and no work item left
-        __syncwarp();
-
-        // ---- T: the pre-walked trees ----
-        if (P.n_pre > 0) {
-            // T1: every live (path, tree) pair tests the tree's root box; hits go to the list
-            int n_list = 0;
-#pragma unroll 1
-            for (int tree = 0; tree < P.n_pre; ++tree) {
-#pragma unroll 1
-                for (int b = 0; b < kBatches; ++b) {
-                    const int slot = b * 32 + lane;
-                    const bool alive = (live[b] >> lane) & 1u;
-                    Ray r;
-                    r.o = v3(ST(F_OX, slot), ST(F_OY, slot), ST(F_OZ, slot));
-                    r.d = v3(ST(F_DX, slot), ST(F_DY, slot), ST(F_DZ, slot));
-                    r.time = ST(F_TIME, slot);
-                    if (P.pre[tree].ctx != 0) r = ray_in_ctx(S, r, P.pre[tree].ctx);
-                    const RayK k = make_rayk(r);
-                    const float4 mn = make_float4(P.pre[tree].mn[0], P.pre[tree].mn[1], P.pre[tree].mn[2], 0.0f);
-                    const float4 mx = make_float4(P.pre[tree].mx[0], P.pre[tree].mx[1], P.pre[tree].mx[2], 0.0f);
-                    const bool hit = alive && box_hit_tight(mn, mx, r, k, kTmin, CUDART_INF_F);
-                    const unsigned m = __ballot_sync(kFull, hit);
-                    const int at = n_list + __popc(m & lt_mask);
-                    const bool listed = hit && at < Sh::kListCap;
-                    if (listed) {
-                        list[2 * at] = make_float4(r.o.x, r.o.y, r.o.z, r.time);
-                        list[2 * at + 1] = make_float4(r.d.x, r.d.y, r.d.z, __int_as_float(slot | (tree << 16)));
-                    }
-                    // missed: no hit; listed: filled in by T2; the list is full: walked inline by the stream walk
-                    pre[slot * kMaxPreTrees + tree] = make_float2(0.0f, __int_as_float(hit && !listed ? kPreNotWalked : kPreNone));
-                    n_list = min(n_list + __popc(m), Sh::kListCap);
-                }
-            }
-            __syncwarp();
-            // T2: persistent lanes pull walks from the list
-            int next = 0;
-            int ref = 0, sp = 0, base = 0, entry = -1;  // entry < 0: this lane is idle
-            Ray cur;
-            cur.o = v3(0.0f, 0.0f, 0.0f); cur.d = v3(1.0f, 1.0f, 1.0f); cur.time = 0.0f;
-            RayK k = make_rayk(cur);
-            TreeHit h;
-            h.t = CUDART_INF_F; h.pc = -1; h.face = 0;
-            float ts = 0.0f, te = 1.0f;
-            int stack_ref[kBvh2Stack];
-            float stack_t[kBvh2Stack];
-            for (;;) {
-                const unsigned idle = __ballot_sync(kFull, entry < 0);
-                if (idle && next < n_list) {
-                    const int e = next + __popc(idle & lt_mask);
-                    next += __popc(idle);
-                    if (entry < 0 && e < n_list) {
-                        const float4 a = list[2 * e], b4 = list[2 * e + 1];
-                        entry = __float_as_int(b4.w);
-                        cur.o = v3(a.x, a.y, a.z); cur.d = v3(b4.x, b4.y, b4.z); cur.time = a.w;
-                        k = make_rayk(cur);
-                        const int tree = entry >> 16;
-                        base = P.pre[tree].base; ts = P.pre[tree].ts; te = P.pre[tree].te;
-                        h.t = CUDART_INF_F; h.pc = -1; h.face = 0;
-                        ref = 0; sp = 0;
-                    }
-                }
-                if (!__any_sync(kFull, entry >= 0)) break;
-                if (entry >= 0) {
-                    if (bvh2_step(S, base, cur, k, kTmin, ts, te, ref, sp, stack_ref, stack_t, h)) {
-                        pre[(entry & 0xffff) * kMaxPreTrees + (entry >> 16)] =
-                            make_float2(h.t, __int_as_float(h.pc < 0 ? kPreNone : (h.pc | (h.face << 24))));
-                        entry = -1;
-                    }
-                }
-            }
-            __syncwarp();
-        }
-
-        // ---- W: stream walk + shading, batch by batch ----
-#pragma unroll
-        for (int b = 0; b < kBatches; ++b) {
-            if (!live[b]) continue;
-            const int slot = b * 32 + lane;
-            float (*bacc)[3] = reinterpret_cast<float (*)[3]>(acc + b * 96);
-            bool active = (live[b] >> lane) & 1u;
-            Ray ray;
-            ray.o = v3(ST(F_OX, slot), ST(F_OY, slot), ST(F_OZ, slot));
-            ray.d = v3(ST(F_DX, slot), ST(F_DY, slot), ST(F_DZ, slot));
-            ray.time = ST(F_TIME, slot);
-            if (!active) { ray.o = v3(0.0f, 0.0f, 0.0f); ray.d = v3(1.0f, 1.0f, 1.0f); ray.time = 0.0f; }
-            const uint32_t bpl = __float_as_uint(ST(F_BOUNCE_PL, slot));
-            uint32_t bounce = bpl & 0xffffu;
-            RngKey key;
-            key.k0 = P.k0; key.k1 = P.k1;
-            key.pixel = __float_as_uint(ST(F_PIXEL, slot));
-            key.sample = __float_as_uint(ST(F_SAMPLE, slot));
-            MediumXi xi;
-            xi.key = key; xi.bounce = bounce; xi.injected = 0.0f; xi.inject = false;
-            Best best;
-            best.pc = -1; best.t = 0.0f; best.face = 0; best.ctx = 0;
-            float closest = CUDART_INF_F;
-            const bool hit = traverse_uniform(S, 0, S.n_ops, active, ray, ray, 0, kTmin, closest, best, ref_boxes, xi,
-                                              pre + slot * kMaxPreTrees, P.n_pre);
-            if (active) {
-                n_rays++;
-                V3 T = v3(ST(F_TX, slot), ST(F_TY, slot), ST(F_TZ, slot));
-                V3 add = v3(0.0f, 0.0f, 0.0f);
-                if (!hit) {
-                    add = T * bg;
-                    active = false;
-                } else {
-                    HitRec hr;
-                    make_hit_record(S, ray, best, false, hr);
-                    const Material m = S.mats[hr.mat];
-                    if (m.kind == MAT_DIFFUSE_LIGHT) {
-                        add = T * material_emitted(S, E, m, hr);
-                        active = false;  // DiffuseLight::scatter -> None
-                    } else {
-                        float u4[4];
-                        rng_block(key, bounce, RNG_BLOCK_SCATTER, u4);
-                        V3 att;
-                        Ray sc;
-                        if (material_scatter(S, E, m, ray, hr, u4, att, sc)) {
-                            T = T * att;
-                            bounce++;
-                            if (bounce >= (uint32_t)P.depth) {  // ray_color(depth == 0) is black
-                                active = false;
-                            } else {
-                                ST(F_OX, slot) = sc.o.x; ST(F_OY, slot) = sc.o.y; ST(F_OZ, slot) = sc.o.z;
-                                ST(F_DX, slot) = sc.d.x; ST(F_DY, slot) = sc.d.y; ST(F_DZ, slot) = sc.d.z;
-                                ST(F_TIME, slot) = sc.time;
-                                ST(F_TX, slot) = T.x; ST(F_TY, slot) = T.y; ST(F_TZ, slot) = T.z;
-                                ST(F_BOUNCE_PL, slot) = __uint_as_float((bpl & 0xffff0000u) | bounce);
-                            }
-                        } else {
-                            active = false;
-                        }
-                    }
-                }
-                const int my_pl = (int)(bpl >> 16);
-                if (add.x != 0.0f) atomicAdd(&bacc[my_pl][0], add.x);
-                if (add.y != 0.0f) atomicAdd(&bacc[my_pl][1], add.y);
-                if (add.z != 0.0f) atomicAdd(&bacc[my_pl][2], add.z);
-            }
-            live[b] = __ballot_sync(kFull, active);
-        }
-        __syncwarp();
-    }
-#undef ST
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        n_rays += __shfl_xor_sync(kFull, n_rays, o);
-        n_paths += __shfl_xor_sync(kFull, n_paths, o);
-    }
-    if (lane == 0) {
-        atomicAdd(P.counters + 1, n_rays);
-        atomicAdd(P.counters + 2, n_paths);
-    }
-}
-
 // The plain variant: every lane runs the per-lane interpreter (`traverse<>`) for one whole ray segment per iteration and
 // the warp re-converges for shading.  Kept selectable (HRT_FLAG_INTERPRETER) for A/B measurements against the scheduler.
 // kUniform: the warp walks the stream together instead (traverse_uniform<>, hrt_device.cuh) — HRT_FLAG_UNIFORM.
@@ -706,6 +399,28 @@ __global__ void __launch_bounds__(kBlock, 2) render_interp_kernel(const __grid_c
     if (lane == 0) {
         atomicAdd(P.counters + 1, n_rays);
         atomicAdd(P.counters + 2, n_paths);
+    }
+}
+
+// Sample range of work item `item` (tile-major inside a chunk; big chunks first, then the shrinking tail chunks).
+__device__ __forceinline__ void decode_item(const RenderParams& P, unsigned long long item, int& tx, int& ty, int& s0, int& s_n) {
+    const int tile = (int)(item % (unsigned long long)P.n_tiles);
+    const int chunk = (int)(item / (unsigned long long)P.n_tiles);
+    tx = tile % P.tiles_x;
+    ty = tile / P.tiles_x;
+    const int tc = chunk - P.n_big;  // >= 0: one of the shrinking tail chunks
+    s0 = P.sample_begin + (tc < 0 ? chunk * P.chunk : P.tail_begin[tc]);
+    s_n = tc < 0 ? P.chunk : P.tail_size[tc];
+}
+// Adds the item's radiance sums (lane = pixel of the 8x4 tile) into the frame accumulator.
+__device__ __forceinline__ void flush_item(const RenderParams& P, int tx, int ty, int s_n, float (*acc)[3], int lane) {
+    const int px = tx * 8 + (lane & 7), py = ty * 4 + (lane >> 3);
+    if (px < P.width && py < P.height) {
+        float* dst = reinterpret_cast<float*>(P.accum + (size_t)py * P.width + px);
+        atomicAdd(dst + 0, acc[lane][0]);
+        atomicAdd(dst + 1, acc[lane][1]);
+        atomicAdd(dst + 2, acc[lane][2]);
+        atomicAdd(dst + 3, (float)s_n);
     }
 }
 
@@ -1000,6 +715,183 @@ __global__ void __launch_bounds__(kPoolBlock, 1) render_pool_kernel(const __grid
     if (lane < 8) atomicAdd(P.counters + 20 + lane, (unsigned long long)st_cycles);
 #endif
 }
+
+// ---- wavefront render: two small kernels per ray segment instead of one big persistent kernel ----
+// Why: the persistent kernels above carry the whole path tracer (camera, stream walk, tree walk, media, hit record,
+// materials, textures: 4 000 - 5 000 SASS instructions = 64 - 80 KB), every warp cycles through all of it once per ray
+// segment on its own schedule, and instruction fetch is then THE top stall: 5 - 11 warps per issue slot waiting in
+// `no_instruction`, growing with the kernel's size (profiles/r02_*).  Here N path slots live in global memory and one
+// iteration is
+//   wave_logic_kernel   shade the segment traced last (emitted + scatter, application.rs:486-494), accumulate finished
+//                       paths, start the next camera sample in every free slot (application.rs:443-448)
+//   wave_trace_kernel   world.hit for every slot's ray segment (warp-uniform walk + tree walks)
+// each a fraction of the code, each run by the whole GPU at once, so the instruction caches hold what is running.
+// Same Philox streams and arithmetic as the other kernels: the same paths, summed in a different order.
+constexpr int kWaveBlock = 256;
+enum WaveField {
+    WF_OX, WF_OY, WF_OZ, WF_DX, WF_DY, WF_DZ, WF_TIME,  // the ray segment to trace / traced last
+    WF_TX, WF_TY, WF_TZ, WF_PIXEL, WF_SAMPLE,           // throughput, Philox key
+    WF_BOUNCE,                                          // >= 0: segments behind this path; -1: free slot
+    WF_HIT_T, WF_HIT_PC, WF_HIT_FC,                     // result of the trace (pc -1: miss; FC = side | ctx << 8)
+    WF_WORDS
+};
+struct WaveParams {
+    DeviceScene S;
+    CameraK cam;
+    int width, height, depth;
+    float bg[3];
+    uint32_t k0, k1;
+    int sample_begin;
+    int n_pixels, n_slots;
+    unsigned long long total_paths;
+    int reference_boxes;
+    float* st;                     // [WF_WORDS][n_slots]
+    unsigned long long* counters;  // [0] next path index, [1] rays, [2] paths
+    float4* accum;
+    int* live_out;                 // when not null: += number of slots that carry a path after this logic pass
+};
+static_assert(WF_WORDS == hrt::kWaveStateWords, "wave state layout");
+#define WST(f, slot) P.st[(size_t)(f) * P.n_slots + (slot)]
+
+__global__ void __launch_bounds__(kWaveBlock, 3) wave_trace_kernel(const __grid_constant__ WaveParams P) {
+    const int slot = blockIdx.x * kWaveBlock + threadIdx.x;
+    const bool in_range = slot < P.n_slots;
+    const int bounce = in_range ? __float_as_int(WST(WF_BOUNCE, slot)) : -1;
+    const bool active = bounce >= 0;
+    Ray ray;
+    ray.o = v3(0.0f, 0.0f, 0.0f); ray.d = v3(1.0f, 1.0f, 1.0f); ray.time = 0.0f;
+    MediumXi xi;
+    xi.key.k0 = P.k0; xi.key.k1 = P.k1; xi.key.pixel = 0; xi.key.sample = 0;
+    xi.bounce = 0; xi.injected = 0.0f; xi.inject = false;
+    if (active) {
+        ray.o = v3(WST(WF_OX, slot), WST(WF_OY, slot), WST(WF_OZ, slot));
+        ray.d = v3(WST(WF_DX, slot), WST(WF_DY, slot), WST(WF_DZ, slot));
+        ray.time = WST(WF_TIME, slot);
+        xi.key.pixel = __float_as_uint(WST(WF_PIXEL, slot));
+        xi.key.sample = __float_as_uint(WST(WF_SAMPLE, slot));
+        xi.bounce = (uint32_t)bounce;
+    }
+    Best best;
+    best.pc = -1; best.t = 0.0f; best.face = 0; best.ctx = 0;
+    float closest = CUDART_INF_F;
+    traverse_uniform(P.S, 0, P.S.n_ops, active, ray, ray, 0, 0.001f, closest, best, P.reference_boxes != 0, xi);
+    if (active) {
+        WST(WF_HIT_T, slot) = best.t;
+        WST(WF_HIT_PC, slot) = __int_as_float(best.pc);
+        WST(WF_HIT_FC, slot) = __int_as_float(best.face | (best.ctx << 8));
+    }
+    const unsigned m = __ballot_sync(kFull, active);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(P.counters + 1, (unsigned long long)__popc(m));
+}
+
+__global__ void __launch_bounds__(kWaveBlock, 3) wave_logic_kernel(const __grid_constant__ WaveParams P) {
+    __shared__ NoiseTable sh_noise[kMaxNoiseTablesShared];
+    TexEnv E;
+    stage_noise(P.S, E, sh_noise, kMaxNoiseTablesShared);
+    const DeviceScene& S = P.S;
+    const int lane = threadIdx.x & 31;
+    const int slot = blockIdx.x * kWaveBlock + threadIdx.x;
+    const bool in_range = slot < P.n_slots;
+    int bounce = in_range ? __float_as_int(WST(WF_BOUNCE, slot)) : -1;
+    RngKey key;
+    key.k0 = P.k0; key.k1 = P.k1; key.pixel = 0; key.sample = 0;
+    if (bounce >= 0) {
+        // ---- emitted + scatter for the segment traced last (application.rs:482-494) ----
+        key.pixel = __float_as_uint(WST(WF_PIXEL, slot));
+        key.sample = __float_as_uint(WST(WF_SAMPLE, slot));
+        Ray ray;
+        ray.o = v3(WST(WF_OX, slot), WST(WF_OY, slot), WST(WF_OZ, slot));
+        ray.d = v3(WST(WF_DX, slot), WST(WF_DY, slot), WST(WF_DZ, slot));
+        ray.time = WST(WF_TIME, slot);
+        V3 T = v3(WST(WF_TX, slot), WST(WF_TY, slot), WST(WF_TZ, slot));
+        const int hit_pc = __float_as_int(WST(WF_HIT_PC, slot));
+        V3 add = v3(0.0f, 0.0f, 0.0f);
+        bool alive = false;
+        if (hit_pc < 0) {
+            add = T * v3(P.bg[0], P.bg[1], P.bg[2]);
+        } else {
+            const int fc = __float_as_int(WST(WF_HIT_FC, slot));
+            Best best;
+            best.t = WST(WF_HIT_T, slot); best.pc = hit_pc; best.face = fc & 0xff; best.ctx = fc >> 8;
+            HitRec h;
+            make_hit_record(S, ray, best, false, h);
+            const Material m = S.mats[h.mat];
+            if (m.kind == MAT_DIFFUSE_LIGHT) {
+                add = T * material_emitted(S, E, m, h);  // DiffuseLight::scatter -> None
+            } else {
+                float u4[4];
+                rng_block(key, (uint32_t)bounce, RNG_BLOCK_SCATTER, u4);
+                V3 att;
+                Ray sc;
+                if (material_scatter(S, E, m, ray, h, u4, att, sc)) {
+                    T = T * att;
+                    bounce++;
+                    if (bounce < P.depth) {  // ray_color(depth == 0) is black
+                        alive = true;
+                        WST(WF_OX, slot) = sc.o.x; WST(WF_OY, slot) = sc.o.y; WST(WF_OZ, slot) = sc.o.z;
+                        WST(WF_DX, slot) = sc.d.x; WST(WF_DY, slot) = sc.d.y; WST(WF_DZ, slot) = sc.d.z;
+                        WST(WF_TIME, slot) = sc.time;
+                        WST(WF_TX, slot) = T.x; WST(WF_TY, slot) = T.y; WST(WF_TZ, slot) = T.z;
+                        WST(WF_BOUNCE, slot) = __int_as_float(bounce);
+                    }
+                }
+            }
+        }
+        if (!alive) {
+            // the path is over: its radiance and its sample count go to the pixel (one 16-byte reduction)
+            atomicAdd(P.accum + key.pixel, make_float4(add.x, add.y, add.z, 1.0f));
+            bounce = -1;
+        }
+    }
+    // ---- free slots start the next camera samples (application.rs:443-448), drawn from one global index ----
+    const bool is_free = in_range && bounce < 0;
+    const unsigned need = __ballot_sync(kFull, is_free);
+    bool started = false;
+    if (need) {
+        unsigned long long base = 0;
+        if (lane == __ffs(need) - 1) base = atomicAdd(P.counters, (unsigned long long)__popc(need));
+        base = __shfl_sync(kFull, base, __ffs(need) - 1);
+        const unsigned long long idx = base + (unsigned long long)__popc(need & ((1u << lane) - 1u));
+        if (is_free && idx < P.total_paths) {
+            key.pixel = (uint32_t)(idx % (unsigned long long)P.n_pixels);
+            key.sample = (uint32_t)P.sample_begin + (uint32_t)(idx / (unsigned long long)P.n_pixels);
+            if (P.depth > 0) {
+                const int px = (int)(key.pixel % (uint32_t)P.width), py = (int)(key.pixel / (uint32_t)P.width);
+                float c4[4];
+                rng_block(key, 0, RNG_BLOCK_CAMERA, c4);  // jitter x, jitter y, shutter time, lens u1
+                float lens_u2 = 0.0f;
+                if (P.cam.lens_radius != 0.0f) {
+                    float l4[4];
+                    rng_block(key, 0, RNG_BLOCK_CAMERA - 1, l4);
+                    lens_u2 = l4[0];
+                }
+                const float u = ((float)px + c4[0]) / ((float)P.width - 1.0f);   // application.rs:444-445
+                const float v = ((float)py + c4[1]) / ((float)P.height - 1.0f);
+                const Ray r = camera_get_ray(P.cam, u, v, c4[3], lens_u2, c4[2]);
+                WST(WF_OX, slot) = r.o.x; WST(WF_OY, slot) = r.o.y; WST(WF_OZ, slot) = r.o.z;
+                WST(WF_DX, slot) = r.d.x; WST(WF_DY, slot) = r.d.y; WST(WF_DZ, slot) = r.d.z;
+                WST(WF_TIME, slot) = r.time;
+                WST(WF_TX, slot) = 1.0f; WST(WF_TY, slot) = 1.0f; WST(WF_TZ, slot) = 1.0f;
+                WST(WF_PIXEL, slot) = __uint_as_float(key.pixel);
+                WST(WF_SAMPLE, slot) = __uint_as_float(key.sample);
+                WST(WF_BOUNCE, slot) = __int_as_float(0);
+                bounce = 0;
+            } else {
+                atomicAdd(P.accum + key.pixel, make_float4(0.0f, 0.0f, 0.0f, 1.0f));  // depth 0: black, but counted
+            }
+            started = true;
+        }
+    }
+    if (in_range && bounce < 0) WST(WF_BOUNCE, slot) = __int_as_float(-1);
+    const unsigned ms = __ballot_sync(kFull, started);
+    if (lane == 0 && ms) atomicAdd(P.counters + 2, (unsigned long long)__popc(ms));
+    if (P.live_out) {
+        // depth 0 never keeps a path, but unstarted samples mean the job is not over
+        const unsigned ml = __ballot_sync(kFull, bounce >= 0 || (started && P.depth <= 0));
+        if (lane == 0 && ml) atomicAdd(P.live_out, __popc(ml));
+    }
+}
+#undef WST
 
 __global__ void __launch_bounds__(256) resolve_kernel(const float4* __restrict__ accum, int n_pixels, float scale,
                                                       float4* __restrict__ out) {
@@ -1337,32 +1229,53 @@ static CameraK to_camera(const hrt_camera_state& c) {
     return k;
 }
 
-// Block shapes of the uniform-walk kernel (HRT_SHAPE; the default is what measured best on C5, profiles/r02_*):
-//   threads per block, blocks per SM, batches of 32 paths per warp
-#define HRT_UNIFORM_SHAPES(X) X(0, 256, 2, 2) X(1, 256, 2, 4) X(2, 256, 2, 1) X(3, 512, 1, 2) X(4, 512, 1, 4) X(5, 128, 4, 2) X(6, 256, 3, 2) X(7, 384, 1, 4)
-static cudaError_t uniform_config(int shape, int& threads, int& blocks_per_sm, size_t& smem, bool set_attr) {
-#define X(ID, T, B, N)                                                                                               \
-    if (shape == ID) {                                                                                                \
-        threads = T; smem = PooledShape<T, B, N>::kBytes;                                                              \
-        cudaError_t e_ = set_attr ? cudaFuncSetAttribute((const void*)render_uniform_kernel<T, B, N>,                  \
-                                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)       \
-                                  : cudaSuccess;                                                                       \
-        if (e_ != cudaSuccess) return e_;                                                                              \
-        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, render_uniform_kernel<T, B, N>, T, smem); \
+// Host loop of the wavefront render: batches of iterations are enqueued ahead; after each batch the number of slots
+// that still carry a path comes back through pinned memory, and the loop ends one batch after it reads zero.  Blocks
+// the calling thread until the render is complete.
+cudaError_t launch_render_wave(hrt::RenderLaunch& L, hrt::WaveBuffers& W, int num_sms, cudaStream_t stream) {
+    (void)num_sms;
+    WaveParams P;
+    P.S = to_device_scene(L.scene);
+    P.cam = to_camera(L.cam);
+    P.width = L.width; P.height = L.height; P.depth = L.depth;
+    P.bg[0] = L.background[0]; P.bg[1] = L.background[1]; P.bg[2] = L.background[2];
+    P.k0 = L.key0; P.k1 = L.key1;
+    P.sample_begin = L.sample_begin;
+    P.n_pixels = L.width * L.height;
+    P.total_paths = (unsigned long long)P.n_pixels * (unsigned long long)L.sample_count;
+    const unsigned long long want = (P.total_paths + kWaveBlock - 1) / kWaveBlock * kWaveBlock;
+    P.n_slots = (int)std::min<unsigned long long>((unsigned long long)W.n_slots, std::max<unsigned long long>(want, kWaveBlock));
+    P.reference_boxes = L.reference_boxes;
+    P.st = W.state;
+    P.counters = L.counters;
+    P.accum = reinterpret_cast<float4*>(L.accum);
+    P.live_out = nullptr;
+    const int grid = (P.n_slots + kWaveBlock - 1) / kWaveBlock;
+    L.grid = grid;
+    L.block = kWaveBlock;
+    L.launches = 0;
+    cudaError_t e;
+    // every slot starts free
+    if ((e = cudaMemsetAsync(W.state + (size_t)WF_BOUNCE * P.n_slots, 0xff, sizeof(float) * (size_t)P.n_slots, stream)) != cudaSuccess) return e;
+    const int kBatch = 16;
+    for (int b = 0;; ++b) {
+        int* live = W.d_live + (b & 1);
+        if ((e = cudaMemsetAsync(live, 0, sizeof(int), stream)) != cudaSuccess) return e;
+        for (int i = 0; i < kBatch; ++i) {
+            P.live_out = i == kBatch - 1 ? live : nullptr;
+            wave_logic_kernel<<<grid, kWaveBlock, 0, stream>>>(P);
+            wave_trace_kernel<<<grid, kWaveBlock, 0, stream>>>(P);
+            L.launches += 2;
+        }
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        if ((e = cudaMemcpyAsync(W.h_live + (b & 1), live, sizeof(int), cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return e;
+        if ((e = cudaEventRecord(W.ev[b & 1], stream)) != cudaSuccess) return e;
+        if (b >= 1) {
+            if ((e = cudaEventSynchronize(W.ev[(b - 1) & 1])) != cudaSuccess) return e;
+            if (W.h_live[(b - 1) & 1] == 0) break;  // the batch enqueued meanwhile found nothing to do
+        }
     }
-    HRT_UNIFORM_SHAPES(X)
-#undef X
-    return cudaErrorInvalidValue;
-}
-static cudaError_t uniform_launch(int shape, int grid, size_t smem, cudaStream_t stream, const RenderParams& P) {
-#define X(ID, T, B, N)                                                       \
-    if (shape == ID) {                                                        \
-        render_uniform_kernel<T, B, N><<<grid, T, smem, stream>>>(P);         \
-        return cudaGetLastError();                                            \
-    }
-    HRT_UNIFORM_SHAPES(X)
-#undef X
-    return cudaErrorInvalidValue;
+    return cudaSuccess;
 }
 
 cudaError_t launch_render(hrt::RenderLaunch& L, int num_sms, cudaStream_t stream) {
@@ -1382,10 +1295,6 @@ cudaError_t launch_render(hrt::RenderLaunch& L, int num_sms, cudaStream_t stream
     P.n_sh_noise = 0;
     cudaError_t e;
     const bool pooled = L.interpreter == 2;
-    int uni_shape = 0, uni_threads = 256;
-    size_t uni_smem = 0;
-    P.n_pre = L.n_pre;
-    for (int i = 0; i < kMaxPreTrees; ++i) P.pre[i] = L.pre[i];
     const void* pool_fn = (const void*)render_pool_kernel;
     if (pooled) {
         // Shared-memory budget of the one resident block: the ray pools, then as much of the Box16 table as fits (all
@@ -1406,8 +1315,7 @@ cudaError_t launch_render(hrt::RenderLaunch& L, int num_sms, cudaStream_t stream
         if (e != cudaSuccess) return e;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, pool_fn, kPoolBlock, pool_smem);
     } else if (L.interpreter == 3) {
-        uni_shape = L.shape;
-        e = uniform_config(uni_shape, uni_threads, blocks_per_sm, uni_smem, true);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, render_interp_kernel<true>, kBlock, 0);
     } else if (L.interpreter == 1) {
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, render_interp_kernel<false>, kBlock, 0);
     } else {
@@ -1421,8 +1329,7 @@ cudaError_t launch_render(hrt::RenderLaunch& L, int num_sms, cudaStream_t stream
     int chunk = L.chunk;
     if (chunk <= 0) {
         chunk = pooled ? 256 : 64;  // the pool kernel keeps 96 rays in flight per warp: larger items
-        // the uniform-walk kernel keeps up to 4 items per warp in flight (one per batch)
-        const long long resident_warps = (long long)grid * (pooled ? kPoolWarps : (L.interpreter == 3 ? 4 * (uni_threads / 32) : kWarpsPerBlock));
+        const long long resident_warps = (long long)grid * (pooled ? kPoolWarps : kWarpsPerBlock);
         while (chunk > 4 && (long long)P.n_tiles * ((L.sample_count + chunk - 1) / chunk) < 8 * resident_warps) chunk /= 2;
     }
     if (chunk > L.sample_count) chunk = L.sample_count;
@@ -1451,13 +1358,10 @@ cudaError_t launch_render(hrt::RenderLaunch& L, int num_sms, cudaStream_t stream
     P.counters = L.counters;
     P.accum = reinterpret_cast<float4*>(L.accum);
     L.grid = grid;
-    L.block = pooled ? kPoolBlock : (L.interpreter == 3 ? uni_threads : kBlock);
+    L.block = pooled ? kPoolBlock : kBlock;
     L.chunk = chunk;
     if (L.interpreter == 2) render_pool_kernel<<<grid, kPoolBlock, pool_smem, stream>>>(P);
-    else if (L.interpreter == 3) {
-        e = uniform_launch(uni_shape, grid, uni_smem, stream, P);
-        if (e != cudaSuccess) return e;
-    }
+    else if (L.interpreter == 3) render_interp_kernel<true><<<grid, kBlock, 0, stream>>>(P);
     else if (L.interpreter == 1) render_interp_kernel<false><<<grid, kBlock, 0, stream>>>(P);
     else render_kernel<<<grid, kBlock, 0, stream>>>(P);
     return cudaGetLastError();

@@ -32,21 +32,30 @@ struct RenderLaunch {
     int32_t chunk;        // samples per work item
     int32_t reference_boxes;
     int32_t n_nodes;      // tree nodes of the scene form being rendered
-    int32_t n_pre;        // OP_BVH trees walked ahead of the stream walk (<= kMaxPreTrees)
-    hrt::PreTree pre[hrt::kMaxPreTrees];
-    int32_t shape;        // uniform-walk kernel: block shape / synchronisation variant (diagnostic)
     int32_t interpreter;  // render kernel variant: 0 warp scheduler, 1 per-lane interpreter, 2 shared-memory ray pool,
                           // 3 warp-uniform walk (production)
     unsigned long long* counters;  // device: [0] work-item cursor, [1] rays, [2] paths
     float* accum;                  // device: width*height*4 f32, added into
     int32_t grid, block;           // out: launch configuration actually used
+    int32_t launches;              // out: kernels launched
 };
+
+// Device buffers of the wavefront render (hrt_kernels.cu launch_render_wave), owned per device.
+struct WaveBuffers {
+    float* state = nullptr;   // [WF_WORDS][n_slots]
+    int32_t n_slots = 0;
+    int* d_live = nullptr;    // 2 counters
+    int* h_live = nullptr;    // pinned mirror
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+};
+constexpr int kWaveStateWords = 16;  // == WF_WORDS
 
 }  // namespace hrt
 
 #define HRT_DECLARE_LAUNCHERS(NS)                                                                                        \
     namespace NS {                                                                                                       \
     cudaError_t launch_render(hrt::RenderLaunch& L, int num_sms, cudaStream_t stream);                                        \
+    cudaError_t launch_render_wave(hrt::RenderLaunch& L, hrt::WaveBuffers& W, int num_sms, cudaStream_t stream);              \
     cudaError_t launch_trace_hits(const hrt::DeviceSceneHost& S, const hrt_ray* d_rays, int n, const float* d_xi,             \
                                   hrt_hit* d_out, int reference_boxes, cudaStream_t stream);                             \
     cudaError_t launch_tex_value(const hrt::DeviceSceneHost& S, int tex, const float* d_uvp, int n, float* d_out,             \

@@ -18,6 +18,7 @@ HRT_FLAG_INTERPRETER = 8
 HRT_FLAG_POOL = 16
 HRT_FLAG_SCHEDULER = 32
 HRT_FLAG_UNIFORM = 64
+HRT_FLAG_WAVEFRONT = 128
 ABI_VERSION = 3  # include/hrt.h HRT_ABI_VERSION
 HRT_BVH_REFERENCE = 0
 HRT_BVH_TREES = 1

@@ -169,6 +169,8 @@ enum {
     HRT_FLAG_INTERPRETER = 8,         /* render: plain per-lane interpreter kernel instead of the warp scheduler  */
     HRT_FLAG_UNIFORM = 64,            /* render / hrt_trace_hits: the warp walks the op stream together (one record per
                                          step for the lanes that are at it; every branch warp-uniform)          */
+    HRT_FLAG_WAVEFRONT = 128,         /* render: the wavefront render (default): path slots in device memory, one shade /
+                                         regenerate kernel and one trace kernel per ray segment                  */
     HRT_FLAG_WARP_SCHEDULER = 4       /* hrt_trace_hits only: run through the render kernel's warp-level op-class
                                          scheduler instead of the plain per-lane interpreter                */
 };

@@ -408,7 +408,7 @@ def test_render_kernel_variants_agree(pkg, orc, built, name):
     outs = []
     # the last entry drives the pool kernel's box loop through the 32-byte records (reference test on every box) instead
     # of the fp16 table in shared memory: same hits, so the same paths
-    for flag in (N.HRT_FLAG_POOL, N.HRT_FLAG_SCHEDULER, N.HRT_FLAG_INTERPRETER, N.HRT_FLAG_UNIFORM,
+    for flag in (N.HRT_FLAG_WAVEFRONT, N.HRT_FLAG_POOL, N.HRT_FLAG_SCHEDULER, N.HRT_FLAG_INTERPRETER, N.HRT_FLAG_UNIFORM,
                  N.HRT_FLAG_POOL | N.HRT_FLAG_REFERENCE_TRAVERSAL):
         acc, st = gb.render(spec.camera, 72, 48, 160, 50, spec.background, seed=31, resolve=False, flags=flag)
         outs.append((np.nan_to_num(acc[..., :3]), st.rays, st.paths))
