@@ -64,7 +64,7 @@ void release_device_state(DeviceState* d) {
         cudaFree(d->d_nodes); cudaFree(d->d_mats); cudaFree(d->d_texs); cudaFree(d->d_noise);
         cudaFree(d->d_counters); cudaFree(d->d_accum); cudaFree(d->d_rgba);
         for (auto e : d->ev) if (e) cudaEventDestroy(e);
-        cudaFree(d->wave.state); cudaFree(d->wave.d_live);
+        cudaFree(d->wave.state); cudaFree(d->wave.d_live); cudaFree(d->wave.acc64);
         if (d->wave.h_live) cudaFreeHost(d->wave.h_live);
         for (auto e : d->wave.ev) if (e) cudaEventDestroy(e);
         for (auto& sl : d->slots) {
@@ -100,7 +100,14 @@ static DeviceState* find_state(hrt_scene* s, int device) {
     return nullptr;
 }
 
-static int32_t ensure_wave(DeviceState* d) {
+static int32_t ensure_wave(DeviceState* d, size_t pixels) {
+    if (d->wave.acc_pixels < pixels) {
+        cudaFree(d->wave.acc64);
+        d->wave.acc64 = nullptr;
+        d->wave.acc_pixels = 0;
+        HRT_CUDA(cudaMalloc((void**)&d->wave.acc64, sizeof(double) * 4 * pixels));
+        d->wave.acc_pixels = pixels;
+    }
     if (d->wave.state) return HRT_OK;
     int n = 1 << 20;  // path slots in flight (64 MB of state)
     if (const char* env = getenv("HRT_WAVE_SLOTS")) n = atoi(env);
@@ -410,7 +417,7 @@ static int32_t render_into(hrt_scene* s, DeviceState* d, const hrt_camera_desc* 
     HRT_CUDA(cudaEventRecord(slot.t0, stream));
     cudaError_t e;
     if (L.interpreter == 5) {
-        if ((rc = ensure_wave(d)) != HRT_OK) return rc;
+        if ((rc = ensure_wave(d, (size_t)rd->width * rd->height)) != HRT_OK) return rc;
         e = (rd->flags & HRT_FLAG_EXACT_MATH) ? hrt_exact::launch_render_wave(L, d->wave, d->num_sms, stream)
                                               : hrt_fast::launch_render_wave(L, d->wave, d->num_sms, stream);
     } else {

@@ -747,9 +747,28 @@ struct WaveParams {
     int reference_boxes;
     float* st;                     // [WF_WORDS][n_slots]
     unsigned long long* counters;  // [0] next path index, [1] rays, [2] paths
+    double* acc64;                 // [n_pixels][4] radiance sums + sample counts of this render (added into `accum` at the end)
     float4* accum;
     int* live_out;                 // when not null: += number of slots that carry a path after this logic pass
 };
+// One reduction per finished path.  In f64: the persistent kernels add a work item's (<= 256 samples') partial sum, here
+// every sample is added on its own, and 10^4 f32 additions of near-equal terms drift by ~1e-4 relative (measured on the
+// constant background of `earth`), enough to show in the pooled z-scores.
+__device__ __forceinline__ void wave_accumulate(const WaveParams& P, uint32_t pixel, V3 add) {
+    double* a = P.acc64 + 4 * (size_t)pixel;
+    if (add.x != 0.0f) atomicAdd(a + 0, (double)add.x);
+    if (add.y != 0.0f) atomicAdd(a + 1, (double)add.y);
+    if (add.z != 0.0f) atomicAdd(a + 2, (double)add.z);
+    atomicAdd(a + 3, 1.0);
+}
+__global__ void __launch_bounds__(256) wave_finish_kernel(double* __restrict__ acc64, int n_pixels, float4* __restrict__ accum) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pixels) return;
+    double* a = acc64 + 4 * (size_t)i;
+    float4 v = accum[i];
+    v.x += (float)a[0]; v.y += (float)a[1]; v.z += (float)a[2]; v.w += (float)a[3];
+    accum[i] = v;
+}
 static_assert(WF_WORDS == hrt::kWaveStateWords, "wave state layout");
 #define WST(f, slot) P.st[(size_t)(f) * P.n_slots + (slot)]
 
@@ -839,7 +858,7 @@ __global__ void __launch_bounds__(kWaveBlock, 3) wave_logic_kernel(const __grid_
         }
         if (!alive) {
             // the path is over: its radiance and its sample count go to the pixel (one 16-byte reduction)
-            atomicAdd(P.accum + key.pixel, make_float4(add.x, add.y, add.z, 1.0f));
+            wave_accumulate(P, key.pixel, add);
             bounce = -1;
         }
     }
@@ -877,7 +896,7 @@ __global__ void __launch_bounds__(kWaveBlock, 3) wave_logic_kernel(const __grid_
                 WST(WF_BOUNCE, slot) = __int_as_float(0);
                 bounce = 0;
             } else {
-                atomicAdd(P.accum + key.pixel, make_float4(0.0f, 0.0f, 0.0f, 1.0f));  // depth 0: black, but counted
+                wave_accumulate(P, key.pixel, v3(0.0f, 0.0f, 0.0f));  // depth 0: black, but counted
             }
             started = true;
         }
@@ -1249,12 +1268,14 @@ cudaError_t launch_render_wave(hrt::RenderLaunch& L, hrt::WaveBuffers& W, int nu
     P.st = W.state;
     P.counters = L.counters;
     P.accum = reinterpret_cast<float4*>(L.accum);
+    P.acc64 = W.acc64;
     P.live_out = nullptr;
     const int grid = (P.n_slots + kWaveBlock - 1) / kWaveBlock;
     L.grid = grid;
     L.block = kWaveBlock;
     L.launches = 0;
     cudaError_t e;
+    if ((e = cudaMemsetAsync(W.acc64, 0, sizeof(double) * 4 * (size_t)P.n_pixels, stream)) != cudaSuccess) return e;
     // every slot starts free
     if ((e = cudaMemsetAsync(W.state + (size_t)WF_BOUNCE * P.n_slots, 0xff, sizeof(float) * (size_t)P.n_slots, stream)) != cudaSuccess) return e;
     const int kBatch = 16;
@@ -1275,7 +1296,9 @@ cudaError_t launch_render_wave(hrt::RenderLaunch& L, hrt::WaveBuffers& W, int nu
             if (W.h_live[(b - 1) & 1] == 0) break;  // the batch enqueued meanwhile found nothing to do
         }
     }
-    return cudaSuccess;
+    wave_finish_kernel<<<(P.n_pixels + 255) / 256, 256, 0, stream>>>(W.acc64, P.n_pixels, P.accum);
+    L.launches += 1;
+    return cudaGetLastError();
 }
 
 cudaError_t launch_render(hrt::RenderLaunch& L, int num_sms, cudaStream_t stream) {

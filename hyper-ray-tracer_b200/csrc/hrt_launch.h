@@ -43,6 +43,8 @@ struct RenderLaunch {
 // Device buffers of the wavefront render (hrt_kernels.cu launch_render_wave), owned per device.
 struct WaveBuffers {
     float* state = nullptr;   // [WF_WORDS][n_slots]
+    double* acc64 = nullptr;  // [acc_pixels][4]
+    size_t acc_pixels = 0;
     int32_t n_slots = 0;
     int* d_live = nullptr;    // 2 counters
     int* h_live = nullptr;    // pinned mirror
