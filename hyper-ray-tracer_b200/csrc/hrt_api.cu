@@ -65,6 +65,7 @@ void release_device_state(DeviceState* d) {
         cudaFree(d->d_counters); cudaFree(d->d_accum); cudaFree(d->d_rgba);
         for (auto e : d->ev) if (e) cudaEventDestroy(e);
         cudaFree(d->wave.state); cudaFree(d->wave.d_live); cudaFree(d->wave.acc64);
+        cudaFree(d->wave.tq); cudaFree(d->wave.pre); cudaFree(d->wave.tq_count);
         if (d->wave.h_live) cudaFreeHost(d->wave.h_live);
         for (auto e : d->wave.ev) if (e) cudaEventDestroy(e);
         for (auto& sl : d->slots) {
@@ -115,6 +116,9 @@ static int32_t ensure_wave(DeviceState* d, size_t pixels) {
     n = (n + 255) / 256 * 256;
     HRT_CUDA(cudaMalloc((void**)&d->wave.state, sizeof(float) * (size_t)kWaveStateWords * (size_t)n));
     HRT_CUDA(cudaMalloc((void**)&d->wave.d_live, 2 * sizeof(int)));
+    HRT_CUDA(cudaMalloc((void**)&d->wave.tq, sizeof(float) * 8 * (size_t)kMaxPreTrees * (size_t)n));
+    HRT_CUDA(cudaMalloc((void**)&d->wave.pre, sizeof(float) * 2 * (size_t)kMaxPreTrees * (size_t)n));
+    HRT_CUDA(cudaMalloc((void**)&d->wave.tq_count, 2 * kMaxPreTrees * sizeof(int)));
     HRT_CUDA(cudaMallocHost((void**)&d->wave.h_live, 2 * sizeof(int)));
     for (auto& e : d->wave.ev) HRT_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     d->wave.n_slots = n;
@@ -388,6 +392,10 @@ static int32_t render_into(hrt_scene* s, DeviceState* d, const hrt_camera_desc* 
     L.reference_boxes = ref_boxes ? 1 : 0;
     L.scene = d->view[ref_boxes ? 0 : 1];  // the reference form of the stream goes with the reference's box test
     L.n_nodes = ref_boxes ? 0 : (int32_t)s->fast.nodes.size();
+    L.n_pre = 0;
+    if (!ref_boxes && !getenv("HRT_NO_TREE_STAGE"))
+        for (const PreTree& t : s->fast.trees)
+            if (L.n_pre < kMaxPreTrees) L.pre[L.n_pre++] = t;
     {
         const char* env = getenv("HRT_KERNEL");  // diagnostic override: "interp" | "sched" | "pool"
         // default: the wavefront render (two small kernels per ray segment)

@@ -465,9 +465,72 @@ __device__ __noinline__ bool tie_goes_to_later(const DeviceScene& S, int later_p
     return box_hit_reference(mn, mx, cur, k, tmin, t);
 }
 
-// Closest hit of the tree whose first node is `base` for t in [tmin, closest]; leaves are primitive records of the op
-// stream.  Box tests only prune (every box is sound), so any visit order finds the same closest t; exact ties are
-// settled by tie_goes_to_later.  (ts, te): the BvhNode's time interval.  Out of line: one copy per kernel.
+// One step of the walk of the tree whose first node is `base`: an inner node (both children's boxes, nearer first, the
+// other postponed on the stack) or a leaf (a primitive record of the op stream), then the next postponed child that can
+// still hold a closer or equal hit.  Returns true when the walk is over.  Box tests only prune (every box is sound), so
+// any visit order finds the same closest t; exact ties are settled by tie_goes_to_later.  (ts, te): the BvhNode's time
+// interval.  `ref` >= 0: node (relative to base), < 0: ~pc of a leaf record; start with ref = 0, sp = 0.
+__device__ __forceinline__ bool bvh2_step(const DeviceScene& S, int base, const Ray& cur, const RayK& k, float tmin, float ts, float te,
+                                          int& ref, int& sp, int* stack_ref, float* stack_t, TreeHit& h) {
+    if (ref >= 0) {
+        uint4 L, R;
+        load_node(S, base + ref, L, R);
+        float llo, lhi, rlo, rhi;
+        slab16(L.x, L.y, L.z, cur, k, tmin, h.t, llo, lhi);
+        slab16(R.x, R.y, R.z, cur, k, tmin, h.t, rlo, rhi);
+        const bool hl = !(lhi < llo), hr = !(rhi < rlo);
+        if (hl && hr) {
+            const bool right_first = rlo < llo;
+            stack_ref[sp] = right_first ? (int)L.w : (int)R.w;
+            stack_t[sp] = right_first ? llo : rlo;
+            sp++;
+            ref = right_first ? (int)R.w : (int)L.w;
+            return false;
+        }
+        if (hl || hr) {
+            ref = hl ? (int)L.w : (int)R.w;
+            return false;
+        }
+    } else {
+        const int pc = ~ref;
+        float4 A, B;
+        load_op(S, pc, A, B);
+        const uint32_t opc = __float_as_uint(B.w) & 0xffu;
+        float t = 0.0f;
+        int face = 0;
+        bool hit;
+        if (opc == OP_SPHERE || opc == OP_MSPHERE) {
+            V3 ctr = v3(A.x, A.y, A.z);
+            if (opc == OP_MSPHERE) {
+                float4 C, D;
+                load_op(S, pc + 1, C, D);
+                ctr = msphere_center(ctr, v3(C.x, C.y, C.z), C.w, D.x, cur.time);
+            }
+            hit = sphere_test(ctr, A.w, cur, k, tmin, h.t, t);
+        } else if (opc == OP_CUBOID) {
+            hit = cuboid_test(v3(A.x, A.y, A.z), v3(B.x, B.y, B.z), cur, k, tmin, h.t, t, face);
+        } else {
+            hit = rect_any(opc, A, B.x, cur, k, tmin, h.t, t);
+        }
+        if (hit) {  // the primitive tests accept t <= closest
+            bool take = t < h.t || h.pc < 0;
+            if (!take && !(t > h.t)) {  // exact tie (or a NaN, Q15) with the hit held so far
+                const bool later_wins = tie_goes_to_later(S, pc > h.pc ? pc : h.pc, cur, tmin, t, ts, te);
+                take = (pc > h.pc) == later_wins;
+            }
+            if (take) { h.t = t; h.pc = pc; h.face = face; }
+        }
+    }
+    // next: the nearest postponed child that can still hold a closer (or equal) hit
+    do {
+        if (sp == 0) return true;
+        --sp;
+        ref = stack_ref[sp];
+    } while (stack_t[sp] > h.t);
+    return false;
+}
+// Closest hit of a whole tree for t in [tmin, closest]; `best_pc`: the record of the hit held so far (-1 none).  Out of
+// line: one copy per kernel.
 __device__ __noinline__ TreeHit bvh2_walk(const DeviceScene& S, int base, Ray cur, float tmin, float closest, int best_pc,
                                           float ts, float te) {
     const RayK k = make_rayk(cur);
@@ -475,65 +538,9 @@ __device__ __noinline__ TreeHit bvh2_walk(const DeviceScene& S, int base, Ray cu
     h.t = closest; h.pc = best_pc; h.face = 0;
     int stack_ref[kBvh2Stack];
     float stack_t[kBvh2Stack];
-    int sp = 0;
-    int ref = 0;  // the tree's first node is its root
-    for (;;) {
-        if (ref >= 0) {
-            uint4 L, R;
-            load_node(S, base + ref, L, R);
-            float llo, lhi, rlo, rhi;
-            slab16(L.x, L.y, L.z, cur, k, tmin, h.t, llo, lhi);
-            slab16(R.x, R.y, R.z, cur, k, tmin, h.t, rlo, rhi);
-            const bool hl = !(lhi < llo), hr = !(rhi < rlo);
-            if (hl && hr) {
-                const bool right_first = rlo < llo;
-                stack_ref[sp] = right_first ? (int)L.w : (int)R.w;
-                stack_t[sp] = right_first ? llo : rlo;
-                sp++;
-                ref = right_first ? (int)R.w : (int)L.w;
-                continue;
-            }
-            if (hl || hr) {
-                ref = hl ? (int)L.w : (int)R.w;
-                continue;
-            }
-        } else {
-            const int pc = ~ref;
-            float4 A, B;
-            load_op(S, pc, A, B);
-            const uint32_t opc = __float_as_uint(B.w) & 0xffu;
-            float t = 0.0f;
-            int face = 0;
-            bool hit;
-            if (opc == OP_SPHERE || opc == OP_MSPHERE) {
-                V3 ctr = v3(A.x, A.y, A.z);
-                if (opc == OP_MSPHERE) {
-                    float4 C, D;
-                    load_op(S, pc + 1, C, D);
-                    ctr = msphere_center(ctr, v3(C.x, C.y, C.z), C.w, D.x, cur.time);
-                }
-                hit = sphere_test(ctr, A.w, cur, k, tmin, h.t, t);
-            } else if (opc == OP_CUBOID) {
-                hit = cuboid_test(v3(A.x, A.y, A.z), v3(B.x, B.y, B.z), cur, k, tmin, h.t, t, face);
-            } else {
-                hit = rect_any(opc, A, B.x, cur, k, tmin, h.t, t);
-            }
-            if (hit) {  // the primitive tests accept t <= closest
-                bool take = t < h.t || h.pc < 0;
-                if (!take && !(t > h.t)) {  // exact tie (or a NaN, Q15) with the hit held so far
-                    const bool later_wins = tie_goes_to_later(S, pc > h.pc ? pc : h.pc, cur, tmin, t, ts, te);
-                    take = (pc > h.pc) == later_wins;
-                }
-                if (take) { h.t = t; h.pc = pc; h.face = face; }
-            }
-        }
-        // next: the nearest postponed child that can still hold a closer (or equal) hit
-        do {
-            if (sp == 0) return h;
-            --sp;
-            ref = stack_ref[sp];
-        } while (stack_t[sp] > h.t);
-    }
+    int sp = 0, ref = 0;
+    while (!bvh2_step(S, base, cur, k, tmin, ts, te, ref, sp, stack_ref, stack_t, h)) {}
+    return h;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -731,9 +738,13 @@ __device__ __noinline__ bool medium_sample(const DeviceScene& S, float4 A, float
 // also the compact forms of the rect / cuboid tests.
 // Every lane of the warp must call it (`active` = this lane carries a ray).
 // ------------------------------------------------------------------------------------------------
+// `pre` / `n_pre`: results of the first n_pre OP_BVH trees of the stream walked AHEAD for this ray over [tmin, +inf)
+// (the wavefront render's tree stage): {t, code} with code = kPreNone: no hit, else leaf pc | side << 24.
+constexpr int kPreNone = -1;
 __device__ __forceinline__ bool traverse_uniform(const DeviceScene& S, const int pc_begin, const int pc_end, const bool active,
                                                  const Ray& world, Ray cur, int cur_ctx, const float tmin_world, float& closest_io,
-                                                 Best& best, const bool reference_boxes, const MediumXi& xi) {
+                                                 Best& best, const bool reference_boxes, const MediumXi& xi,
+                                                 const float2* pre = nullptr, const int n_pre = 0) {
     const unsigned kAll = 0xffffffffu;
     int pc = active ? pc_begin : pc_end;
     RayK k = make_rayk(cur);
@@ -813,6 +824,28 @@ __device__ __forceinline__ bool traverse_uniform(const DeviceScene& S, const int
                 if (me) hit = cuboid_test(v3(A.x, A.y, A.z), v3(B.x, B.y, B.z), cur, k, tmin, closest, t, face);
                 break;
             case OP_BVH: {  // a sound BvhNode as a two-child tree: every ray walks it on its own (bvh2_walk)
+                const int tree = __float_as_int(B.z);
+                if (mode == 0 && tree >= 0 && tree < n_pre) {
+                    // walked ahead over [tmin, +inf): its closest hit t* is the tree's closest hit in [tmin, closest] iff
+                    // t* <= closest (the tree is sound), and an exact tie with the hit held so far — an earlier record —
+                    // is settled the reference's way
+                    if (me) {
+                        const float2 r = pre[tree];
+                        const int code = __float_as_int(r.y);
+                        if (code != kPreNone) {
+                            const float tt = r.x;
+                            const int leaf = code & 0xffffff;
+                            bool take = tt < closest;
+                            if (!take && !(tt > closest)) take = best.pc < 0 || tie_goes_to_later(S, leaf, cur, tmin, tt, B.x, B.y);
+                            if (take) {
+                                closest = tt; hitf = true;
+                                best.t = tt; best.pc = leaf; best.face = code >> 24; best.ctx = cur_ctx;
+                            }
+                        }
+                        pc = (int)(w7 >> 8);
+                    }
+                    break;
+                }
                 if (me) {
                     const int held = mode == 0 ? best.pc : -1;
                     const TreeHit th = bvh2_walk(S, __float_as_int(A.x), cur, tmin, closest, held, B.x, B.y);

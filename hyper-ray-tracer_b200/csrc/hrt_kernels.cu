@@ -747,6 +747,12 @@ struct WaveParams {
     int reference_boxes;
     float* st;                     // [WF_WORDS][n_slots]
     unsigned long long* counters;  // [0] next path index, [1] rays, [2] paths
+    // the tree stage: the first n_pre OP_BVH trees of the stream are walked for all slots together, compacted
+    int n_pre;
+    PreTree pre[kMaxPreTrees];
+    float4* tq;                    // [kMaxPreTrees][n_slots][2]: {o.xyz, time}, {d.xyz, slot} in the tree's ray space
+    float2* pre_res;               // [n_slots][kMaxPreTrees]: {t, code} (traverse_uniform)
+    int* tq_count;                 // [kMaxPreTrees] queued, then [kMaxPreTrees] taken
     double* acc64;                 // [n_pixels][4] radiance sums + sample counts of this render (added into `accum` at the end)
     float4* accum;
     int* live_out;                 // when not null: += number of slots that carry a path after this logic pass
@@ -793,7 +799,9 @@ __global__ void __launch_bounds__(kWaveBlock, 3) wave_trace_kernel(const __grid_
     Best best;
     best.pc = -1; best.t = 0.0f; best.face = 0; best.ctx = 0;
     float closest = CUDART_INF_F;
-    traverse_uniform(P.S, 0, P.S.n_ops, active, ray, ray, 0, 0.001f, closest, best, P.reference_boxes != 0, xi);
+    traverse_uniform(P.S, 0, P.S.n_ops, active, ray, ray, 0, 0.001f, closest, best, P.reference_boxes != 0, xi,
+                     P.pre_res + (size_t)(in_range ? slot : 0) * kMaxPreTrees, P.n_pre);
+    if (blockIdx.x == 0 && threadIdx.x < 2 * kMaxPreTrees) P.tq_count[threadIdx.x] = 0;  // the queues are consumed
     if (active) {
         WST(WF_HIT_T, slot) = best.t;
         WST(WF_HIT_PC, slot) = __int_as_float(best.pc);
@@ -801,6 +809,57 @@ __global__ void __launch_bounds__(kWaveBlock, 3) wave_trace_kernel(const __grid_
     }
     const unsigned m = __ballot_sync(kFull, active);
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(P.counters + 1, (unsigned long long)__popc(m));
+}
+
+// Tree stage, part 2: persistent warps pull walks from the tree's queue — a lane that finishes its walk takes the next
+// entry — so the lanes stay filled however much the walks differ in length.  (Inside wave_trace_kernel the same walks
+// were 64 % of its issued instructions at 3 - 7 of 32 lanes: only the few rays of a warp that reach one tree walk
+// together, profiles/r02_w1_*.)
+__global__ void __launch_bounds__(kWaveBlock, 3) wave_tree_kernel(const __grid_constant__ WaveParams P, const int tree) {
+    const DeviceScene& S = P.S;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const int n_entries = P.tq_count[tree];
+    int* const next = P.tq_count + kMaxPreTrees + tree;
+    const float4* const queue = P.tq + 2 * (size_t)tree * P.n_slots;
+    const int base = P.pre[tree].base;
+    const float ts = P.pre[tree].ts, te = P.pre[tree].te;
+    int slot = -1;  // < 0: this lane is idle
+    int ref = 0, sp = 0;
+    Ray cur;
+    cur.o = v3(0.0f, 0.0f, 0.0f); cur.d = v3(1.0f, 1.0f, 1.0f); cur.time = 0.0f;
+    RayK k = make_rayk(cur);
+    TreeHit h;
+    h.t = CUDART_INF_F; h.pc = -1; h.face = 0;
+    int stack_ref[kBvh2Stack];
+    float stack_t[kBvh2Stack];
+    bool drained = false;  // warp-uniform: the queue has no entry left
+    for (;;) {
+        const unsigned idle = __ballot_sync(kFull, slot < 0);
+        if (idle && !drained) {
+            int e0 = 0;
+            if (lane == 0) e0 = atomicAdd(next, __popc(idle));
+            e0 = __shfl_sync(kFull, e0, 0);
+            const int e = e0 + __popc(idle & lt_mask);
+            if (e0 + __popc(idle) >= n_entries) drained = true;
+            if (slot < 0 && e < n_entries) {
+                const float4 a = __ldg(queue + 2 * (size_t)e), b = __ldg(queue + 2 * (size_t)e + 1);
+                slot = __float_as_int(b.w);
+                cur.o = v3(a.x, a.y, a.z); cur.d = v3(b.x, b.y, b.z); cur.time = a.w;
+                k = make_rayk(cur);
+                h.t = CUDART_INF_F; h.pc = -1; h.face = 0;
+                ref = 0; sp = 0;
+            }
+        }
+        if (!__any_sync(kFull, slot >= 0)) break;
+        if (slot >= 0) {
+            if (bvh2_step(S, base, cur, k, 0.001f, ts, te, ref, sp, stack_ref, stack_t, h)) {
+                P.pre_res[(size_t)slot * kMaxPreTrees + tree] =
+                    make_float2(h.t, __int_as_float(h.pc < 0 ? kPreNone : (h.pc | (h.face << 24))));
+                slot = -1;
+            }
+        }
+    }
 }
 
 __global__ void __launch_bounds__(kWaveBlock, 3) wave_logic_kernel(const __grid_constant__ WaveParams P) {
@@ -902,6 +961,37 @@ __global__ void __launch_bounds__(kWaveBlock, 3) wave_logic_kernel(const __grid_
         }
     }
     if (in_range && bounce < 0) WST(WF_BOUNCE, slot) = __int_as_float(-1);
+    // ---- tree stage, part 1: the ray this slot traces next against the root box of every pre-walked tree ----
+    if (P.n_pre > 0) {
+        const bool live = bounce >= 0;
+        Ray w;
+        w.o = v3(0.0f, 0.0f, 0.0f); w.d = v3(1.0f, 1.0f, 1.0f); w.time = 0.0f;
+        if (live) {
+            w.o = v3(WST(WF_OX, slot), WST(WF_OY, slot), WST(WF_OZ, slot));
+            w.d = v3(WST(WF_DX, slot), WST(WF_DY, slot), WST(WF_DZ, slot));
+            w.time = WST(WF_TIME, slot);
+        }
+#pragma unroll 1
+        for (int tree = 0; tree < P.n_pre; ++tree) {
+            const Ray r = P.pre[tree].ctx != 0 ? ray_in_ctx(S, w, P.pre[tree].ctx) : w;
+            const RayK k = make_rayk(r);
+            const float4 mn = make_float4(P.pre[tree].mn[0], P.pre[tree].mn[1], P.pre[tree].mn[2], 0.0f);
+            const float4 mx = make_float4(P.pre[tree].mx[0], P.pre[tree].mx[1], P.pre[tree].mx[2], 0.0f);
+            const bool hit = live && box_hit_tight(mn, mx, r, k, 0.001f, CUDART_INF_F);
+            const unsigned m = __ballot_sync(kFull, hit);
+            if (m) {
+                int at = 0;
+                if (lane == __ffs(m) - 1) at = atomicAdd(P.tq_count + tree, __popc(m));
+                at = __shfl_sync(kFull, at, __ffs(m) - 1) + __popc(m & ((1u << lane) - 1u));
+                if (hit) {
+                    float4* q = P.tq + 2 * ((size_t)tree * P.n_slots + at);
+                    q[0] = make_float4(r.o.x, r.o.y, r.o.z, r.time);
+                    q[1] = make_float4(r.d.x, r.d.y, r.d.z, __int_as_float(slot));
+                }
+            }
+            if (live) P.pre_res[(size_t)slot * kMaxPreTrees + tree] = make_float2(0.0f, __int_as_float(kPreNone));
+        }
+    }
     const unsigned ms = __ballot_sync(kFull, started);
     if (lane == 0 && ms) atomicAdd(P.counters + 2, (unsigned long long)__popc(ms));
     if (P.live_out) {
@@ -1252,7 +1342,6 @@ static CameraK to_camera(const hrt_camera_state& c) {
 // that still carry a path comes back through pinned memory, and the loop ends one batch after it reads zero.  Blocks
 // the calling thread until the render is complete.
 cudaError_t launch_render_wave(hrt::RenderLaunch& L, hrt::WaveBuffers& W, int num_sms, cudaStream_t stream) {
-    (void)num_sms;
     WaveParams P;
     P.S = to_device_scene(L.scene);
     P.cam = to_camera(L.cam);
@@ -1269,6 +1358,11 @@ cudaError_t launch_render_wave(hrt::RenderLaunch& L, hrt::WaveBuffers& W, int nu
     P.counters = L.counters;
     P.accum = reinterpret_cast<float4*>(L.accum);
     P.acc64 = W.acc64;
+    P.n_pre = L.n_pre;
+    for (int i = 0; i < kMaxPreTrees; ++i) P.pre[i] = L.pre[i];
+    P.tq = reinterpret_cast<float4*>(W.tq);
+    P.pre_res = reinterpret_cast<float2*>(W.pre);
+    P.tq_count = W.tq_count;
     P.live_out = nullptr;
     const int grid = (P.n_slots + kWaveBlock - 1) / kWaveBlock;
     L.grid = grid;
@@ -1276,6 +1370,11 @@ cudaError_t launch_render_wave(hrt::RenderLaunch& L, hrt::WaveBuffers& W, int nu
     L.launches = 0;
     cudaError_t e;
     if ((e = cudaMemsetAsync(W.acc64, 0, sizeof(double) * 4 * (size_t)P.n_pixels, stream)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(W.tq_count, 0, sizeof(int) * 2 * kMaxPreTrees, stream)) != cudaSuccess) return e;
+    // persistent tree-walk warps: as many blocks as are resident at once
+    int tree_blocks_per_sm = 1;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tree_blocks_per_sm, wave_tree_kernel, kWaveBlock, 0)) != cudaSuccess) return e;
+    const int tree_grid = std::min(grid, num_sms * std::max(1, tree_blocks_per_sm));
     // every slot starts free
     if ((e = cudaMemsetAsync(W.state + (size_t)WF_BOUNCE * P.n_slots, 0xff, sizeof(float) * (size_t)P.n_slots, stream)) != cudaSuccess) return e;
     const int kBatch = 16;
@@ -1285,8 +1384,9 @@ cudaError_t launch_render_wave(hrt::RenderLaunch& L, hrt::WaveBuffers& W, int nu
         for (int i = 0; i < kBatch; ++i) {
             P.live_out = i == kBatch - 1 ? live : nullptr;
             wave_logic_kernel<<<grid, kWaveBlock, 0, stream>>>(P);
+            for (int t = 0; t < P.n_pre; ++t) wave_tree_kernel<<<tree_grid, kWaveBlock, 0, stream>>>(P, t);
             wave_trace_kernel<<<grid, kWaveBlock, 0, stream>>>(P);
-            L.launches += 2;
+            L.launches += 2 + P.n_pre;
         }
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         if ((e = cudaMemcpyAsync(W.h_live + (b & 1), live, sizeof(int), cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return e;

@@ -32,6 +32,8 @@ struct RenderLaunch {
     int32_t chunk;        // samples per work item
     int32_t reference_boxes;
     int32_t n_nodes;      // tree nodes of the scene form being rendered
+    int32_t n_pre;        // OP_BVH trees the wavefront render walks in its own stage (<= kMaxPreTrees)
+    hrt::PreTree pre[hrt::kMaxPreTrees];
     int32_t interpreter;  // render kernel variant: 0 warp scheduler, 1 per-lane interpreter, 2 shared-memory ray pool,
                           // 3 warp-uniform walk (production)
     unsigned long long* counters;  // device: [0] work-item cursor, [1] rays, [2] paths
@@ -43,6 +45,9 @@ struct RenderLaunch {
 // Device buffers of the wavefront render (hrt_kernels.cu launch_render_wave), owned per device.
 struct WaveBuffers {
     float* state = nullptr;   // [WF_WORDS][n_slots]
+    float* tq = nullptr;      // tree-walk queues: [kMaxPreTrees][n_slots] entries of 8 words
+    float* pre = nullptr;     // tree-walk results: [n_slots][kMaxPreTrees] x {t, code}
+    int* tq_count = nullptr;  // [kMaxPreTrees] entries queued + [kMaxPreTrees] entries taken
     double* acc64 = nullptr;  // [acc_pixels][4]
     size_t acc_pixels = 0;
     int32_t n_slots = 0;

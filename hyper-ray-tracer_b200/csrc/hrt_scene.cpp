@@ -505,6 +505,13 @@ struct Flattener {
         op.i[2] = (int32_t)order.size();
         op.i[3] = max_depth;
         op.f[4] = o.t0; op.f[5] = o.t1;  // the BvhNode's time interval: moving-sphere leaf boxes depend on it
+        op.i[6] = in_medium ? -1 : (int32_t)f.trees.size();
+        if (!in_medium) {
+            PreTree t;
+            t.pc = at; t.ctx = ctx; t.base = base; t.ts = o.t0; t.te = o.t1;
+            for (int a = 0; a < 3; ++a) { t.mn[a] = root.box.mn[a]; t.mx[a] = root.box.mx[a]; }
+            f.trees.push_back(t);
+        }
         op.u[7] = OP_BVH | ((uint32_t)pc() << 8);
         f.ops[box_at].u[7] = OP_BOX | ((uint32_t)pc() << 8);
         f.n_bvh_trees++;

@@ -55,6 +55,7 @@ struct FlatScene {
     std::vector<Box16> box16;  // derived from ops at commit
     std::vector<Ctx> ctxs;
     std::vector<Bvh2Node> nodes;
+    std::vector<PreTree> trees;  // the OP_BVH trees outside medium boundaries, in stream order
     int32_t n_box_ops = 0, n_loose_boxes = 0, n_prim_ops = 0, n_media = 0, max_ctx_depth = 0;
     int32_t n_bvh_trees = 0, max_tree_depth = 0;
 };

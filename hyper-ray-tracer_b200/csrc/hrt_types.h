@@ -46,7 +46,8 @@ enum Opcode : uint32_t {
 //   POP         w3 ctx to restore                              w7 = op | run<<8   } first one enters/leaves the whole chain
 //   MEDIUM      w0 -1/density, w1 mat, w2 medium idx, w3 prim  w7 = op | end_pc<<8
 //   BVH         w0 first node (index into the node table), w1 node count, w2 leaf count, w3 tree depth
-//               w4 time_start, w5 time_end of the BvhNode      w7 = op | end_pc<<8
+//               w4 time_start, w5 time_end of the BvhNode, w6 index of the tree among those outside medium
+//               boundaries (stream order; -1 inside one)       w7 = op | end_pc<<8
 struct alignas(16) Op {
     union {
         float f[8];
@@ -84,6 +85,16 @@ struct alignas(16) Bvh2Node {
 static_assert(sizeof(Bvh2Node) == 32, "bvh2 node must be 32 bytes");
 constexpr int kBvh2SahDepth = 24;  // SAH splits down to this depth, then balanced median splits: depth <= 24 + log2(n)
 constexpr int kBvh2Stack = 48;     // per-ray stack entries (one per tree level at most)
+constexpr int kMaxPreTrees = 2;    // OP_BVH trees the wavefront render walks in its own, compacted stage AHEAD of the stream
+                                   // walk (the first ones of the world ray's stream; later ones are walked inline)
+// Where such a tree sits (render kernel parameters): its record, the ray space it lives in and its root box.
+struct PreTree {
+    int32_t pc;       // the OP_BVH record (its OP_BOX root record is pc - 1)
+    int32_t ctx;      // ray-space context of the record
+    int32_t base;     // first node
+    float ts, te;     // the BvhNode's time interval
+    float mn[3], mx[3];
+};
 
 constexpr int kMaxCtxDepth = 6;
 // A ray-space context = the chain of TRANSLATE/ROTATE records (outermost first) that maps the world ray
