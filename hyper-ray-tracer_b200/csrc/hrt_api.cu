@@ -68,6 +68,9 @@ void release_device_state(DeviceState* d) {
         cudaFree(d->wave.tq); cudaFree(d->wave.pre); cudaFree(d->wave.tq_count);
         if (d->wave.h_live) cudaFreeHost(d->wave.h_live);
         for (auto e : d->wave.ev) if (e) cudaEventDestroy(e);
+        for (auto e : d->wave.ev_end) if (e) cudaEventDestroy(e);
+        if (d->wave.ev_begin) cudaEventDestroy(d->wave.ev_begin);
+        for (auto st : d->wave.streams) if (st) cudaStreamDestroy(st);
         for (auto& sl : d->slots) {
             if (sl.t0) cudaEventDestroy(sl.t0);
             if (sl.t1) cudaEventDestroy(sl.t1);
@@ -110,17 +113,20 @@ static int32_t ensure_wave(DeviceState* d, size_t pixels) {
         d->wave.acc_pixels = pixels;
     }
     if (d->wave.state) return HRT_OK;
-    int n = 1 << 20;  // path slots in flight (64 MB of state)
+    int n = 4 << 20;  // path slots in flight, all partitions together (64 B of state + 80 B of tree-stage buffers each)
     if (const char* env = getenv("HRT_WAVE_SLOTS")) n = atoi(env);
-    if (n < 256) n = 256;
-    n = (n + 255) / 256 * 256;
+    if (n < 256 * kWaveParts) n = 256 * kWaveParts;
+    n = (n + 256 * kWaveParts - 1) / (256 * kWaveParts) * (256 * kWaveParts);
     HRT_CUDA(cudaMalloc((void**)&d->wave.state, sizeof(float) * (size_t)kWaveStateWords * (size_t)n));
-    HRT_CUDA(cudaMalloc((void**)&d->wave.d_live, 2 * sizeof(int)));
+    HRT_CUDA(cudaMalloc((void**)&d->wave.d_live, 2 * kWaveParts * sizeof(int)));
     HRT_CUDA(cudaMalloc((void**)&d->wave.tq, sizeof(float) * 8 * (size_t)kMaxPreTrees * (size_t)n));
     HRT_CUDA(cudaMalloc((void**)&d->wave.pre, sizeof(float) * 2 * (size_t)kMaxPreTrees * (size_t)n));
-    HRT_CUDA(cudaMalloc((void**)&d->wave.tq_count, 2 * kMaxPreTrees * sizeof(int)));
-    HRT_CUDA(cudaMallocHost((void**)&d->wave.h_live, 2 * sizeof(int)));
+    HRT_CUDA(cudaMalloc((void**)&d->wave.tq_count, 2 * kMaxPreTrees * kWaveParts * sizeof(int)));
+    HRT_CUDA(cudaMallocHost((void**)&d->wave.h_live, 2 * kWaveParts * sizeof(int)));
     for (auto& e : d->wave.ev) HRT_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : d->wave.ev_end) HRT_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    HRT_CUDA(cudaEventCreateWithFlags(&d->wave.ev_begin, cudaEventDisableTiming));
+    for (auto& st : d->wave.streams) HRT_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     d->wave.n_slots = n;
     return HRT_OK;
 }

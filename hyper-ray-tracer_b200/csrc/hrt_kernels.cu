@@ -753,6 +753,7 @@ struct WaveParams {
     float4* tq;                    // [kMaxPreTrees][n_slots][2]: {o.xyz, time}, {d.xyz, slot} in the tree's ray space
     float2* pre_res;               // [n_slots][kMaxPreTrees]: {t, code} (traverse_uniform)
     int* tq_count;                 // [kMaxPreTrees] queued, then [kMaxPreTrees] taken
+    int tree_refill;               // idle lanes at which a tree-walk warp pulls new entries
     double* acc64;                 // [n_pixels][4] radiance sums + sample counts of this render (added into `accum` at the end)
     float4* accum;
     int* live_out;                 // when not null: += number of slots that carry a path after this logic pass
@@ -836,7 +837,9 @@ __global__ void __launch_bounds__(kWaveBlock, 3) wave_tree_kernel(const __grid_c
     bool drained = false;  // warp-uniform: the queue has no entry left
     for (;;) {
         const unsigned idle = __ballot_sync(kFull, slot < 0);
-        if (idle && !drained) {
+        // refill when enough lanes are idle: one atomic on the queue head per refill, shared by every warp of the GPU, so
+        // refilling single lanes makes that counter the bottleneck (measured: 836 us per tree and iteration)
+        if (!drained && __popc(idle) >= P.tree_refill) {
             int e0 = 0;
             if (lane == 0) e0 = atomicAdd(next, __popc(idle));
             e0 = __shfl_sync(kFull, e0, 0);
@@ -1338,9 +1341,13 @@ static CameraK to_camera(const hrt_camera_state& c) {
     return k;
 }
 
-// Host loop of the wavefront render: batches of iterations are enqueued ahead; after each batch the number of slots
-// that still carry a path comes back through pinned memory, and the loop ends one batch after it reads zero.  Blocks
-// the calling thread until the render is complete.
+// Host loop of the wavefront render.  The path slots are split into kWaveParts partitions, each iterating on its own
+// stream: every iteration ends with the slowest walk of its wave (a ray with a NaN component passes every box test and
+// visits a whole 2000-node tree: ~0.8 ms against ~0.1 ms for the rest of the wave, and a million rays nearly always hold
+// one), and while one partition sits in such a tail the others keep the SMs busy.  All partitions draw camera samples
+// from the same global index, so a partition is finished for good when it ends a batch of iterations with no path left:
+// batches are enqueued ahead and the count comes back through pinned memory.  Blocks the calling thread until the
+// render is complete; on return the work is ordered before anything enqueued on `stream` afterwards.
 cudaError_t launch_render_wave(hrt::RenderLaunch& L, hrt::WaveBuffers& W, int num_sms, cudaStream_t stream) {
     WaveParams P;
     P.S = to_device_scene(L.scene);
@@ -1351,50 +1358,80 @@ cudaError_t launch_render_wave(hrt::RenderLaunch& L, hrt::WaveBuffers& W, int nu
     P.sample_begin = L.sample_begin;
     P.n_pixels = L.width * L.height;
     P.total_paths = (unsigned long long)P.n_pixels * (unsigned long long)L.sample_count;
-    const unsigned long long want = (P.total_paths + kWaveBlock - 1) / kWaveBlock * kWaveBlock;
-    P.n_slots = (int)std::min<unsigned long long>((unsigned long long)W.n_slots, std::max<unsigned long long>(want, kWaveBlock));
     P.reference_boxes = L.reference_boxes;
-    P.st = W.state;
     P.counters = L.counters;
     P.accum = reinterpret_cast<float4*>(L.accum);
     P.acc64 = W.acc64;
     P.n_pre = L.n_pre;
     for (int i = 0; i < kMaxPreTrees; ++i) P.pre[i] = L.pre[i];
-    P.tq = reinterpret_cast<float4*>(W.tq);
-    P.pre_res = reinterpret_cast<float2*>(W.pre);
-    P.tq_count = W.tq_count;
+    P.tree_refill = 12;
+    if (const char* env = getenv("HRT_TREE_REFILL")) P.tree_refill = std::max(1, std::min(32, atoi(env)));
     P.live_out = nullptr;
+    // slots per partition: all of them for a big job, no more than the job has paths for a small one
+    int parts = hrt::kWaveParts;
+    if (const char* env = getenv("HRT_WAVE_PARTS")) parts = std::max(1, std::min(hrt::kWaveParts, atoi(env)));
+    const int cap = W.n_slots / hrt::kWaveParts / kWaveBlock * kWaveBlock;  // the buffers are laid out for kWaveParts partitions
+    const unsigned long long share = (P.total_paths + parts - 1) / parts;
+    const unsigned long long want = (share + kWaveBlock - 1) / kWaveBlock * kWaveBlock;
+    P.n_slots = (int)std::min<unsigned long long>((unsigned long long)cap, std::max<unsigned long long>(want, kWaveBlock));
     const int grid = (P.n_slots + kWaveBlock - 1) / kWaveBlock;
     L.grid = grid;
     L.block = kWaveBlock;
     L.launches = 0;
     cudaError_t e;
     if ((e = cudaMemsetAsync(W.acc64, 0, sizeof(double) * 4 * (size_t)P.n_pixels, stream)) != cudaSuccess) return e;
-    if ((e = cudaMemsetAsync(W.tq_count, 0, sizeof(int) * 2 * kMaxPreTrees, stream)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(W.tq_count, 0, sizeof(int) * 2 * kMaxPreTrees * hrt::kWaveParts, stream)) != cudaSuccess) return e;
+    // every slot starts free
+    if ((e = cudaMemsetAsync(W.state, 0xff, sizeof(float) * (size_t)WF_WORDS * (size_t)cap * hrt::kWaveParts, stream)) != cudaSuccess) return e;
+    if ((e = cudaEventRecord(W.ev_begin, stream)) != cudaSuccess) return e;
     // persistent tree-walk warps: as many blocks as are resident at once
     int tree_blocks_per_sm = 1;
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tree_blocks_per_sm, wave_tree_kernel, kWaveBlock, 0)) != cudaSuccess) return e;
     const int tree_grid = std::min(grid, num_sms * std::max(1, tree_blocks_per_sm));
-    // every slot starts free
-    if ((e = cudaMemsetAsync(W.state + (size_t)WF_BOUNCE * P.n_slots, 0xff, sizeof(float) * (size_t)P.n_slots, stream)) != cudaSuccess) return e;
+    WaveParams PP[hrt::kWaveParts];
+    bool running[hrt::kWaveParts];
+    for (int p = 0; p < parts; ++p) {
+        PP[p] = P;
+        PP[p].st = W.state + (size_t)p * WF_WORDS * cap;
+        PP[p].tq = reinterpret_cast<float4*>(W.tq) + (size_t)p * 2 * kMaxPreTrees * cap;
+        PP[p].pre_res = reinterpret_cast<float2*>(W.pre) + (size_t)p * kMaxPreTrees * cap;
+        PP[p].tq_count = W.tq_count + p * 2 * kMaxPreTrees;
+        running[p] = true;
+        if ((e = cudaStreamWaitEvent(W.streams[p], W.ev_begin, 0)) != cudaSuccess) return e;
+    }
     const int kBatch = 16;
-    for (int b = 0;; ++b) {
-        int* live = W.d_live + (b & 1);
-        if ((e = cudaMemsetAsync(live, 0, sizeof(int), stream)) != cudaSuccess) return e;
-        for (int i = 0; i < kBatch; ++i) {
-            P.live_out = i == kBatch - 1 ? live : nullptr;
-            wave_logic_kernel<<<grid, kWaveBlock, 0, stream>>>(P);
-            for (int t = 0; t < P.n_pre; ++t) wave_tree_kernel<<<tree_grid, kWaveBlock, 0, stream>>>(P, t);
-            wave_trace_kernel<<<grid, kWaveBlock, 0, stream>>>(P);
-            L.launches += 2 + P.n_pre;
+    int n_running = parts;
+    for (int b = 0; n_running > 0; ++b) {
+        for (int p = 0; p < parts; ++p) {
+            if (!running[p]) continue;
+            cudaStream_t sp = W.streams[p];
+            int* live = W.d_live + 2 * p + (b & 1);
+            if ((e = cudaMemsetAsync(live, 0, sizeof(int), sp)) != cudaSuccess) return e;
+            for (int i = 0; i < kBatch; ++i) {
+                PP[p].live_out = i == kBatch - 1 ? live : nullptr;
+                wave_logic_kernel<<<grid, kWaveBlock, 0, sp>>>(PP[p]);
+                for (int t = 0; t < P.n_pre; ++t) wave_tree_kernel<<<tree_grid, kWaveBlock, 0, sp>>>(PP[p], t);
+                wave_trace_kernel<<<grid, kWaveBlock, 0, sp>>>(PP[p]);
+                L.launches += 2 + P.n_pre;
+            }
+            if ((e = cudaGetLastError()) != cudaSuccess) return e;
+            if ((e = cudaMemcpyAsync(W.h_live + 2 * p + (b & 1), live, sizeof(int), cudaMemcpyDeviceToHost, sp)) != cudaSuccess) return e;
+            if ((e = cudaEventRecord(W.ev[2 * p + (b & 1)], sp)) != cudaSuccess) return e;
         }
-        if ((e = cudaGetLastError()) != cudaSuccess) return e;
-        if ((e = cudaMemcpyAsync(W.h_live + (b & 1), live, sizeof(int), cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return e;
-        if ((e = cudaEventRecord(W.ev[b & 1], stream)) != cudaSuccess) return e;
         if (b >= 1) {
-            if ((e = cudaEventSynchronize(W.ev[(b - 1) & 1])) != cudaSuccess) return e;
-            if (W.h_live[(b - 1) & 1] == 0) break;  // the batch enqueued meanwhile found nothing to do
+            for (int p = 0; p < parts; ++p) {
+                if (!running[p]) continue;
+                if ((e = cudaEventSynchronize(W.ev[2 * p + ((b - 1) & 1)])) != cudaSuccess) return e;
+                if (W.h_live[2 * p + ((b - 1) & 1)] == 0) {  // (the batch enqueued meanwhile finds nothing to do)
+                    running[p] = false;
+                    n_running--;
+                }
+            }
         }
+    }
+    for (int p = 0; p < parts; ++p) {
+        if ((e = cudaEventRecord(W.ev_end[p], W.streams[p])) != cudaSuccess) return e;
+        if ((e = cudaStreamWaitEvent(stream, W.ev_end[p], 0)) != cudaSuccess) return e;
     }
     wave_finish_kernel<<<(P.n_pixels + 255) / 256, 256, 0, stream>>>(W.acc64, P.n_pixels, P.accum);
     L.launches += 1;

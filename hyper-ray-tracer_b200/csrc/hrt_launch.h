@@ -43,17 +43,21 @@ struct RenderLaunch {
 };
 
 // Device buffers of the wavefront render (hrt_kernels.cu launch_render_wave), owned per device.
+constexpr int kWaveParts = 4;  // partitions of the path slots, each iterating on its own stream
 struct WaveBuffers {
-    float* state = nullptr;   // [WF_WORDS][n_slots]
-    float* tq = nullptr;      // tree-walk queues: [kMaxPreTrees][n_slots] entries of 8 words
-    float* pre = nullptr;     // tree-walk results: [n_slots][kMaxPreTrees] x {t, code}
-    int* tq_count = nullptr;  // [kMaxPreTrees] entries queued + [kMaxPreTrees] entries taken
+    float* state = nullptr;   // [kWaveParts][WF_WORDS][n_slots / kWaveParts]
+    int32_t n_slots = 0;      // all partitions together
+    float* tq = nullptr;      // tree-walk queues: [kWaveParts][kMaxPreTrees][n_slots / kWaveParts] entries of 8 words
+    float* pre = nullptr;     // tree-walk results: [kWaveParts][n_slots / kWaveParts][kMaxPreTrees] x {t, code}
+    int* tq_count = nullptr;  // per partition: [kMaxPreTrees] entries queued + [kMaxPreTrees] entries taken
     double* acc64 = nullptr;  // [acc_pixels][4]
     size_t acc_pixels = 0;
-    int32_t n_slots = 0;
-    int* d_live = nullptr;    // 2 counters
+    int* d_live = nullptr;    // per partition: 2 counters
     int* h_live = nullptr;    // pinned mirror
-    cudaEvent_t ev[2] = {nullptr, nullptr};
+    cudaStream_t streams[kWaveParts] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[2 * kWaveParts] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_end[kWaveParts] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_begin = nullptr;
 };
 constexpr int kWaveStateWords = 16;  // == WF_WORDS
 
