@@ -465,69 +465,79 @@ __device__ __noinline__ bool tie_goes_to_later(const DeviceScene& S, int later_p
     return box_hit_reference(mn, mx, cur, k, tmin, t);
 }
 
-// One step of the walk of the tree whose first node is `base`: an inner node (both children's boxes, nearer first, the
-// other postponed on the stack) or a leaf (a primitive record of the op stream), then the next postponed child that can
-// still hold a closer or equal hit.  Returns true when the walk is over.  Box tests only prune (every box is sound), so
-// any visit order finds the same closest t; exact ties are settled by tie_goes_to_later.  (ts, te): the BvhNode's time
-// interval.  `ref` >= 0: node (relative to base), < 0: ~pc of a leaf record; start with ref = 0, sp = 0.
-__device__ __forceinline__ bool bvh2_step(const DeviceScene& S, int base, const Ray& cur, const RayK& k, float tmin, float ts, float te,
-                                          int& ref, int& sp, int* stack_ref, float* stack_t, TreeHit& h) {
-    if (ref >= 0) {
-        uint4 L, R;
-        load_node(S, base + ref, L, R);
-        float llo, lhi, rlo, rhi;
-        slab16(L.x, L.y, L.z, cur, k, tmin, h.t, llo, lhi);
-        slab16(R.x, R.y, R.z, cur, k, tmin, h.t, rlo, rhi);
-        const bool hl = !(lhi < llo), hr = !(rhi < rlo);
-        if (hl && hr) {
-            const bool right_first = rlo < llo;
-            stack_ref[sp] = right_first ? (int)L.w : (int)R.w;
-            stack_t[sp] = right_first ? llo : rlo;
-            sp++;
-            ref = right_first ? (int)R.w : (int)L.w;
-            return false;
-        }
-        if (hl || hr) {
-            ref = hl ? (int)L.w : (int)R.w;
-            return false;
-        }
-    } else {
-        const int pc = ~ref;
-        float4 A, B;
-        load_op(S, pc, A, B);
-        const uint32_t opc = __float_as_uint(B.w) & 0xffu;
-        float t = 0.0f;
-        int face = 0;
-        bool hit;
-        if (opc == OP_SPHERE || opc == OP_MSPHERE) {
-            V3 ctr = v3(A.x, A.y, A.z);
-            if (opc == OP_MSPHERE) {
-                float4 C, D;
-                load_op(S, pc + 1, C, D);
-                ctr = msphere_center(ctr, v3(C.x, C.y, C.z), C.w, D.x, cur.time);
-            }
-            hit = sphere_test(ctr, A.w, cur, k, tmin, h.t, t);
-        } else if (opc == OP_CUBOID) {
-            hit = cuboid_test(v3(A.x, A.y, A.z), v3(B.x, B.y, B.z), cur, k, tmin, h.t, t, face);
-        } else {
-            hit = rect_any(opc, A, B.x, cur, k, tmin, h.t, t);
-        }
-        if (hit) {  // the primitive tests accept t <= closest
-            bool take = t < h.t || h.pc < 0;
-            if (!take && !(t > h.t)) {  // exact tie (or a NaN, Q15) with the hit held so far
-                const bool later_wins = tie_goes_to_later(S, pc > h.pc ? pc : h.pc, cur, tmin, t, ts, te);
-                take = (pc > h.pc) == later_wins;
-            }
-            if (take) { h.t = t; h.pc = pc; h.face = face; }
-        }
-    }
-    // next: the nearest postponed child that can still hold a closer (or equal) hit
+// The walk of the tree whose first node is `base`, one step at a time.  `ref` >= 0: an inner node (relative to base),
+// < 0: ~pc of a leaf record; start with ref = 0, sp = 0.  Box tests only prune (every box is sound), so any visit order
+// finds the same closest t; exact ties are settled by tie_goes_to_later.  (ts, te): the BvhNode's time interval.
+//
+// Next postponed child that can still hold a closer or equal hit; true when the walk is over.
+__device__ __forceinline__ bool bvh2_pop(int& ref, int& sp, const int* stack_ref, const float* stack_t, const TreeHit& h) {
     do {
         if (sp == 0) return true;
         --sp;
         ref = stack_ref[sp];
     } while (stack_t[sp] > h.t);
     return false;
+}
+// Inner node: both children's boxes, the nearer one first, the other postponed on the stack.
+__device__ __forceinline__ bool bvh2_inner(const DeviceScene& S, int base, const Ray& cur, const RayK& k, float tmin, int& ref, int& sp,
+                                           int* stack_ref, float* stack_t, const TreeHit& h) {
+    uint4 L, R;
+    load_node(S, base + ref, L, R);
+    float llo, lhi, rlo, rhi;
+    slab16(L.x, L.y, L.z, cur, k, tmin, h.t, llo, lhi);
+    slab16(R.x, R.y, R.z, cur, k, tmin, h.t, rlo, rhi);
+    const bool hl = !(lhi < llo), hr = !(rhi < rlo);
+    if (hl && hr) {
+        const bool right_first = rlo < llo;
+        stack_ref[sp] = right_first ? (int)L.w : (int)R.w;
+        stack_t[sp] = right_first ? llo : rlo;
+        sp++;
+        ref = right_first ? (int)R.w : (int)L.w;
+        return false;
+    }
+    if (hl || hr) {
+        ref = hl ? (int)L.w : (int)R.w;
+        return false;
+    }
+    return bvh2_pop(ref, sp, stack_ref, stack_t, h);
+}
+// Leaf: a primitive record of the op stream.
+__device__ __forceinline__ bool bvh2_leaf(const DeviceScene& S, const Ray& cur, const RayK& k, float tmin, float ts, float te, int& ref,
+                                          int& sp, const int* stack_ref, const float* stack_t, TreeHit& h) {
+    const int pc = ~ref;
+    float4 A, B;
+    load_op(S, pc, A, B);
+    const uint32_t opc = __float_as_uint(B.w) & 0xffu;
+    float t = 0.0f;
+    int face = 0;
+    bool hit;
+    if (opc == OP_SPHERE || opc == OP_MSPHERE) {
+        V3 ctr = v3(A.x, A.y, A.z);
+        if (opc == OP_MSPHERE) {
+            float4 C, D;
+            load_op(S, pc + 1, C, D);
+            ctr = msphere_center(ctr, v3(C.x, C.y, C.z), C.w, D.x, cur.time);
+        }
+        hit = sphere_test(ctr, A.w, cur, k, tmin, h.t, t);
+    } else if (opc == OP_CUBOID) {
+        hit = cuboid_test(v3(A.x, A.y, A.z), v3(B.x, B.y, B.z), cur, k, tmin, h.t, t, face);
+    } else {
+        hit = rect_any(opc, A, B.x, cur, k, tmin, h.t, t);
+    }
+    if (hit) {  // the primitive tests accept t <= closest
+        bool take = t < h.t || h.pc < 0;
+        if (!take && !(t > h.t)) {  // exact tie (or a NaN, Q15) with the hit held so far
+            const bool later_wins = tie_goes_to_later(S, pc > h.pc ? pc : h.pc, cur, tmin, t, ts, te);
+            take = (pc > h.pc) == later_wins;
+        }
+        if (take) { h.t = t; h.pc = pc; h.face = face; }
+    }
+    return bvh2_pop(ref, sp, stack_ref, stack_t, h);
+}
+__device__ __forceinline__ bool bvh2_step(const DeviceScene& S, int base, const Ray& cur, const RayK& k, float tmin, float ts, float te,
+                                          int& ref, int& sp, int* stack_ref, float* stack_t, TreeHit& h) {
+    return ref >= 0 ? bvh2_inner(S, base, cur, k, tmin, ref, sp, stack_ref, stack_t, h)
+                    : bvh2_leaf(S, cur, k, tmin, ts, te, ref, sp, stack_ref, stack_t, h);
 }
 // Closest hit of a whole tree for t in [tmin, closest]; `best_pc`: the record of the hit held so far (-1 none).  Out of
 // line: one copy per kernel.

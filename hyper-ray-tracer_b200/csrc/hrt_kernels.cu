@@ -754,6 +754,7 @@ struct WaveParams {
     float2* pre_res;               // [n_slots][kMaxPreTrees]: {t, code} (traverse_uniform)
     int* tq_count;                 // [kMaxPreTrees] queued, then [kMaxPreTrees] taken
     int tree_refill;               // idle lanes at which a tree-walk warp pulls new entries
+    int tree_inner_min;            // lanes at an inner node for which the walk stays in its inner-node loop
     double* acc64;                 // [n_pixels][4] radiance sums + sample counts of this render (added into `accum` at the end)
     float4* accum;
     int* live_out;                 // when not null: += number of slots that carry a path after this logic pass
@@ -855,6 +856,18 @@ __global__ void __launch_bounds__(kWaveBlock, 3) wave_tree_kernel(const __grid_c
             }
         }
         if (!__any_sync(kFull, slot >= 0)) break;
+        // "while-while": inner nodes for as long as most busy lanes stand at one (a lane that has reached a leaf waits),
+        // then the leaves — a step that mixed both would run each with only the lanes that are at it
+        for (;;) {
+            const bool at_inner = slot >= 0 && ref >= 0;
+            const int n_inner = __popc(__ballot_sync(kFull, at_inner));
+            if (n_inner < P.tree_inner_min) break;
+            if (at_inner && bvh2_inner(S, base, cur, k, 0.001f, ref, sp, stack_ref, stack_t, h)) {
+                P.pre_res[(size_t)slot * kMaxPreTrees + tree] =
+                    make_float2(h.t, __int_as_float(h.pc < 0 ? kPreNone : (h.pc | (h.face << 24))));
+                slot = -1;
+            }
+        }
         if (slot >= 0) {
             if (bvh2_step(S, base, cur, k, 0.001f, ts, te, ref, sp, stack_ref, stack_t, h)) {
                 P.pre_res[(size_t)slot * kMaxPreTrees + tree] =
@@ -980,7 +993,13 @@ __global__ void __launch_bounds__(kWaveBlock, 3) wave_logic_kernel(const __grid_
             const RayK k = make_rayk(r);
             const float4 mn = make_float4(P.pre[tree].mn[0], P.pre[tree].mn[1], P.pre[tree].mn[2], 0.0f);
             const float4 mx = make_float4(P.pre[tree].mx[0], P.pre[tree].mx[1], P.pre[tree].mx[2], 0.0f);
-            const bool hit = live && box_hit_tight(mn, mx, r, k, 0.001f, CUDART_INF_F);
+            // A ray whose origin (or direction) is all NaN — the continuation of a path that hit something at t = NaN, Q15 —
+            // passes every box test and is accepted by every primitive test, each accepted hit replacing the one before
+            // (the reference's `t <= t_max` is never false): it visits the whole tree (~2000 steps against ~14 for an
+            // ordinary ray, and a wave of a million rays nearly always holds one) to end at the last leaf of the
+            // reference's order with t = NaN.  That answer is written directly.
+            const bool all_nan = (r.o.x != r.o.x && r.o.y != r.o.y && r.o.z != r.o.z) || (r.d.x != r.d.x && r.d.y != r.d.y && r.d.z != r.d.z);
+            const bool hit = live && !all_nan && box_hit_tight(mn, mx, r, k, 0.001f, CUDART_INF_F);
             const unsigned m = __ballot_sync(kFull, hit);
             if (m) {
                 int at = 0;
@@ -992,7 +1011,10 @@ __global__ void __launch_bounds__(kWaveBlock, 3) wave_logic_kernel(const __grid_
                     q[1] = make_float4(r.d.x, r.d.y, r.d.z, __int_as_float(slot));
                 }
             }
-            if (live) P.pre_res[(size_t)slot * kMaxPreTrees + tree] = make_float2(0.0f, __int_as_float(kPreNone));
+            if (live)
+                P.pre_res[(size_t)slot * kMaxPreTrees + tree] =
+                    all_nan ? make_float2(CUDART_NAN_F, __int_as_float(P.pre[tree].last_pc | (P.pre[tree].last_face << 24)))
+                            : make_float2(0.0f, __int_as_float(kPreNone));
         }
     }
     const unsigned ms = __ballot_sync(kFull, started);
@@ -1366,6 +1388,8 @@ cudaError_t launch_render_wave(hrt::RenderLaunch& L, hrt::WaveBuffers& W, int nu
     for (int i = 0; i < kMaxPreTrees; ++i) P.pre[i] = L.pre[i];
     P.tree_refill = 12;
     if (const char* env = getenv("HRT_TREE_REFILL")) P.tree_refill = std::max(1, std::min(32, atoi(env)));
+    P.tree_inner_min = 12;
+    if (const char* env = getenv("HRT_TREE_INNER")) P.tree_inner_min = std::max(1, std::min(33, atoi(env)));
     P.live_out = nullptr;
     // slots per partition: all of them for a big job, no more than the job has paths for a small one
     int parts = hrt::kWaveParts;
@@ -1387,6 +1411,7 @@ cudaError_t launch_render_wave(hrt::RenderLaunch& L, hrt::WaveBuffers& W, int nu
     // persistent tree-walk warps: as many blocks as are resident at once
     int tree_blocks_per_sm = 1;
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tree_blocks_per_sm, wave_tree_kernel, kWaveBlock, 0)) != cudaSuccess) return e;
+    if (const char* env = getenv("HRT_TREE_BLOCKS")) tree_blocks_per_sm = std::max(1, std::min(tree_blocks_per_sm, atoi(env)));
     const int tree_grid = std::min(grid, num_sms * std::max(1, tree_blocks_per_sm));
     WaveParams PP[hrt::kWaveParts];
     bool running[hrt::kWaveParts];

@@ -510,6 +510,8 @@ struct Flattener {
             PreTree t;
             t.pc = at; t.ctx = ctx; t.base = base; t.ts = o.t0; t.te = o.t1;
             for (int a = 0; a < 3; ++a) { t.mn[a] = root.box.mn[a]; t.mx[a] = root.box.mx[a]; }
+            t.last_pc = leaf_pc[order.back()];
+            t.last_face = s.objects[order.back()].kind == OBJ_CUBOID ? 5 : 0;
             f.trees.push_back(t);
         }
         op.u[7] = OP_BVH | ((uint32_t)pc() << 8);

@@ -94,6 +94,8 @@ struct PreTree {
     int32_t base;     // first node
     float ts, te;     // the BvhNode's time interval
     float mn[3], mx[3];
+    int32_t last_pc;  // the tree's last leaf record in the reference's order and, when it is a cuboid, its last side (5):
+    int32_t last_face;  // what a ray whose origin or direction is all NaN "hits" (every test accepts it, the last one wins)
 };
 
 constexpr int kMaxCtxDepth = 6;
