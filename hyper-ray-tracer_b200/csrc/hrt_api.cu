@@ -65,7 +65,7 @@ void release_device_state(DeviceState* d) {
         cudaFree(d->d_counters); cudaFree(d->d_accum); cudaFree(d->d_rgba);
         for (auto e : d->ev) if (e) cudaEventDestroy(e);
         cudaFree(d->wave.state); cudaFree(d->wave.d_live); cudaFree(d->wave.acc64);
-        cudaFree(d->wave.tq); cudaFree(d->wave.pre); cudaFree(d->wave.tq_count);
+        cudaFree(d->wave.tq); cudaFree(d->wave.pre); cudaFree(d->wave.tq_count); cudaFree(d->wave.xq);
         if (d->wave.h_live) cudaFreeHost(d->wave.h_live);
         for (auto e : d->wave.ev) if (e) cudaEventDestroy(e);
         for (auto e : d->wave.ev_end) if (e) cudaEventDestroy(e);
@@ -116,12 +116,14 @@ static int32_t ensure_wave(DeviceState* d, size_t pixels) {
     int n = 4 << 20;  // path slots in flight, all partitions together (64 B of state + 80 B of tree-stage buffers each)
     if (const char* env = getenv("HRT_WAVE_SLOTS")) n = atoi(env);
     if (n < 256 * kWaveParts) n = 256 * kWaveParts;
+    if (n > (4 << 20) * kWaveParts) n = (4 << 20) * kWaveParts;  // slot ids share a word with a texture id (wave_noise_kernel)
     n = (n + 256 * kWaveParts - 1) / (256 * kWaveParts) * (256 * kWaveParts);
     HRT_CUDA(cudaMalloc((void**)&d->wave.state, sizeof(float) * (size_t)kWaveStateWords * (size_t)n));
     HRT_CUDA(cudaMalloc((void**)&d->wave.d_live, 2 * kWaveParts * sizeof(int)));
     HRT_CUDA(cudaMalloc((void**)&d->wave.tq, sizeof(float) * 8 * (size_t)kMaxPreTrees * (size_t)n));
     HRT_CUDA(cudaMalloc((void**)&d->wave.pre, sizeof(float) * 2 * (size_t)kMaxPreTrees * (size_t)n));
-    HRT_CUDA(cudaMalloc((void**)&d->wave.tq_count, 2 * kMaxPreTrees * kWaveParts * sizeof(int)));
+    HRT_CUDA(cudaMalloc((void**)&d->wave.tq_count, kWaveCounters * kWaveParts * sizeof(int)));
+    HRT_CUDA(cudaMalloc((void**)&d->wave.xq, sizeof(float) * 4 * (size_t)n));
     HRT_CUDA(cudaMallocHost((void**)&d->wave.h_live, 2 * kWaveParts * sizeof(int)));
     for (auto& e : d->wave.ev) HRT_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto& e : d->wave.ev_end) HRT_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));

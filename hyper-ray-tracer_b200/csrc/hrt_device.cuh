@@ -1173,13 +1173,18 @@ __device__ __forceinline__ V3 material_emitted(const DeviceScene& S, const TexEn
     return v3(0.0f, 0.0f, 0.0f);
 }
 // Material::scatter with uniforms u[0..3].  Returns false for "None".
+// `defer_noise` (wavefront render): when the albedo is a NoiseTexture, do not evaluate it — 7 octaves of perlin noise
+// for the few lanes of a warp that hit such a surface — but report its id; the caller queues (slot, texture, point) and
+// a compacted kernel multiplies the path's throughput by the value afterwards.
 __device__ __forceinline__ bool material_scatter(const DeviceScene& S, const TexEnv E, const Material& m, const Ray& ray,
-                                                 const HitRec& h, const float u[4], V3& attenuation, Ray& scattered) {
+                                                 const HitRec& h, const float u[4], V3& attenuation, Ray& scattered,
+                                                 int* defer_noise = nullptr) {
     switch (m.kind) {
         case MAT_LAMBERTIAN: {  // lambertian.rs:27-38
             V3 dir = h.n + sample_unit_vector(u[0], u[1]);
             if (near_zero(dir)) dir = h.n;
-            attenuation = texture_value(S, E, m.tex, h.u, h.v, h.p);
+            if (defer_noise && m.tex < 1024 && S.texs[m.tex].kind == TEX_NOISE) { *defer_noise = m.tex; attenuation = v3(1.0f, 1.0f, 1.0f); }
+            else attenuation = texture_value(S, E, m.tex, h.u, h.v, h.p);
             scattered = Ray{h.p, dir, ray.time};
             return true;
         }
@@ -1207,7 +1212,8 @@ __device__ __forceinline__ bool material_scatter(const DeviceScene& S, const Tex
             return true;
         }
         case MAT_ISOTROPIC: {  // isotropic.rs:27-33
-            attenuation = texture_value(S, E, m.tex, h.u, h.v, h.p);
+            if (defer_noise && m.tex < 1024 && S.texs[m.tex].kind == TEX_NOISE) { *defer_noise = m.tex; attenuation = v3(1.0f, 1.0f, 1.0f); }
+            else attenuation = texture_value(S, E, m.tex, h.u, h.v, h.p);
             scattered = Ray{h.p, sample_in_unit_sphere(u[0], u[1], u[2]), ray.time};
             return true;
         }

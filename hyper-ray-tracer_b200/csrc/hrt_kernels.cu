@@ -752,7 +752,8 @@ struct WaveParams {
     PreTree pre[kMaxPreTrees];
     float4* tq;                    // [kMaxPreTrees][n_slots][2]: {o.xyz, time}, {d.xyz, slot} in the tree's ray space
     float2* pre_res;               // [n_slots][kMaxPreTrees]: {t, code} (traverse_uniform)
-    int* tq_count;                 // [kMaxPreTrees] queued, then [kMaxPreTrees] taken
+    float4* xq;                    // [n_slots] deferred NoiseTexture evaluations: {p.xyz, slot | texture << 22}
+    int* tq_count;                 // [kMaxPreTrees] tree walks queued, [kMaxPreTrees] taken, [1] noise evaluations queued
     int tree_refill;               // idle lanes at which a tree-walk warp pulls new entries
     int tree_inner_min;            // lanes at an inner node for which the walk stays in its inner-node loop
     double* acc64;                 // [n_pixels][4] radiance sums + sample counts of this render (added into `accum` at the end)
@@ -803,7 +804,7 @@ __global__ void __launch_bounds__(kWaveBlock, 3) wave_trace_kernel(const __grid_
     float closest = CUDART_INF_F;
     traverse_uniform(P.S, 0, P.S.n_ops, active, ray, ray, 0, 0.001f, closest, best, P.reference_boxes != 0, xi,
                      P.pre_res + (size_t)(in_range ? slot : 0) * kMaxPreTrees, P.n_pre);
-    if (blockIdx.x == 0 && threadIdx.x < 2 * kMaxPreTrees) P.tq_count[threadIdx.x] = 0;  // the queues are consumed
+    if (blockIdx.x == 0 && threadIdx.x < hrt::kWaveCounters) P.tq_count[threadIdx.x] = 0;  // the queues are consumed
     if (active) {
         WST(WF_HIT_T, slot) = best.t;
         WST(WF_HIT_PC, slot) = __int_as_float(best.pc);
@@ -811,6 +812,21 @@ __global__ void __launch_bounds__(kWaveBlock, 3) wave_trace_kernel(const __grid_
     }
     const unsigned m = __ballot_sync(kFull, active);
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(P.counters + 1, (unsigned long long)__popc(m));
+}
+
+// Deferred NoiseTexture albedos (material_scatter): throughput *= value, one queued evaluation per thread.
+__global__ void __launch_bounds__(kWaveBlock) wave_noise_kernel(const __grid_constant__ WaveParams P) {
+    __shared__ NoiseTable sh_noise[kMaxNoiseTablesShared];
+    TexEnv E;
+    stage_noise(P.S, E, sh_noise, kMaxNoiseTablesShared);
+    const int n = P.tq_count[2 * kMaxPreTrees];
+    for (int i = blockIdx.x * kWaveBlock + threadIdx.x; i < n; i += gridDim.x * kWaveBlock) {
+        const float4 q = P.xq[i];
+        const int code = __float_as_int(q.w);
+        const int slot = code & ((1 << 22) - 1);
+        const V3 c = texture_value(P.S, E, code >> 22, 0.0f, 0.0f, v3(q.x, q.y, q.z));
+        WST(WF_TX, slot) *= c.x; WST(WF_TY, slot) *= c.y; WST(WF_TZ, slot) *= c.z;
+    }
 }
 
 // Tree stage, part 2: persistent warps pull walks from the tree's queue — a lane that finishes its walk takes the next
@@ -917,11 +933,15 @@ __global__ void __launch_bounds__(kWaveBlock, 3) wave_logic_kernel(const __grid_
                 rng_block(key, (uint32_t)bounce, RNG_BLOCK_SCATTER, u4);
                 V3 att;
                 Ray sc;
-                if (material_scatter(S, E, m, ray, h, u4, att, sc)) {
+                int noise_tex = -1;
+                if (material_scatter(S, E, m, ray, h, u4, att, sc, &noise_tex)) {
                     T = T * att;
                     bounce++;
                     if (bounce < P.depth) {  // ray_color(depth == 0) is black
                         alive = true;
+                        if (noise_tex >= 0)  // the albedo is applied by wave_noise_kernel
+                            P.xq[atomicAdd(P.tq_count + 2 * kMaxPreTrees, 1)] =
+                                make_float4(h.p.x, h.p.y, h.p.z, __int_as_float(slot | (noise_tex << 22)));
                         WST(WF_OX, slot) = sc.o.x; WST(WF_OY, slot) = sc.o.y; WST(WF_OZ, slot) = sc.o.z;
                         WST(WF_DX, slot) = sc.d.x; WST(WF_DY, slot) = sc.d.y; WST(WF_DZ, slot) = sc.d.z;
                         WST(WF_TIME, slot) = sc.time;
@@ -1404,7 +1424,7 @@ cudaError_t launch_render_wave(hrt::RenderLaunch& L, hrt::WaveBuffers& W, int nu
     L.launches = 0;
     cudaError_t e;
     if ((e = cudaMemsetAsync(W.acc64, 0, sizeof(double) * 4 * (size_t)P.n_pixels, stream)) != cudaSuccess) return e;
-    if ((e = cudaMemsetAsync(W.tq_count, 0, sizeof(int) * 2 * kMaxPreTrees * hrt::kWaveParts, stream)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(W.tq_count, 0, sizeof(int) * hrt::kWaveCounters * hrt::kWaveParts, stream)) != cudaSuccess) return e;
     // every slot starts free
     if ((e = cudaMemsetAsync(W.state, 0xff, sizeof(float) * (size_t)WF_WORDS * (size_t)cap * hrt::kWaveParts, stream)) != cudaSuccess) return e;
     if ((e = cudaEventRecord(W.ev_begin, stream)) != cudaSuccess) return e;
@@ -1420,7 +1440,8 @@ cudaError_t launch_render_wave(hrt::RenderLaunch& L, hrt::WaveBuffers& W, int nu
         PP[p].st = W.state + (size_t)p * WF_WORDS * cap;
         PP[p].tq = reinterpret_cast<float4*>(W.tq) + (size_t)p * 2 * kMaxPreTrees * cap;
         PP[p].pre_res = reinterpret_cast<float2*>(W.pre) + (size_t)p * kMaxPreTrees * cap;
-        PP[p].tq_count = W.tq_count + p * 2 * kMaxPreTrees;
+        PP[p].tq_count = W.tq_count + p * hrt::kWaveCounters;
+        PP[p].xq = reinterpret_cast<float4*>(W.xq) + (size_t)p * cap;
         running[p] = true;
         if ((e = cudaStreamWaitEvent(W.streams[p], W.ev_begin, 0)) != cudaSuccess) return e;
     }
@@ -1435,9 +1456,10 @@ cudaError_t launch_render_wave(hrt::RenderLaunch& L, hrt::WaveBuffers& W, int nu
             for (int i = 0; i < kBatch; ++i) {
                 PP[p].live_out = i == kBatch - 1 ? live : nullptr;
                 wave_logic_kernel<<<grid, kWaveBlock, 0, sp>>>(PP[p]);
+                if (P.S.n_noise > 0) wave_noise_kernel<<<num_sms, kWaveBlock, 0, sp>>>(PP[p]);
                 for (int t = 0; t < P.n_pre; ++t) wave_tree_kernel<<<tree_grid, kWaveBlock, 0, sp>>>(PP[p], t);
                 wave_trace_kernel<<<grid, kWaveBlock, 0, sp>>>(PP[p]);
-                L.launches += 2 + P.n_pre;
+                L.launches += 2 + P.n_pre + (P.S.n_noise > 0 ? 1 : 0);
             }
             if ((e = cudaGetLastError()) != cudaSuccess) return e;
             if ((e = cudaMemcpyAsync(W.h_live + 2 * p + (b & 1), live, sizeof(int), cudaMemcpyDeviceToHost, sp)) != cudaSuccess) return e;

@@ -44,12 +44,14 @@ struct RenderLaunch {
 
 // Device buffers of the wavefront render (hrt_kernels.cu launch_render_wave), owned per device.
 constexpr int kWaveParts = 4;  // partitions of the path slots, each iterating on its own stream
+constexpr int kWaveCounters = 8;  // queue counters per partition (2 per pre-walked tree, 1 for deferred noise, padding)
 struct WaveBuffers {
     float* state = nullptr;   // [kWaveParts][WF_WORDS][n_slots / kWaveParts]
     int32_t n_slots = 0;      // all partitions together
     float* tq = nullptr;      // tree-walk queues: [kWaveParts][kMaxPreTrees][n_slots / kWaveParts] entries of 8 words
     float* pre = nullptr;     // tree-walk results: [kWaveParts][n_slots / kWaveParts][kMaxPreTrees] x {t, code}
-    int* tq_count = nullptr;  // per partition: [kMaxPreTrees] entries queued + [kMaxPreTrees] entries taken
+    float* xq = nullptr;      // deferred noise-texture evaluations: [kWaveParts][n_slots / kWaveParts] x 4 words
+    int* tq_count = nullptr;  // per partition: kWaveCounters queue counters
     double* acc64 = nullptr;  // [acc_pixels][4]
     size_t acc_pixels = 0;
     int* d_live = nullptr;    // per partition: 2 counters
