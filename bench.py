@@ -245,7 +245,7 @@ def run_b200(args, scene_name, width, height, samples, depth):
     def resident_step(i):
         st = dr.step(samples, depth, seed=i, want_stats=(rank == 0))
         if st is not None and rank == 0:
-            stats.append((st.kernel_ms, st.rays, st.paths, st.grid, st.block))
+            stats.append((st.kernel_ms, st.rays, st.paths, st.grid, st.block, st.launches))
     ms_total = timed(resident_step, args.steps)
     clocks = sampler.stop() if sampler else None
     ms_per_step = ms_total / args.steps
@@ -280,6 +280,21 @@ def run_b200(args, scene_name, width, height, samples, depth):
                "api": "hrt_scene_refresh (H2D tables) + hrt_render (host RGBA-f32 out)" if world == 1 else
                       "hrt_scene_refresh + hrt_render_accum_device + NCCL all_reduce + hrt_resolve_device + D2H"}
 
+    # ---- outside the timed region: the N-rank frame against the 1-rank frame of the same sample set ----
+    # (spp sharding + one all-reduce must give the 1-GPU image up to f32 summation order)
+    chk_spp = 16 * world
+    dr.step(chk_spp, depth, seed=4242, to_host=True)
+    torch.cuda.current_stream().synchronize()
+    parity = None
+    if rank == 0:
+        sharded = dr.host.numpy().copy()
+        solo, _ = dr.r.render(width, height, chk_spp, depth, seed=4242)
+        fin = np.isfinite(sharded).all(axis=-1) & np.isfinite(solo).all(axis=-1)
+        diff = np.abs(sharded[fin] - solo[fin])
+        parity = {"ok": bool(np.allclose(sharded[fin], solo[fin], rtol=3e-4, atol=3e-4)), "max_abs_diff": float(diff.max()) if diff.size else 0.0,
+                  "spp": chk_spp, "what": f"{world}-rank sharded frame vs rank 0 alone, same seed, resolved RGBA"}
+    barrier()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -308,10 +323,11 @@ def run_b200(args, scene_name, width, height, samples, depth):
         traffic = None
         issue = None
         try:  # DRAM bytes per launch of the dominant kernel, from a committed ncu metric pass of this very workload
-            with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-                t = json.load(f).get(f"{args.config}@{samples}")
+            with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
+                t = json.load(f).get(args.config)
             if t and world == 1:
-                traffic = t["dram_bytes_per_launch"]
+                # DRAM bytes per path (ncu, summed over every launch of a short frame) x the paths of one step
+                traffic = t["dram_bytes_per_path"] * my_paths
                 if "issue_active_pct" in t:  # measured issue-slot utilisation of the same kernel (not algorithmic work)
                     issue = {"issue_active_pct": t["issue_active_pct"], "source": t["issue_source"]}
         except OSError:
@@ -320,8 +336,11 @@ def run_b200(args, scene_name, width, height, samples, depth):
                     "frac": achieved / peaks.fp32_tflops, "traffic": traffic,
                     "peak_source": "measured live by hrt_measure_peaks (FFMA chains, CUDA events); MEASURED_PEAKS.json has "
                                    "no FP32 figure",
-                    # hrt_api.cu render_into: the ray-pool kernel from 128 samples per launch, else the warp scheduler
-                    "kernel": "render_pool_kernel" if -(-samples // world) >= 128 else "render_kernel", "kernel_ms": kernel_ms, "flops_per_path": wm["flops_per_path"],
+                    # hrt_api.cu render_into: the wavefront render for big jobs on scenes with OP_BVH trees (kernel_ms is then the
+                    # whole pipeline: wave_logic + wave_noise + wave_tree per tree + wave_trace per iteration; shares in
+                    # profiles/r02_wave_window_*.txt), else the persistent uniform-walk kernel
+                    "kernel": "wavefront render (wave_logic / wave_tree / wave_trace kernels)" if stats and stats[0][5] > 2 else "render_interp_kernel<true> (uniform walk)",
+                    "kernel_ms": kernel_ms, "flops_per_path": wm["flops_per_path"],
                     "work_model": wm["source"], "issue": issue,
                     "l2": {"achieved_gbs": l2_ach, "peak_gbs": peaks.l2_read_gbs, "frac": l2_ach / peaks.l2_read_gbs,
                            "bytes_per_path": wm["bytes_per_path"]},
@@ -337,8 +356,8 @@ def run_b200(args, scene_name, width, height, samples, depth):
                                     "kernel is compute/latency-bound, not HBM-bound, so no L2 flush applies",
                        "grid": stats[0][3] if stats else None, "block": stats[0][4] if stats else None},
             "mrays_per_s": (value * rays_per_path) if rays_per_path else None, "rays_per_path": rays_per_path,
-            "kernel_ms": kernel_ms, "gpu_launches": 2 * args.steps, "clocks": clocks, "e2e": e2e, "roofline": roofline,
-            "cpu_baseline": cpu}
+            "kernel_ms": kernel_ms, "gpu_launches": int(sum(s[5] for s in stats)) + args.steps, "clocks": clocks, "e2e": e2e,
+            "roofline": roofline, "parity_vs_n1": parity["ok"] if parity else None, "parity": parity, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

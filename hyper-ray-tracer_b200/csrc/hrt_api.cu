@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/hrt.h"
@@ -523,6 +524,49 @@ int32_t hrt_render_accum(hrt_scene* s, int32_t device, const hrt_camera_desc* ca
     return render_host(s, device, cam, rd, out_sum, stats, false);
 }
 
+// Progressive delivery (application.rs:284-306: the reference shows tiles as they finish) and early exit
+// (application.rs:357-391: a resize abandons the frame).  The frame is rendered in batches of `batch_samples` samples —
+// disjoint slices of ONE render's sample set, accumulated on the device — and after every batch the frame of the samples
+// so far is resolved on the device, copied to `out_rgba` and handed to `on_frame`; a non-zero return cancels the render.
+int32_t hrt_render_progressive(hrt_scene* s, int32_t device, const hrt_camera_desc* cam, const hrt_render_desc* rd,
+                               int32_t batch_samples, hrt_progress_fn on_frame, void* user, float* out_rgba, hrt_stats* stats) {
+    if (!out_rgba) return fail(HRT_ERR_INVALID, "null output buffer");
+    if (batch_samples <= 0) return fail(HRT_ERR_INVALID, "render_progressive: batch_samples must be positive");
+    DeviceState* d = nullptr;
+    int32_t rc = get_state(s, device, &d);
+    if (rc != HRT_OK) return rc;
+    if ((rc = check_render_args(s, cam, rd)) != HRT_OK) return rc;
+    const size_t pixels = (size_t)rd->width * rd->height;
+    if ((rc = ensure_scratch(d, pixels)) != HRT_OK) return rc;
+    const int begin = rd->sample_count > 0 ? rd->sample_begin : 0;
+    const int total = rd->sample_count > 0 ? rd->sample_count : rd->samples;
+    hrt_stats agg;
+    std::memset(&agg, 0, sizeof(agg));
+    cudaStream_t stream = 0;
+    HRT_CUDA(cudaMemsetAsync(d->d_accum, 0, pixels * 16, stream));
+    int done = 0;
+    while (done < total) {
+        hrt_render_desc slice = *rd;
+        slice.sample_begin = begin + done;
+        slice.sample_count = std::min(batch_samples, total - done);
+        hrt_stats local;
+        std::memset(&local, 0, sizeof(local));
+        LaunchSlot* slot = nullptr;
+        if ((rc = render_into(s, d, cam, &slice, d->d_accum, stream, &local, &slot)) != HRT_OK) return rc;
+        done += slice.sample_count;
+        // resolve what has been accumulated so far: sqrt(sum / samples_done) (application.rs:451-456)
+        cudaError_t e = hrt_fast::launch_resolve(d->d_accum, (int)pixels, done, d->d_rgba, stream);
+        if (e != cudaSuccess) return cuda_fail(e, "resolve_kernel launch");
+        HRT_CUDA(cudaMemcpyAsync(out_rgba, d->d_rgba, pixels * 16, cudaMemcpyDeviceToHost, stream));
+        if ((rc = finish_stats(slot, stream, &local)) != HRT_OK) return rc;  // synchronises the stream
+        agg.paths += local.paths; agg.rays += local.rays; agg.kernel_ms += local.kernel_ms;
+        agg.launches += local.launches + 1; agg.grid = local.grid; agg.block = local.block;
+        if (on_frame && on_frame(user, done, total, out_rgba) != 0) break;  // cancelled by the front end
+    }
+    if (stats) *stats = agg;
+    return done < total ? HRT_CANCELLED : HRT_OK;
+}
+
 // Single-process multi-GPU render (the reference is ONE process): device k renders the k-th sample slice into its own
 // accumulator, all devices run concurrently, and the first device sums the others' accumulators over NVLink peer memory
 // inside the resolve kernel.
@@ -557,18 +601,39 @@ static int32_t render_multi(hrt_scene* s, const int32_t* devices, int32_t n, con
     LaunchSlot* slots[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     const int total = rd->sample_count > 0 ? rd->sample_count : rd->samples;
     const int base = rd->sample_count > 0 ? rd->sample_begin : 0;
-    for (int i = 0; i < n; ++i) {  // launch everything first: the devices render concurrently
-        std::memset(&local[i], 0, sizeof(hrt_stats));
-        HRT_CUDA(cudaSetDevice(devices[i]));
-        HRT_CUDA(cudaMemsetAsync(st[i]->d_accum, 0, pixels * 16, 0));
-        hrt_render_desc slice = *rd;
-        const int q = total / n, r = total % n;
-        slice.sample_begin = base + i * q + (i < r ? i : r);
-        slice.sample_count = q + (i < r ? 1 : 0);
-        if (slice.sample_count > 0 && (rc = render_into(s, st[i], cam, &slice, st[i]->d_accum, 0, &local[i], &slots[i])) != HRT_OK)
-            return rc;
-        HRT_CUDA(cudaEventRecord(st[i]->ev[2], 0));  // "my slice is in my accumulator"
+    // One host thread per device: the wavefront render drives its iterations from the host (hrt_kernels.cu
+    // launch_render_wave) and returns when its slice is complete, so the devices only render concurrently when their
+    // loops run concurrently.
+    int32_t rcs[8];
+    std::string errs[8];
+    {
+        std::vector<std::thread> workers;
+        for (int i = 0; i < n; ++i) {
+            std::memset(&local[i], 0, sizeof(hrt_stats));
+            rcs[i] = HRT_OK;
+            workers.emplace_back([&, i]() {
+                auto body = [&]() -> int32_t {
+                    HRT_CUDA(cudaSetDevice(devices[i]));
+                    HRT_CUDA(cudaMemsetAsync(st[i]->d_accum, 0, pixels * 16, 0));
+                    hrt_render_desc slice = *rd;
+                    const int q = total / n, r = total % n;
+                    slice.sample_begin = base + i * q + (i < r ? i : r);
+                    slice.sample_count = q + (i < r ? 1 : 0);
+                    if (slice.sample_count > 0) {
+                        const int32_t rc_i = render_into(s, st[i], cam, &slice, st[i]->d_accum, 0, &local[i], &slots[i]);
+                        if (rc_i != HRT_OK) return rc_i;
+                    }
+                    HRT_CUDA(cudaEventRecord(st[i]->ev[2], 0));  // "my slice is in my accumulator"
+                    return HRT_OK;
+                };
+                rcs[i] = body();
+                if (rcs[i] != HRT_OK) errs[i] = hrt_last_error();  // the message is thread-local
+            });
+        }
+        for (auto& w : workers) w.join();
     }
+    for (int i = 0; i < n; ++i)
+        if (rcs[i] != HRT_OK) return fail(rcs[i], errs[i]);
     HRT_CUDA(cudaSetDevice(devices[0]));
     for (int i = 1; i < n; ++i) HRT_CUDA(cudaStreamWaitEvent(0, st[i]->ev[2], 0));
     HRT_CUDA(cudaEventRecord(st[0]->ev[3], 0));

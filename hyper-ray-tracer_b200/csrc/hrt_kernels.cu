@@ -728,6 +728,9 @@ __global__ void __launch_bounds__(kPoolBlock, 1) render_pool_kernel(const __grid
 // each a fraction of the code, each run by the whole GPU at once, so the instruction caches hold what is running.
 // Same Philox streams and arithmetic as the other kernels: the same paths, summed in a different order.
 constexpr int kWaveBlock = 256;
+#ifndef HRT_LOGIC_BLOCKS
+#define HRT_LOGIC_BLOCKS 3
+#endif
 enum WaveField {
     WF_OX, WF_OY, WF_OZ, WF_DX, WF_DY, WF_DZ, WF_TIME,  // the ray segment to trace / traced last
     WF_TX, WF_TY, WF_TZ, WF_PIXEL, WF_SAMPLE,           // throughput, Philox key
@@ -894,7 +897,7 @@ __global__ void __launch_bounds__(kWaveBlock, 3) wave_tree_kernel(const __grid_c
     }
 }
 
-__global__ void __launch_bounds__(kWaveBlock, 3) wave_logic_kernel(const __grid_constant__ WaveParams P) {
+__global__ void __launch_bounds__(kWaveBlock, HRT_LOGIC_BLOCKS) wave_logic_kernel(const __grid_constant__ WaveParams P) {
     __shared__ NoiseTable sh_noise[kMaxNoiseTablesShared];
     TexEnv E;
     stage_noise(P.S, E, sh_noise, kMaxNoiseTablesShared);

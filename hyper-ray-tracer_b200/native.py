@@ -26,6 +26,19 @@ HRT_STREAM_REFERENCE = 0
 HRT_STREAM_FAST = 1
 
 
+PROGRESS_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p)
+
+
+def _check_frame(out, width, height):
+    """A caller-provided frame buffer goes to C as a raw pointer: it must be exactly (height, width, 4) float32, C order."""
+    if out is None:
+        return np.empty((height, width, 4), dtype=np.float32)
+    if not (isinstance(out, np.ndarray) and out.dtype == np.float32 and out.shape == (height, width, 4) and out.flags.c_contiguous
+            and out.flags.writeable):
+        raise ValueError(f"out must be a writable C-contiguous float32 array of shape ({height}, {width}, 4)")
+    return out
+
+
 class HrtError(RuntimeError):
     def __init__(self, code: int, message: str):
         super().__init__(f"libhrt error {code}: {message}")
@@ -89,7 +102,7 @@ EXPORTS = [
     "hrt_render_accum", "hrt_render_accum_device", "hrt_resolve_device", "hrt_trace_hits", "hrt_tex_value",
     "hrt_scatter", "hrt_camera_rays", "hrt_philox_uniforms", "hrt_scene_evict", "hrt_scene_device_bytes",
     "hrt_measure_peaks", "hrt_scene_refresh", "hrt_render_multi", "hrt_render_accum_multi", "hrt_scene_get_box16",
-    "hrt_scene_set_bvh_builder", "hrt_scene_get_tree_nodes",
+    "hrt_scene_set_bvh_builder", "hrt_scene_get_tree_nodes", "hrt_render_progressive",
 ]
 
 _lib = None
@@ -155,6 +168,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.hrt_camera_rays.argtypes = [i32, C.POINTER(CameraDesc), vp, i32, vp, C.c_uint32]
     lib.hrt_philox_uniforms.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, f3]
     lib.hrt_scene_evict.argtypes = [vp, i32]
+    lib.hrt_render_progressive.argtypes = [vp, i32, C.POINTER(CameraDesc), C.POINTER(RenderDesc), i32, PROGRESS_FN, vp, vp, C.POINTER(Stats)]
     lib.hrt_render_multi.argtypes = [vp, C.POINTER(i32), i32, C.POINTER(CameraDesc), C.POINTER(RenderDesc), vp, C.POINTER(Stats)]
     lib.hrt_render_accum_multi.argtypes = [vp, C.POINTER(i32), i32, C.POINTER(CameraDesc), C.POINTER(RenderDesc), vp, C.POINTER(Stats)]
     lib.hrt_scene_refresh.argtypes = [vp, i32]
@@ -349,19 +363,34 @@ class HrtBackend:
         """`Application::render` through the C ABI with HOST buffers; returns (h, w, 4) float32, rows bottom-up."""
         cd = camera_desc(cam, width, height)
         rd = self._render_desc(width, height, samples, depth, background, seed, 0, 0, flags)
-        if out is None:
-            out = np.empty((height, width, 4), dtype=np.float32)
+        out = _check_frame(out, width, height)
         st = Stats()
         fn = self.lib.hrt_render if resolve else self.lib.hrt_render_accum
         self._check(fn(self.handle, device, C.byref(cd), C.byref(rd), _ptr(out), C.byref(st)))
         return out, st
 
+    def render_progressive(self, cam, width, height, samples, depth, background, batch, on_frame=None, seed=0, device=0, flags=0,
+                           out=None):
+        """hrt_render_progressive: `on_frame(samples_done, samples_total, frame)` after every `batch` samples (frame is a
+        view of `out`, valid during the call); a truthy return cancels.  Returns (out, stats, cancelled)."""
+        cd = camera_desc(cam, width, height)
+        rd = self._render_desc(width, height, samples, depth, background, seed, 0, 0, flags)
+        out = _check_frame(out, width, height)
+        st = Stats()
+
+        def trampoline(_user, done, total, _ptr_):
+            return 1 if (on_frame is not None and on_frame(int(done), int(total), out)) else 0
+        cb = PROGRESS_FN(trampoline)
+        rc = self.lib.hrt_render_progressive(self.handle, device, C.byref(cd), C.byref(rd), int(batch), cb, None, _ptr(out), C.byref(st))
+        if rc < 0:
+            self._check(rc)
+        return out, st, rc == 1
+
     def render_multi(self, devices, cam, width, height, samples, depth, background, seed=0, flags=0, resolve=True, out=None):
         """Single-process multi-GPU render (hrt_render_multi): samples sharded over `devices`, fused peer reduce+resolve."""
         cd = camera_desc(cam, width, height)
         rd = self._render_desc(width, height, samples, depth, background, seed, 0, 0, flags)
-        if out is None:
-            out = np.empty((height, width, 4), dtype=np.float32)
+        out = _check_frame(out, width, height)
         devs = (C.c_int32 * len(devices))(*devices)
         st = Stats()
         fn = self.lib.hrt_render_multi if resolve else self.lib.hrt_render_accum_multi

@@ -47,29 +47,21 @@ class Renderer:
         return self.backend.render(self.spec.camera, width, height, samples, depth, self.spec.background, seed=seed,
                                    device=self.device, flags=flags, resolve=resolve, out=out)
 
-    def render_progressive(self, width: int, height: int, samples: int, depth: int, batch: int, seed: int = 0, flags: int = 0):
-        """Progressive delivery: the reference shows tiles as they finish (application.rs:284-306); the
-        GPU equivalent is sample batches.  Yields (samples_done, frame) after every `batch` samples, where frame is the
-        gamma-resolved RGBA-f32 image of the samples so far (same layout as `render`).  The batches are disjoint Philox
+    def render_progressive(self, width: int, height: int, samples: int, depth: int, batch: int, seed: int = 0, flags: int = 0,
+                           on_frame=None):
+        """Progressive delivery through hrt_render_progressive: the reference shows tiles as they finish
+        (application.rs:284-306) and abandons the frame on a resize (:357-391); here the frame of the samples so far is
+        delivered after every `batch` samples and `on_frame(done, total, frame)` may cancel by returning True.  Returns the
+        list of (samples_done, frame copy) delivered and whether the render was cancelled.  The batches are disjoint Philox
         sample slices of ONE render, so the last frame equals `render(...)` up to f32 summation order."""
-        import ctypes as C
-        b = self.backend
-        acc = np.zeros((height, width, 4), dtype=np.float32)
-        part = np.empty_like(acc)
-        cd = native.camera_desc(self.spec.camera, width, height)
-        done = 0
-        while done < samples:
-            count = min(batch, samples - done)
-            rd = b._render_desc(width, height, samples, depth, self.spec.background, seed, done, count, flags)
-            st = native.Stats()
-            b._check(b.lib.hrt_render_accum(b.handle, self.device, C.byref(cd), C.byref(rd), part.ctypes.data_as(C.c_void_p),
-                                            C.byref(st)))
-            acc += part
-            done += count
-            frame = np.empty_like(acc)
-            frame[..., :3] = np.sqrt(acc[..., :3] * np.float32(1.0 / done))  # application.rs:451-453 on the samples so far
-            frame[..., 3] = 1.0
-            yield done, frame
+        frames = []
+
+        def cb(done, total, frame):
+            frames.append((done, frame.copy()))
+            return bool(on_frame(done, total, frame)) if on_frame is not None else False
+        _, _, cancelled = self.backend.render_progressive(self.spec.camera, width, height, samples, depth, self.spec.background,
+                                                          batch, cb, seed=seed, device=self.device, flags=flags)
+        return frames, cancelled
 
     # ---- device-resident pieces for the distributed path ----
     def render_slice_into(self, accum, width, height, samples, depth, seed, sample_begin, sample_count, stream_ptr=0,

@@ -206,6 +206,18 @@ int32_t hrt_render(hrt_scene*, int32_t device, const hrt_camera_desc*, const hrt
 int32_t hrt_render_accum(hrt_scene*, int32_t device, const hrt_camera_desc*, const hrt_render_desc*, float* out_sum,
                          hrt_stats* stats);
 
+/* Progressive delivery and early exit.  The reference hands finished tiles to the display loop one by one
+ * (src/application.rs:284-306) and abandons a frame when the window is resized (:357-391).  Here the frame is rendered in
+ * batches of `batch_samples` samples — disjoint slices of ONE render's sample set, accumulated on the device — and after
+ * every batch the frame of the samples so far (gamma-resolved with the count so far, same layout as hrt_render) is
+ * copied to `out_rgba` and `on_frame(user, samples_done, samples_total, out_rgba)` is called on the calling thread; a
+ * non-zero return cancels the render (HRT_CANCELLED; out_rgba keeps the last delivered frame).  on_frame may be NULL.
+ * The last frame equals hrt_render's up to f32 summation order. */
+#define HRT_CANCELLED 1
+typedef int32_t (*hrt_progress_fn)(void* user, int32_t samples_done, int32_t samples_total, const float* rgba);
+int32_t hrt_render_progressive(hrt_scene*, int32_t device, const hrt_camera_desc*, const hrt_render_desc*, int32_t batch_samples,
+                               hrt_progress_fn on_frame, void* user, float* out_rgba, hrt_stats* stats);
+
 /* Single-process multi-GPU render on `n_devices` (1..8) CUDA devices of one node — the shape the reference needs, being one
  * process (src/main.rs:24-32): device k renders the k-th disjoint sample slice into its own accumulator, all devices run
  * concurrently, and devices[0] sums the peers' accumulators over NVLink peer memory INSIDE the gamma-resolve kernel (no
@@ -217,8 +229,11 @@ int32_t hrt_render_accum_multi(hrt_scene*, const int32_t* devices, int32_t n_dev
                                const hrt_render_desc*, float* out_sum, hrt_stats* stats);
 
 /* Device-resident variants for multi-GPU sample sharding: `d_accum` is a device pointer on `device` to
- * width*height*4 f32 that the call ADDS into (zero it first); `stream` is a cudaStream_t (0 = default).
- * Asynchronous w.r.t. the host except for the stats read-back when stats != NULL. */
+ * width*height*4 f32 that the call ADDS into (zero it first); `stream` is a cudaStream_t (0 = default): the work is
+ * ordered after what `stream` holds at the call and before anything enqueued on it afterwards.  A big render on a scene
+ * with OP_BVH trees is driven from the host in iterations (the wavefront render) and the call then returns when it is
+ * complete; otherwise it only enqueues one kernel and returns (it blocks for the stats read-back when stats != NULL).
+ * Renders of one scene on one device may overlap on different streams: every launch owns its counters. */
 int32_t hrt_render_accum_device(hrt_scene*, int32_t device, const hrt_camera_desc*, const hrt_render_desc*,
                                 void* d_accum, void* stream, hrt_stats* stats);
 /* Gamma resolve (src/application.rs:451-456): d_out_rgba[i] = (sqrt(sum.rgb * (1/samples)), 1.0). */

@@ -418,15 +418,33 @@ def test_render_kernel_variants_agree(pkg, orc, built, name):
 
 
 def test_progressive_delivery_converges_to_the_full_render(pkg, orc, built):
-    """Sample-batch progressive delivery (the GPU analogue of the reference's per-tile delivery): batches are disjoint
-    slices of one render, so the last progressive frame equals the one-shot frame."""
+    """hrt_render_progressive (the GPU analogue of the reference's per-tile delivery, application.rs:284-306): batches are
+    disjoint slices of one render accumulated on the device, every delivered frame is the resolved image of the samples
+    so far, the last one equals the one-shot frame AND is the oracle's image (z-scores against a live oracle render);
+    a callback that returns non-zero cancels (the resize early-exit, application.rs:357-391)."""
     spec, gb, ob, _, _ = built("cornell")
     r = pkg.renderer.Renderer(spec, device=0)
-    full, _ = r.render(48, 48, 200, 50, seed=3)
-    frames = list(r.render_progressive(48, 48, 200, 50, batch=64, seed=3))
-    assert [d for d, _ in frames] == [64, 128, 192, 200]
+    w = h = 48
+    full, _ = r.render(w, h, 200, 50, seed=3)
+    frames, cancelled = r.render_progressive(w, h, 200, 50, batch=64, seed=3)
+    assert not cancelled and [d for d, _ in frames] == [64, 128, 192, 200]
     assert np.allclose(np.nan_to_num(frames[-1][1]), np.nan_to_num(full), rtol=2e-4, atol=2e-4)
     assert not np.allclose(np.nan_to_num(frames[0][1]), np.nan_to_num(full), rtol=2e-4, atol=2e-4)
+    assert np.all(frames[0][1][..., 3] == 1.0)
+    # the first frame is the 64-sample render of the same sample slice, resolved with ITS count
+    first, _ = r.render(w, h, 64, 50, seed=3)
+    assert np.allclose(np.nan_to_num(frames[0][1]), np.nan_to_num(first), rtol=2e-4, atol=2e-4)
+    # against the oracle: the final progressive frame is a Monte-Carlo estimate of the oracle's image
+    frames2, _ = r.render_progressive(w, h, 4096, 50, batch=1024, seed=5)
+    ref_sum, ref_sq, _ = ob.render(spec.camera, w, h, 512, 50, spec.background, seed=21, want_sumsq=True)
+    g = np.nan_to_num(frames2[-1][1][..., :3].astype(np.float64)) ** 2  # undo the gamma resolve
+    zb, _, _, _, _ = _zscores(g * 4096, 4096, np.nan_to_num(ref_sum), np.nan_to_num(ref_sq), 512, pool=8)
+    assert zb.size >= 20 and np.sqrt((zb ** 2).mean()) < 1.6 and abs(zb.mean()) < 0.5, (np.sqrt((zb ** 2).mean()), zb.mean())
+    # early exit: cancel after the second batch
+    seen = []
+    frames3, cancelled = r.render_progressive(w, h, 200, 50, batch=64, seed=3, on_frame=lambda d, t, f: seen.append(d) or d >= 128)
+    assert cancelled and seen == [64, 128] and [d for d, _ in frames3] == [64, 128]
+    assert np.allclose(np.nan_to_num(frames3[-1][1]), np.nan_to_num(frames[1][1]), rtol=2e-4, atol=2e-4)
 
 
 def test_exact_and_production_renders_agree(pkg, orc, built):
