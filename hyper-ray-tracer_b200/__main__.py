@@ -16,7 +16,8 @@ import time
 
 import numpy as np
 
-from . import native, renderer, scene_io, scenes
+from . import native, scene_io, scenes
+from . import scene as scene_mod
 
 
 def parse(argv=None):
@@ -60,17 +61,37 @@ def main(argv=None) -> int:
         print("error: no CUDA device — this renderer has no CPU fallback", file=sys.stderr)
         return 2
     print("Generating world...")                                    # application.rs:131
-    spec = scene_io.load_scene(a.load_scene) if a.load_scene else scenes.make_scene(a.scene, a.seed)
-    if a.save_scene:
-        scene_io.save_scene(spec, a.save_scene)
-    r = renderer.Renderer(spec, device=a.device, bvh_builder={"reference": native.HRT_BVH_REFERENCE, "trees": native.HRT_BVH_TREES}.get(a.bvh))
+    builder = {"reference": native.HRT_BVH_REFERENCE, "trees": native.HRT_BVH_TREES}[a.bvh]
+    if a.load_scene and a.load_scene.endswith(".npz"):  # the Python harness's instance format (scene_io.py)
+        spec = scene_io.load_scene(a.load_scene)
+        gb = native.HrtBackend()
+        gb.set_bvh_builder(builder)
+        scene_mod.emit(spec.world, gb)
+        cam, background = spec.camera, spec.background
+        if a.save_scene:
+            scene_io.save_scene(spec, a.save_scene)
+    else:
+        # the library's own scene generators and scene-instance files (hrt_make_scene / hrt_scene_load, include/hrt.h)
+        if a.load_scene:
+            gb, root, view = native.HrtBackend.load(a.load_scene)
+        else:
+            gb = native.HrtBackend()
+            root, view = gb.make_scene(a.scene, a.seed, scenes.load_earthmap() if a.scene in ("earth", "final") else None)
+        if a.save_scene:
+            gb.save(root, view, a.save_scene)
+        gb.set_bvh_builder(builder)
+        gb.commit(root)
+        cam = scene_mod.Camera(tuple(view.look_from), tuple(view.look_at), view.vfov, view.aperture, view.focus_dist, view.time0,
+                               view.time1)
+        background = tuple(view.background)
+    gb.upload(a.device)
     print("Generated world")                                        # application.rs:199
     print("Rendering image...")                                     # application.rs:387
     t0 = time.time()
-    frame, st = r.render(a.width, a.height, a.samples, a.depth, seed=a.render_seed)
+    frame, st = gb.render(cam, a.width, a.height, a.samples, a.depth, background, seed=a.render_seed, device=a.device)
     dt = time.time() - t0
     print(f"Rendered image in {int(dt) // 60:02d}:{int(dt) % 60:02d}! ({dt * 1e3:.0f} ms, kernel {st.kernel_ms:.1f} ms)")  # :266-271
-    print(f"  Width: {a.width}\n  Height: {a.height}\n  Samples: {a.samples}\n  Depth: {a.depth}\n  Objects: {r.backend.count()}")  # :272-277
+    print(f"  Width: {a.width}\n  Height: {a.height}\n  Samples: {a.samples}\n  Depth: {a.depth}\n  Objects: {gb.count()}")  # :272-277
     print(f"  Paths: {st.paths}  Rays: {st.rays}  ({st.paths / max(st.kernel_ms, 1e-6) / 1e3:.1f} Mpaths/s)")
     write_frame(a.out, frame)
     print(f"wrote {a.out}")

@@ -639,6 +639,19 @@ static int32_t add_mat(hrt_scene* s, const Material& m) {
     return (int32_t)s->materials.size() - 1;
 }
 
+namespace hrt {
+int32_t add_medium_with_material(hrt_scene* s, int32_t boundary, float density, int32_t mat) {
+    if (!s || s->committed || !obj_ok(s, boundary) || !mat_ok(s, mat)) return fail(HRT_ERR_INVALID, "constant_medium: bad argument");
+    Obj o;
+    o.kind = OBJ_MEDIUM;
+    o.child = boundary;
+    o.density = density;
+    o.neg_inv_density = -1.0f / density;
+    o.mat = mat;
+    return add_obj(s, std::move(o));
+}
+}  // namespace hrt
+
 extern "C" {
 
 const char* hrt_last_error(void) { return g_last_error.c_str(); }
@@ -811,6 +824,7 @@ int32_t hrt_rotate(hrt_scene* s, int32_t axis, int32_t child, float degrees) {
     o.kind = OBJ_ROTATE;
     o.child = child;
     o.plane_or_axis = axis;
+    o.angle_degrees = degrees;
     float radians = (PI_F / 180.0f) * degrees;  // rotation.rs:40-42
     o.sin_theta = sinf(radians);
     o.cos_theta = cosf(radians);
@@ -829,6 +843,7 @@ int32_t hrt_constant_medium(hrt_scene* s, int32_t boundary, float density, int32
     Obj o;
     o.kind = OBJ_MEDIUM;
     o.child = boundary;
+    o.density = density;
     o.neg_inv_density = -1.0f / density;  // constant_medium.rs:27
     o.mat = add_mat(s, m);
     return add_obj(s, std::move(o));

@@ -34,6 +34,7 @@ struct Obj {
     float a0 = 0, a1 = 0, b0 = 0, b1 = 0, k = 0; // rect
     float sin_theta = 0, cos_theta = 1;          // rotate
     float neg_inv_density = 0;                   // medium
+    float density = 0, angle_degrees = 0;        // as passed to the builder (scene-instance files)
     int32_t plane_or_axis = 0;
     int32_t mat = -1;
     int32_t child = -1;
@@ -91,4 +92,6 @@ namespace hrt {
 void set_error(const std::string& msg);
 int32_t fail(int32_t code, const std::string& msg);
 void release_device_state(DeviceState*);
+// hrt_constant_medium with its Isotropic material already in the material table (hrt_scene_load)
+int32_t add_medium_with_material(hrt_scene*, int32_t boundary, float density, int32_t mat);
 }  // namespace hrt

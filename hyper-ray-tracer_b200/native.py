@@ -70,6 +70,11 @@ class Stats(C.Structure):
                 ("block", C.c_int32)]
 
 
+class SceneView(C.Structure):
+    _fields_ = [("look_from", C.c_float * 3), ("look_at", C.c_float * 3), ("vfov", C.c_float), ("aperture", C.c_float),
+                ("focus_dist", C.c_float), ("time0", C.c_float), ("time1", C.c_float), ("background", C.c_float * 3)]
+
+
 class Peaks(C.Structure):
     _fields_ = [("fp32_tflops", C.c_float), ("l2_read_gbs", C.c_float), ("fma_ms", C.c_float), ("l2_ms", C.c_float),
                 ("sm_count", C.c_int32), ("clock_khz", C.c_int32)]
@@ -102,7 +107,8 @@ EXPORTS = [
     "hrt_render_accum", "hrt_render_accum_device", "hrt_resolve_device", "hrt_trace_hits", "hrt_tex_value",
     "hrt_scatter", "hrt_camera_rays", "hrt_philox_uniforms", "hrt_scene_evict", "hrt_scene_device_bytes",
     "hrt_measure_peaks", "hrt_scene_refresh", "hrt_render_multi", "hrt_render_accum_multi", "hrt_scene_get_box16",
-    "hrt_scene_set_bvh_builder", "hrt_scene_get_tree_nodes", "hrt_render_progressive",
+    "hrt_scene_set_bvh_builder", "hrt_scene_get_tree_nodes", "hrt_render_progressive", "hrt_make_scene", "hrt_scene_save",
+    "hrt_scene_load",
 ]
 
 _lib = None
@@ -168,6 +174,10 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.hrt_camera_rays.argtypes = [i32, C.POINTER(CameraDesc), vp, i32, vp, C.c_uint32]
     lib.hrt_philox_uniforms.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, f3]
     lib.hrt_scene_evict.argtypes = [vp, i32]
+    lib.hrt_make_scene.argtypes = [vp, C.c_char_p, C.c_uint64, C.POINTER(C.c_uint8), C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(i32),
+                                   C.POINTER(SceneView)]
+    lib.hrt_scene_save.argtypes = [vp, i32, C.POINTER(SceneView), C.c_char_p]
+    lib.hrt_scene_load.argtypes = [C.c_char_p, C.POINTER(vp), C.POINTER(i32), C.POINTER(SceneView)]
     lib.hrt_render_progressive.argtypes = [vp, i32, C.POINTER(CameraDesc), C.POINTER(RenderDesc), i32, PROGRESS_FN, vp, vp, C.POINTER(Stats)]
     lib.hrt_render_multi.argtypes = [vp, C.POINTER(i32), i32, C.POINTER(CameraDesc), C.POINTER(RenderDesc), vp, C.POINTER(Stats)]
     lib.hrt_render_accum_multi.argtypes = [vp, C.POINTER(i32), i32, C.POINTER(CameraDesc), C.POINTER(RenderDesc), vp, C.POINTER(Stats)]
@@ -285,6 +295,36 @@ class HrtBackend:
     def bvh(self, ids: Sequence[int], t0, t1):
         arr = (C.c_int32 * max(1, len(ids)))(*ids)
         return self._check(self.lib.hrt_bvh(self.handle, arr, len(ids), float(t0), float(t1)))
+
+    # ---- the scene library (hrt_make_scene / hrt_scene_save / hrt_scene_load) ----
+    def make_scene(self, name: str, seed: int = 1, image: Optional[np.ndarray] = None):
+        """The reference's generator `name` (src/arguments.rs:10-19) with an explicit seed, issued on this (uncommitted)
+        scene; `image` = decoded texels (h, w, 3|4) uint8 for `earth` / `final`.  Returns (root id, SceneView)."""
+        root, view = C.c_int32(-1), SceneView()
+        if image is not None:
+            d = np.ascontiguousarray(image, dtype=np.uint8)
+            h, w, comps = d.shape
+            ptr = d.ctypes.data_as(C.POINTER(C.c_uint8))
+        else:
+            ptr, w, h, comps = None, 0, 0, 0
+        self._check(self.lib.hrt_make_scene(self.handle, name.encode(), int(seed), ptr, w, h, comps, C.byref(root), C.byref(view)))
+        return int(root.value), view
+
+    def save(self, root: int, view: "SceneView", path: str):
+        self._check(self.lib.hrt_scene_save(self.handle, int(root), C.byref(view), path.encode()))
+
+    @classmethod
+    def load(cls, path: str):
+        """A stored scene instance as a fresh, uncommitted backend: (backend, root id, SceneView)."""
+        lib = load_library()
+        handle, root, view = C.c_void_p(), C.c_int32(-1), SceneView()
+        rc = lib.hrt_scene_load(path.encode(), C.byref(handle), C.byref(root), C.byref(view))
+        if rc < 0:
+            raise HrtError(rc, lib.hrt_last_error().decode())
+        self = cls.__new__(cls)
+        self.lib = lib
+        self.handle = handle
+        return self, int(root.value), view
 
     def set_bvh_builder(self, builder: int):
         """HRT_BVH_TREES (1, default: sound BVHs become OP_BVH trees in the fast form) or HRT_BVH_REFERENCE (0); before

@@ -97,6 +97,32 @@ int32_t hrt_list(hrt_scene*, const int32_t* children, int32_t n);               
  * refused (the reference panics in partial_cmp().unwrap()). */
 int32_t hrt_bvh(hrt_scene*, const int32_t* children, int32_t n, float time_start, float time_end);
 
+/* ---- scene library (src/application.rs:497-935, :132-197) ------------------------------------------- */
+/* What Application::new picks per scene next to the world: Camera::new's arguments and the background colour
+ * (src/application.rs:132-211; focus_dist 10, shutter [0, 1) for every scene). */
+typedef struct hrt_scene_view {
+    float look_from[3], look_at[3];
+    float vfov, aperture, focus_dist, time0, time1;
+    float background[3];
+} hrt_scene_view;
+/* The reference's scene generators — `--scene` of src/arguments.rs:10-19: "random" (generate_random_scene, application.rs:497),
+ * "two-spheres" (:567), "two-perlin-spheres" (:589), "earth" (:604), "simple-light" (:614), "cornell" (:639),
+ * "cornell-smoke" (:723), "final" (:817) — issued as builder calls on `scene` (not committed; *root_out is the world).
+ * The reference draws sphere positions, box heights and perlin tables from an unseeded thread_rng, so no two of its runs
+ * render the same world; here `seed` fixes the instance (the draws are those of numpy's PCG64 seeded with `seed`, 24 / 23
+ * bit f32 uniforms as rand 0.8.5's gen / gen_range — hrt_rng.hpp — so the instances equal the ones the round-1 Python
+ * harness generated and the committed goldens were rendered from).  `image`: the decoded texels of assets/earthmap.jpg for
+ * "earth" and "final" (the front end's `image` crate stays the decoder); NULL gives the reference's empty-image colour. */
+int32_t hrt_make_scene(hrt_scene*, const char* name, uint64_t seed, const uint8_t* image, uint32_t image_width, uint32_t image_height,
+                       uint32_t image_components, int32_t* root_out, hrt_scene_view* view_out);
+/* A scene INSTANCE on disk: every builder call made on `scene` so far (textures, materials, perlin tables, image texels,
+ * hittables in creation order), the root and the view, as one flat little-endian file.  hrt_scene_load re-issues the
+ * hittable calls in the same order on a fresh scene — same ids, same bounding boxes, same BvhNode trees, hence the same
+ * flattened streams — and leaves it uncommitted.  (The reference never stores a world: Application::new generates it
+ * and drops the generator's state, application.rs:132-199.) */
+int32_t hrt_scene_save(const hrt_scene*, int32_t root, const hrt_scene_view* view, const char* path);
+int32_t hrt_scene_load(const char* path, hrt_scene** out, int32_t* root_out, hrt_scene_view* view_out);
+
 /* Flatten the tree under `root` into the device op stream + material/texture tables (host only). */
 int32_t hrt_scene_commit(hrt_scene*, int32_t root);
 

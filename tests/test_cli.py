@@ -60,8 +60,14 @@ def test_cli_renders_a_frame(pkg, tmp_path):
 def test_cli_stored_scene_renders_the_same_frame(pkg, tmp_path):
     """--save-scene / --load-scene: the stored instance renders the same frame as the generated one (same render seed)."""
     cli = _cli(pkg)
-    scene, a, b = str(tmp_path / "s.npz"), str(tmp_path / "a.npy"), str(tmp_path / "b.npy")
+    scene, a, b = str(tmp_path / "s.hrts"), str(tmp_path / "a.npy"), str(tmp_path / "b.npy")
     common = "--width 48 --height 32 --samples 16 --depth 20 --render-seed 5"
     assert cli.main(f"--scene random --seed 9 {common} --save-scene {scene} --out {a}".split()) == 0
     assert cli.main(f"--load-scene {scene} {common} --out {b}".split()) == 0
     assert np.allclose(np.nan_to_num(np.load(a)), np.nan_to_num(np.load(b)), rtol=2e-4, atol=2e-4)
+    # ... and the Python harness's .npz instance format still loads (scene_io.py)
+    spec = pkg.make_scene("random", 9)
+    npz, c = str(tmp_path / "s.npz"), str(tmp_path / "c.npy")
+    pkg.scene_io.save_scene(spec, npz)
+    assert cli.main(f"--load-scene {npz} {common} --out {c}".split()) == 0
+    assert np.allclose(np.nan_to_num(np.load(a)), np.nan_to_num(np.load(c)), rtol=2e-4, atol=2e-4)
