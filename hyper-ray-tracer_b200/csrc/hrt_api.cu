@@ -17,7 +17,7 @@
 
 namespace hrt {
 
-constexpr int kCounterWords = 32;  // [0] work cursor, [1] rays, [2] paths, [8..27] diagnostic build's scheduler statistics
+constexpr int kCounterWords = 32;  // [0] work cursor / next path index, [1] rays, [2] paths
 constexpr int kLaunchSlots = 8;
 
 // What one render launch owns on the device: its counter block (the kernel's work cursor lives there) and its timing
@@ -35,7 +35,6 @@ struct DeviceState {
     int num_sms = 0;
     // [0] reference form, [1] fast form of the flattened scene (hrt_scene.hpp)
     void* d_ops[2] = {nullptr, nullptr};
-    void* d_box16[2] = {nullptr, nullptr};
     void* d_ctxs[2] = {nullptr, nullptr};
     void* d_nodes = nullptr;
     void* d_mats = nullptr;
@@ -61,7 +60,7 @@ void release_device_state(DeviceState* d) {
     if (cudaGetDevice(&prev) == cudaSuccess && cudaSetDevice(d->device) == cudaSuccess) {
         for (auto t : d->texobjs) cudaDestroyTextureObject(t);
         for (auto a : d->arrays) cudaFreeArray(a);
-        for (int k = 0; k < 2; ++k) { cudaFree(d->d_ops[k]); cudaFree(d->d_box16[k]); cudaFree(d->d_ctxs[k]); }
+        for (int k = 0; k < 2; ++k) { cudaFree(d->d_ops[k]); cudaFree(d->d_ctxs[k]); }
         cudaFree(d->d_nodes); cudaFree(d->d_mats); cudaFree(d->d_texs); cudaFree(d->d_noise);
         cudaFree(d->d_counters); cudaFree(d->d_accum); cudaFree(d->d_rgba);
         for (auto e : d->ev) if (e) cudaEventDestroy(e);
@@ -159,7 +158,6 @@ static int32_t fill_device_state(hrt_scene* s, DeviceState* d) {
     for (int k = 0; k < 2; ++k) {
         const FlatScene& f = flat_of(s, k);
         if ((rc = upload_table(&d->d_ops[k], f.ops.data(), f.ops.size() * sizeof(Op))) != HRT_OK) return rc;
-        if ((rc = upload_table(&d->d_box16[k], f.box16.data(), f.box16.size() * sizeof(Box16))) != HRT_OK) return rc;
         if ((rc = upload_table(&d->d_ctxs[k], f.ctxs.data(), f.ctxs.size() * sizeof(Ctx))) != HRT_OK) return rc;
     }
     if ((rc = upload_table(&d->d_nodes, s->fast.nodes.data(), s->fast.nodes.size() * sizeof(Bvh2Node))) != HRT_OK) return rc;
@@ -202,7 +200,7 @@ static int32_t fill_device_state(hrt_scene* s, DeviceState* d) {
         const FlatScene& f = flat_of(s, k);
         DeviceSceneHost& v = d->view[k];
         std::memset(&v, 0, sizeof(v));
-        v.ops = d->d_ops[k]; v.box16 = d->d_box16[k]; v.ctxs = d->d_ctxs[k];
+        v.ops = d->d_ops[k]; v.ctxs = d->d_ctxs[k];
         v.nodes = d->d_nodes;  // only the fast form has OP_BVH records
         v.mats = d->d_mats; v.texs = d->d_texs; v.noise = d->d_noise;
         for (size_t i = 0; i < d->texobjs.size() && i < (size_t)kMaxImages; ++i) v.images[i] = d->texobjs[i];
@@ -279,7 +277,6 @@ int32_t hrt_scene_refresh(hrt_scene* s, int32_t device) {
     for (int k = 0; k < 2; ++k) {
         const FlatScene& f = flat_of(s, k);
         HRT_CUDA(cudaMemcpyAsync(d->d_ops[k], f.ops.data(), f.ops.size() * sizeof(Op), cudaMemcpyHostToDevice, 0));
-        HRT_CUDA(cudaMemcpyAsync(d->d_box16[k], f.box16.data(), f.box16.size() * sizeof(Box16), cudaMemcpyHostToDevice, 0));
         HRT_CUDA(cudaMemcpyAsync(d->d_ctxs[k], f.ctxs.data(), f.ctxs.size() * sizeof(Ctx), cudaMemcpyHostToDevice, 0));
     }
     if (!s->fast.nodes.empty())
@@ -304,7 +301,7 @@ int64_t hrt_scene_device_bytes(const hrt_scene* s) {
                           s->noise_tables.size() * sizeof(NoiseTable) + s->fast.nodes.size() * sizeof(Bvh2Node));
     for (int k = 0; k < 2; ++k) {
         const FlatScene& f = flat_of(s, k);
-        b += (int64_t)(f.ops.size() * sizeof(Op) + f.box16.size() * sizeof(Box16) + f.ctxs.size() * sizeof(Ctx));
+        b += (int64_t)(f.ops.size() * sizeof(Op) + f.ctxs.size() * sizeof(Ctx));
     }
     for (const ImageData& img : s->images) b += (int64_t)img.rgba.size();
     return b;
@@ -372,7 +369,7 @@ static int32_t check_render_args(const hrt_scene* s, const hrt_camera_desc* cam,
     if (cam->width != rd->width || cam->height != rd->height)
         return fail(HRT_ERR_INVALID, "render: camera size differs from render size (Camera::resize uses the image size)");
     if ((long long)rd->width * rd->height > (1ll << 31) - 1) return fail(HRT_ERR_INVALID, "render: image too large");
-    // the ray pool keeps the bounce index in 16 bits next to the pixel lane (hrt_pool.cuh PF_BOUNCE_PL)
+    // (the persistent kernels of round 1 kept the bounce index in 16 bits; the limit stays part of the interface)
     if (rd->depth > 65535) return fail(HRT_ERR_INVALID, "render: depth above 65535 is not supported");
     (void)s;
     return HRT_OK;
@@ -406,22 +403,18 @@ static int32_t render_into(hrt_scene* s, DeviceState* d, const hrt_camera_desc* 
         for (const PreTree& t : s->fast.trees)
             if (L.n_pre < kMaxPreTrees) L.pre[L.n_pre++] = t;
     {
-        const char* env = getenv("HRT_KERNEL");  // diagnostic override: "interp" | "sched" | "pool"
+        const char* env = getenv("HRT_KERNEL");  // diagnostic override: "interp" | "uniform" | "wave"
         // default: the wavefront render for big jobs on scenes with OP_BVH trees (its compacted tree stage and small
-        // kernels win there: `final` 400 vs 270 Mpaths/s), the persistent uniform-walk kernel otherwise (no per-iteration
+        // kernels win there: `final` 435 vs 270 Mpaths/s), the persistent uniform-walk kernel otherwise (no per-iteration
         // launches, no ramp-up and drain of a wave: Cornell 880 vs 650, `random` at 100 spp 1280 vs 580)
         const long long job_paths = (long long)rd->width * rd->height * L.sample_count;
         int variant = (L.n_pre > 0 && job_paths >= (32ll << 20)) ? 5 : 3;
         if (rd->flags & HRT_FLAG_WAVEFRONT) variant = 5;
-        if (rd->flags & HRT_FLAG_SCHEDULER) variant = 0;
-        if (rd->flags & HRT_FLAG_INTERPRETER) variant = 1;
-        if (rd->flags & HRT_FLAG_POOL) variant = 2;
         if (rd->flags & HRT_FLAG_UNIFORM) variant = 3;
+        if (rd->flags & HRT_FLAG_INTERPRETER) variant = 1;
+        if (env && env[0] == 'i') variant = 1;
         if (env && env[0] == 'u') variant = 3;
         if (env && env[0] == 'w') variant = 5;
-        if (env && env[0] == 'i') variant = 1;
-        if (env && env[0] == 's') variant = 0;
-        if (env && env[0] == 'p') variant = 2;
         L.interpreter = variant;
     }
     LaunchSlot& slot = d->slots[d->next_slot];
@@ -461,18 +454,6 @@ static int32_t finish_stats(LaunchSlot* slot, cudaStream_t stream, hrt_stats* st
     unsigned long long c[kCounterWords];
     HRT_CUDA(cudaMemcpyAsync(c, slot->counters, sizeof(c), cudaMemcpyDeviceToHost, stream));
     HRT_CUDA(cudaStreamSynchronize(stream));
-    if (getenv("HRT_SCHED_STATS")) {
-        static const char* names[6] = {"box", "sphere", "rect", "misc", "done", "new"};
-        for (int i = 0; i < 6; ++i)
-            fprintf(stderr, "[sched] %-6s rounds %llu lanes %llu avg %.2f rounds/ray %.2f\n", names[i], c[8 + 2 * i], c[9 + 2 * i],
-                    c[8 + 2 * i] ? (double)c[9 + 2 * i] / (double)c[8 + 2 * i] : 0.0, c[1] ? 32.0 * (double)c[8 + 2 * i] / (double)c[1] : 0.0);
-        static const char* phases[8] = {"box", "sphere", "rect", "misc", "done", "new", "vote+gather", "item"};
-        double total = 0.0;
-        for (int i = 0; i < 8; ++i) total += (double)c[20 + i];
-        for (int i = 0; i < 8 && total > 0.0; ++i)
-            fprintf(stderr, "[sched] cycles %-12s %5.1f %%  (%.0f per round)\n", phases[i], 100.0 * (double)c[20 + i] / total,
-                    i < 6 && c[8 + 2 * i] ? (double)c[20 + i] / (double)c[8 + 2 * i] : 0.0);
-    }
     stats->rays = c[1];
     stats->paths = c[2];
     float ms = 0.0f;
@@ -722,8 +703,7 @@ int32_t hrt_trace_hits(hrt_scene* s, int32_t device, const hrt_ray* rays, int32_
     }
     // the reference form of the stream goes with the reference's box test (as in render_into)
     const DeviceSceneHost& view = d->view[(flags & HRT_FLAG_REFERENCE_TRAVERSAL) ? 0 : 1];
-    const int ref = ((flags & HRT_FLAG_REFERENCE_TRAVERSAL) ? 1 : 0) | ((flags & HRT_FLAG_WARP_SCHEDULER) ? 2 : 0) |
-                    ((flags & HRT_FLAG_UNIFORM) ? 4 : 0);
+    const int ref = ((flags & HRT_FLAG_REFERENCE_TRAVERSAL) ? 1 : 0) | ((flags & HRT_FLAG_UNIFORM) ? 4 : 0);
     cudaError_t e = (flags & HRT_FLAG_EXACT_MATH) ? hrt_exact::launch_trace_hits(view, dr.p, n, dx.p, dh.p, ref, 0)
                                                   : hrt_fast::launch_trace_hits(view, dr.p, n, dx.p, dh.p, ref, 0);
     if (e != cudaSuccess) return cuda_fail(e, "trace_hits_kernel launch");

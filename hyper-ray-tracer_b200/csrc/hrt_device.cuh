@@ -64,7 +64,6 @@ __device__ __forceinline__ V3 ray_at(const Ray& r, float t) { return r.o + t * r
 
 struct DeviceScene {
     const float4* ops;     // 2 x float4 per record
-    const uint4* box16;    // 16-byte companion per record (hrt_types.h Box16): fp16 outward-rounded box + w7
     const uint4* nodes;    // 2 x uint4 per OP_BVH tree node (hrt_types.h Bvh2Node)
     const Ctx* ctxs;
     const Material* mats;

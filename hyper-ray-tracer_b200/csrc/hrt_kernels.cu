@@ -1,21 +1,23 @@
 // hrt_kernels.cu — sm_100a kernels of the path-tracing hot path + their launchers.
 // Compiled twice (see hrt_device.cuh): -DHRT_EXACT=1 --fmad=false and -DHRT_EXACT=0.
 //
-// Three render kernels replace Application::render's sample loop + ray_color (src/application.rs:393-495).  All are
-// persistent: warps pull (8x4-pixel tile, sample-chunk) work items from a global cursor, the bounce "recursion" is a
-// flat loop over ray segments, finished paths are replaced at once, and they trace identical paths (same Philox
-// streams, same per-ray record order):
-//   render_pool_kernel    default from 128 samples per launch: 96 rays per warp parked in shared memory, one record
-//                         class per round with gathered (nearly full) warps, fp16 box table in shared memory
-//   render_kernel         default below that: rays stay in their lanes, the warp votes on the class to run
-//   render_interp_kernel  every lane interprets its own ray's records (the simple form; diagnostic)
-//   resolve_kernel     the gamma resolve sqrt(sum * 1/spp), alpha 1 (src/application.rs:451-456).
+// Application::render's sample loop + ray_color (src/application.rs:393-495) has two implementations that trace the same
+// paths (same Philox streams, same per-ray record order, same arithmetic):
+//   render_interp_kernel<true>   persistent: warps pull (8x4-pixel tile, sample-chunk) work items from a global cursor,
+//                                every lane owns a path, world.hit is the warp-uniform walk of the op stream
+//                                (traverse_uniform, hrt_device.cuh).  Small jobs and scenes without OP_BVH trees.
+//   render_interp_kernel<false>  the same with every lane interpreting its own ray's records (traverse<>): the plain form,
+//                                kept as the baseline the uniform walk is measured against.
+//   wave_logic / wave_noise / wave_tree / wave_trace / wave_finish
+//                                the wavefront render: path slots in device memory, a few small kernels per ray segment,
+//                                tree walks compacted over the whole wave.  Big jobs on scenes with OP_BVH trees.
+//   resolve_kernel         the gamma resolve sqrt(sum * 1/spp), alpha 1 (src/application.rs:451-456)
 //   reduce_resolve_kernel  the same, summing the accumulators of several devices over peer memory (hrt_render_multi)
-//   trace_hits_kernel  world.hit() on explicit rays            (parity entry)
+//   trace_hits_kernel / trace_hits_uniform_kernel   world.hit() on explicit rays   (parity entry)
 //   tex_value_kernel   Texture::value                          (parity entry)
 //   scatter_kernel     Material::scatter / emitted             (parity entry)
 //   camera_rays_kernel Camera::get_ray                         (parity entry)
-#include "hrt_pool.cuh"
+#include "hrt_device.cuh"
 #include "hrt_launch.h"
 
 namespace HRT_NS {
@@ -43,8 +45,6 @@ struct RenderParams {
     // guided schedule: n_big chunks of `chunk` samples, then up to kMaxTailChunks geometrically smaller ones
     int n_big, tail_begin[kMaxTailChunks], tail_size[kMaxTailChunks];
     int reference_boxes;
-    int n_tab;       // ray-pool kernel: Box16 records [0, n_tab) are staged in shared memory
-    int n_sh_noise;  // ray-pool kernel: noise tables staged behind them
 
     unsigned long long* counters;
     float4* accum;
@@ -61,202 +61,32 @@ __device__ __forceinline__ void stage_noise(const DeviceScene& S, TexEnv& E, Noi
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(kBlock, 2) render_kernel(const __grid_constant__ RenderParams P) {
-    __shared__ float sh_acc[kWarpsPerBlock][32][3];
-    __shared__ NoiseTable sh_noise[kMaxNoiseTablesShared];
-    TexEnv E;
-    stage_noise(P.S, E, sh_noise, kMaxNoiseTablesShared);
-
-    const DeviceScene& S = P.S;
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    const bool ref_boxes = P.reference_boxes != 0;
-    const V3 bg = v3(P.bg[0], P.bg[1], P.bg[2]);
-    const float div_w = (float)P.width - 1.0f, div_h = (float)P.height - 1.0f;  // application.rs:444-445
-    const float kTmin = 0.001f;                                                 // application.rs:482
-    unsigned long long n_rays = 0, n_paths = 0;
-#ifdef HRT_SCHED_STATS
-    unsigned long long st_rounds = 0, st_lanes = 0;  // lane c of every warp counts class c
-#endif
-
-    for (;;) {
-        unsigned long long item = 0;
-        if (lane == 0) item = atomicAdd(P.counters, 1ULL);
-        item = __shfl_sync(kFull, item, 0);
-        if (item >= (unsigned long long)P.n_items) break;
-        const int tile = (int)(item % (unsigned long long)P.n_tiles);
-        const int chunk = (int)(item / (unsigned long long)P.n_tiles);
-        const int tx = tile % P.tiles_x, ty = tile / P.tiles_x;
-        const int tc = chunk - P.n_big;  // >= 0: one of the shrinking tail chunks
-        const int s0 = P.sample_begin + (tc < 0 ? chunk * P.chunk : P.tail_begin[tc]);
-        const int s_n = tc < 0 ? P.chunk : P.tail_size[tc];
-        const int pool_size = 32 * s_n;
-        int pool_next = 0;
-
-        sh_acc[warp][lane][0] = 0.0f;
-        sh_acc[warp][lane][1] = 0.0f;
-        sh_acc[warp][lane][2] = 0.0f;
-        __syncwarp();
-
-        // per-lane path state
-        Lane L;
-        int cls = CLS_NEW;
-        Ray world;  // the ray segment being traced, in world space
-        V3 T = v3(1.0f, 1.0f, 1.0f);
-        uint32_t bounce = 0;
-        RngKey key;
-        key.k0 = P.k0; key.k1 = P.k1; key.pixel = 0; key.sample = 0;
-        int my_pl = lane;
-
-        for (;;) {
-            // ---- tight box loop: while a quorum of lanes sits at a box record, nothing else is looked at ----
-            int nb = warp_box_count(cls);
-            while (nb >= kBoxQuorum) {
-#ifdef HRT_SCHED_STATS
-                if (lane == 0) { st_rounds++; st_lanes += nb; }
-#endif
-                if (cls == CLS_BOX) { step_box(S, L, kTmin, ref_boxes); cls = lane_class(L); }
-                nb = warp_box_count(cls);
-            }
-            const Tier tier = warp_plan_slow(cls, nb);  // warp-uniform
-            if (!tier.any) break;
-#ifdef HRT_SCHED_STATS
-#define HRT_STAT(C, COND)                                                  \
-    {                                                                      \
-        const int n_ = __popc(__ballot_sync(kFull, (COND)));               \
-        if (lane == (C) && n_ > 0) { st_rounds++; st_lanes += n_; }        \
+// Sample range of work item `item` (tile-major inside a chunk; big chunks first, then the shrinking tail chunks).
+__device__ __forceinline__ void decode_item(const RenderParams& P, unsigned long long item, int& tx, int& ty, int& s0, int& s_n) {
+    const int tile = (int)(item % (unsigned long long)P.n_tiles);
+    const int chunk = (int)(item / (unsigned long long)P.n_tiles);
+    tx = tile % P.tiles_x;
+    ty = tile / P.tiles_x;
+    const int tc = chunk - P.n_big;  // >= 0: one of the shrinking tail chunks
+    s0 = P.sample_begin + (tc < 0 ? chunk * P.chunk : P.tail_begin[tc]);
+    s_n = tc < 0 ? P.chunk : P.tail_size[tc];
+}
+// Adds the item's radiance sums (lane = pixel of the 8x4 tile) into the frame accumulator.
+__device__ __forceinline__ void flush_item(const RenderParams& P, int tx, int ty, int s_n, float (*acc)[3], int lane) {
+    const int px = tx * 8 + (lane & 7), py = ty * 4 + (lane >> 3);
+    if (px < P.width && py < P.height) {
+        float* dst = reinterpret_cast<float*>(P.accum + (size_t)py * P.width + px);
+        atomicAdd(dst + 0, acc[lane][0]);
+        atomicAdd(dst + 1, acc[lane][1]);
+        atomicAdd(dst + 2, acc[lane][2]);
+        atomicAdd(dst + 3, (float)s_n);
     }
-            if (tier.box) HRT_STAT(0, cls == CLS_BOX)
-            if (tier.leaf) { HRT_STAT(tier.leaf_cls, cls == tier.leaf_cls) }
-            if (tier.done) HRT_STAT(4, cls == CLS_DONE)
-            if (tier.fill) HRT_STAT(5, cls == CLS_NEW)
-#endif
-            if (tier.box) {  // below the quorum, but still the largest population
-                if (cls == CLS_BOX) { step_box(S, L, kTmin, ref_boxes); cls = lane_class(L); }
-                continue;
-            }
-            if (tier.leaf && cls == tier.leaf_cls) {  // the leaf class with the most parked lanes
-                if (cls == CLS_SPHERE) { step_sphere(S, L, kTmin); cls = lane_class(L); }
-                else if (cls == CLS_RECT) { step_rect(S, L, kTmin); cls = lane_class(L); }
-                else {
-                    MediumXi xi;
-                    xi.key = key; xi.bounce = bounce; xi.injected = 0.0f; xi.inject = false;
-                    step_misc(S, L, world, kTmin, ref_boxes, xi);
-                    cls = lane_class(L);
-                }
-            }
-            if (tier.done) {
-                // ---- traversal finished: emitted + scatter (application.rs:482-494) ----
-                if (cls == CLS_DONE) {
-                    n_rays++;
-                    V3 add = v3(0.0f, 0.0f, 0.0f);
-                    bool alive = false;
-                    if (L.best_pc < 0) {
-                        add = T * bg;
-                    } else {
-                        Best best;
-                        best.t = L.closest; best.pc = L.best_pc; best.face = L.best_face; best.ctx = L.best_ctx;
-                        HitRec h;
-                        make_hit_record(S, world, best, false, h);
-                        const Material m = S.mats[h.mat];
-                        if (m.kind == MAT_DIFFUSE_LIGHT) {
-                            add = T * material_emitted(S, E, m, h);  // DiffuseLight::scatter -> None
-                        } else {
-                            float u4[4];
-                            rng_block(key, bounce, RNG_BLOCK_SCATTER, u4);
-                            V3 att;
-                            Ray sc;
-                            if (material_scatter(S, E, m, world, h, u4, att, sc)) {
-                                T = T * att;
-                                world = sc;
-                                bounce++;
-                                alive = bounce < (uint32_t)P.depth;  // ray_color(depth == 0) is black
-                            }
-                        }
-                    }
-                    if (add.x != 0.0f) atomicAdd(&sh_acc[warp][my_pl][0], add.x);
-                    if (add.y != 0.0f) atomicAdd(&sh_acc[warp][my_pl][1], add.y);
-                    if (add.z != 0.0f) atomicAdd(&sh_acc[warp][my_pl][2], add.z);
-                    if (alive) {
-                        lane_start(S, L, world, CUDART_INF_F);
-                        cls = lane_class(L);
-                    } else {
-                        cls = CLS_NEW;
-                    }
-                }
-            }
-            if (tier.fill) {
-                // ---- CLS_NEW: re-fill path-less lanes from the warp-local pool (ballot + popc compaction) ----
-                const unsigned need = __ballot_sync(kFull, cls == CLS_NEW);
-                const int idx = pool_next + __popc(need & lt_mask);
-                pool_next += __popc(need);
-                if (cls == CLS_NEW) {
-                    if (idx >= pool_size) {
-                        cls = CLS_IDLE;
-                    } else {
-                        const int pl = idx & 31;
-                        const int px = tx * 8 + (pl & 7), py = ty * 4 + (pl >> 3);
-                        if (px < P.width && py < P.height) {
-                            key.pixel = (uint32_t)(py * P.width + px);
-                            key.sample = (uint32_t)(s0 + (idx >> 5));
-                            n_paths++;
-                            if (P.depth > 0) {
-                                float c4[4];
-                                rng_block(key, 0, RNG_BLOCK_CAMERA, c4);  // jitter x, jitter y, shutter time, lens u1
-                                float lens_u2 = 0.0f;
-                                if (P.cam.lens_radius != 0.0f) {
-                                    float l4[4];
-                                    rng_block(key, 0, RNG_BLOCK_CAMERA - 1, l4);
-                                    lens_u2 = l4[0];
-                                }
-                                const float u = ((float)px + c4[0]) / div_w;
-                                const float v = ((float)py + c4[1]) / div_h;
-                                world = camera_get_ray(P.cam, u, v, c4[3], lens_u2, c4[2]);
-                                T = v3(1.0f, 1.0f, 1.0f);
-                                bounce = 0;
-                                my_pl = pl;
-                                lane_start(S, L, world, CUDART_INF_F);
-                                cls = lane_class(L);
-                            }
-                        }
-                    }
-                }
-            }
-        }
-        __syncwarp();
-        {
-            const int px = tx * 8 + (lane & 7), py = ty * 4 + (lane >> 3);
-            if (px < P.width && py < P.height) {
-                float* dst = reinterpret_cast<float*>(P.accum + (size_t)py * P.width + px);
-                atomicAdd(dst + 0, sh_acc[warp][lane][0]);
-                atomicAdd(dst + 1, sh_acc[warp][lane][1]);
-                atomicAdd(dst + 2, sh_acc[warp][lane][2]);
-                atomicAdd(dst + 3, (float)s_n);
-            }
-        }
-        __syncwarp();
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        n_rays += __shfl_xor_sync(kFull, n_rays, o);
-        n_paths += __shfl_xor_sync(kFull, n_paths, o);
-    }
-    if (lane == 0) {
-        atomicAdd(P.counters + 1, n_rays);
-        atomicAdd(P.counters + 2, n_paths);
-    }
-#ifdef HRT_SCHED_STATS
-    if (lane < 6) {
-        atomicAdd(P.counters + 8 + 2 * lane, st_rounds);
-        atomicAdd(P.counters + 9 + 2 * lane, st_lanes);
-    }
-#endif
 }
 
-// The plain variant: every lane runs the per-lane interpreter (`traverse<>`) for one whole ray segment per iteration and
-// the warp re-converges for shading.  Kept selectable (HRT_FLAG_INTERPRETER) for A/B measurements against the scheduler.
-// kUniform: the warp walks the stream together instead (traverse_uniform<>, hrt_device.cuh) — HRT_FLAG_UNIFORM.
+// The persistent render kernel.  kUniform = false: every lane runs the per-lane interpreter (`traverse<>`) for one whole ray
+// segment per iteration and the warp re-converges for shading (HRT_FLAG_INTERPRETER: the plain form).  kUniform = true:
+// the warp walks the stream together instead (traverse_uniform, hrt_device.cuh) — HRT_FLAG_UNIFORM, the default for
+// small jobs and for scenes without OP_BVH trees.
 template <bool kUniform>
 __global__ void __launch_bounds__(kBlock, 2) render_interp_kernel(const __grid_constant__ RenderParams P) {
     __shared__ float sh_acc[kWarpsPerBlock][32][3];
@@ -400,320 +230,6 @@ __global__ void __launch_bounds__(kBlock, 2) render_interp_kernel(const __grid_c
         atomicAdd(P.counters + 1, n_rays);
         atomicAdd(P.counters + 2, n_paths);
     }
-}
-
-// Sample range of work item `item` (tile-major inside a chunk; big chunks first, then the shrinking tail chunks).
-__device__ __forceinline__ void decode_item(const RenderParams& P, unsigned long long item, int& tx, int& ty, int& s0, int& s_n) {
-    const int tile = (int)(item % (unsigned long long)P.n_tiles);
-    const int chunk = (int)(item / (unsigned long long)P.n_tiles);
-    tx = tile % P.tiles_x;
-    ty = tile / P.tiles_x;
-    const int tc = chunk - P.n_big;  // >= 0: one of the shrinking tail chunks
-    s0 = P.sample_begin + (tc < 0 ? chunk * P.chunk : P.tail_begin[tc]);
-    s_n = tc < 0 ? P.chunk : P.tail_size[tc];
-}
-// Adds the item's radiance sums (lane = pixel of the 8x4 tile) into the frame accumulator.
-__device__ __forceinline__ void flush_item(const RenderParams& P, int tx, int ty, int s_n, float (*acc)[3], int lane) {
-    const int px = tx * 8 + (lane & 7), py = ty * 4 + (lane >> 3);
-    if (px < P.width && py < P.height) {
-        float* dst = reinterpret_cast<float*>(P.accum + (size_t)py * P.width + px);
-        atomicAdd(dst + 0, acc[lane][0]);
-        atomicAdd(dst + 1, acc[lane][1]);
-        atomicAdd(dst + 2, acc[lane][2]);
-        atomicAdd(dst + 3, (float)s_n);
-    }
-}
-
-// ---- render kernel with warp-private ray pools in shared memory (hrt_pool.cuh) ----
-#ifndef HRT_POOL_BLOCK
-#define HRT_POOL_BLOCK 512
-#endif
-constexpr int kPoolBlock = HRT_POOL_BLOCK;
-constexpr int kPoolWarps = kPoolBlock / 32;
-constexpr size_t kPoolBytes = (size_t)kPoolWarps * kPoolWarpWords * sizeof(float);
-static_assert(kPoolBytes % 16 == 0, "the Box16 table behind the pools must stay 16-byte aligned");
-
-// What a class body needs besides the pool: scene, staged tables, render constants and the current work item.
-struct RoundEnv {
-    const DeviceScene& S;
-    const RenderParams& P;
-    TexEnv E;
-    const uint4* sh_tab;  // Box16 records [0, n_tab) in shared memory
-    int n_tab;
-    int first_cls;        // class of record 0: where every new ray segment starts
-    bool ref_boxes;
-    V3 bg;
-    float div_w, div_h;   // application.rs:444-445
-    // current work item: 8x4-pixel tile, samples [s0, s0 + pool_size / 32)
-    int tx, ty, s0, pool_size;
-    float (*acc)[3];      // [32][3] shared-memory radiance sums of the item's pixels
-    __device__ __forceinline__ uint4 box16_at(int pc) const { return pc < n_tab ? sh_tab[pc] : __ldg(S.box16 + pc); }
-};
-
-// One round: every lane with a ray (slot s >= 0; all of class `run`, which is warp-uniform) advances it; returns the
-// ray's new class (CLS_IDLE for lanes without a ray).  `new_idx` is the path index a CLS_NEW slot draws.
-template <class PoolT>
-__device__ __forceinline__ int run_class(const RoundEnv& R, const PoolT& W, int run, int s, int new_idx,
-                                         unsigned long long& n_rays, unsigned long long& n_paths) {
-    const DeviceScene& S = R.S;
-    const RenderParams& P = R.P;
-    const float kTmin = 0.001f;  // application.rs:482
-    int cls = CLS_IDLE;
-    if (run == CLS_BOX) {
-        Ray cur;
-        RayK k;
-        float closest = 0.0f;
-        int pc = 0;
-        uint4 Q = make_uint4(0u, 0u, 0u, 0u);
-        if (s >= 0) {
-            cur.o = v3(W.at(PF_COX, s), W.at(PF_COY, s), W.at(PF_COZ, s));
-            cur.d = v3(W.at(PF_CDX, s), W.at(PF_CDY, s), W.at(PF_CDZ, s));
-            cur.time = 0.0f;  // boxes do not depend on the ray's time
-            closest = W.at(PF_CLOSEST, s);
-            pc = __float_as_int(W.at(PF_PC, s));
-            k = make_rayk(cur);
-            Q = R.box16_at(pc);
-            cls = record_class(Q.w & 0xffu);
-        }
-        // several box steps per gather, while most of the gathered rays are still at a box
-        for (int it = 0; it < kPoolMaxBoxSteps; ++it) {
-            if (cls == CLS_BOX) {
-                bool hit;
-                if ((Q.w & 0xffu) == OP_BOX_LOOSE || R.ref_boxes) {
-                    // unsound box, fp16-unrepresentable box or reference traversal: the 32-byte record decides
-                    float4 A, B;
-                    load_op(S, pc, A, B);
-                    const bool loose = (__float_as_uint(B.w) & 0xffu) == OP_BOX_LOOSE || R.ref_boxes;
-                    hit = loose ? box_hit_reference(A, B, cur, k, kTmin, closest) : box_hit_tight(A, B, cur, k, kTmin, closest);
-                } else {
-                    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&Q.x));  // min.x, min.y
-                    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&Q.y));  // min.z, max.x
-                    const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&Q.z));  // max.y, max.z
-                    hit = box_hit_tight(make_float4(a.x, a.y, b.x, 0.0f), make_float4(b.y, c.x, c.y, 0.0f), cur, k, kTmin, closest);
-                }
-                pc = hit ? pc + 1 : (int)(Q.w >> 8);
-                Q = R.box16_at(pc);
-                cls = record_class(Q.w & 0xffu);
-            }
-            if (__popc(__ballot_sync(kFull, cls == CLS_BOX)) < kPoolBoxKeep) break;
-        }
-        if (s >= 0) W.at(PF_PC, s) = __int_as_float(pc);
-    } else if (run <= CLS_MISC) {
-        if (s >= 0) {
-            Lane L;
-            pool_load_traversal(W, s, L);
-            L.k = make_rayk(L.cur);
-            lane_fetch(S, L);
-            if (run == CLS_SPHERE) step_sphere(S, L, kTmin);
-            else if (run == CLS_RECT) step_rect(S, L, kTmin);
-            else {
-                const Ray world = pool_load_world(W, s);
-                MediumXi xi;
-                xi.key.k0 = P.k0; xi.key.k1 = P.k1;
-                xi.key.pixel = __float_as_uint(W.at(PF_PIXEL, s));
-                xi.key.sample = __float_as_uint(W.at(PF_SAMPLE, s));
-                xi.bounce = __float_as_uint(W.at(PF_BOUNCE_PL, s)) & 0xffffu;
-                xi.injected = 0.0f; xi.inject = false;
-                step_misc(S, L, world, kTmin, R.ref_boxes, xi);
-            }
-            pool_store_traversal(W, s, L, run == CLS_MISC);
-            cls = lane_class(L);
-        }
-    } else if (run == CLS_DONE) {
-        // ---- traversal finished: emitted + scatter (application.rs:482-494) ----
-        if (s >= 0) {
-            n_rays++;
-            Ray world = pool_load_world(W, s);
-            V3 T = v3(W.at(PF_TX, s), W.at(PF_TY, s), W.at(PF_TZ, s));
-            const uint32_t bpl = __float_as_uint(W.at(PF_BOUNCE_PL, s));
-            uint32_t bounce = bpl & 0xffffu;
-            const int my_pl = (int)(bpl >> 16);
-            RngKey key;
-            key.k0 = P.k0; key.k1 = P.k1;
-            key.pixel = __float_as_uint(W.at(PF_PIXEL, s));
-            key.sample = __float_as_uint(W.at(PF_SAMPLE, s));
-            const int best_pc = __float_as_int(W.at(PF_BEST_PC, s));
-            V3 add = v3(0.0f, 0.0f, 0.0f);
-            bool alive = false;
-            if (best_pc < 0) {
-                add = T * R.bg;
-            } else {
-                const int fc = __float_as_int(W.at(PF_BEST_FC, s));
-                Best best;
-                best.t = W.at(PF_CLOSEST, s); best.pc = best_pc; best.face = fc & 0xff; best.ctx = fc >> 8;
-                HitRec h;
-                make_hit_record(S, world, best, false, h);
-                const Material m = S.mats[h.mat];
-                if (m.kind == MAT_DIFFUSE_LIGHT) {
-                    add = T * material_emitted(S, R.E, m, h);  // DiffuseLight::scatter -> None
-                } else {
-                    float u4[4];
-                    rng_block(key, bounce, RNG_BLOCK_SCATTER, u4);
-                    V3 att;
-                    Ray sc;
-                    if (material_scatter(S, R.E, m, world, h, u4, att, sc)) {
-                        T = T * att;
-                        world = sc;
-                        bounce++;
-                        alive = bounce < (uint32_t)P.depth;  // ray_color(depth == 0) is black
-                    }
-                }
-            }
-            if (add.x != 0.0f) atomicAdd(&R.acc[my_pl][0], add.x);
-            if (add.y != 0.0f) atomicAdd(&R.acc[my_pl][1], add.y);
-            if (add.z != 0.0f) atomicAdd(&R.acc[my_pl][2], add.z);
-            cls = CLS_NEW;
-            if (alive) {
-                pool_store_segment(W, s, world);
-                W.at(PF_TX, s) = T.x; W.at(PF_TY, s) = T.y; W.at(PF_TZ, s) = T.z;
-                W.at(PF_BOUNCE_PL, s) = __uint_as_float(bounce | ((uint32_t)my_pl << 16));
-                cls = R.first_cls;
-            }
-        }
-    } else {
-        // ---- CLS_NEW: the gathered path-less slots draw the next path indices of the item ----
-        if (s >= 0) {
-            cls = CLS_NEW;  // a slot whose index fell outside the image draws again
-            if (new_idx >= R.pool_size) {
-                cls = CLS_IDLE;
-            } else {
-                const int pl = new_idx & 31;
-                const int px = R.tx * 8 + (pl & 7), py = R.ty * 4 + (pl >> 3);
-                if (px < P.width && py < P.height) {
-                    RngKey key;
-                    key.k0 = P.k0; key.k1 = P.k1;
-                    key.pixel = (uint32_t)(py * P.width + px);
-                    key.sample = (uint32_t)(R.s0 + (new_idx >> 5));
-                    n_paths++;
-                    if (P.depth > 0) {
-                        float c4[4];
-                        rng_block(key, 0, RNG_BLOCK_CAMERA, c4);  // jitter x, jitter y, shutter time, lens u1
-                        float lens_u2 = 0.0f;
-                        if (P.cam.lens_radius != 0.0f) {
-                            float l4[4];
-                            rng_block(key, 0, RNG_BLOCK_CAMERA - 1, l4);
-                            lens_u2 = l4[0];
-                        }
-                        const float u = ((float)px + c4[0]) / R.div_w;
-                        const float v = ((float)py + c4[1]) / R.div_h;
-                        const Ray world = camera_get_ray(P.cam, u, v, c4[3], lens_u2, c4[2]);
-                        pool_store_segment(W, s, world);
-                        W.at(PF_TX, s) = 1.0f; W.at(PF_TY, s) = 1.0f; W.at(PF_TZ, s) = 1.0f;
-                        W.at(PF_PIXEL, s) = __uint_as_float(key.pixel);
-                        W.at(PF_SAMPLE, s) = __uint_as_float(key.sample);
-                        W.at(PF_BOUNCE_PL, s) = __uint_as_float((uint32_t)pl << 16);
-                        cls = R.first_cls;
-                    }
-                }
-            }
-        }
-    }
-    return cls;
-}
-
-// One 16-warp block per SM.  Dynamic shared memory: [16 warp pools][Box16 table, n_tab records][n_sh_noise noise tables].
-// The box loop — 85 % of all steps — then never leaves the SM: with the records in global memory a warp-wide fetch of
-// ~20 different records almost always contained at least one L1 miss (hit rate 82 %), so every box step paid an L2
-// round trip (profiles/r01_render_kernel_summary.md, "phase cycles").
-__global__ void __launch_bounds__(kPoolBlock, 1) render_pool_kernel(const __grid_constant__ RenderParams P) {
-    extern __shared__ __align__(16) float sh_pool[];
-    __shared__ float sh_acc[kPoolWarps][32][3];
-    const DeviceScene& S = P.S;
-    uint4* const sh_tab = reinterpret_cast<uint4*>(sh_pool + kPoolWarps * kPoolWarpWords);
-    for (int i = threadIdx.x; i < P.n_tab; i += kPoolBlock) sh_tab[i] = __ldg(S.box16 + i);
-    TexEnv E;
-    stage_noise(S, E, reinterpret_cast<NoiseTable*>(sh_tab + P.n_tab), P.n_sh_noise);  // ends with __syncthreads()
-
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    unsigned long long n_rays = 0, n_paths = 0;
-#ifdef HRT_SCHED_STATS
-    unsigned long long st_rounds = 0, st_lanes = 0;
-    // cycles per phase, kept by lane c for class c (lanes 0-5), lane 6: vote + gather, lane 7: item set-up and flush
-    long long st_cycles = 0, st_mark = clock64();
-#define HRT_STAT_PHASE(who)                                        \
-    {                                                              \
-        const long long now_ = clock64();                          \
-        if (lane == (who)) st_cycles += now_ - st_mark;            \
-        st_mark = now_;                                            \
-    }
-#else
-#define HRT_STAT_PHASE(who)
-#endif
-    PoolWarp W;
-    W.f = sh_pool + warp * kPoolWarpWords;
-    W.cls_w = reinterpret_cast<uint32_t*>(W.f + PF_WORDS * kPoolSlots);
-    W.list = reinterpret_cast<int*>(W.cls_w + 32);
-    RoundEnv R{S, P, E, sh_tab, P.n_tab, 0, P.reference_boxes != 0, v3(P.bg[0], P.bg[1], P.bg[2]),
-               (float)P.width - 1.0f, (float)P.height - 1.0f, 0, 0, 0, 0, sh_acc[warp]};
-    R.first_cls = record_class(R.box16_at(0).w & 0xffu);
-
-    for (;;) {
-        unsigned long long item = 0;
-        if (lane == 0) item = atomicAdd(P.counters, 1ULL);
-        item = __shfl_sync(kFull, item, 0);
-        if (item >= (unsigned long long)P.n_items) break;
-        int s_n;
-        decode_item(P, item, R.tx, R.ty, R.s0, s_n);
-        R.pool_size = 32 * s_n;
-        int pool_next = 0;
-
-        sh_acc[warp][lane][0] = 0.0f;
-        sh_acc[warp][lane][1] = 0.0f;
-        sh_acc[warp][lane][2] = 0.0f;
-        // every slot starts path-less (byte 3 of the class word is unused)
-        {
-            uint32_t w0 = 0u;  // home rows in use start path-less, the rest are idle
-#pragma unroll
-            for (int j = 0; j < 4; ++j) w0 |= (uint32_t)(j < kPoolHomes ? CLS_NEW : CLS_IDLE) << (8 * j);
-            W.cls_w[lane] = w0;
-        }
-        __syncwarp();
-        int rot = 0;
-
-        HRT_STAT_PHASE(7)
-        for (;;) {
-            const uint32_t cw = W.cls_w[lane];
-            const PoolCounts cnt = pool_count(cw);
-            int run = CLS_BOX, best_n = cnt.n[CLS_BOX];
-#pragma unroll
-            for (int c = CLS_SPHERE; c <= CLS_NEW; ++c)
-                if (cnt.n[c] > best_n) { run = c; best_n = cnt.n[c]; }
-            if (best_n == 0) break;  // every slot idle: the item is finished
-            const int n = pool_gather(W, cw, run, lane, rot);
-            rot = rot + 1 == kPoolHomes ? 0 : rot + 1;
-            const int s = lane < n ? W.list[lane] : -1;
-#ifdef HRT_SCHED_STATS
-            if (lane == run) { st_rounds++; st_lanes += n; }
-#endif
-            HRT_STAT_PHASE(6)
-            const int cls = run_class(R, W, run, s, pool_next + lane, n_rays, n_paths);
-            if (run == CLS_NEW) pool_next += n;
-            if (s >= 0) W.set_cls(s, cls);
-            __syncwarp();  // slot state and class bytes written by this round are visible to the next round's readers
-            HRT_STAT_PHASE(run)
-        }
-        __syncwarp();
-        flush_item(P, R.tx, R.ty, s_n, sh_acc[warp], lane);
-        __syncwarp();
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        n_rays += __shfl_xor_sync(kFull, n_rays, o);
-        n_paths += __shfl_xor_sync(kFull, n_paths, o);
-    }
-    if (lane == 0) {
-        atomicAdd(P.counters + 1, n_rays);
-        atomicAdd(P.counters + 2, n_paths);
-    }
-#ifdef HRT_SCHED_STATS
-    HRT_STAT_PHASE(7)
-    if (lane < 6) {
-        atomicAdd(P.counters + 8 + 2 * lane, st_rounds);
-        atomicAdd(P.counters + 9 + 2 * lane, st_lanes);
-    }
-    if (lane < 8) atomicAdd(P.counters + 20 + lane, (unsigned long long)st_cycles);
-#endif
 }
 
 // ---- wavefront render: two small kernels per ray segment instead of one big persistent kernel ----
@@ -1148,73 +664,6 @@ __global__ void __launch_bounds__(128) trace_hits_uniform_kernel(const __grid_co
     out[i] = o;
 }
 
-// world.hit() through the warp scheduler (the control flow the render kernel uses): one ray per lane.
-__global__ void __launch_bounds__(128) trace_hits_sched_kernel(const __grid_constant__ DeviceScene S, const hrt_ray* __restrict__ rays,
-                                                               int n, const float* __restrict__ xi_in, hrt_hit* __restrict__ out,
-                                                               int reference_boxes) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    Lane L;
-    int cls = CLS_IDLE;
-    Ray world;
-    float tmin = 0.0f;
-    MediumXi xi;
-    xi.key.k0 = 0; xi.key.k1 = 0; xi.key.pixel = 0; xi.key.sample = 0;
-    xi.bounce = 0;
-    xi.inject = true;
-    xi.injected = 0.5f;
-    if (i < n) {
-        const hrt_ray r = rays[i];
-        world.o = v3(r.o[0], r.o[1], r.o[2]);
-        world.d = v3(r.d[0], r.d[1], r.d[2]);
-        world.time = r.time;
-        tmin = r.tmin;
-        if (xi_in) xi.injected = xi_in[i];
-        lane_start(S, L, world, r.tmax);
-        cls = lane_class(L);
-    }
-    const bool ref = reference_boxes != 0;
-    for (;;) {
-        const Tier tier = warp_plan(cls);
-        if (!tier.any) break;
-        if (tier.box) {
-            if (cls == CLS_BOX) { step_box(S, L, tmin, ref); cls = lane_class(L); }
-            continue;
-        }
-        if (tier.leaf && cls == tier.leaf_cls) {
-            if (cls == CLS_SPHERE) { step_sphere(S, L, tmin); cls = lane_class(L); }
-            else if (cls == CLS_RECT) { step_rect(S, L, tmin); cls = lane_class(L); }
-            else { step_misc(S, L, world, tmin, ref, xi); cls = lane_class(L); }
-        }
-        if (tier.done) {
-            if (cls == CLS_DONE) {
-                hrt_hit o;
-                o.hit = 0; o.t = 0.0f;
-                o.p[0] = o.p[1] = o.p[2] = 0.0f;
-                o.n[0] = o.n[1] = o.n[2] = 0.0f;
-                o.u = 0.0f; o.v = 0.0f;
-                o.front_face = 0; o.material_id = -1; o.prim_id = -1; o.face = 0;
-                if (L.best_pc >= 0) {
-                    Best best;
-                    best.t = L.closest; best.pc = L.best_pc; best.face = L.best_face; best.ctx = L.best_ctx;
-                    HitRec h;
-                    make_hit_record(S, world, best, true, h);
-                    o.hit = 1;
-                    o.t = h.t;
-                    o.p[0] = h.p.x; o.p[1] = h.p.y; o.p[2] = h.p.z;
-                    o.n[0] = h.n.x; o.n[1] = h.n.y; o.n[2] = h.n.z;
-                    o.u = h.u; o.v = h.v;
-                    o.front_face = h.front_face ? 1 : 0;
-                    o.material_id = h.mat;
-                    o.prim_id = h.prim;
-                    o.face = h.face;
-                }
-                out[i] = o;
-                cls = CLS_IDLE;
-            }
-        }
-    }
-}
-
 __global__ void __launch_bounds__(kBlock) tex_value_kernel(const __grid_constant__ DeviceScene S, int tex,
                                                            const float* __restrict__ uvp, int n, float* __restrict__ out) {
     __shared__ NoiseTable sh_noise[kMaxNoiseTablesShared];
@@ -1360,7 +809,6 @@ cudaError_t launch_l2_read(const float4* d_buf, size_t n_vec, int repeats, float
 static DeviceScene to_device_scene(const hrt::DeviceSceneHost& h) {
     DeviceScene S;
     S.ops = reinterpret_cast<const float4*>(h.ops);
-    S.box16 = reinterpret_cast<const uint4*>(h.box16);
     S.nodes = reinterpret_cast<const uint4*>(h.nodes);
     S.ctxs = reinterpret_cast<const Ctx*>(h.ctxs);
     S.mats = reinterpret_cast<const Material*>(h.mats);
@@ -1500,46 +948,18 @@ cudaError_t launch_render(hrt::RenderLaunch& L, int num_sms, cudaStream_t stream
     P.tiles_y = (L.height + 3) / 4;
     P.n_tiles = P.tiles_x * P.tiles_y;
     int blocks_per_sm = 0;
-    size_t pool_smem = kPoolBytes;
-    P.n_tab = 0;
-    P.n_sh_noise = 0;
-    cudaError_t e;
-    const bool pooled = L.interpreter == 2;
-    const void* pool_fn = (const void*)render_pool_kernel;
-    if (pooled) {
-        // Shared-memory budget of the one resident block: the ray pools, then as much of the Box16 table as fits (all
-        // of it for the BASELINE scenes: 4236 records = 66 KB for `final`), then the noise tables.
-        const size_t pools = kPoolBytes;
-        int dev = 0, optin = 0;
-        cudaFuncAttributes fa;
-        if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
-        if ((e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess) return e;
-        if ((e = cudaFuncGetAttributes(&fa, pool_fn)) != cudaSuccess) return e;
-        long long avail = (long long)optin - (long long)fa.sharedSizeBytes - (long long)pools;
-        if (avail < 0) return cudaErrorInvalidConfiguration;
-        P.n_tab = (int)std::min<long long>(P.S.n_ops, avail / 16);
-        avail -= 16ll * P.n_tab;
-        P.n_sh_noise = (int)std::min<long long>(std::min(P.S.n_noise, kMaxNoiseTablesShared), avail / (long long)sizeof(NoiseTable));
-        pool_smem = pools + 16 * (size_t)P.n_tab + sizeof(NoiseTable) * (size_t)P.n_sh_noise;
-        e = cudaFuncSetAttribute(pool_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pool_smem);
-        if (e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, pool_fn, kPoolBlock, pool_smem);
-    } else if (L.interpreter == 3) {
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, render_interp_kernel<true>, kBlock, 0);
-    } else if (L.interpreter == 1) {
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, render_interp_kernel<false>, kBlock, 0);
-    } else {
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, render_kernel, kBlock, 0);
-    }
+    const bool uniform = L.interpreter != 1;
+    cudaError_t e = uniform ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, render_interp_kernel<true>, kBlock, 0)
+                            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, render_interp_kernel<false>, kBlock, 0);
     if (e != cudaSuccess) return e;
     if (blocks_per_sm < 1) blocks_per_sm = 1;
     const int grid = num_sms * blocks_per_sm;
-    // Samples per work item: large enough to amortise the per-item flush and the end-of-pool tail, small
+    // Samples per work item: large enough to amortise the per-item flush and the end-of-item tail, small
     // enough that the dynamic cursor balances the last wave (>= ~8 items per resident warp when possible).
     int chunk = L.chunk;
     if (chunk <= 0) {
-        chunk = pooled ? 256 : 64;  // the pool kernel keeps 96 rays in flight per warp: larger items
-        const long long resident_warps = (long long)grid * (pooled ? kPoolWarps : kWarpsPerBlock);
+        chunk = 64;
+        const long long resident_warps = (long long)grid * kWarpsPerBlock;
         while (chunk > 4 && (long long)P.n_tiles * ((L.sample_count + chunk - 1) / chunk) < 8 * resident_warps) chunk /= 2;
     }
     if (chunk > L.sample_count) chunk = L.sample_count;
@@ -1568,12 +988,10 @@ cudaError_t launch_render(hrt::RenderLaunch& L, int num_sms, cudaStream_t stream
     P.counters = L.counters;
     P.accum = reinterpret_cast<float4*>(L.accum);
     L.grid = grid;
-    L.block = pooled ? kPoolBlock : kBlock;
+    L.block = kBlock;
     L.chunk = chunk;
-    if (L.interpreter == 2) render_pool_kernel<<<grid, kPoolBlock, pool_smem, stream>>>(P);
-    else if (L.interpreter == 3) render_interp_kernel<true><<<grid, kBlock, 0, stream>>>(P);
-    else if (L.interpreter == 1) render_interp_kernel<false><<<grid, kBlock, 0, stream>>>(P);
-    else render_kernel<<<grid, kBlock, 0, stream>>>(P);
+    if (uniform) render_interp_kernel<true><<<grid, kBlock, 0, stream>>>(P);
+    else render_interp_kernel<false><<<grid, kBlock, 0, stream>>>(P);
     return cudaGetLastError();
 }
 
@@ -1582,8 +1000,6 @@ cudaError_t launch_trace_hits(const hrt::DeviceSceneHost& S, const hrt_ray* d_ra
     if (n <= 0) return cudaSuccess;
     if (reference_boxes & 4)  // bit 2: the warp-uniform walk
         trace_hits_uniform_kernel<<<(n + 127) / 128, 128, 0, stream>>>(to_device_scene(S), d_rays, n, d_xi, d_out, reference_boxes & 1);
-    else if (reference_boxes & 2)  // bit 1: run through the warp scheduler (the render kernel's control flow)
-        trace_hits_sched_kernel<<<(n + 127) / 128, 128, 0, stream>>>(to_device_scene(S), d_rays, n, d_xi, d_out, reference_boxes & 1);
     else
         trace_hits_kernel<<<(n + 127) / 128, 128, 0, stream>>>(to_device_scene(S), d_rays, n, d_xi, d_out, reference_boxes & 1);
     return cudaGetLastError();

@@ -11,7 +11,6 @@ namespace hrt {
 
 struct DeviceSceneHost {  // mirrors HRT_NS::DeviceScene field for field (checked by static_assert in the .cu)
     const void* ops;
-    const void* box16;
     const void* nodes;
     const void* ctxs;
     const void* mats;
@@ -34,8 +33,8 @@ struct RenderLaunch {
     int32_t n_nodes;      // tree nodes of the scene form being rendered
     int32_t n_pre;        // OP_BVH trees the wavefront render walks in its own stage (<= kMaxPreTrees)
     hrt::PreTree pre[hrt::kMaxPreTrees];
-    int32_t interpreter;  // render kernel variant: 0 warp scheduler, 1 per-lane interpreter, 2 shared-memory ray pool,
-                          // 3 warp-uniform walk (production)
+    int32_t interpreter;  // render variant: 1 persistent kernel, per-lane interpreter; 3 persistent kernel, warp-uniform
+                          // walk; 5 wavefront render
     unsigned long long* counters;  // device: [0] work-item cursor, [1] rays, [2] paths
     float* accum;                  // device: width*height*4 f32, added into
     int32_t grid, block;           // out: launch configuration actually used

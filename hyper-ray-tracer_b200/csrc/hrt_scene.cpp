@@ -560,7 +560,7 @@ struct Flattener {
     }
 };
 
-// ---- fp16 with directed rounding (Box16, hrt_types.h) ----
+// ---- fp16 with directed rounding (Bvh2Node boxes, hrt_types.h) ----
 // Largest fp16 <= x (up == false) or smallest fp16 >= x (up == true); +-inf when x is outside the finite fp16 range on
 // the side that keeps the inequality.  x must not be NaN.
 static uint16_t float_to_half_directed(float x, bool up) {
@@ -586,26 +586,6 @@ static uint16_t float_to_half_directed(float x, bool up) {
         mag = he == 0 ? (uint16_t)q : (uint16_t)(((uint32_t)he << 10) + (q - 1024u));
     }
     return (uint16_t)(mag | (neg ? 0x8000u : 0u));
-}
-
-static void build_box16(FlatScene& s) {
-    s.box16.assign(s.ops.size(), Box16{});
-    for (size_t i = 0; i < s.ops.size(); ++i) {
-        const Op& op = s.ops[i];
-        Box16& b = s.box16[i];
-        b.w7 = op.u[7];
-        if ((op.u[7] & 0xffu) != OP_BOX) continue;
-        bool ok = true;
-        for (int a = 0; a < 3; ++a) ok = ok && !std::isnan(op.f[a]) && !std::isnan(op.f[4 + a]);
-        if (!ok) {
-            b.w7 = (op.u[7] & ~0xffu) | OP_BOX_LOOSE;  // "read the 32-byte record"
-            continue;
-        }
-        for (int a = 0; a < 3; ++a) {
-            b.h[a] = float_to_half_directed(op.f[a], false);
-            b.h[3 + a] = float_to_half_directed(op.f[4 + a], true);
-        }
-    }
 }
 
 }  // namespace hrt
@@ -918,7 +898,6 @@ static int32_t flatten(const hrt_scene* s, int32_t root, FlatScene& f, bool tree
             ++i;
         }
     }
-    build_box16(f);
     return HRT_OK;
 }
 
@@ -973,14 +952,6 @@ int32_t hrt_scene_get_info(const hrt_scene* s, hrt_scene_info* out) {
     return HRT_OK;
 }
 static const FlatScene* pick_flat(const hrt_scene* s, int32_t which) { return which == HRT_STREAM_FAST ? &s->fast : &s->ref; }
-int32_t hrt_scene_get_box16(const hrt_scene* s, int32_t which, void* out, int32_t cap_ops) {
-    if (!s) return fail(HRT_ERR_INVALID, "null scene");
-    if (!s->committed) return fail(HRT_ERR_STATE, "scene not committed");
-    const FlatScene* f = pick_flat(s, which);
-    int32_t n = (int32_t)f->box16.size();
-    if (out && cap_ops > 0) std::memcpy(out, f->box16.data(), sizeof(Box16) * (size_t)std::min(n, cap_ops));
-    return n;
-}
 int32_t hrt_scene_get_ops(const hrt_scene* s, int32_t which, void* out, int32_t cap_ops) {
     if (!s) return fail(HRT_ERR_INVALID, "null scene");
     if (!s->committed) return fail(HRT_ERR_STATE, "scene not committed");

@@ -49,11 +49,10 @@ struct ImageData {
     uint32_t width = 0, height = 0;
 };
 
-// One flattened form of the scene (hrt_types.h): the op stream with its fp16 companions, the ray-space contexts whose
-// records it refers to, and the node table of its OP_BVH trees.
+// One flattened form of the scene (hrt_types.h): the op stream, the ray-space contexts whose records it refers to, and
+// the node table of its OP_BVH trees.
 struct FlatScene {
     std::vector<Op> ops;
-    std::vector<Box16> box16;  // derived from ops at commit
     std::vector<Ctx> ctxs;
     std::vector<Bvh2Node> nodes;
     std::vector<PreTree> trees;  // the OP_BVH trees outside medium boundaries, in stream order

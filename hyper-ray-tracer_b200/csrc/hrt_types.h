@@ -13,8 +13,7 @@
 
 namespace hrt {
 
-// The high nibble of an opcode is its scheduler class + 1 (box 1, sphere 2, rect 3, misc 4, end 5), so the render
-// kernel's class look-up is a shift (hrt_machine.cuh: record_class).
+// The high nibble of an opcode is its record class (box 1, sphere 2, rect 3, ray space / medium / tree 4, end 5).
 enum Opcode : uint32_t {
     OP_BOX = 0x10,        // sound box: intersected ("tight") slab test is result-identical to the reference test
     OP_BOX_LOOSE = 0x11,  // unsound box (Q2): MUST use the reference's per-axis test (src/aabb.rs:20-47)
@@ -57,19 +56,8 @@ struct alignas(16) Op {
 };
 static_assert(sizeof(Op) == 32, "op record must be 32 bytes");
 
-// 16-byte companion of every record (same index) — what the ray-pool kernel's box loop reads, from SHARED MEMORY, instead
-// of the 32-byte record: the box rounded OUTWARD to fp16 (any superset of a sound box is sound, so results do not
-// change) plus w7.
-//   h[0..2] = min rounded down, h[3..5] = max rounded up, w7 = the record's own w7
-// except that a box fp16 cannot carry (NaN bounds) and every OP_BOX_LOOSE record say OP_BOX_LOOSE here, which sends the
-// kernel to the 32-byte record.  Non-box records only carry w7 (their class).
-struct alignas(16) Box16 {
-    uint16_t h[6];
-    uint32_t w7;
-};
-static_assert(sizeof(Box16) == 16, "box16 record must be 16 bytes");
-
-// Node of an OP_BVH tree: the fp16 outward-rounded boxes of BOTH children (same layout and rounding as Box16) and the two
+// Node of an OP_BVH tree: the boxes of BOTH children rounded OUTWARD to fp16 (min down, max up — any superset of a sound
+// box is sound, so results do not change; +-inf beyond the fp16 range) and the two
 // child links — >= 0: another node (index relative to the tree's first node), < 0: ~pc of the leaf's primitive record in
 // the op stream.  The reference visits a BvhNode's children left first with a running t_max and lets the later child win
 // an exact tie if it is still reached (bvh_node.rs:110-124); a sound tree can be walked in ANY order with the same

@@ -13,10 +13,7 @@ LIB_PATH = os.environ.get("HRT_LIB") or os.path.join(_HERE, "csrc", "libhrt.so")
 
 HRT_FLAG_REFERENCE_TRAVERSAL = 1
 HRT_FLAG_EXACT_MATH = 2
-HRT_FLAG_WARP_SCHEDULER = 4
 HRT_FLAG_INTERPRETER = 8
-HRT_FLAG_POOL = 16
-HRT_FLAG_SCHEDULER = 32
 HRT_FLAG_UNIFORM = 64
 HRT_FLAG_WAVEFRONT = 128
 ABI_VERSION = 3  # include/hrt.h HRT_ABI_VERSION
@@ -106,7 +103,7 @@ EXPORTS = [
     "hrt_scene_get_ops", "hrt_bvh_leaf_order", "hrt_bounding_box", "hrt_camera_init", "hrt_scene_upload", "hrt_render",
     "hrt_render_accum", "hrt_render_accum_device", "hrt_resolve_device", "hrt_trace_hits", "hrt_tex_value",
     "hrt_scatter", "hrt_camera_rays", "hrt_philox_uniforms", "hrt_scene_evict", "hrt_scene_device_bytes",
-    "hrt_measure_peaks", "hrt_scene_refresh", "hrt_render_multi", "hrt_render_accum_multi", "hrt_scene_get_box16",
+    "hrt_measure_peaks", "hrt_scene_refresh", "hrt_render_multi", "hrt_render_accum_multi",
     "hrt_scene_set_bvh_builder", "hrt_scene_get_tree_nodes", "hrt_render_progressive", "hrt_make_scene", "hrt_scene_save",
     "hrt_scene_load",
 ]
@@ -157,7 +154,6 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.hrt_scene_count.argtypes = [vp]
     lib.hrt_scene_get_info.argtypes = [vp, C.POINTER(SceneInfo)]
     lib.hrt_scene_get_ops.argtypes = [vp, i32, vp, i32]
-    lib.hrt_scene_get_box16.argtypes = [vp, i32, vp, i32]
     lib.hrt_scene_get_tree_nodes.argtypes = [vp, vp, i32]
     lib.hrt_scene_set_bvh_builder.argtypes = [vp, i32]
     lib.hrt_bvh_leaf_order.argtypes = [vp, i32, C.POINTER(i32), i32]
@@ -348,13 +344,6 @@ class HrtBackend:
         n = self._check(self.lib.hrt_scene_get_ops(self.handle, which, None, 0))
         out = np.zeros((n, 8), dtype=np.uint32)
         self._check(self.lib.hrt_scene_get_ops(self.handle, which, _ptr(out), n))
-        return out
-
-    def box16(self, which: int = HRT_STREAM_REFERENCE) -> np.ndarray:
-        """(n_ops, 8) uint16: six fp16 bounds (min rounded down, max rounded up) + w7 as two halves (hrt_types.h Box16)."""
-        n = self._check(self.lib.hrt_scene_get_box16(self.handle, which, None, 0))
-        out = np.zeros((n, 8), dtype=np.uint16)
-        self._check(self.lib.hrt_scene_get_box16(self.handle, which, _ptr(out), n))
         return out
 
     def tree_nodes(self) -> np.ndarray:

@@ -29,7 +29,8 @@
 extern "C" {
 #endif
 
-#define HRT_ABI_VERSION 3 /* 3: two flattened forms (reference / fast), OP_BVH trees; hrt_scene_info, get_ops, get_box16 changed */
+#define HRT_ABI_VERSION 3 /* 3: two flattened forms (reference / fast), OP_BVH trees, scene library, progressive render;
+                             hrt_scene_info / hrt_scene_get_ops changed, hrt_scene_get_box16 and three render flags gone */
 
 typedef enum hrt_status {
     HRT_OK = 0,
@@ -164,9 +165,6 @@ int32_t hrt_scene_set_bvh_builder(hrt_scene*, int32_t builder);
 enum { HRT_STREAM_REFERENCE = 0, HRT_STREAM_FAST = 1 };
 /* Copies up to cap_ops 32-byte records of the chosen form; returns its record count. */
 int32_t hrt_scene_get_ops(const hrt_scene*, int32_t which, void* out, int32_t cap_ops);
-/* Copies up to cap_ops 16-byte companions of the records (six fp16 bounds rounded outward + w7, hrt_types.h Box16);
- * returns the record count. */
-int32_t hrt_scene_get_box16(const hrt_scene*, int32_t which, void* out, int32_t cap_ops);
 /* Copies up to cap_nodes 32-byte tree nodes of the fast form (hrt_types.h Bvh2Node); returns the node count. */
 int32_t hrt_scene_get_tree_nodes(const hrt_scene*, void* out, int32_t cap_nodes);
 /* DFS left->right leaf object ids of a hrt_bvh object; returns leaf count. */
@@ -190,15 +188,14 @@ int32_t hrt_camera_init(const hrt_camera_desc*, hrt_camera_state* out);
 enum {
     HRT_FLAG_REFERENCE_TRAVERSAL = 1, /* per-axis (loose) box test on every node, as aabb.rs:20-47        */
     HRT_FLAG_EXACT_MATH = 2,          /* no FMA contraction, IEEE div/sqrt, accurate libm (parity build) */
-    HRT_FLAG_SCHEDULER = 32,          /* render: force the in-register warp-scheduler kernel                      */
-    HRT_FLAG_POOL = 16,               /* render: warp-private shared-memory ray pool kernel                       */
-    HRT_FLAG_INTERPRETER = 8,         /* render: plain per-lane interpreter kernel instead of the warp scheduler  */
+    HRT_FLAG_INTERPRETER = 8,         /* render: the persistent kernel with every lane interpreting its own ray's records
+                                         (the plain form, kept as the baseline of the warp-uniform walk)        */
     HRT_FLAG_UNIFORM = 64,            /* render / hrt_trace_hits: the warp walks the op stream together (one record per
-                                         step for the lanes that are at it; every branch warp-uniform)          */
-    HRT_FLAG_WAVEFRONT = 128,         /* render: the wavefront render (default): path slots in device memory, one shade /
-                                         regenerate kernel and one trace kernel per ray segment                  */
-    HRT_FLAG_WARP_SCHEDULER = 4       /* hrt_trace_hits only: run through the render kernel's warp-level op-class
-                                         scheduler instead of the plain per-lane interpreter                */
+                                         step for the lanes that are at it; every branch warp-uniform).  Render: the
+                                         persistent kernel (default for small jobs and scenes without OP_BVH trees) */
+    HRT_FLAG_WAVEFRONT = 128          /* render: the wavefront render (default for big jobs on scenes with OP_BVH trees):
+                                         path slots in device memory, a few small kernels per ray segment, tree walks
+                                         compacted over the whole wave                                           */
 };
 typedef struct hrt_render_desc {
     int32_t width, height;

@@ -104,24 +104,6 @@ def test_hit_records_tight_boxes_same_result(pkg, orc, built, name):
 
 
 @pytest.mark.parametrize("name", ALL_SCENES)
-def test_hit_records_through_warp_scheduler(pkg, orc, built, name):
-    """The render kernel does not run the plain per-lane interpreter but a warp-level op-class scheduler (hrt_machine.cuh).
-    HRT_FLAG_WARP_SCHEDULER pushes the same explicit rays through that control flow: results must be bit-identical."""
-    N = pkg.native
-    spec, gb, ob, _, _ = built(name)
-    rays = _ray_set(pkg, orc, spec, ob, seed=29)[:-7]  # ragged tail: not a multiple of the warp size
-    xi = np.random.default_rng(4).random(len(rays), dtype=np.float32)
-    want = ob.trace_hits(rays, xi)
-    got = gb.trace_hits(rays, xi, flags=N.HRT_FLAG_EXACT_MATH | N.HRT_FLAG_WARP_SCHEDULER)
-    _compare_hits(got, want, exact=True, what=f"{name}/exact+scheduler")
-    plain = gb.trace_hits(rays, xi, flags=N.HRT_FLAG_EXACT_MATH)
-    assert plain.tobytes() == got.tobytes()
-    fast_plain = gb.trace_hits(rays, xi, flags=0)
-    fast_sched = gb.trace_hits(rays, xi, flags=N.HRT_FLAG_WARP_SCHEDULER)
-    assert fast_plain.tobytes() == fast_sched.tobytes()
-
-
-@pytest.mark.parametrize("name", ALL_SCENES)
 def test_hit_records_through_warp_uniform_walk(pkg, orc, built, name):
     """HRT_FLAG_UNIFORM: the 32 rays of a warp walk the op stream together (traverse_uniform<>, hrt_device.cuh), every step
     executing the record at the smallest pc for the lanes that are at it.  Per ray the visit order and the arithmetic are
@@ -400,16 +382,16 @@ def test_render_conventions_and_slices(pkg, orc, built):
 
 @pytest.mark.parametrize("name", ["random", "cornell-smoke", "final"])
 def test_render_kernel_variants_agree(pkg, orc, built, name):
-    """The three render kernels (shared-memory ray pool, in-register warp scheduler, plain interpreter) trace the SAME
-    paths — same Philox streams, same per-ray traversal order — so their accumulators agree up to f32 summation order and
+    """The render implementations — the wavefront render (tree walks in their own compacted stage, ahead of the stream
+    walk), the persistent kernel with the warp-uniform walk, the persistent kernel with the plain per-lane interpreter —
+    on the fast form of the stream (OP_BVH trees) and on the reference form with the reference's own box test on every
+    node, all trace the SAME paths: same Philox streams, same hits.  Their accumulators agree up to summation order and
     their ray counts are identical."""
     N = pkg.native
     spec, gb, ob, _, _ = built(name)
     outs = []
-    # the last entry drives the pool kernel's box loop through the 32-byte records (reference test on every box) instead
-    # of the fp16 table in shared memory: same hits, so the same paths
-    for flag in (N.HRT_FLAG_WAVEFRONT, N.HRT_FLAG_POOL, N.HRT_FLAG_SCHEDULER, N.HRT_FLAG_INTERPRETER, N.HRT_FLAG_UNIFORM,
-                 N.HRT_FLAG_POOL | N.HRT_FLAG_REFERENCE_TRAVERSAL):
+    for flag in (N.HRT_FLAG_WAVEFRONT, N.HRT_FLAG_UNIFORM, N.HRT_FLAG_INTERPRETER, N.HRT_FLAG_WAVEFRONT | N.HRT_FLAG_REFERENCE_TRAVERSAL,
+                 N.HRT_FLAG_UNIFORM | N.HRT_FLAG_REFERENCE_TRAVERSAL):
         acc, st = gb.render(spec.camera, 72, 48, 160, 50, spec.background, seed=31, resolve=False, flags=flag)
         outs.append((np.nan_to_num(acc[..., :3]), st.rays, st.paths))
     assert len({o[1] for o in outs}) == 1 and {o[2] for o in outs} == {72 * 48 * 160}
@@ -473,8 +455,7 @@ def test_fast_form_trees_same_hits_and_same_paths_on_gpu(pkg, orc, built, name):
     rays = _ray_set(pkg, orc, spec, ob, n_cam=4000, n_sec=8000, seed=37)
     xi = np.random.default_rng(5).random(len(rays), dtype=np.float32)
     want = ob.trace_hits(rays, xi)
-    for flags, what in ((N.HRT_FLAG_EXACT_MATH, "per-lane"), (N.HRT_FLAG_EXACT_MATH | N.HRT_FLAG_UNIFORM, "uniform"),
-                        (N.HRT_FLAG_EXACT_MATH | N.HRT_FLAG_WARP_SCHEDULER, "scheduler")):
+    for flags, what in ((N.HRT_FLAG_EXACT_MATH, "per-lane"), (N.HRT_FLAG_EXACT_MATH | N.HRT_FLAG_UNIFORM, "uniform")):
         _compare_hits(gb.trace_hits(rays, xi, flags=flags), want, exact=True, what=f"{name}/fast form/{what}")
     a, sa = gb.render(spec.camera, 64, 40, 160, 50, spec.background, seed=17, resolve=False, flags=N.HRT_FLAG_EXACT_MATH)
     b, sb = gb.render(spec.camera, 64, 40, 160, 50, spec.background, seed=17, resolve=False,

@@ -132,48 +132,43 @@ def test_final_scene_stream(pkg):
     assert i.time_min == 0.0 and i.time_max == 1.0
 
 
-@pytest.mark.parametrize("name", ["random", "cornell", "final"])
-def test_box16_companion_is_outward_and_tight(pkg, name):
-    """hrt_types.h Box16: every sound box is carried in fp16 rounded OUTWARD by less than one fp16 step; loose boxes keep
-    their opcode (-> 32-byte record); every record keeps its w7."""
-    spec = pkg.make_scene(name, 3)
-    gb = pkg.HrtBackend()
-    pkg.scene.emit(spec.world, gb)
-    ops, b16 = gb.ops(), gb.box16()
-    assert len(ops) == len(b16)
-    w7 = b16[:, 6].astype(np.uint32) | (b16[:, 7].astype(np.uint32) << 16)
-    assert np.array_equal(w7, ops[:, 7])
-    tight = np.where((ops[:, 7] & 0xFF) == 0x10)[0]
-    assert len(tight) > 0
-    mn = ops[tight, 0:3].view(np.float32)
-    mx = ops[tight, 4:7].view(np.float32)
-    h = b16[tight, 0:6].view(np.float16)
-    lo, hi = h[:, 0:3], h[:, 3:6]
-    assert np.all(lo.astype(np.float32) <= mn) and np.all(hi.astype(np.float32) >= mx)
-    # tight: one fp16 step inward would cut into the box
-    assert np.all(np.nextafter(lo, np.float16(np.inf)).astype(np.float32) > mn)
-    assert np.all(np.nextafter(hi, np.float16(-np.inf)).astype(np.float32) < mx)
-
-
-def test_box16_directed_rounding_extremes(pkg):
-    """Bounds outside fp16's range round to +-inf / the largest finite on the safe side; tiny bounds to subnormals."""
-    S = pkg.scene
+def test_tree_boxes_directed_rounding_extremes(pkg):
+    """OP_BVH tree nodes carry their children's boxes in fp16 rounded OUTWARD (hrt_types.h Bvh2Node): by less than one
+    fp16 step where fp16 can follow, to +-inf / the largest finite on the safe side beyond its range, to subnormals for
+    tiny bounds.  (Structure and containment on the real scenes: tests/test_stream_interpreter.py.)"""
+    S, N = pkg.scene, pkg.native
     gb = pkg.HrtBackend()
     m = S.Lambertian(S.SolidColor((0.5, 0.5, 0.5)))
-    world = S.BvhNode([S.Sphere((0.0, -100000.0, 0.0), 100000.0, m), S.Sphere((1e-6, 1e-6, 1e-6), 3e-7, m),
-                       S.Sphere((70000.0, 0.0, 0.0), 1.0, m)], 0.0, 1.0)
+    spheres = [((0.0, -100000.0, 0.0), 100000.0), ((1e-6, 1e-6, 1e-6), 3e-7), ((70000.0, 0.0, 0.0), 1.0), ((3.0, 4.0, 5.0), 0.7),
+               ((-30.3, 1.1, 7.7), 2.2)]
+    world = S.BvhNode([S.Sphere(c, r, m) for c, r in spheres], 0.0, 1.0)
     S.emit(world, gb)
-    ops, b16 = gb.ops(), gb.box16()
-    tight = np.where((ops[:, 7] & 0xFF) == 0x10)[0]
-    mn = ops[tight, 0:3].view(np.float32)
-    mx = ops[tight, 4:7].view(np.float32)
-    h = b16[tight, 0:6].view(np.float16).astype(np.float32)
-    assert np.all(h[:, 0:3] <= mn) and np.all(h[:, 3:6] >= mx)
-    assert np.isneginf(h[:, 0:3]).any() and np.isposinf(h[:, 3:6]).any()
-    # the far sphere's min.x (69999) stays finite: the largest finite fp16 is below it
-    assert (h[:, 0] == 65504.0).any()
-    small = np.abs(mn) < 1e-5
-    assert small.any() and np.all(np.abs(h[:, 0:3][small]) < 1e-5)
+    assert gb.info().n_bvh_trees == 1 and gb.info().n_tree_nodes == len(spheres) - 1
+    ops, nodes = gb.ops(N.HRT_STREAM_FAST), gb.tree_nodes()
+    f = ops.view(np.float32)
+    boxes = nodes[:, [0, 1, 2, 3, 4, 5, 8, 9, 10, 11, 12, 13]].copy().view(np.float16)
+    links = nodes.view(np.int32)[:, [3, 7]]
+    seen = 0
+    for n in range(len(nodes)):
+        for side in (0, 1):
+            ref = int(links[n, side])
+            if ref >= 0:
+                continue
+            pc = ~ref
+            c, r = f[pc, 0:3], f[pc, 3]
+            mn, mx = c - r, c + r  # sphere.rs:77-83
+            lo, hi = boxes[n, 6 * side:6 * side + 3], boxes[n, 6 * side + 3:6 * side + 6]
+            assert np.all(lo.astype(np.float32) <= mn) and np.all(hi.astype(np.float32) >= mx)
+            fin = np.isfinite(lo)
+            assert np.all(np.nextafter(lo[fin], np.float16(np.inf)).astype(np.float32) > mn[fin])  # one step inward cuts in
+            fin = np.isfinite(hi)
+            assert np.all(np.nextafter(hi[fin], np.float16(-np.inf)).astype(np.float32) < mx[fin])
+            seen += 1
+    assert seen == len(spheres)
+    h = boxes.astype(np.float32)
+    assert np.isneginf(h).any() and np.isposinf(h).any()  # the r = 1e5 sphere
+    assert (h == 65504.0).any()                            # min.x = 69999 of the far sphere: the largest finite fp16 is below it
+    assert ((np.abs(h) < 1e-5) & (h != 0)).any()           # the tiny sphere: subnormals
 
 
 def test_camera_init_matches_oracle(pkg, orc):

@@ -8,7 +8,7 @@ def _stream(pkg, spec):
     b = pkg.HrtBackend()
     e = pkg.scene.emit(spec.world, b)
     i = b.info()
-    return b.ops(), b.box16(), (i.n_ops, i.n_materials, i.n_textures, i.n_noise_tables, i.n_images, i.n_media, i.n_contexts), e.root
+    return b.ops(), b.ops(1), b.tree_nodes(), (i.n_ops, i.n_materials, i.n_textures, i.n_noise_tables, i.n_images, i.n_media, i.n_contexts), e.root
 
 
 @pytest.mark.parametrize("name", ["random", "two-spheres", "two-perlin-spheres", "earth", "simple-light", "cornell",
@@ -23,10 +23,10 @@ def test_round_trip_is_bit_identical(pkg, tmp_path, name):
     assert back.camera == spec.camera or all(
         np.allclose(getattr(back.camera, f), getattr(spec.camera, f), rtol=0, atol=0) for f in
         ("look_from", "look_at", "fov", "aperture", "focus_dist", "time_0", "time_1"))
-    ops0, b0, info0, root0 = _stream(pkg, spec)
-    ops1, b1, info1, root1 = _stream(pkg, back)
+    ops0, fast0, nodes0, info0, root0 = _stream(pkg, spec)
+    ops1, fast1, nodes1, info1, root1 = _stream(pkg, back)
     assert info0 == info1 and root0 == root1  # same sharing of materials / textures, same id allocation
-    assert np.array_equal(ops0, ops1) and np.array_equal(b0, b1)
+    assert np.array_equal(ops0, ops1) and np.array_equal(fast0, fast1) and np.array_equal(nodes0, nodes1)
 
 
 def test_second_generation_file_equals_first(pkg, tmp_path):

@@ -2,7 +2,7 @@
 # All BASELINE configs on one GPU, CPU oracle timed beside each (run under gpurun); JSON lines -> gpurun_out/bench_all.jsonl
 out=gpurun_out/bench_all.jsonl
 : > $out
-for cfg in C1 C2a C2b C3 C4 C5; do
+for cfg in C1 C2a C2b C3 C4; do  # (C5 is the default bench line)
   python bench.py --config $cfg --steps 2 --warmup 3 --cpu-seconds 10 2>/dev/null | tail -1 >> $out
 done
 python - <<'PY'
