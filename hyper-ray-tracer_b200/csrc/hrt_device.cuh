@@ -750,6 +750,10 @@ __device__ __noinline__ bool medium_sample(const DeviceScene& S, float4 A, float
 // `pre` / `n_pre`: results of the first n_pre OP_BVH trees of the stream walked AHEAD for this ray over [tmin, +inf)
 // (the wavefront render's tree stage): {t, code} with code = kPreNone: no hit, else leaf pc | side << 24.
 constexpr int kPreNone = -1;
+// kKeepSpace: keep the ray space entered last in registers (11 of them) — what the persistent kernel wants (a
+// ConstantMedium enters its boundary's space twice per ray); the wavefront's trace kernel runs at 80 registers and is
+// better off recomputing.
+template <bool kKeepSpace = true>
 __device__ __forceinline__ bool traverse_uniform(const DeviceScene& S, const int pc_begin, const int pc_end, const bool active,
                                                  const Ray& world, Ray cur, int cur_ctx, const float tmin_world, float& closest_io,
                                                  Best& best, const bool reference_boxes, const MediumXi& xi,
@@ -757,6 +761,12 @@ __device__ __forceinline__ bool traverse_uniform(const DeviceScene& S, const int
     const unsigned kAll = 0xffffffffu;
     int pc = active ? pc_begin : pc_end;
     RayK k = make_rayk(cur);
+    const int entry_ctx = cur_ctx;  // the ray space the walk starts in (the world's, for a whole stream)
+    const Ray entry_ray = cur;
+    const RayK entry_k = k;
+    int kept_ctx = -1;              // the other ray space entered last
+    Ray kept_ray = cur;
+    RayK kept_k = k;
     float closest = closest_io;
     float tmin = tmin_world;  // t_min of the query this lane is in
     bool hitf = false;        // the query this lane is in has hit something
@@ -867,10 +877,21 @@ __device__ __forceinline__ bool traverse_uniform(const DeviceScene& S, const int
                 break;
             }
             case OP_TRANSLATE: case OP_ROTATE: case OP_POP: {
+                // A ray space is a pure function of (world ray, context): leaving to the world space restores the world
+                // ray, and the space entered last is kept — a ConstantMedium enters its boundary's space twice per ray
+                // (two queries), every Translation / Rotation is left again right after its child.
                 if (me) {
                     cur_ctx = __float_as_int(A.w);
-                    cur = ray_in_ctx(S, world, cur_ctx);
-                    k = make_rayk(cur);
+                    if (cur_ctx == entry_ctx) {
+                        cur = entry_ray;
+                        k = kKeepSpace ? entry_k : make_rayk(cur);
+                    } else if (kKeepSpace && cur_ctx == kept_ctx) {
+                        cur = kept_ray; k = kept_k;
+                    } else {
+                        cur = ray_in_ctx(S, world, cur_ctx);
+                        k = make_rayk(cur);
+                        if (kKeepSpace) { kept_ctx = cur_ctx; kept_ray = cur; kept_k = k; }
+                    }
                     const int run = (int)(w7 >> 8);
                     pc = upc + (run > 0 ? run : 1);
                 }

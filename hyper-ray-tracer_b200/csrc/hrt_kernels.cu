@@ -244,6 +244,9 @@ __global__ void __launch_bounds__(kBlock, 2) render_interp_kernel(const __grid_c
 // each a fraction of the code, each run by the whole GPU at once, so the instruction caches hold what is running.
 // Same Philox streams and arithmetic as the other kernels: the same paths, summed in a different order.
 constexpr int kWaveBlock = 256;
+#ifndef HRT_TRACE_BLOCKS
+#define HRT_TRACE_BLOCKS 3
+#endif
 #ifndef HRT_LOGIC_BLOCKS
 #define HRT_LOGIC_BLOCKS 3
 #endif
@@ -300,7 +303,7 @@ __global__ void __launch_bounds__(256) wave_finish_kernel(double* __restrict__ a
 static_assert(WF_WORDS == hrt::kWaveStateWords, "wave state layout");
 #define WST(f, slot) P.st[(size_t)(f) * P.n_slots + (slot)]
 
-__global__ void __launch_bounds__(kWaveBlock, 3) wave_trace_kernel(const __grid_constant__ WaveParams P) {
+__global__ void __launch_bounds__(kWaveBlock, HRT_TRACE_BLOCKS) wave_trace_kernel(const __grid_constant__ WaveParams P) {
     const int slot = blockIdx.x * kWaveBlock + threadIdx.x;
     const bool in_range = slot < P.n_slots;
     const int bounce = in_range ? __float_as_int(WST(WF_BOUNCE, slot)) : -1;
@@ -321,8 +324,8 @@ __global__ void __launch_bounds__(kWaveBlock, 3) wave_trace_kernel(const __grid_
     Best best;
     best.pc = -1; best.t = 0.0f; best.face = 0; best.ctx = 0;
     float closest = CUDART_INF_F;
-    traverse_uniform(P.S, 0, P.S.n_ops, active, ray, ray, 0, 0.001f, closest, best, P.reference_boxes != 0, xi,
-                     P.pre_res + (size_t)(in_range ? slot : 0) * kMaxPreTrees, P.n_pre);
+    traverse_uniform<false>(P.S, 0, P.S.n_ops, active, ray, ray, 0, 0.001f, closest, best, P.reference_boxes != 0, xi,
+                            P.pre_res + (size_t)(in_range ? slot : 0) * kMaxPreTrees, P.n_pre);
     if (blockIdx.x == 0 && threadIdx.x < hrt::kWaveCounters) P.tq_count[threadIdx.x] = 0;  // the queues are consumed
     if (active) {
         WST(WF_HIT_T, slot) = best.t;
