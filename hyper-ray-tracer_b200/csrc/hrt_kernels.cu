@@ -480,13 +480,27 @@ __global__ void __launch_bounds__(kWaveBlock, HRT_LOGIC_BLOCKS) wave_logic_kerne
         }
     }
     // ---- free slots start the next camera samples (application.rs:443-448), drawn from one global index ----
+    // ONE atomic per block: every warp of the GPU draws from the same counter, and a returning atomic per warp on one
+    // address was 38 % of this kernel's stall samples (profiles/r02_wave_logic_kernel_by_function.txt)
+    __shared__ int sh_cnt[kWaveBlock / 32];
+    __shared__ unsigned long long sh_base64;
+    __shared__ int sh_base32;
+    const int warp = threadIdx.x >> 5;
     const bool is_free = in_range && bounce < 0;
     const unsigned need = __ballot_sync(kFull, is_free);
+    if (lane == 0) sh_cnt[warp] = __popc(need);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+#pragma unroll
+        for (int ww = 0; ww < kWaveBlock / 32; ++ww) tot += sh_cnt[ww];
+        sh_base64 = tot ? atomicAdd(P.counters, (unsigned long long)tot) : 0ULL;
+    }
+    __syncthreads();
     bool started = false;
     if (need) {
-        unsigned long long base = 0;
-        if (lane == __ffs(need) - 1) base = atomicAdd(P.counters, (unsigned long long)__popc(need));
-        base = __shfl_sync(kFull, base, __ffs(need) - 1);
+        unsigned long long base = sh_base64;
+        for (int ww = 0; ww < warp; ++ww) base += (unsigned long long)sh_cnt[ww];
         const unsigned long long idx = base + (unsigned long long)__popc(need & ((1u << lane) - 1u));
         if (is_free && idx < P.total_paths) {
             key.pixel = (uint32_t)(idx % (unsigned long long)P.n_pixels);
@@ -543,15 +557,22 @@ __global__ void __launch_bounds__(kWaveBlock, HRT_LOGIC_BLOCKS) wave_logic_kerne
             const bool all_nan = (r.o.x != r.o.x && r.o.y != r.o.y && r.o.z != r.o.z) || (r.d.x != r.d.x && r.d.y != r.d.y && r.d.z != r.d.z);
             const bool hit = live && !all_nan && box_hit_tight(mn, mx, r, k, 0.001f, CUDART_INF_F);
             const unsigned m = __ballot_sync(kFull, hit);
-            if (m) {
-                int at = 0;
-                if (lane == __ffs(m) - 1) at = atomicAdd(P.tq_count + tree, __popc(m));
-                at = __shfl_sync(kFull, at, __ffs(m) - 1) + __popc(m & ((1u << lane) - 1u));
-                if (hit) {
-                    float4* q = P.tq + 2 * ((size_t)tree * P.n_slots + at);
-                    q[0] = make_float4(r.o.x, r.o.y, r.o.z, r.time);
-                    q[1] = make_float4(r.d.x, r.d.y, r.d.z, __int_as_float(slot));
-                }
+            __syncthreads();  // (sh_cnt / sh_base32 of the previous round are read)
+            if (lane == 0) sh_cnt[warp] = __popc(m);
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                int tot = 0;
+#pragma unroll
+                for (int ww = 0; ww < kWaveBlock / 32; ++ww) tot += sh_cnt[ww];
+                sh_base32 = tot ? atomicAdd(P.tq_count + tree, tot) : 0;
+            }
+            __syncthreads();
+            if (hit) {
+                int at = sh_base32 + __popc(m & ((1u << lane) - 1u));
+                for (int ww = 0; ww < warp; ++ww) at += sh_cnt[ww];
+                float4* q = P.tq + 2 * ((size_t)tree * P.n_slots + at);
+                q[0] = make_float4(r.o.x, r.o.y, r.o.z, r.time);
+                q[1] = make_float4(r.d.x, r.d.y, r.d.z, __int_as_float(slot));
             }
             if (live)
                 P.pre_res[(size_t)slot * kMaxPreTrees + tree] =
