@@ -645,7 +645,7 @@ __device__ __forceinline__ bool traverse(const DeviceScene& S, int pc, const int
                 pc = (int)(w7 >> 8);
                 break;
             }
-            case OP_MEDIUM: case OP_MEDIUM_SPHERE: {
+            case OP_MEDIUM: case OP_MEDIUM_SPHERE: case OP_MEDIUM_CUBOID: {
                 const int end = (int)(w7 >> 8);
                 if (!kInner) {
                     // constant_medium.rs:34-76
@@ -897,9 +897,46 @@ __device__ __forceinline__ bool traverse_uniform(const DeviceScene& S, const int
                 }
                 break;
             }
-            case OP_MEDIUM: case OP_MEDIUM_SPHERE: {  // constant_medium.rs:34-76; media do not nest, so mode == 0 here
+            case OP_MEDIUM: case OP_MEDIUM_SPHERE: case OP_MEDIUM_CUBOID: {  // constant_medium.rs:34-76; media do not nest: mode == 0
                 const int end = (int)(w7 >> 8);
                 bool generic = me;
+                if (opc == OP_MEDIUM_CUBOID) {
+                    // Boundary = one cuboid in its own ray space: both boundary queries here, with the very calls the
+                    // sub-stream walk would make (cuboid_test over (-inf, +inf), then over (t1 + 1e-4, +inf)) — one step
+                    // instead of two walks over push / cuboid / pop records.
+                    float4 P0, P1;
+                    load_op(S, upc + 1, P0, P1);
+                    const uint32_t first = __float_as_uint(P1.w);
+                    const bool pushed = (first & 0xffu) != OP_CUBOID;
+                    const int box_pc = upc + 1 + (pushed ? (int)(first >> 8) : 0);
+                    float4 C, D;
+                    load_op(S, box_pc, C, D);
+                    generic = false;
+                    if (me) {
+                        Ray r = cur;
+                        RayK kr = k;
+                        if (pushed) {
+                            const int target = __float_as_int(P0.w);
+                            if (kKeepSpace && target == kept_ctx) {
+                                r = kept_ray; kr = kept_k;
+                            } else {
+                                r = ray_in_ctx(S, world, target);
+                                kr = make_rayk(r);
+                                if (kKeepSpace) { kept_ctx = target; kept_ray = r; kept_k = kr; }
+                            }
+                        }
+                        float t1, t2;
+                        int face;
+                        if (cuboid_test(v3(C.x, C.y, C.z), v3(D.x, D.y, D.z), r, kr, -CUDART_INF_F, CUDART_INF_F, t1, face) && t1 == t1 &&
+                            cuboid_test(v3(C.x, C.y, C.z), v3(D.x, D.y, D.z), r, kr, t1 + 0.0001f, CUDART_INF_F, t2, face) && t2 == t2) {
+                            float tm;
+                            if (medium_sample(S, A, k.dd, t1, t2, tmin, closest, xi, tm)) {
+                                closest = tm; hitf = true;
+                                best.t = tm; best.pc = upc; best.face = 0; best.ctx = cur_ctx;
+                            }
+                        }
+                    }
+                }
                 if (opc == OP_MEDIUM_SPHERE) {
                     // Boundary = one plain sphere: both boundary queries in closed form with sphere_test's arithmetic
                     // (query 1 over (-inf, +inf) always takes the near root; query 2 over (t1 + 1e-4, +inf) takes the
@@ -1011,7 +1048,7 @@ __device__ __noinline__ void make_hit_record(const DeviceScene& S, const Ray& wo
         if (want_uv || (S.mats[h.mat].flags & MATF_NEEDS_UV)) sphere_uv(outward, h.u, h.v);
         set_face_normal(h, r.d, outward);
         h.prim = __float_as_int(B.y);
-    } else if (opc == OP_MEDIUM || opc == OP_MEDIUM_SPHERE) {  // constant_medium.rs:67-75
+    } else if (opc == OP_MEDIUM || opc == OP_MEDIUM_SPHERE || opc == OP_MEDIUM_CUBOID) {  // constant_medium.rs:67-75
         h.n = v3(0.0f, 0.0f, 0.0f);
         h.front_face = false;
         h.mat = __float_as_int(A.y);

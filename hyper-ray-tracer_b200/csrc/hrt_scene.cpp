@@ -408,7 +408,18 @@ struct Flattener {
                 if (pc() >= (1 << 24)) { error = "op stream longer than 2^24 records"; return false; }
                 {
                     const bool single_sphere = (pc() == at + 2) && ((f.ops[at + 1].u[7] & 0xffu) == OP_SPHERE);
-                    f.ops[at].u[7] = (single_sphere ? OP_MEDIUM_SPHERE : OP_MEDIUM) | ((uint32_t)pc() << 8);
+                    // [push x r] CUBOID [pop x r]: one cuboid in its own ray space (r = 0: bare)
+                    bool boxed = false;
+                    {
+                        auto opc = [&](int32_t i) { return f.ops[i].u[7] & 0xffu; };
+                        int32_t r = 0;
+                        while (at + 1 + r < pc() && (opc(at + 1 + r) == OP_TRANSLATE || opc(at + 1 + r) == OP_ROTATE)) ++r;
+                        if (pc() == at + 2 + 2 * r && opc(at + 1 + r) == OP_CUBOID) {
+                            boxed = true;
+                            for (int32_t i = 0; i < r; ++i) boxed = boxed && opc(at + 2 + r + i) == OP_POP;
+                        }
+                    }
+                    f.ops[at].u[7] = (single_sphere ? OP_MEDIUM_SPHERE : (boxed ? OP_MEDIUM_CUBOID : OP_MEDIUM)) | ((uint32_t)pc() << 8);
                 }
                 return true;
             }

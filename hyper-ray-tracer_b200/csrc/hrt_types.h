@@ -29,6 +29,8 @@ enum Opcode : uint32_t {
     OP_POP = 0x42,        // leave child ray space (restore context in w3)
     OP_MEDIUM = 0x43,
     OP_MEDIUM_SPHERE = 0x44,  // OP_MEDIUM whose boundary sub-stream is exactly one OP_SPHERE record (closed-form path)
+    OP_MEDIUM_CUBOID = 0x46,  // OP_MEDIUM whose boundary sub-stream is one OP_CUBOID, bare or inside one run of ray-space pushes
+                              // (Translation(Rotation(Cuboid)): the smoke blocks of Cornell-smoke) — both queries in one step
     OP_BVH = 0x45,            // a whole sound BvhNode as a binary tree of Bvh2Node records walked with a per-ray stack,
                               // nearer child first; its leaves are the primitive records [pc+1, end)
     OP_END = 0x50,

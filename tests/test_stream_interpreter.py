@@ -13,7 +13,7 @@ from conftest import build_both, make_rays
 
 OP_BOX, OP_BOX_LOOSE, OP_SPHERE, OP_MSPHERE = 0x10, 0x11, 0x20, 0x21
 OP_RECT_XY, OP_RECT_YZ, OP_RECT_ZX, OP_CUBOID = 0x30, 0x31, 0x32, 0x33
-OP_TRANSLATE, OP_ROTATE, OP_POP, OP_MEDIUM, OP_MEDIUM_SPHERE, OP_BVH, OP_END = 0x40, 0x41, 0x42, 0x43, 0x44, 0x45, 0x50
+OP_TRANSLATE, OP_ROTATE, OP_POP, OP_MEDIUM, OP_MEDIUM_SPHERE, OP_BVH, OP_MEDIUM_CUBOID, OP_END = 0x40, 0x41, 0x42, 0x43, 0x44, 0x45, 0x46, 0x50
 F = np.float32
 
 
@@ -251,7 +251,7 @@ def trace_stream(ops, rays, nodes=None, stats=None):
                     pc_of[idx] = pc + run
                     pc += 1
                     continue
-                elif op in (OP_MEDIUM, OP_MEDIUM_SPHERE):
+                elif op in (OP_MEDIUM, OP_MEDIUM_SPHERE, OP_MEDIUM_CUBOID):
                     pc_of[idx] = payload  # skip the boundary sub-stream
                     pc += 1
                     continue
@@ -321,7 +321,7 @@ def test_fast_form_finds_the_same_hits(pkg, orc, name):
     # the trees replace the box records of those BVHs: one root box + one OP_BVH record per tree instead of 2n-1 boxes
     kinds = fast_ops[:, 7] & 0xFF
     assert (kinds == OP_BVH).sum() == i.n_bvh_trees and i.n_fast_box_ops < i.n_box_ops // 10
-    for k in (OP_SPHERE, OP_MSPHERE, OP_CUBOID, OP_RECT_XY, OP_RECT_YZ, OP_RECT_ZX, OP_MEDIUM, OP_MEDIUM_SPHERE):
+    for k in (OP_SPHERE, OP_MSPHERE, OP_CUBOID, OP_RECT_XY, OP_RECT_YZ, OP_RECT_ZX, OP_MEDIUM, OP_MEDIUM_SPHERE, OP_MEDIUM_CUBOID):
         assert (kinds == k).sum() == ((ref_ops[:, 7] & 0xFF) == k).sum()
     rays = _rays(orc, ob, spec, n=700)
     want = ob.trace_hits(rays, np.full(len(rays), 0.5, dtype=np.float32))
@@ -333,6 +333,24 @@ def test_fast_form_finds_the_same_hits(pkg, orc, name):
     assert m.sum() > len(rays) // 10
     assert np.array_equal(prim[m], want["prim_id"][m]), (name, int((prim[m] != want["prim_id"][m]).sum()))
     assert np.allclose(t[m], want["t"][m], rtol=1e-5, atol=0)
+
+
+def test_medium_records_name_their_boundary_shape(pkg, orc):
+    """A ConstantMedium whose boundary is one plain sphere / one cuboid (bare or inside one run of ray-space pushes) is
+    flagged for the closed-form paths (hrt_types.h OP_MEDIUM_SPHERE / OP_MEDIUM_CUBOID); its sub-stream stays in place."""
+    kinds = lambda name: [int(x) & 0xFF for x in _both_forms(pkg, orc, pkg.make_scene(name, 1).world)[3][:, 7]]  # noqa: E731
+    smoke = kinds("cornell-smoke")
+    assert smoke.count(OP_MEDIUM_CUBOID) == 2 and smoke.count(OP_MEDIUM) == 0
+    i = smoke.index(OP_MEDIUM_CUBOID)
+    assert smoke[i + 1:i + 6] == [OP_TRANSLATE, OP_ROTATE, OP_CUBOID, OP_POP, OP_POP]
+    final = kinds("final")
+    assert final.count(OP_MEDIUM_SPHERE) == 2 and final.count(OP_MEDIUM) == 0 and final.count(OP_MEDIUM_CUBOID) == 0
+    S = pkg.scene
+    m = S.Lambertian(S.SolidColor((0.5, 0.5, 0.5)))
+    bare = S.ConstantMedium(S.Cuboid((0, 0, 0), (1, 1, 1), m), 0.5, S.SolidColor((1, 1, 1)))
+    lst = S.ConstantMedium(S.List([S.Cuboid((0, 0, 0), (1, 1, 1), m), S.Sphere((3, 0, 0), 1.0, m)]), 0.5, S.SolidColor((1, 1, 1)))
+    ks = [int(x) & 0xFF for x in _both_forms(pkg, orc, S.List([bare, lst]))[3][:, 7]]
+    assert ks.count(OP_MEDIUM_CUBOID) == 1 and ks.count(OP_MEDIUM) == 1  # a two-object boundary stays generic
 
 
 def test_tree_structure_is_well_formed(pkg, orc):
