@@ -727,6 +727,21 @@ __device__ __noinline__ bool medium_sample(const DeviceScene& S, float4 A, float
     return true;
 }
 
+// The two boundary queries of a ConstantMedium whose boundary is one cuboid (constant_medium.rs:37-38): (t1, t2), t2 = NaN
+// when either misses (or is NaN, which the walk of the sub-stream treats as a miss too).  Out of line: cold for every
+// scene without such a medium.
+__device__ __noinline__ float2 cuboid_boundary(float4 C, float4 D, Ray r, float4 kq) {
+    RayK k;
+    k.inv = v3(kq.x, kq.y, kq.z);
+    k.dd = kq.w;
+    float t1, t2;
+    int face;
+    if (cuboid_test(v3(C.x, C.y, C.z), v3(D.x, D.y, D.z), r, k, -CUDART_INF_F, CUDART_INF_F, t1, face) && t1 == t1 &&
+        cuboid_test(v3(C.x, C.y, C.z), v3(D.x, D.y, D.z), r, k, t1 + 0.0001f, CUDART_INF_F, t2, face))
+        return make_float2(t1, t2);
+    return make_float2(0.0f, CUDART_NAN_F);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Warp-uniform traversal of the op stream.
 //
@@ -925,12 +940,10 @@ __device__ __forceinline__ bool traverse_uniform(const DeviceScene& S, const int
                                 if (kKeepSpace) { kept_ctx = target; kept_ray = r; kept_k = kr; }
                             }
                         }
-                        float t1, t2;
-                        int face;
-                        if (cuboid_test(v3(C.x, C.y, C.z), v3(D.x, D.y, D.z), r, kr, -CUDART_INF_F, CUDART_INF_F, t1, face) && t1 == t1 &&
-                            cuboid_test(v3(C.x, C.y, C.z), v3(D.x, D.y, D.z), r, kr, t1 + 0.0001f, CUDART_INF_F, t2, face) && t2 == t2) {
+                        const float2 tt = cuboid_boundary(C, D, r, make_float4(kr.inv.x, kr.inv.y, kr.inv.z, kr.dd));
+                        if (tt.y == tt.y) {
                             float tm;
-                            if (medium_sample(S, A, k.dd, t1, t2, tmin, closest, xi, tm)) {
+                            if (medium_sample(S, A, k.dd, tt.x, tt.y, tmin, closest, xi, tm)) {
                                 closest = tm; hitf = true;
                                 best.t = tm; best.pc = upc; best.face = 0; best.ctx = cur_ctx;
                             }
