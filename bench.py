@@ -58,6 +58,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="frames of the e2e leg (default max(2, steps // 8))")
+    ap.add_argument("--single-process", action="store_true",
+                    help="N GPUs from ONE process through hrt_render_multi (one host thread per device, peers' accumulators summed "
+                         "over NVLink peer memory inside the resolve kernel) instead of torchrun + NCCL; prints the same line")
     return ap.parse_args()
 
 
@@ -190,6 +193,50 @@ def run_reference(args, scene_name, width, height, samples, depth):
                        "scene_seed": args.seed},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": last["cores"], "kind": "port", "sample": last["sample"]},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ---- single-process multi-GPU arm (hrt_render_multi) ------------------------------------------------------------------
+def run_single_process(args, scene_name, width, height, samples, depth):
+    """The shape the reference needs (it is one process): devices 0..N-1 driven by hrt_render_multi.  Every step is the
+    whole public call with HOST output, so `value` and `e2e` are the same measurement (host wall clock around blocking
+    calls; each device's render is CUDA-event-timed inside and reported as kernel_ms = the slowest device)."""
+    pkg = graft.load_package()
+    n = args.gpus
+    if pkg.native.device_count() < n:
+        raise SystemExit(f"bench.py: {n} CUDA devices needed, {pkg.native.device_count()} visible")
+    spec = pkg.make_scene(scene_name, args.seed)
+    r = pkg.renderer.Renderer(spec, device=0)
+    devs = list(range(n))
+    out = np.empty((height, width, 4), dtype=np.float32)
+    total_paths = width * height * samples
+    for i in range(args.warmup):
+        r.backend.render_multi(devs, spec.camera, width, height, samples, depth, spec.background, seed=1000 + i, out=out)
+    sampler = ClockSampler(0)
+    sampler.start()
+    kernel_ms, launches = [], 0
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        _, st = r.backend.render_multi(devs, spec.camera, width, height, samples, depth, spec.background, seed=i, out=out)
+        kernel_ms.append(st.kernel_ms)
+        launches += st.launches
+    ms_per_step = (time.perf_counter() - t0) * 1e3 / args.steps
+    clocks = sampler.stop()
+    value = total_paths / (ms_per_step * 1e-3) / 1e6
+    chk = 16 * n
+    a, _ = r.backend.render_multi(devs, spec.camera, width, height, chk, depth, spec.background, seed=4242)
+    b, _ = r.render(width, height, chk, depth, seed=4242)
+    fin = np.isfinite(a).all(axis=-1) & np.isfinite(b).all(axis=-1)
+    parity = bool(np.allclose(a[fin], b[fin], rtol=3e-4, atol=3e-4))
+    line = {"metric": metric_name(args.config, scene_name, width, height), "value": value, "unit": UNIT, "n_gpus": n, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.config}: {scene_name} {width}x{height}, {samples} spp, depth {depth}", "scene_seed": args.seed,
+                       "bvh": args.bvh, "parallelism": f"single process, hrt_render_multi over {n} devices (peer-memory reduce + resolve)"},
+            "kernel_ms": float(np.mean(kernel_ms)), "gpu_launches": int(launches), "clocks": clocks,
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": width * height * 16, "ms_per_step": ms_per_step,
+                    "api": "hrt_render_multi (host RGBA-f32 out); scene tables resident"},
+            "parity_vs_n1": parity}
     print(json.dumps(line), flush=True)
 
 
@@ -373,6 +420,8 @@ def main():
         samples = args.samples
     if args.impl == "reference":
         run_reference(args, scene_name, width, height, samples, depth)
+    elif args.single_process:
+        run_single_process(args, scene_name, width, height, samples, depth)
     else:
         run_b200(args, scene_name, width, height, samples, depth)
 

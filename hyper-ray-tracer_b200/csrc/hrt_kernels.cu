@@ -858,7 +858,7 @@ static CameraK to_camera(const hrt_camera_state& c) {
     return k;
 }
 
-// Host loop of the wavefront render.  The path slots are split into kWaveParts partitions, each iterating on its own
+// Host loop of the wavefront render.  The path slots are split into partitions (4; HRT_WAVE_PARTS), each iterating on its own
 // stream: every iteration ends with the slowest walk of its wave (a ray with a NaN component passes every box test and
 // visits a whole 2000-node tree: ~0.8 ms against ~0.1 ms for the rest of the wave, and a million rays nearly always hold
 // one), and while one partition sits in such a tail the others keep the SMs busy.  All partitions draw camera samples
@@ -887,9 +887,10 @@ cudaError_t launch_render_wave(hrt::RenderLaunch& L, hrt::WaveBuffers& W, int nu
     if (const char* env = getenv("HRT_TREE_INNER")) P.tree_inner_min = std::max(1, std::min(33, atoi(env)));
     P.live_out = nullptr;
     // slots per partition: all of them for a big job, no more than the job has paths for a small one
-    int parts = hrt::kWaveParts;
+    int parts = 4;
     if (const char* env = getenv("HRT_WAVE_PARTS")) parts = std::max(1, std::min(hrt::kWaveParts, atoi(env)));
-    const int cap = W.n_slots / hrt::kWaveParts / kWaveBlock * kWaveBlock;  // the buffers are laid out for kWaveParts partitions
+    // the buffers are split evenly among the partitions in use; slot ids share a word with a texture id (wave_noise_kernel)
+    const int cap = std::min(W.n_slots / parts, 1 << 22) / kWaveBlock * kWaveBlock;
     const unsigned long long share = (P.total_paths + parts - 1) / parts;
     const unsigned long long want = (share + kWaveBlock - 1) / kWaveBlock * kWaveBlock;
     P.n_slots = (int)std::min<unsigned long long>((unsigned long long)cap, std::max<unsigned long long>(want, kWaveBlock));
@@ -901,7 +902,7 @@ cudaError_t launch_render_wave(hrt::RenderLaunch& L, hrt::WaveBuffers& W, int nu
     if ((e = cudaMemsetAsync(W.acc64, 0, sizeof(double) * 4 * (size_t)P.n_pixels, stream)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(W.tq_count, 0, sizeof(int) * hrt::kWaveCounters * hrt::kWaveParts, stream)) != cudaSuccess) return e;
     // every slot starts free
-    if ((e = cudaMemsetAsync(W.state, 0xff, sizeof(float) * (size_t)WF_WORDS * (size_t)cap * hrt::kWaveParts, stream)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(W.state, 0xff, sizeof(float) * (size_t)WF_WORDS * (size_t)cap * parts, stream)) != cudaSuccess) return e;
     if ((e = cudaEventRecord(W.ev_begin, stream)) != cudaSuccess) return e;
     // persistent tree-walk warps: as many blocks as are resident at once
     int tree_blocks_per_sm = 1;

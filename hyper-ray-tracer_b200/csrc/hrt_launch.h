@@ -42,7 +42,7 @@ struct RenderLaunch {
 };
 
 // Device buffers of the wavefront render (hrt_kernels.cu launch_render_wave), owned per device.
-constexpr int kWaveParts = 4;  // partitions of the path slots, each iterating on its own stream
+constexpr int kWaveParts = 8;  // most partitions of the path slots, each iterating on its own stream (default 4 in use)
 constexpr int kWaveCounters = 8;  // queue counters per partition (2 per pre-walked tree, 1 for deferred noise, padding)
 struct WaveBuffers {
     float* state = nullptr;   // [kWaveParts][WF_WORDS][n_slots / kWaveParts]
@@ -55,9 +55,9 @@ struct WaveBuffers {
     size_t acc_pixels = 0;
     int* d_live = nullptr;    // per partition: 2 counters
     int* h_live = nullptr;    // pinned mirror
-    cudaStream_t streams[kWaveParts] = {nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t ev[2 * kWaveParts] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t ev_end[kWaveParts] = {nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t streams[kWaveParts] = {};
+    cudaEvent_t ev[2 * kWaveParts] = {};
+    cudaEvent_t ev_end[kWaveParts] = {};
     cudaEvent_t ev_begin = nullptr;
 };
 constexpr int kWaveStateWords = 16;  // == WF_WORDS

@@ -429,6 +429,35 @@ def test_progressive_delivery_converges_to_the_full_render(pkg, orc, built):
     assert np.allclose(np.nan_to_num(frames3[-1][1]), np.nan_to_num(frames[1][1]), rtol=2e-4, atol=2e-4)
 
 
+def test_renders_in_flight_on_two_streams_do_not_disturb_each_other(pkg, orc, built):
+    """hrt_render_accum_device returns before the persistent kernel finishes; every launch owns its counter block (work
+    cursor, ray / path counts), so two renders of ONE scene on ONE device may be in flight on different streams.  Both must
+    equal the renders done one after the other."""
+    torch = pytest.importorskip("torch")
+    spec, gb, ob, _, _ = built("cornell")
+    w, h, spp = 96, 96, 192
+    dev = torch.device("cuda", 0)
+
+    def render(seed, stream):
+        acc = torch.zeros((h, w, 4), dtype=torch.float32, device=dev)
+        with torch.cuda.stream(stream):
+            gb.render_accum_device(spec.camera, w, h, spp, 50, spec.background, seed, 0, acc.data_ptr(), stream.cuda_stream,
+                                   flags=pkg.native.HRT_FLAG_UNIFORM)
+        return acc
+    s0 = torch.cuda.Stream(device=dev)
+    alone = []
+    for seed in (11, 12):
+        alone.append(render(seed, s0))
+        s0.synchronize()
+    s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    for _ in range(3):  # several rounds: an overlap that matters is a matter of timing
+        a, b = render(11, s1), render(12, s2)
+        torch.cuda.synchronize()
+        for got, want in ((a, alone[0]), (b, alone[1])):
+            assert torch.all(got[..., 3] == spp)
+            assert torch.allclose(torch.nan_to_num(got), torch.nan_to_num(want), rtol=2e-4, atol=2e-4)
+
+
 def test_exact_and_production_renders_agree(pkg, orc, built):
     """Same seed, same Philox streams: the parity build and the production build trace the same paths except where an
     ulp flips a decision; the images must agree far inside the noise."""
