@@ -33,8 +33,8 @@ struct LaunchSlot {
 struct DeviceState {
     int device = -1;
     int num_sms = 0;
-    // [0] reference form, [1] fast form of the flattened scene (hrt_scene.hpp)
-    void* d_ops[2] = {nullptr, nullptr};
+    // [0] reference form, [1] fast form of the flattened scene (hrt_scene.hpp), [2] the fast form's wave variant (ops only)
+    void* d_ops[3] = {nullptr, nullptr, nullptr};
     void* d_ctxs[2] = {nullptr, nullptr};
     void* d_nodes = nullptr;
     void* d_mats = nullptr;
@@ -51,7 +51,7 @@ struct DeviceState {
     float* d_rgba = nullptr;
     size_t accum_pixels = 0;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    DeviceSceneHost view[2];
+    DeviceSceneHost view[3];
 };
 
 void release_device_state(DeviceState* d) {
@@ -61,6 +61,7 @@ void release_device_state(DeviceState* d) {
         for (auto t : d->texobjs) cudaDestroyTextureObject(t);
         for (auto a : d->arrays) cudaFreeArray(a);
         for (int k = 0; k < 2; ++k) { cudaFree(d->d_ops[k]); cudaFree(d->d_ctxs[k]); }
+        cudaFree(d->d_ops[2]);
         cudaFree(d->d_nodes); cudaFree(d->d_mats); cudaFree(d->d_texs); cudaFree(d->d_noise);
         cudaFree(d->d_counters); cudaFree(d->d_accum); cudaFree(d->d_rgba);
         for (auto e : d->ev) if (e) cudaEventDestroy(e);
@@ -113,7 +114,7 @@ static int32_t ensure_wave(DeviceState* d, size_t pixels) {
         d->wave.acc_pixels = pixels;
     }
     if (d->wave.state) return HRT_OK;
-    int n = 4 << 20;  // path slots in flight, all partitions together (64 B of state + 80 B of tree-stage buffers each)
+    int n = 8 << 20;  // most path slots in flight, all partitions together (64 B of state + 96 B of stage buffers each: 1.3 GB)
     if (const char* env = getenv("HRT_WAVE_SLOTS")) n = atoi(env);
     if (n < 256 * kWaveParts) n = 256 * kWaveParts;
     if (n > (4 << 20) * kWaveParts) n = (4 << 20) * kWaveParts;  // slot ids share a word with a texture id (wave_noise_kernel)
@@ -160,6 +161,8 @@ static int32_t fill_device_state(hrt_scene* s, DeviceState* d) {
         if ((rc = upload_table(&d->d_ops[k], f.ops.data(), f.ops.size() * sizeof(Op))) != HRT_OK) return rc;
         if ((rc = upload_table(&d->d_ctxs[k], f.ctxs.data(), f.ctxs.size() * sizeof(Ctx))) != HRT_OK) return rc;
     }
+    if (!s->fast.wave_ops.empty() &&
+        (rc = upload_table(&d->d_ops[2], s->fast.wave_ops.data(), s->fast.wave_ops.size() * sizeof(Op))) != HRT_OK) return rc;
     if ((rc = upload_table(&d->d_nodes, s->fast.nodes.data(), s->fast.nodes.size() * sizeof(Bvh2Node))) != HRT_OK) return rc;
     if ((rc = upload_table(&d->d_mats, s->materials.data(), s->materials.size() * sizeof(Material))) != HRT_OK) return rc;
     if ((rc = upload_table(&d->d_texs, s->textures.data(), s->textures.size() * sizeof(Texture))) != HRT_OK) return rc;
@@ -209,6 +212,8 @@ static int32_t fill_device_state(hrt_scene* s, DeviceState* d) {
         v.n_media = f.n_media;
         v.ln_e = logf(2.71828182845904523536f);
     }
+    d->view[2] = d->view[1];
+    if (d->d_ops[2]) d->view[2].ops = d->d_ops[2];
     return HRT_OK;
 }
 
@@ -279,6 +284,8 @@ int32_t hrt_scene_refresh(hrt_scene* s, int32_t device) {
         HRT_CUDA(cudaMemcpyAsync(d->d_ops[k], f.ops.data(), f.ops.size() * sizeof(Op), cudaMemcpyHostToDevice, 0));
         HRT_CUDA(cudaMemcpyAsync(d->d_ctxs[k], f.ctxs.data(), f.ctxs.size() * sizeof(Ctx), cudaMemcpyHostToDevice, 0));
     }
+    if (d->d_ops[2] && !s->fast.wave_ops.empty())
+        HRT_CUDA(cudaMemcpyAsync(d->d_ops[2], s->fast.wave_ops.data(), s->fast.wave_ops.size() * sizeof(Op), cudaMemcpyHostToDevice, 0));
     if (!s->fast.nodes.empty())
         HRT_CUDA(cudaMemcpyAsync(d->d_nodes, s->fast.nodes.data(), s->fast.nodes.size() * sizeof(Bvh2Node), cudaMemcpyHostToDevice, 0));
     if (!s->materials.empty())
@@ -303,6 +310,7 @@ int64_t hrt_scene_device_bytes(const hrt_scene* s) {
         const FlatScene& f = flat_of(s, k);
         b += (int64_t)(f.ops.size() * sizeof(Op) + f.ctxs.size() * sizeof(Ctx));
     }
+    b += (int64_t)(s->fast.wave_ops.size() * sizeof(Op));
     for (const ImageData& img : s->images) b += (int64_t)img.rgba.size();
     return b;
 }
@@ -431,6 +439,8 @@ static int32_t render_into(hrt_scene* s, DeviceState* d, const hrt_camera_desc* 
     cudaError_t e;
     if (L.interpreter == 5) {
         if ((rc = ensure_wave(d, (size_t)rd->width * rd->height)) != HRT_OK) return rc;
+        // the stream walk meets the trees walked ahead where their spans begin (HRT_NO_SPANS: diagnostic, at their OP_BVH records)
+        if (!ref_boxes && L.n_pre > 0 && !getenv("HRT_NO_SPANS")) L.scene = d->view[2];
         e = (rd->flags & HRT_FLAG_EXACT_MATH) ? hrt_exact::launch_render_wave(L, d->wave, d->num_sms, stream)
                                               : hrt_fast::launch_render_wave(L, d->wave, d->num_sms, stream);
     } else {

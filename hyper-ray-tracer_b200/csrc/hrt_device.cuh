@@ -891,6 +891,30 @@ __device__ __forceinline__ bool traverse_uniform(const DeviceScene& S, const int
                 }
                 break;
             }
+            case OP_BVH_PRE: {
+                // (wave form of the stream) A tree walked ahead, met where the records that exist only for it begin: its
+                // answer is merged as above and the walk goes on behind them — the sound boxes in between only prune what
+                // `t* < closest` rejects anyway, and the tree's ray space is entered only to settle an exact tie.
+                if (me) {
+                    const float2 r = pre[__float_as_int(A.x)];
+                    const int code = __float_as_int(r.y);
+                    if (code != kPreNone) {
+                        const float tt = r.x;
+                        const int leaf = code & 0xffffff;
+                        const int tctx = __float_as_int(A.y);
+                        bool take = tt < closest;
+                        if (!take && !(tt > closest))
+                            take = best.pc < 0 ||
+                                   tie_goes_to_later(S, leaf, tctx == cur_ctx ? cur : ray_in_ctx(S, world, tctx), tmin, tt, B.x, B.y);
+                        if (take) {
+                            closest = tt; hitf = true;
+                            best.t = tt; best.pc = leaf; best.face = code >> 24; best.ctx = tctx;
+                        }
+                    }
+                    pc = (int)(w7 >> 8);
+                }
+                break;
+            }
             case OP_TRANSLATE: case OP_ROTATE: case OP_POP: {
                 // A ray space is a pure function of (world ray, context): leaving to the world space restores the world
                 // ray, and the space entered last is kept — a ConstantMedium enters its boundary's space twice per ray

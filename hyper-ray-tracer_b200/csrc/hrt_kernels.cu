@@ -248,7 +248,10 @@ constexpr int kWaveBlock = 256;
 #define HRT_TRACE_BLOCKS 3
 #endif
 #ifndef HRT_LOGIC_BLOCKS
-#define HRT_LOGIC_BLOCKS 3
+#define HRT_LOGIC_BLOCKS 4  // 64 registers, 32 warps per SM: the kernel waits on memory (C5 499 -> 521 Mpaths/s against 3 blocks)
+#endif
+#ifndef HRT_LOGIC_PREFETCH
+#define HRT_LOGIC_PREFETCH 1  // diagnostic builds: 0 = plain loads of the slot state (which ptxas sinks into their branches)
 #endif
 enum WaveField {
     WF_OX, WF_OY, WF_OZ, WF_DX, WF_DY, WF_DZ, WF_TIME,  // the ray segment to trace / traced last
@@ -301,6 +304,11 @@ __global__ void __launch_bounds__(256) wave_finish_kernel(double* __restrict__ a
     accum[i] = v;
 }
 static_assert(WF_WORDS == hrt::kWaveStateWords, "wave state layout");
+__device__ __forceinline__ float ld_volatile(const float* p) {
+    float v;
+    asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
 #define WST(f, slot) P.st[(size_t)(f) * P.n_slots + (slot)]
 
 __global__ void __launch_bounds__(kWaveBlock, HRT_TRACE_BLOCKS) wave_trace_kernel(const __grid_constant__ WaveParams P) {
@@ -351,20 +359,26 @@ __global__ void __launch_bounds__(kWaveBlock) wave_noise_kernel(const __grid_con
     }
 }
 
-// Tree stage, part 2: persistent warps pull walks from the tree's queue — a lane that finishes its walk takes the next
+// Tree stage, part 2: persistent warps pull walks from the trees' queues — a lane that finishes its walk takes the next
 // entry — so the lanes stay filled however much the walks differ in length.  (Inside wave_trace_kernel the same walks
 // were 64 % of its issued instructions at 3 - 7 of 32 lanes: only the few rays of a warp that reach one tree walk
-// together, profiles/r02_w1_*.)
+// together, profiles/r02_w1_*.)  tree >= 0: that tree's queue only; tree < 0: the queues of all pre-walked trees one
+// behind the other in ONE launch (one ramp-up and one drain per iteration instead of one per tree; the walks of different
+// trees run the same code, only the first node differs).
 __global__ void __launch_bounds__(kWaveBlock, 3) wave_tree_kernel(const __grid_constant__ WaveParams P, const int tree) {
     const DeviceScene& S = P.S;
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
-    const int n_entries = P.tq_count[tree];
-    int* const next = P.tq_count + kMaxPreTrees + tree;
-    const float4* const queue = P.tq + 2 * (size_t)tree * P.n_slots;
-    const int base = P.pre[tree].base;
-    const float ts = P.pre[tree].ts, te = P.pre[tree].te;
+    const int first = tree < 0 ? 0 : tree, last = tree < 0 ? P.n_pre : tree + 1;
+    int n_before[kMaxPreTrees + 1];  // entries of the queues in front of each tree's
+    n_before[0] = 0;
+#pragma unroll
+    for (int t = 0; t < kMaxPreTrees; ++t) n_before[t + 1] = n_before[t] + ((t >= first && t < last) ? P.tq_count[t] : 0);
+    const int n_entries = n_before[kMaxPreTrees];
+    int* const next = P.tq_count + kMaxPreTrees + first;
     int slot = -1;  // < 0: this lane is idle
+    int my_tree = first, base = P.pre[first].base;
+    float ts = P.pre[first].ts, te = P.pre[first].te;
     int ref = 0, sp = 0;
     Ray cur;
     cur.o = v3(0.0f, 0.0f, 0.0f); cur.d = v3(1.0f, 1.0f, 1.0f); cur.time = 0.0f;
@@ -385,12 +399,19 @@ __global__ void __launch_bounds__(kWaveBlock, 3) wave_tree_kernel(const __grid_c
             const int e = e0 + __popc(idle & lt_mask);
             if (e0 + __popc(idle) >= n_entries) drained = true;
             if (slot < 0 && e < n_entries) {
-                const float4 a = __ldg(queue + 2 * (size_t)e), b = __ldg(queue + 2 * (size_t)e + 1);
+                my_tree = first;
+                int before = 0;
+#pragma unroll
+                for (int t = 1; t < kMaxPreTrees; ++t)
+                    if (t > first && t < last && e >= n_before[t]) { my_tree = t; before = n_before[t]; }
+                const float4* const q = P.tq + 2 * ((size_t)my_tree * P.n_slots + (size_t)(e - before));
+                const float4 a = __ldg(q), b = __ldg(q + 1);
                 slot = __float_as_int(b.w);
                 cur.o = v3(a.x, a.y, a.z); cur.d = v3(b.x, b.y, b.z); cur.time = a.w;
                 k = make_rayk(cur);
                 h.t = CUDART_INF_F; h.pc = -1; h.face = 0;
                 ref = 0; sp = 0;
+                base = P.pre[my_tree].base; ts = P.pre[my_tree].ts; te = P.pre[my_tree].te;
             }
         }
         if (!__any_sync(kFull, slot >= 0)) break;
@@ -401,14 +422,14 @@ __global__ void __launch_bounds__(kWaveBlock, 3) wave_tree_kernel(const __grid_c
             const int n_inner = __popc(__ballot_sync(kFull, at_inner));
             if (n_inner < P.tree_inner_min) break;
             if (at_inner && bvh2_inner(S, base, cur, k, 0.001f, ref, sp, stack_ref, stack_t, h)) {
-                P.pre_res[(size_t)slot * kMaxPreTrees + tree] =
+                P.pre_res[(size_t)slot * kMaxPreTrees + my_tree] =
                     make_float2(h.t, __int_as_float(h.pc < 0 ? kPreNone : (h.pc | (h.face << 24))));
                 slot = -1;
             }
         }
         if (slot >= 0) {
             if (bvh2_step(S, base, cur, k, 0.001f, ts, te, ref, sp, stack_ref, stack_t, h)) {
-                P.pre_res[(size_t)slot * kMaxPreTrees + tree] =
+                P.pre_res[(size_t)slot * kMaxPreTrees + my_tree] =
                     make_float2(h.t, __int_as_float(h.pc < 0 ? kPreNone : (h.pc | (h.face << 24))));
                 slot = -1;
             }
@@ -417,34 +438,49 @@ __global__ void __launch_bounds__(kWaveBlock, 3) wave_tree_kernel(const __grid_c
 }
 
 __global__ void __launch_bounds__(kWaveBlock, HRT_LOGIC_BLOCKS) wave_logic_kernel(const __grid_constant__ WaveParams P) {
-    __shared__ NoiseTable sh_noise[kMaxNoiseTablesShared];
+    // NoiseTexture albedos are deferred to wave_noise_kernel, so no perlin table is staged here (9.7 KB per block and a
+    // barrier before the first state load); a checker over noise or an emitting noise texture reads the tables in place
     TexEnv E;
-    stage_noise(P.S, E, sh_noise, kMaxNoiseTablesShared);
+    E.sh_noise = nullptr; E.n_shared_noise = 0;
     const DeviceScene& S = P.S;
     const int lane = threadIdx.x & 31;
     const int slot = blockIdx.x * kWaveBlock + threadIdx.x;
     const bool in_range = slot < P.n_slots;
-    int bounce = in_range ? __float_as_int(WST(WF_BOUNCE, slot)) : -1;
+    // the whole slot is fetched at once, not behind the test of its bounce word (a second trip to HBM on the critical
+    // path of every block); free slots exist only while a render ramps up and drains
+    // (ld.volatile: ptxas sinks plain loads back into the branches that use their values)
+    const int ld = in_range ? slot : 0;
+#if HRT_LOGIC_PREFETCH
+#define WLD(f) ld_volatile(&WST(f, ld))
+#else
+#define WLD(f) WST(f, ld)
+#endif
+    int bounce = in_range ? __float_as_int(WLD(WF_BOUNCE)) : -1;
     RngKey key;
-    key.k0 = P.k0; key.k1 = P.k1; key.pixel = 0; key.sample = 0;
+    key.k0 = P.k0; key.k1 = P.k1;
+    key.pixel = __float_as_uint(WLD(WF_PIXEL));
+    key.sample = __float_as_uint(WLD(WF_SAMPLE));
+    Ray ray;
+    ray.o = v3(WLD(WF_OX), WLD(WF_OY), WLD(WF_OZ));
+    ray.d = v3(WLD(WF_DX), WLD(WF_DY), WLD(WF_DZ));
+    ray.time = WLD(WF_TIME);
+    V3 T = v3(WLD(WF_TX), WLD(WF_TY), WLD(WF_TZ));
+    const int hit_pc = __float_as_int(WLD(WF_HIT_PC));
+    const int hit_fc = __float_as_int(WLD(WF_HIT_FC));
+    const float hit_t = WLD(WF_HIT_T);
+#undef WLD
+    Ray nxt;  // the segment this slot traces next (when it still carries a path after this pass)
+    nxt.o = v3(0.0f, 0.0f, 0.0f); nxt.d = v3(1.0f, 1.0f, 1.0f); nxt.time = 0.0f;
     if (bounce >= 0) {
         // ---- emitted + scatter for the segment traced last (application.rs:482-494) ----
-        key.pixel = __float_as_uint(WST(WF_PIXEL, slot));
-        key.sample = __float_as_uint(WST(WF_SAMPLE, slot));
-        Ray ray;
-        ray.o = v3(WST(WF_OX, slot), WST(WF_OY, slot), WST(WF_OZ, slot));
-        ray.d = v3(WST(WF_DX, slot), WST(WF_DY, slot), WST(WF_DZ, slot));
-        ray.time = WST(WF_TIME, slot);
-        V3 T = v3(WST(WF_TX, slot), WST(WF_TY, slot), WST(WF_TZ, slot));
-        const int hit_pc = __float_as_int(WST(WF_HIT_PC, slot));
         V3 add = v3(0.0f, 0.0f, 0.0f);
         bool alive = false;
         if (hit_pc < 0) {
             add = T * v3(P.bg[0], P.bg[1], P.bg[2]);
         } else {
-            const int fc = __float_as_int(WST(WF_HIT_FC, slot));
+            const int fc = hit_fc;
             Best best;
-            best.t = WST(WF_HIT_T, slot); best.pc = hit_pc; best.face = fc & 0xff; best.ctx = fc >> 8;
+            best.t = hit_t; best.pc = hit_pc; best.face = fc & 0xff; best.ctx = fc >> 8;
             HitRec h;
             make_hit_record(S, ray, best, false, h);
             const Material m = S.mats[h.mat];
@@ -464,6 +500,7 @@ __global__ void __launch_bounds__(kWaveBlock, HRT_LOGIC_BLOCKS) wave_logic_kerne
                         if (noise_tex >= 0)  // the albedo is applied by wave_noise_kernel
                             P.xq[atomicAdd(P.tq_count + 2 * kMaxPreTrees, 1)] =
                                 make_float4(h.p.x, h.p.y, h.p.z, __int_as_float(slot | (noise_tex << 22)));
+                        nxt = sc;
                         WST(WF_OX, slot) = sc.o.x; WST(WF_OY, slot) = sc.o.y; WST(WF_OZ, slot) = sc.o.z;
                         WST(WF_DX, slot) = sc.d.x; WST(WF_DY, slot) = sc.d.y; WST(WF_DZ, slot) = sc.d.z;
                         WST(WF_TIME, slot) = sc.time;
@@ -484,7 +521,6 @@ __global__ void __launch_bounds__(kWaveBlock, HRT_LOGIC_BLOCKS) wave_logic_kerne
     // address was 38 % of this kernel's stall samples (profiles/r02_wave_logic_kernel_by_function.txt)
     __shared__ int sh_cnt[kWaveBlock / 32];
     __shared__ unsigned long long sh_base64;
-    __shared__ int sh_base32;
     const int warp = threadIdx.x >> 5;
     const bool is_free = in_range && bounce < 0;
     const unsigned need = __ballot_sync(kFull, is_free);
@@ -517,10 +553,10 @@ __global__ void __launch_bounds__(kWaveBlock, HRT_LOGIC_BLOCKS) wave_logic_kerne
                 }
                 const float u = ((float)px + c4[0]) / ((float)P.width - 1.0f);   // application.rs:444-445
                 const float v = ((float)py + c4[1]) / ((float)P.height - 1.0f);
-                const Ray r = camera_get_ray(P.cam, u, v, c4[3], lens_u2, c4[2]);
-                WST(WF_OX, slot) = r.o.x; WST(WF_OY, slot) = r.o.y; WST(WF_OZ, slot) = r.o.z;
-                WST(WF_DX, slot) = r.d.x; WST(WF_DY, slot) = r.d.y; WST(WF_DZ, slot) = r.d.z;
-                WST(WF_TIME, slot) = r.time;
+                nxt = camera_get_ray(P.cam, u, v, c4[3], lens_u2, c4[2]);
+                WST(WF_OX, slot) = nxt.o.x; WST(WF_OY, slot) = nxt.o.y; WST(WF_OZ, slot) = nxt.o.z;
+                WST(WF_DX, slot) = nxt.d.x; WST(WF_DY, slot) = nxt.d.y; WST(WF_DZ, slot) = nxt.d.z;
+                WST(WF_TIME, slot) = nxt.time;
                 WST(WF_TX, slot) = 1.0f; WST(WF_TY, slot) = 1.0f; WST(WF_TZ, slot) = 1.0f;
                 WST(WF_PIXEL, slot) = __uint_as_float(key.pixel);
                 WST(WF_SAMPLE, slot) = __uint_as_float(key.sample);
@@ -534,50 +570,58 @@ __global__ void __launch_bounds__(kWaveBlock, HRT_LOGIC_BLOCKS) wave_logic_kerne
     }
     if (in_range && bounce < 0) WST(WF_BOUNCE, slot) = __int_as_float(-1);
     // ---- tree stage, part 1: the ray this slot traces next against the root box of every pre-walked tree ----
+    // (all trees in ONE round of block-wide counting: one barrier pair and one atomic per tree and block)
     if (P.n_pre > 0) {
+        __shared__ int sh_tcnt[kMaxPreTrees][kWaveBlock / 32];
+        __shared__ int sh_tbase[kMaxPreTrees];
         const bool live = bounce >= 0;
-        Ray w;
-        w.o = v3(0.0f, 0.0f, 0.0f); w.d = v3(1.0f, 1.0f, 1.0f); w.time = 0.0f;
-        if (live) {
-            w.o = v3(WST(WF_OX, slot), WST(WF_OY, slot), WST(WF_OZ, slot));
-            w.d = v3(WST(WF_DX, slot), WST(WF_DY, slot), WST(WF_DZ, slot));
-            w.time = WST(WF_TIME, slot);
-        }
-#pragma unroll 1
-        for (int tree = 0; tree < P.n_pre; ++tree) {
-            const Ray r = P.pre[tree].ctx != 0 ? ray_in_ctx(S, w, P.pre[tree].ctx) : w;
-            const RayK k = make_rayk(r);
-            const float4 mn = make_float4(P.pre[tree].mn[0], P.pre[tree].mn[1], P.pre[tree].mn[2], 0.0f);
-            const float4 mx = make_float4(P.pre[tree].mx[0], P.pre[tree].mx[1], P.pre[tree].mx[2], 0.0f);
-            // A ray whose origin (or direction) is all NaN — the continuation of a path that hit something at t = NaN, Q15 —
-            // passes every box test and is accepted by every primitive test, each accepted hit replacing the one before
-            // (the reference's `t <= t_max` is never false): it visits the whole tree (~2000 steps against ~14 for an
-            // ordinary ray, and a wave of a million rays nearly always holds one) to end at the last leaf of the
-            // reference's order with t = NaN.  That answer is written directly.
-            const bool all_nan = (r.o.x != r.o.x && r.o.y != r.o.y && r.o.z != r.o.z) || (r.d.x != r.d.x && r.d.y != r.d.y && r.d.z != r.d.z);
-            const bool hit = live && !all_nan && box_hit_tight(mn, mx, r, k, 0.001f, CUDART_INF_F);
-            const unsigned m = __ballot_sync(kFull, hit);
-            __syncthreads();  // (sh_cnt / sh_base32 of the previous round are read)
-            if (lane == 0) sh_cnt[warp] = __popc(m);
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                int tot = 0;
+        Ray rr[kMaxPreTrees];
+        unsigned mm[kMaxPreTrees];
+        bool hit[kMaxPreTrees], nan_ray[kMaxPreTrees];
 #pragma unroll
-                for (int ww = 0; ww < kWaveBlock / 32; ++ww) tot += sh_cnt[ww];
-                sh_base32 = tot ? atomicAdd(P.tq_count + tree, tot) : 0;
+        for (int tree = 0; tree < kMaxPreTrees; ++tree) {
+            rr[tree] = nxt; mm[tree] = 0u; hit[tree] = false; nan_ray[tree] = false;
+            if (tree < P.n_pre) {
+                const Ray r = P.pre[tree].ctx != 0 ? ray_in_ctx(S, nxt, P.pre[tree].ctx) : nxt;
+                const RayK k = make_rayk(r);
+                const float4 mn = make_float4(P.pre[tree].mn[0], P.pre[tree].mn[1], P.pre[tree].mn[2], 0.0f);
+                const float4 mx = make_float4(P.pre[tree].mx[0], P.pre[tree].mx[1], P.pre[tree].mx[2], 0.0f);
+                // A ray whose origin (or direction) is all NaN — the continuation of a path that hit something at t = NaN,
+                // Q15 — passes every box test and is accepted by every primitive test, each accepted hit replacing the one
+                // before (the reference's `t <= t_max` is never false): it visits the whole tree (~2000 steps against ~14
+                // for an ordinary ray, and a wave of a million rays nearly always holds one) to end at the last leaf of the
+                // reference's order with t = NaN.  That answer is written directly.
+                nan_ray[tree] = (r.o.x != r.o.x && r.o.y != r.o.y && r.o.z != r.o.z) || (r.d.x != r.d.x && r.d.y != r.d.y && r.d.z != r.d.z);
+                hit[tree] = live && !nan_ray[tree] && box_hit_tight(mn, mx, r, k, 0.001f, CUDART_INF_F);
+                mm[tree] = __ballot_sync(kFull, hit[tree]);
+                if (lane == 0) sh_tcnt[tree][warp] = __popc(mm[tree]);
+                rr[tree] = r;
             }
-            __syncthreads();
-            if (hit) {
-                int at = sh_base32 + __popc(m & ((1u << lane) - 1u));
-                for (int ww = 0; ww < warp; ++ww) at += sh_cnt[ww];
-                float4* q = P.tq + 2 * ((size_t)tree * P.n_slots + at);
-                q[0] = make_float4(r.o.x, r.o.y, r.o.z, r.time);
-                q[1] = make_float4(r.d.x, r.d.y, r.d.z, __int_as_float(slot));
+        }
+        __syncthreads();
+        if (threadIdx.x < P.n_pre) {
+            int tot = 0;
+#pragma unroll
+            for (int ww = 0; ww < kWaveBlock / 32; ++ww) tot += sh_tcnt[threadIdx.x][ww];
+            sh_tbase[threadIdx.x] = tot ? atomicAdd(P.tq_count + threadIdx.x, tot) : 0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int tree = 0; tree < kMaxPreTrees; ++tree) {
+            if (tree < P.n_pre) {
+                if (hit[tree]) {
+                    int at = sh_tbase[tree] + __popc(mm[tree] & ((1u << lane) - 1u));
+                    for (int ww = 0; ww < warp; ++ww) at += sh_tcnt[tree][ww];
+                    float4* q = P.tq + 2 * ((size_t)tree * P.n_slots + at);
+                    const Ray& r = rr[tree];
+                    q[0] = make_float4(r.o.x, r.o.y, r.o.z, r.time);
+                    q[1] = make_float4(r.d.x, r.d.y, r.d.z, __int_as_float(slot));
+                }
+                if (live)
+                    P.pre_res[(size_t)slot * kMaxPreTrees + tree] =
+                        nan_ray[tree] ? make_float2(CUDART_NAN_F, __int_as_float(P.pre[tree].last_pc | (P.pre[tree].last_face << 24)))
+                                      : make_float2(0.0f, __int_as_float(kPreNone));
             }
-            if (live)
-                P.pre_res[(size_t)slot * kMaxPreTrees + tree] =
-                    all_nan ? make_float2(CUDART_NAN_F, __int_as_float(P.pre[tree].last_pc | (P.pre[tree].last_face << 24)))
-                            : make_float2(0.0f, __int_as_float(kPreNone));
         }
     }
     const unsigned ms = __ballot_sync(kFull, started);
@@ -858,7 +902,7 @@ static CameraK to_camera(const hrt_camera_state& c) {
     return k;
 }
 
-// Host loop of the wavefront render.  The path slots are split into partitions (4; HRT_WAVE_PARTS), each iterating on its own
+// Host loop of the wavefront render.  The path slots are split into partitions (2; HRT_WAVE_PARTS), each iterating on its own
 // stream: every iteration ends with the slowest walk of its wave (a ray with a NaN component passes every box test and
 // visits a whole 2000-node tree: ~0.8 ms against ~0.1 ms for the rest of the wave, and a million rays nearly always hold
 // one), and while one partition sits in such a tail the others keep the SMs busy.  All partitions draw camera samples
@@ -881,16 +925,23 @@ cudaError_t launch_render_wave(hrt::RenderLaunch& L, hrt::WaveBuffers& W, int nu
     P.acc64 = W.acc64;
     P.n_pre = L.n_pre;
     for (int i = 0; i < kMaxPreTrees; ++i) P.pre[i] = L.pre[i];
+    const bool one_tree_launch = !getenv("HRT_TREE_SPLIT");  // diagnostic: one wave_tree_kernel launch per tree
     P.tree_refill = 12;
     if (const char* env = getenv("HRT_TREE_REFILL")) P.tree_refill = std::max(1, std::min(32, atoi(env)));
     P.tree_inner_min = 12;
     if (const char* env = getenv("HRT_TREE_INNER")) P.tree_inner_min = std::max(1, std::min(33, atoi(env)));
     P.live_out = nullptr;
-    // slots per partition: all of them for a big job, no more than the job has paths for a small one
-    int parts = 4;
+    // Two partitions: enough to fill one's end-of-iteration tails with the other's work, and the fewer the partitions the
+    // larger (and the fewer) the launches (C5 at 2048 spp: 1 / 2 / 3 / 4 / 8 partitions of 4 Mi slots in all = 443 / 447 /
+    // 436 / 430 / 410 Mpaths/s).  Slots in flight: every iteration costs a pass over ALL slots, also while a render ramps up
+    // and drains (~50 iterations whatever its size), so a mid-size job gets fewer of them (C5 at 64 spp = 41 M paths: 404
+    // Mpaths/s with 4 Mi slots, 337 with 8 Mi; at 2048 spp: 521 against 529).
+    int parts = 2;
     if (const char* env = getenv("HRT_WAVE_PARTS")) parts = std::max(1, std::min(hrt::kWaveParts, atoi(env)));
+    long long budget = W.n_slots;
+    if (!getenv("HRT_WAVE_SLOTS")) budget = std::min<long long>(budget, std::max<long long>(4ll << 20, (long long)(P.total_paths / 128)));
     // the buffers are split evenly among the partitions in use; slot ids share a word with a texture id (wave_noise_kernel)
-    const int cap = std::min(W.n_slots / parts, 1 << 22) / kWaveBlock * kWaveBlock;
+    const int cap = (int)std::min<long long>(budget / parts, 1 << 22) / kWaveBlock * kWaveBlock;
     const unsigned long long share = (P.total_paths + parts - 1) / parts;
     const unsigned long long want = (share + kWaveBlock - 1) / kWaveBlock * kWaveBlock;
     P.n_slots = (int)std::min<unsigned long long>((unsigned long long)cap, std::max<unsigned long long>(want, kWaveBlock));
@@ -933,9 +984,15 @@ cudaError_t launch_render_wave(hrt::RenderLaunch& L, hrt::WaveBuffers& W, int nu
                 PP[p].live_out = i == kBatch - 1 ? live : nullptr;
                 wave_logic_kernel<<<grid, kWaveBlock, 0, sp>>>(PP[p]);
                 if (P.S.n_noise > 0) wave_noise_kernel<<<num_sms, kWaveBlock, 0, sp>>>(PP[p]);
-                for (int t = 0; t < P.n_pre; ++t) wave_tree_kernel<<<tree_grid, kWaveBlock, 0, sp>>>(PP[p], t);
+                if (one_tree_launch && P.n_pre > 1) {
+                    wave_tree_kernel<<<tree_grid, kWaveBlock, 0, sp>>>(PP[p], -1);
+                    L.launches += 1;
+                } else {
+                    for (int t = 0; t < P.n_pre; ++t) wave_tree_kernel<<<tree_grid, kWaveBlock, 0, sp>>>(PP[p], t);
+                    L.launches += P.n_pre;
+                }
                 wave_trace_kernel<<<grid, kWaveBlock, 0, sp>>>(PP[p]);
-                L.launches += 2 + P.n_pre + (P.S.n_noise > 0 ? 1 : 0);
+                L.launches += 2 + (P.S.n_noise > 0 ? 1 : 0);
             }
             if ((e = cudaGetLastError()) != cudaSuccess) return e;
             if ((e = cudaMemcpyAsync(W.h_live + 2 * p + (b & 1), live, sizeof(int), cudaMemcpyDeviceToHost, sp)) != cudaSuccess) return e;

@@ -42,7 +42,7 @@ struct RenderLaunch {
 };
 
 // Device buffers of the wavefront render (hrt_kernels.cu launch_render_wave), owned per device.
-constexpr int kWaveParts = 8;  // most partitions of the path slots, each iterating on its own stream (default 4 in use)
+constexpr int kWaveParts = 8;  // most partitions of the path slots, each iterating on its own stream (default 2 in use)
 constexpr int kWaveCounters = 8;  // queue counters per partition (2 per pre-walked tree, 1 for deferred noise, padding)
 struct WaveBuffers {
     float* state = nullptr;   // [kWaveParts][WF_WORDS][n_slots / kWaveParts]

@@ -312,6 +312,9 @@ struct Flattener {
     const hrt_scene& s;
     FlatScene& f;
     const bool trees;  // sound BVHs of plain primitives become OP_BVH trees
+    // inner boxes over at most this many leaves are left out of the fast form (HRT_ELIDE_BOXES=0: diagnostic, keep all)
+    static constexpr int32_t kElideInnerMaxLeaves = 16;
+    const bool elide_boxes = [] { const char* e = std::getenv("HRT_ELIDE_BOXES"); return !(e && e[0] == '0'); }();
     std::string error;
     bool in_medium = false;
     Flattener(const hrt_scene& sc, FlatScene& out, bool bvh_trees) : s(sc), f(out), trees(bvh_trees) {}
@@ -542,14 +545,26 @@ struct Flattener {
         // Soundness: does the reference box contain everything hit() can accept beneath this node?
         Box3 truth;
         bool sound = true_extent(tree, t0, t1, node_index, truth) && contains(n.box, truth);
+        // The fast form leaves out sound boxes that rarely spare a warp anything.  A sound box only prunes — whatever it
+        // rejects cannot be hit beneath it, and a box beneath it that is kept rejects at least as much on every axis
+        // (nested intervals, monotone rounding), exact ties included — so the hits do not change.  The warp-uniform walk
+        // executes every record ANY of its rays reaches: an inner box of a small BVH (the 11-object top level of `final`)
+        // is reached by some ray of nearly every warp, so it is a step for the warp that spares only single lanes the leaf
+        // boxes beneath; without the inner boxes all lanes meet the same leaf boxes together.  Leaf boxes stay (they do
+        // spare whole warps the primitive), except above an OP_BVH tree, whose own root box is the same box.
+        bool elide = false;
+        if (trees && sound && elide_boxes) {
+            if (n.leaf_obj < 0) elide = leaves_of(tree, node_index) <= kElideInnerMaxLeaves;
+            else elide = s.objects[n.leaf_obj].kind == OBJ_BVH && tree_eligible(s.objects[n.leaf_obj]);
+        }
         int32_t at = pc();
-        {
+        if (!elide) {
             Op& op = push(sound ? OP_BOX : OP_BOX_LOOSE);
             op.f[0] = n.box.mn[0]; op.f[1] = n.box.mn[1]; op.f[2] = n.box.mn[2];
             op.f[4] = n.box.mx[0]; op.f[5] = n.box.mx[1]; op.f[6] = n.box.mx[2];
+            f.n_box_ops++;
+            if (!sound) f.n_loose_boxes++;
         }
-        f.n_box_ops++;
-        if (!sound) f.n_loose_boxes++;
         if (n.leaf_obj >= 0) {
             if (!emit(n.leaf_obj, ctx)) return false;
         } else {
@@ -557,8 +572,13 @@ struct Flattener {
             if (!emit_bvh(tree, t0, t1, n.right, ctx)) return false;
         }
         if (pc() >= (1 << 24)) { error = "op stream longer than 2^24 records"; return false; }
-        f.ops[at].u[7] = (f.ops[at].u[7] & 0xffu) | ((uint32_t)pc() << 8);
+        if (!elide) f.ops[at].u[7] = (f.ops[at].u[7] & 0xffu) | ((uint32_t)pc() << 8);
         return true;
+    }
+
+    static int32_t leaves_of(const BvhTree& tree, int32_t node_index) {
+        const BvhTreeNode& n = tree.nodes[node_index];
+        return n.leaf_obj >= 0 ? 1 : leaves_of(tree, n.left) + leaves_of(tree, n.right);
     }
 
     bool true_extent(const BvhTree& tree, float t0, float t1, int32_t node_index, Box3& out) {
@@ -909,6 +929,41 @@ static int32_t flatten(const hrt_scene* s, int32_t root, FlatScene& f, bool tree
             ++i;
         }
     }
+    // The records around each OP_BVH tree that exist only for it (PreTree::from_pc / to_pc): enclosing sound boxes that
+    // cover nothing else (they only prune, and the tree's own closest hit decides what they would have pruned), and whole
+    // runs of ray-space pushes in front matched by as many pops behind.
+    for (PreTree& t : f.trees) {
+        auto opc = [&](int32_t i) { return f.ops[i].u[7] & 0xffu; };
+        auto payload = [&](int32_t i) { return (int32_t)(f.ops[i].u[7] >> 8); };
+        int32_t from = t.pc - 1, to = payload(t.pc);
+        for (;;) {
+            if (from >= 1 && opc(from - 1) == OP_BOX && payload(from - 1) == to) { --from; continue; }
+            int32_t pushes = 0, pops = 0;
+            while (from - pushes >= 1 && is_push(opc(from - pushes - 1))) ++pushes;
+            while (to + pops < (int32_t)n && opc(to + pops) == OP_POP) ++pops;
+            // only a WHOLE run of pushes (its first record is where a walk arrives and carries the run length)
+            if (pushes > 0 && pushes <= pops && payload(from - pushes) == pushes) { from -= pushes; to += pushes; continue; }
+            break;
+        }
+        // a span begins at a box (the first record of a push run stays in place: ray_in_ctx reads it as data)
+        while (is_push(opc(from))) { const int32_t run = payload(from); from += run; to -= run; }
+        t.from_pc = from;
+        t.to_pc = to;
+    }
+    // The WAVE form: the stream walk of the wavefront render holds the answers of the first kMaxPreTrees trees before it
+    // starts, takes each where its span begins and goes on behind it (OP_BVH_PRE, hrt_types.h).
+    f.wave_ops.clear();
+    if (!f.trees.empty()) {
+        f.wave_ops = f.ops;
+        for (size_t i = 0; i < f.trees.size() && i < (size_t)kMaxPreTrees; ++i) {
+            const PreTree& t = f.trees[i];
+            Op op;
+            std::memset(&op, 0, sizeof(op));
+            op.i[0] = (int32_t)i; op.i[1] = t.ctx; op.f[4] = t.ts; op.f[5] = t.te;
+            op.u[7] = OP_BVH_PRE | ((uint32_t)t.to_pc << 8);
+            f.wave_ops[(size_t)t.from_pc] = op;
+        }
+    }
     return HRT_OK;
 }
 
@@ -966,9 +1021,12 @@ static const FlatScene* pick_flat(const hrt_scene* s, int32_t which) { return wh
 int32_t hrt_scene_get_ops(const hrt_scene* s, int32_t which, void* out, int32_t cap_ops) {
     if (!s) return fail(HRT_ERR_INVALID, "null scene");
     if (!s->committed) return fail(HRT_ERR_STATE, "scene not committed");
-    const FlatScene* f = pick_flat(s, which);
-    int32_t n = (int32_t)f->ops.size();
-    if (out && cap_ops > 0) std::memcpy(out, f->ops.data(), sizeof(Op) * (size_t)std::min(n, cap_ops));
+    if (which != HRT_STREAM_REFERENCE && which != HRT_STREAM_FAST && which != HRT_STREAM_WAVE)
+        return fail(HRT_ERR_INVALID, "get_ops: unknown form of the stream");
+    const FlatScene* f = pick_flat(s, which == HRT_STREAM_WAVE ? HRT_STREAM_FAST : which);
+    const std::vector<Op>& ops = (which == HRT_STREAM_WAVE && !f->wave_ops.empty()) ? f->wave_ops : f->ops;
+    int32_t n = (int32_t)ops.size();
+    if (out && cap_ops > 0) std::memcpy(out, ops.data(), sizeof(Op) * (size_t)std::min(n, cap_ops));
     return n;
 }
 int32_t hrt_scene_get_tree_nodes(const hrt_scene* s, void* out, int32_t cap_nodes) {
@@ -976,6 +1034,17 @@ int32_t hrt_scene_get_tree_nodes(const hrt_scene* s, void* out, int32_t cap_node
     if (!s->committed) return fail(HRT_ERR_STATE, "scene not committed");
     int32_t n = (int32_t)s->fast.nodes.size();
     if (out && cap_nodes > 0) std::memcpy(out, s->fast.nodes.data(), sizeof(Bvh2Node) * (size_t)std::min(n, cap_nodes));
+    return n;
+}
+
+int32_t hrt_scene_get_tree_spans(const hrt_scene* s, int32_t* out, int32_t cap_trees) {
+    if (!s) return fail(HRT_ERR_INVALID, "null scene");
+    if (!s->committed) return fail(HRT_ERR_STATE, "scene not committed");
+    const int32_t n = (int32_t)s->fast.trees.size();
+    for (int32_t i = 0; out && i < std::min(n, cap_trees); ++i) {
+        const PreTree& t = s->fast.trees[(size_t)i];
+        out[4 * i + 0] = t.pc; out[4 * i + 1] = t.ctx; out[4 * i + 2] = t.from_pc; out[4 * i + 3] = t.to_pc;
+    }
     return n;
 }
 

@@ -56,6 +56,8 @@ struct FlatScene {
     std::vector<Ctx> ctxs;
     std::vector<Bvh2Node> nodes;
     std::vector<PreTree> trees;  // the OP_BVH trees outside medium boundaries, in stream order
+    std::vector<Op> wave_ops;    // the WAVE form: `ops` with an OP_BVH_PRE record at the from_pc of each of the first
+                                 // kMaxPreTrees trees (what the wavefront render's stream walk reads; empty without trees)
     int32_t n_box_ops = 0, n_loose_boxes = 0, n_prim_ops = 0, n_media = 0, max_ctx_depth = 0;
     int32_t n_bvh_trees = 0, max_tree_depth = 0;
 };

@@ -33,6 +33,8 @@ enum Opcode : uint32_t {
                               // (Translation(Rotation(Cuboid)): the smoke blocks of Cornell-smoke) — both queries in one step
     OP_BVH = 0x45,            // a whole sound BvhNode as a binary tree of Bvh2Node records walked with a per-ray stack,
                               // nearer child first; its leaves are the primitive records [pc+1, end)
+    OP_BVH_PRE = 0x47,        // WAVE form only: stands where the records that exist only for one pre-walked tree begin
+                              // (PreTree::from_pc) — the tree's answer is merged there and the walk goes on at to_pc
     OP_END = 0x50,
 };
 
@@ -49,6 +51,8 @@ enum Opcode : uint32_t {
 //   BVH         w0 first node (index into the node table), w1 node count, w2 leaf count, w3 tree depth
 //               w4 time_start, w5 time_end of the BvhNode, w6 index of the tree among those outside medium
 //               boundaries (stream order; -1 inside one)       w7 = op | end_pc<<8
+//   BVH_PRE     w0 index of the tree among the pre-walked ones, w1 its ray-space context
+//               w4 time_start, w5 time_end                     w7 = op | to_pc<<8
 struct alignas(16) Op {
     union {
         float f[8];
@@ -86,6 +90,10 @@ struct PreTree {
     float mn[3], mx[3];
     int32_t last_pc;  // the tree's last leaf record in the reference's order and, when it is a cuboid, its last side (5):
     int32_t last_face;  // what a ray whose origin or direction is all NaN "hits" (every test accepts it, the last one wins)
+    // [from_pc, to_pc): the records that exist ONLY for this tree — its root box and OP_BVH record, the leaves, and around
+    // them every sound OP_BOX whose skip is to_pc and every run of ray-space pushes matched by the pops behind the leaves.
+    // A walk that already holds the tree's answer takes it at from_pc and goes on at to_pc (traverse_uniform).
+    int32_t from_pc, to_pc;
 };
 
 constexpr int kMaxCtxDepth = 6;

@@ -21,6 +21,7 @@ HRT_BVH_REFERENCE = 0
 HRT_BVH_TREES = 1
 HRT_STREAM_REFERENCE = 0
 HRT_STREAM_FAST = 1
+HRT_STREAM_WAVE = 2
 
 
 PROGRESS_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p)
@@ -104,7 +105,7 @@ EXPORTS = [
     "hrt_render_accum", "hrt_render_accum_device", "hrt_resolve_device", "hrt_trace_hits", "hrt_tex_value",
     "hrt_scatter", "hrt_camera_rays", "hrt_philox_uniforms", "hrt_scene_evict", "hrt_scene_device_bytes",
     "hrt_measure_peaks", "hrt_scene_refresh", "hrt_render_multi", "hrt_render_accum_multi",
-    "hrt_scene_set_bvh_builder", "hrt_scene_get_tree_nodes", "hrt_render_progressive", "hrt_make_scene", "hrt_scene_save",
+    "hrt_scene_set_bvh_builder", "hrt_scene_get_tree_nodes", "hrt_scene_get_tree_spans", "hrt_render_progressive", "hrt_make_scene", "hrt_scene_save",
     "hrt_scene_load",
 ]
 
@@ -155,6 +156,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.hrt_scene_get_info.argtypes = [vp, C.POINTER(SceneInfo)]
     lib.hrt_scene_get_ops.argtypes = [vp, i32, vp, i32]
     lib.hrt_scene_get_tree_nodes.argtypes = [vp, vp, i32]
+    lib.hrt_scene_get_tree_spans.argtypes = [vp, C.POINTER(i32), i32]
     lib.hrt_scene_set_bvh_builder.argtypes = [vp, i32]
     lib.hrt_bvh_leaf_order.argtypes = [vp, i32, C.POINTER(i32), i32]
     lib.hrt_bounding_box.argtypes = [vp, i32, f3]
@@ -353,6 +355,15 @@ class HrtBackend:
         out = np.zeros((max(n, 1), 16), dtype=np.uint16)
         self._check(self.lib.hrt_scene_get_tree_nodes(self.handle, _ptr(out), n))
         return out[:n]
+
+    def tree_spans(self) -> np.ndarray:
+        """(n, 4) int32 rows {OP_BVH pc, context, from_pc, to_pc} of the fast form's trees outside medium boundaries
+        (include/hrt.h hrt_scene_get_tree_spans)."""
+        n = self._check(self.lib.hrt_scene_get_tree_spans(self.handle, None, 0))
+        out = np.zeros((n, 4), dtype=np.int32)
+        if n:
+            self._check(self.lib.hrt_scene_get_tree_spans(self.handle, out.ctypes.data_as(C.POINTER(C.c_int32)), n))
+        return out
 
     def bvh_leaf_order(self, bvh: int):
         n = self._check(self.lib.hrt_bvh_leaf_order(self.handle, bvh, None, 0))

@@ -162,11 +162,18 @@ int32_t hrt_scene_get_info(const hrt_scene*, hrt_scene_info* out);
  * Call before hrt_scene_commit.  hrt_bvh_leaf_order / hrt_bounding_box always describe the reference trees. */
 enum { HRT_BVH_REFERENCE = 0, HRT_BVH_TREES = 1 };
 int32_t hrt_scene_set_bvh_builder(hrt_scene*, int32_t builder);
-enum { HRT_STREAM_REFERENCE = 0, HRT_STREAM_FAST = 1 };
+enum { HRT_STREAM_REFERENCE = 0, HRT_STREAM_FAST = 1,
+       HRT_STREAM_WAVE = 2 /* the fast form as the wavefront render's stream walk reads it: an OP_BVH_PRE record where the
+                              span of each tree it walks ahead begins (hrt_scene_get_tree_spans); same length */ };
 /* Copies up to cap_ops 32-byte records of the chosen form; returns its record count. */
 int32_t hrt_scene_get_ops(const hrt_scene*, int32_t which, void* out, int32_t cap_ops);
 /* Copies up to cap_nodes 32-byte tree nodes of the fast form (hrt_types.h Bvh2Node); returns the node count. */
 int32_t hrt_scene_get_tree_nodes(const hrt_scene*, void* out, int32_t cap_nodes);
+/* The OP_BVH trees of the fast form outside medium boundaries, in stream order: up to cap_trees rows of four int32
+ * {pc of the OP_BVH record, ray-space context, from_pc, to_pc} where [from_pc, to_pc) are the records that exist only
+ * for that tree (hrt_types.h PreTree: what the wavefront render's stream walk steps over once the tree has been
+ * walked ahead); returns the tree count. */
+int32_t hrt_scene_get_tree_spans(const hrt_scene*, int32_t* out, int32_t cap_trees);
 /* DFS left->right leaf object ids of a hrt_bvh object; returns leaf count. */
 int32_t hrt_bvh_leaf_order(const hrt_scene*, int32_t bvh, int32_t* out, int32_t cap);
 /* Reference bounding box of any hittable over time [0,1] (what `bounding_box(0.0, 1.0)` returns). */

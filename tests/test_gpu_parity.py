@@ -5,7 +5,7 @@ bit-exact on t / point / normal / front_face / ids); images statistically indist
 import numpy as np
 import pytest
 
-from conftest import build_both, make_rays
+from conftest import build_both, make_rays, nested_tree_world
 
 pytestmark = pytest.mark.gpu
 
@@ -397,6 +397,31 @@ def test_render_kernel_variants_agree(pkg, orc, built, name):
     assert len({o[1] for o in outs}) == 1 and {o[2] for o in outs} == {72 * 48 * 160}
     for other in outs[1:]:
         assert np.allclose(outs[0][0], other[0], rtol=2e-4, atol=2e-4)
+
+
+def test_wavefront_steps_over_tree_spans(pkg, orc):
+    """Trees behind ray-space pushes, beside siblings and under extra boxes (conftest.nested_tree_world): the wavefront
+    render — whose stream walk takes each pre-walked tree's answer at PreTree::from_pc and goes on at to_pc, and which
+    walks the trees beyond the first kMaxPreTrees inline — traces the same paths as the persistent kernels and as the
+    reference form, and its image is the oracle's (pooled z-scores against a live oracle render)."""
+    N = pkg.native
+    S = pkg.scene
+    world = nested_tree_world(pkg)
+    gb, ob, _, _ = build_both(pkg, orc, world)
+    assert len(gb.tree_spans()) == 4
+    cam = S.Camera((0.0, 7.0, 22.0), (0.0, 0.0, 0.0), 40.0, 0.0)
+    bg = (0.7, 0.8, 1.0)
+    w, h, spp = 96, 64, 128
+    outs = []
+    for flag in (N.HRT_FLAG_WAVEFRONT, N.HRT_FLAG_UNIFORM, N.HRT_FLAG_WAVEFRONT | N.HRT_FLAG_REFERENCE_TRAVERSAL):
+        acc, st = gb.render(cam, w, h, spp, 50, bg, seed=13, resolve=False, flags=flag)
+        outs.append((np.nan_to_num(acc[..., :3]), st.rays, st.paths))
+    assert len({o[1] for o in outs}) == 1 and {o[2] for o in outs} == {w * h * spp}
+    for other in outs[1:]:
+        assert np.allclose(outs[0][0], other[0], rtol=2e-4, atol=2e-4)
+    ref_sum, ref_sq, _ = ob.render(cam, w, h, 64, 50, bg, seed=2, want_sumsq=True)
+    zb, _, _, _, _ = _zscores(outs[0][0].astype(np.float64), spp, np.nan_to_num(ref_sum), np.nan_to_num(ref_sq), 64, pool=8)
+    assert zb.size >= 20 and np.sqrt((zb ** 2).mean()) < 1.6 and abs(zb.mean()) < 0.5, (np.sqrt((zb ** 2).mean()), zb.mean())
 
 
 def test_progressive_delivery_converges_to_the_full_render(pkg, orc, built):

@@ -9,11 +9,12 @@ going to the later record) are interpreted too, one ray at a time.
 import numpy as np
 import pytest
 
-from conftest import build_both, make_rays
+from conftest import build_both, make_rays, nested_tree_world
 
 OP_BOX, OP_BOX_LOOSE, OP_SPHERE, OP_MSPHERE = 0x10, 0x11, 0x20, 0x21
 OP_RECT_XY, OP_RECT_YZ, OP_RECT_ZX, OP_CUBOID = 0x30, 0x31, 0x32, 0x33
 OP_TRANSLATE, OP_ROTATE, OP_POP, OP_MEDIUM, OP_MEDIUM_SPHERE, OP_BVH, OP_MEDIUM_CUBOID, OP_END = 0x40, 0x41, 0x42, 0x43, 0x44, 0x45, 0x46, 0x50
+OP_BVH_PRE = 0x47
 F = np.float32
 
 
@@ -163,9 +164,26 @@ def _rect(o, d, ik, ia, ib, a0, a1, b0, b1, k, tmin, closest):
     return ok, t
 
 
-def trace_stream(ops, rays, nodes=None, stats=None):
+def _apply_push(ops, f, q, o, d):
+    """One OP_TRANSLATE / OP_ROTATE record applied to copies of (o, d) (translation.rs:25-29, rotation.rs:103-116)."""
+    o, d = o.copy(), d.copy()
+    if (int(ops[q, 7]) & 0xFF) == OP_TRANSLATE:
+        o = o - f[q, 0:3]
+    else:
+        sn, cs, axis = f[q, 0], f[q, 1], int(ops[q, 2])
+        ia, ib = (axis + 1) % 3, (axis + 2) % 3
+        for v in (o, d):
+            va, vb = v[ia].copy(), v[ib].copy()
+            v[ia] = cs * va + sn * vb
+            v[ib] = -sn * va + cs * vb
+    return o, d
+
+
+def trace_stream(ops, rays, nodes=None, stats=None, spans=None):
     """Closest hit of every ray against the op stream; returns (hit mask, t, prim id).  `nodes`: the tree-node table of
-    the fast form; `stats[0]` counts box tests."""
+    the fast form; `stats[0]` counts box tests.  `spans` (hrt_scene_get_tree_spans) with the WAVE form of the stream: walk
+    as the wavefront render's stream walk does — at an OP_BVH_PRE record the tree's closest hit over [tmin, +inf), computed
+    on its own (the tree stage), is merged, and the walk goes on behind the records that exist only for the tree."""
     f = ops.view(np.float32)
     n = len(rays)
     o = rays["o"].astype(F).copy()
@@ -186,6 +204,31 @@ def trace_stream(ops, rays, nodes=None, stats=None):
             nxt = pc + 1
             if op == OP_END:
                 break
+            if op == OP_BVH_PRE:  # the WAVE form: w0 = index of the tree among the pre-walked ones, payload = to_pc
+                span = spans[int(ops[pc, 0])]
+                assert int(span[2]) == pc and int(span[3]) == payload and int(ops[pc, 1]) == int(span[1])
+                bvh_pc, to_pc = int(span[0]), payload
+                assert f[pc, 4] == f[bvh_pc, 4] and f[pc, 5] == f[bvh_pc, 5]
+                for i in idx:
+                    oi, di = o[i], d[i]
+                    for q in range(pc, bvh_pc):  # the ray spaces entered between from_pc and the tree
+                        if (int(ops[q, 7]) & 0xFF) in (OP_TRANSLATE, OP_ROTATE):
+                            oi, di = _apply_push(ops, f, q, oi, di)
+                    ts, te = f[bvh_pc, 4], f[bvh_pc, 5]
+                    tt, leaf, pid = walk_tree(ops, f, nodes, int(ops[bvh_pc, 0]), oi, di, time[i], tmin[i], F(np.inf), -1, stats, ts, te)
+                    if leaf < 0:
+                        continue
+                    take = tt < closest[i]
+                    if not take and not (tt > closest[i]):  # exact tie with an earlier record (hrt_device.cuh traverse_uniform)
+                        take = best_pc[i] < 0
+                        if not take:
+                            mn, mx = _ref_leaf_box(ops, f, leaf, ts, te)
+                            take = bool(_box(oi[None, :], di[None, :], mn, mx, np.asarray([[tmin[i]]], F), np.asarray([tt], F), True)[0])
+                    if take:
+                        closest[i], best_pc[i], prim[i] = tt, leaf, pid
+                pc_of[idx] = to_pc
+                pc += 1
+                continue
             if idx.size:
                 oo, dd, cl, tm = o[idx], d[idx], closest[idx], tmin[idx]
                 if op in (OP_BOX, OP_BOX_LOOSE):
@@ -313,19 +356,73 @@ def test_fast_form_finds_the_same_hits(pkg, orc, name):
     spec = pkg.make_scene(name, seed=4)
     gb, ob, ref_ops, fast_ops, nodes = _both_forms(pkg, orc, spec.world)
     i = gb.info()
-    if name == "cornell":  # its one BVH holds the ZX light: untouched
-        assert i.n_bvh_trees == 0 and i.n_tree_nodes == 0 and np.array_equal(ref_ops, fast_ops)
-        return
-    assert i.n_bvh_trees == {"random": 1, "final": 2}[name]
-    assert i.n_fast_ops == len(fast_ops) and i.n_tree_nodes == len(nodes) and 0 < i.max_tree_depth <= 48
-    # the trees replace the box records of those BVHs: one root box + one OP_BVH record per tree instead of 2n-1 boxes
-    kinds = fast_ops[:, 7] & 0xFF
-    assert (kinds == OP_BVH).sum() == i.n_bvh_trees and i.n_fast_box_ops < i.n_box_ops // 10
-    for k in (OP_SPHERE, OP_MSPHERE, OP_CUBOID, OP_RECT_XY, OP_RECT_YZ, OP_RECT_ZX, OP_MEDIUM, OP_MEDIUM_SPHERE, OP_MEDIUM_CUBOID):
-        assert (kinds == k).sum() == ((ref_ops[:, 7] & 0xFF) == k).sum()
+    kinds, ref_kinds = fast_ops[:, 7] & 0xFF, ref_ops[:, 7] & 0xFF
+    if name == "cornell":
+        # its one BVH holds the ZX light (an unsound box): no tree.  What the fast form leaves out are SOUND inner boxes
+        # only (they spare a warp nothing, hrt_scene.cpp emit_bvh); every loose box and every leaf box stays in place
+        assert i.n_bvh_trees == 0 and i.n_tree_nodes == 0
+        assert (kinds == OP_BOX_LOOSE).sum() == (ref_kinds == OP_BOX_LOOSE).sum() == 2
+        assert 0 < (ref_kinds == OP_BOX).sum() - (kinds == OP_BOX).sum() == len(ref_ops) - len(fast_ops)
+        assert kinds[kinds != OP_BOX].tolist() == ref_kinds[ref_kinds != OP_BOX].tolist()
+    else:
+        assert i.n_bvh_trees == {"random": 1, "final": 2}[name]
+        assert i.n_fast_ops == len(fast_ops) and i.n_tree_nodes == len(nodes) and 0 < i.max_tree_depth <= 48
+        # the trees replace the box records of those BVHs: one root box + one OP_BVH record per tree instead of 2n-1 boxes
+        assert (kinds == OP_BVH).sum() == i.n_bvh_trees and i.n_fast_box_ops < i.n_box_ops // 10
+    for k in (OP_BOX_LOOSE, OP_SPHERE, OP_MSPHERE, OP_CUBOID, OP_RECT_XY, OP_RECT_YZ, OP_RECT_ZX, OP_MEDIUM, OP_MEDIUM_SPHERE, OP_MEDIUM_CUBOID):
+        assert (kinds == k).sum() == (ref_kinds == k).sum()
     rays = _rays(orc, ob, spec, n=700)
     want = ob.trace_hits(rays, np.full(len(rays), 0.5, dtype=np.float32))
     hit, t, prim = trace_stream(fast_ops, rays, nodes)
+    medium = (want["hit"] == 1) & np.all(want["n"] == 0.0, axis=1)
+    keep = ~medium & np.isfinite(want["t"])
+    assert np.array_equal(hit[keep], want["hit"][keep] == 1)
+    m = keep & (want["hit"] == 1)
+    assert m.sum() > len(rays) // 10
+    assert np.array_equal(prim[m], want["prim_id"][m]), (name, int((prim[m] != want["prim_id"][m]).sum()))
+    assert np.allclose(t[m], want["t"][m], rtol=1e-5, atol=0)
+
+
+@pytest.mark.parametrize("name", ["random", "final", "nested"])
+def test_tree_spans_step_over_only_what_belongs_to_the_tree(pkg, orc, name):
+    """hrt_scene_get_tree_spans (hrt_types.h PreTree::from_pc / to_pc): the records of a span besides the tree itself are
+    sound boxes that cover nothing else and balanced ray-space pushes / pops, and a stream walk that merges each tree's own
+    closest hit at from_pc and goes on at to_pc — what wave_trace_kernel does — finds the oracle's hits, primitive ids
+    included."""
+    world = nested_tree_world(pkg) if name == "nested" else pkg.make_scene(name, seed=4).world
+    gb, ob, ref_ops, ops, nodes = _both_forms(pkg, orc, world)
+    spans = gb.tree_spans()
+    assert len(spans) == gb.info().n_bvh_trees >= 1
+    kinds = ops[:, 7] & 0xFF
+    for bvh_pc, ctx, a, b in spans.tolist():
+        assert kinds[bvh_pc] == OP_BVH and kinds[bvh_pc - 1] == OP_BOX and 0 <= a < bvh_pc
+        end = int(ops[bvh_pc, 7]) >> 8
+        assert end <= b <= len(ops)
+        front, back = kinds[a:bvh_pc - 1], kinds[end:b]
+        assert all(k in (OP_BOX, OP_TRANSLATE, OP_ROTATE) for k in front) and all(k == OP_POP for k in back)
+        assert sum(k in (OP_TRANSLATE, OP_ROTATE) for k in front) == len(back)
+        for q in range(a, bvh_pc):
+            if kinds[q] == OP_BOX:  # every box of the span closes at the span's end or at the tree's
+                assert (int(ops[q, 7]) >> 8) in (b, end) or kinds[(int(ops[q, 7]) >> 8):b].tolist() == [OP_POP] * (b - (int(ops[q, 7]) >> 8))
+        # nothing jumps INTO the span: no earlier box skips to a record inside it
+        skips = np.array([int(w) >> 8 for w, k in zip(ops[:a, 7], kinds[:a]) if k in (OP_BOX, 0x11)])
+        assert not np.any((skips > a) & (skips < b))
+    if name == "final":  # the ground boxes: root box + tree; the sphere cluster: a leaf box and Translation(Rotation(.)) around them
+        ends = np.array([int(ops[p, 7]) >> 8 for p in spans[:, 0]])
+        assert (spans[:, 0] - 1 - spans[:, 2]).tolist() == [0, 3] and (spans[:, 3] - ends).tolist() == [0, 2]
+    if name == "nested":
+        rng = np.random.default_rng(3)
+        n = 600
+        rays = make_rays(orc, rng.uniform(-12, 12, (n, 3)).astype(np.float32) + np.array([0, 6, 0], np.float32),
+                         rng.normal(size=(n, 3)).astype(np.float32) - np.array([0, 0.6, 0], np.float32), time=rng.random(n, dtype=np.float32))
+    else:
+        rays = _rays(orc, ob, pkg.make_scene(name, seed=4), n=500)
+    want = ob.trace_hits(rays, np.full(len(rays), 0.5, dtype=np.float32))
+    wave = gb.ops(pkg.native.HRT_STREAM_WAVE)
+    pre = np.nonzero((wave[:, 7] & 0xFF) == OP_BVH_PRE)[0]
+    assert pre.tolist() == sorted(spans[:2, 2].tolist()) and len(wave) == len(ops)  # the first kMaxPreTrees (2) trees
+    assert np.array_equal(np.delete(wave, pre, axis=0), np.delete(ops, pre, axis=0)) and np.all((ops[pre, 7] & 0xFF) == OP_BOX)
+    hit, t, prim = trace_stream(wave, rays, nodes, spans=spans)
     medium = (want["hit"] == 1) & np.all(want["n"] == 0.0, axis=1)
     keep = ~medium & np.isfinite(want["t"])
     assert np.array_equal(hit[keep], want["hit"][keep] == 1)
