@@ -250,6 +250,11 @@ constexpr int kWaveBlock = 256;
 #ifndef HRT_LOGIC_BLOCKS
 #define HRT_LOGIC_BLOCKS 4  // 64 registers, 32 warps per SM: the kernel waits on memory (C5 499 -> 521 Mpaths/s against 3 blocks)
 #endif
+#ifndef HRT_LOGIC_THREADS
+#define HRT_LOGIC_THREADS 256  // threads per block of wave_logic_kernel (its barriers couple the warps of a block)
+#endif
+constexpr int kLogicBlock = HRT_LOGIC_THREADS;
+static_assert(kWaveBlock % kLogicBlock == 0 && kLogicBlock % 32 == 0, "logic block size");
 #ifndef HRT_LOGIC_PREFETCH
 #define HRT_LOGIC_PREFETCH 1  // diagnostic builds: 0 = plain loads of the slot state (which ptxas sinks into their branches)
 #endif
@@ -437,14 +442,14 @@ __global__ void __launch_bounds__(kWaveBlock, 3) wave_tree_kernel(const __grid_c
     }
 }
 
-__global__ void __launch_bounds__(kWaveBlock, HRT_LOGIC_BLOCKS) wave_logic_kernel(const __grid_constant__ WaveParams P) {
+__global__ void __launch_bounds__(kLogicBlock, HRT_LOGIC_BLOCKS * (kWaveBlock / kLogicBlock)) wave_logic_kernel(const __grid_constant__ WaveParams P) {
     // NoiseTexture albedos are deferred to wave_noise_kernel, so no perlin table is staged here (9.7 KB per block and a
     // barrier before the first state load); a checker over noise or an emitting noise texture reads the tables in place
     TexEnv E;
     E.sh_noise = nullptr; E.n_shared_noise = 0;
     const DeviceScene& S = P.S;
     const int lane = threadIdx.x & 31;
-    const int slot = blockIdx.x * kWaveBlock + threadIdx.x;
+    const int slot = blockIdx.x * kLogicBlock + threadIdx.x;
     const bool in_range = slot < P.n_slots;
     // the whole slot is fetched at once, not behind the test of its bounce word (a second trip to HBM on the critical
     // path of every block); free slots exist only while a render ramps up and drains
@@ -519,7 +524,7 @@ __global__ void __launch_bounds__(kWaveBlock, HRT_LOGIC_BLOCKS) wave_logic_kerne
     // ---- free slots start the next camera samples (application.rs:443-448), drawn from one global index ----
     // ONE atomic per block: every warp of the GPU draws from the same counter, and a returning atomic per warp on one
     // address was 38 % of this kernel's stall samples (profiles/r02_wave_logic_kernel_by_function.txt)
-    __shared__ int sh_cnt[kWaveBlock / 32];
+    __shared__ int sh_cnt[kLogicBlock / 32];
     __shared__ unsigned long long sh_base64;
     const int warp = threadIdx.x >> 5;
     const bool is_free = in_range && bounce < 0;
@@ -529,7 +534,7 @@ __global__ void __launch_bounds__(kWaveBlock, HRT_LOGIC_BLOCKS) wave_logic_kerne
     if (threadIdx.x == 0) {
         int tot = 0;
 #pragma unroll
-        for (int ww = 0; ww < kWaveBlock / 32; ++ww) tot += sh_cnt[ww];
+        for (int ww = 0; ww < kLogicBlock / 32; ++ww) tot += sh_cnt[ww];
         sh_base64 = tot ? atomicAdd(P.counters, (unsigned long long)tot) : 0ULL;
     }
     __syncthreads();
@@ -572,7 +577,7 @@ __global__ void __launch_bounds__(kWaveBlock, HRT_LOGIC_BLOCKS) wave_logic_kerne
     // ---- tree stage, part 1: the ray this slot traces next against the root box of every pre-walked tree ----
     // (all trees in ONE round of block-wide counting: one barrier pair and one atomic per tree and block)
     if (P.n_pre > 0) {
-        __shared__ int sh_tcnt[kMaxPreTrees][kWaveBlock / 32];
+        __shared__ int sh_tcnt[kMaxPreTrees][kLogicBlock / 32];
         __shared__ int sh_tbase[kMaxPreTrees];
         const bool live = bounce >= 0;
         Ray rr[kMaxPreTrees];
@@ -602,7 +607,7 @@ __global__ void __launch_bounds__(kWaveBlock, HRT_LOGIC_BLOCKS) wave_logic_kerne
         if (threadIdx.x < P.n_pre) {
             int tot = 0;
 #pragma unroll
-            for (int ww = 0; ww < kWaveBlock / 32; ++ww) tot += sh_tcnt[threadIdx.x][ww];
+            for (int ww = 0; ww < kLogicBlock / 32; ++ww) tot += sh_tcnt[threadIdx.x][ww];
             sh_tbase[threadIdx.x] = tot ? atomicAdd(P.tq_count + threadIdx.x, tot) : 0;
         }
         __syncthreads();
@@ -960,6 +965,11 @@ cudaError_t launch_render_wave(hrt::RenderLaunch& L, hrt::WaveBuffers& W, int nu
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tree_blocks_per_sm, wave_tree_kernel, kWaveBlock, 0)) != cudaSuccess) return e;
     if (const char* env = getenv("HRT_TREE_BLOCKS")) tree_blocks_per_sm = std::max(1, std::min(tree_blocks_per_sm, atoi(env)));
     const int tree_grid = std::min(grid, num_sms * std::max(1, tree_blocks_per_sm));
+    // deferred noise evaluations: a few hundred thousand per iteration, each a long dependent chain (7 octaves of table
+    // lookups) — several blocks per SM to hide it (HRT_NOISE_BLOCKS: diagnostic)
+    int noise_blocks_per_sm = 4;
+    if (const char* env = getenv("HRT_NOISE_BLOCKS")) noise_blocks_per_sm = std::max(1, std::min(8, atoi(env)));
+    const int noise_grid = std::min(grid, num_sms * noise_blocks_per_sm);
     WaveParams PP[hrt::kWaveParts];
     bool running[hrt::kWaveParts];
     for (int p = 0; p < parts; ++p) {
@@ -982,8 +992,8 @@ cudaError_t launch_render_wave(hrt::RenderLaunch& L, hrt::WaveBuffers& W, int nu
             if ((e = cudaMemsetAsync(live, 0, sizeof(int), sp)) != cudaSuccess) return e;
             for (int i = 0; i < kBatch; ++i) {
                 PP[p].live_out = i == kBatch - 1 ? live : nullptr;
-                wave_logic_kernel<<<grid, kWaveBlock, 0, sp>>>(PP[p]);
-                if (P.S.n_noise > 0) wave_noise_kernel<<<num_sms, kWaveBlock, 0, sp>>>(PP[p]);
+                wave_logic_kernel<<<grid * (kWaveBlock / kLogicBlock), kLogicBlock, 0, sp>>>(PP[p]);
+                if (P.S.n_noise > 0) wave_noise_kernel<<<noise_grid, kWaveBlock, 0, sp>>>(PP[p]);
                 if (one_tree_launch && P.n_pre > 1) {
                     wave_tree_kernel<<<tree_grid, kWaveBlock, 0, sp>>>(PP[p], -1);
                     L.launches += 1;
