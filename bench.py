@@ -370,7 +370,7 @@ def run_b200(args, scene_name, width, height, samples, depth):
         traffic = None
         issue = None
         try:  # DRAM bytes per launch of the dominant kernel, from a committed ncu metric pass of this very workload
-            with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
+            with open(os.path.join(ROOT, "profiles", "r02b_traffic.json")) as f:
                 t = json.load(f).get(args.config)
             if t and world == 1:
                 # DRAM bytes per path (ncu, summed over every launch of a short frame) x the paths of one step
@@ -385,7 +385,7 @@ def run_b200(args, scene_name, width, height, samples, depth):
                                    "no FP32 figure",
                     # hrt_api.cu render_into: the wavefront render for big jobs on scenes with OP_BVH trees (kernel_ms is then the
                     # whole pipeline: wave_logic + wave_noise + wave_tree per tree + wave_trace per iteration; shares in
-                    # profiles/r02_wave_window_*.txt), else the persistent uniform-walk kernel
+                    # profiles/r02b_wave_window_*.txt), else the persistent uniform-walk kernel
                     "kernel": "wavefront render (wave_logic / wave_tree / wave_trace kernels)" if stats and stats[0][5] > 2 else "render_interp_kernel<true> (uniform walk)",
                     "kernel_ms": kernel_ms, "flops_per_path": wm["flops_per_path"],
                     "work_model": wm["source"], "issue": issue,

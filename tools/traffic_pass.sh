@@ -18,13 +18,17 @@ for r in rows[1:]:
     d[(int(r[ii]), r[ki].split('(')[0])][r[ni]]=v
 b=json.loads([l for l in open('gpurun_out/traffic_%s.log' % cfg) if l.startswith('{')][-1])
 paths=b['value']*1e6*b['ms_per_step']*1e-3
+# the frame itself: when it ran as a wavefront, only the wave kernels (bench.py's parity check renders a few samples
+# with the persistent kernel after the timed step)
+if any(k.startswith('wave_') for (_, k) in d):
+    d={ik: m for ik, m in d.items() if ik[1].startswith('wave_')}
 agg=collections.defaultdict(lambda: collections.Counter())
 for (i,k),m in d.items():
     a=agg[k]; a['n']+=1; a['bytes']+=m['dram__bytes_read.sum']+m['dram__bytes_write.sum']; a['us']+=m['gpu__time_duration.sum']/1e3
     a['issue_x_us']+=m['smsp__issue_active.avg.pct_of_peak_sustained_active']*m['gpu__time_duration.sum']/1e3; a['inst']+=m['smsp__inst_executed.sum']
 tot_b=sum(a['bytes'] for a in agg.values()); tot_us=sum(a['us'] for a in agg.values())
 out={"dram_bytes_per_path": tot_b/paths, "paths_measured": paths, "spp": spp, "issue_active_pct": sum(a['issue_x_us'] for a in agg.values())/tot_us,
-     "issue_source": "profiles/r02_traffic_%s.csv (time-weighted over all launches of a %d-spp frame)" % (cfg, spp),
+     "issue_source": "profiles/r02b_traffic_%s.csv.gz (time-weighted over all launches of a %d-spp frame)" % (cfg, spp),
      "kernels": {k: {"launches": a['n'], "time_share": a['us']/tot_us, "dram_bytes": a['bytes'], "warp_inst_per_path": a['inst']/paths} for k,a in agg.items()}}
 print(json.dumps({cfg: out}))
 PY
