@@ -155,8 +155,10 @@ int32_t hrt_scene_get_info(const hrt_scene*, hrt_scene_info* out);
  * per-ray stack, nearer child first.  Box tests only prune, so the closest hit is the same; on an EXACT tie between two
  * surfaces the reference keeps the leaf that comes later in ITS depth-first order (bvh_node.rs:110-124: `t <= t_max`), and
  * so does the tree walk: the leaf records stay in the stream in the reference's order and an equal-t hit only replaces
- * an earlier record's.  BVHs that are not sound (the Cornell / final top levels, above the ceiling light) keep the
- * reference form in both.
+ * an earlier record's.  BVHs that are not sound (the Cornell / final top levels, above the ceiling light) stay box records
+ * in both forms; of those the fast form leaves out the SOUND inner boxes of small BVHs (at most 16 leaves beneath) and the
+ * leaf box above a tree: a sound box only prunes, a kept box beneath it rejects at least as much on every axis, and the
+ * warp-uniform walk pays for every record any of its 32 rays reaches.  Every loose box and every leaf box stays.
  *   HRT_BVH_TREES (default)  as above
  *   HRT_BVH_REFERENCE        the fast form is the reference form
  * Call before hrt_scene_commit.  hrt_bvh_leaf_order / hrt_bounding_box always describe the reference trees. */
