@@ -55,9 +55,16 @@ def test_error_behaviour(pkg):
     s = b.sphere((0, 0, 0), 1.0, m)
     with pytest.raises(pkg.HrtError):
         b.rect(7, 0, 1, 0, 1, 0, m)
+    with pytest.raises(pkg.HrtError):
+        b.tree_spans()  # not committed
     b.commit(b.bvh([s], 0.0, 1.0))
     with pytest.raises(pkg.HrtError):
         b.sphere((0, 0, 0), 1.0, m)  # immutable after commit
+    # a scene without trees: no spans, and its wave form is its fast form; an unknown form of the stream is an error
+    N = pkg.native
+    assert b.tree_spans().shape == (0, 4) and np.array_equal(b.ops(N.HRT_STREAM_WAVE), b.ops(N.HRT_STREAM_FAST))
+    with pytest.raises(pkg.HrtError):
+        b.ops(3)
     # ConstantMedium nested in a ConstantMedium boundary is rejected with a message
     b2 = pkg.HrtBackend()
     inner = S.ConstantMedium(S.Sphere((0, 0, 0), 1.0, S.Dielectric(1.5)), 0.1, S.SolidColor((1, 1, 1)))

@@ -432,6 +432,46 @@ def test_tree_spans_step_over_only_what_belongs_to_the_tree(pkg, orc, name):
     assert np.allclose(t[m], want["t"][m], rtol=1e-5, atol=0)
 
 
+def test_fast_form_leaves_out_only_sound_inner_boxes_of_small_subtrees(pkg, orc):
+    """hrt_scene.cpp emit_bvh: in a BVH that is not a tree (its leaves are translated cuboids) the fast form drops the sound
+    inner boxes with at most 16 leaves beneath and keeps the larger ones, every leaf box and every loose box; the hits —
+    primitive ids included — are the oracle's, and the library's own count of box records is what the stream holds."""
+    S = pkg.scene
+    rng = np.random.default_rng(17)
+    white = S.Lambertian(S.SolidColor((0.7, 0.7, 0.7)))
+    objs = []
+    for _ in range(40):
+        lo = rng.uniform(-1.0, 0.0, 3)
+        objs.append(S.Translation(S.Cuboid(tuple(lo), tuple(lo + rng.uniform(0.3, 1.2, 3)), white), tuple(rng.uniform(-9, 9, 3))))
+    objs.append(S.Rect(S.Plane.ZX, -3.0, -1.0, 1.0, 4.0, 9.5, S.DiffuseLight(S.SolidColor((4.0, 4.0, 4.0)))))  # an unsound leaf box
+    world = S.BvhNode(objs, 0.0, 1.0)
+    gb, ob, ref_ops, ops, nodes = _both_forms(pkg, orc, world)
+    kinds, ref_kinds = ops[:, 7] & 0xFF, ref_ops[:, 7] & 0xFF
+    i = gb.info()
+    assert i.n_bvh_trees == 0 and i.n_fast_box_ops == int(((kinds == OP_BOX) | (kinds == OP_BOX_LOOSE)).sum())
+    n_leaves = len(objs)
+    assert (ref_kinds == OP_BOX).sum() + (ref_kinds == OP_BOX_LOOSE).sum() == 2 * n_leaves - 1
+    assert (kinds == OP_BOX_LOOSE).sum() == (ref_kinds == OP_BOX_LOOSE).sum() >= 1
+    assert kinds[kinds != OP_BOX].tolist() == ref_kinds[ref_kinds != OP_BOX].tolist()  # nothing else moved
+    # every leaf box is still there: a box record right in front of each leaf's first record
+    first_of_leaf = [pc for pc in range(len(ops)) if kinds[pc] in (OP_TRANSLATE, OP_RECT_ZX) and (pc == 0 or kinds[pc - 1] != OP_TRANSLATE)]
+    assert len(first_of_leaf) == n_leaves and all(kinds[pc - 1] in (OP_BOX, OP_BOX_LOOSE) for pc in first_of_leaf)
+    # the inner boxes that stay cover more than 16 leaves (or are loose); some were dropped, some kept
+    leaf_pcs = np.array(first_of_leaf)
+    inner = [pc for pc in range(len(ops)) if kinds[pc] == OP_BOX and pc + 1 not in first_of_leaf]
+    assert 0 < len(inner) < n_leaves - 1 - int((kinds == OP_BOX_LOOSE).sum())
+    for pc in inner:
+        assert ((leaf_pcs > pc) & (leaf_pcs < (int(ops[pc, 7]) >> 8))).sum() > 16
+    org = rng.uniform(-14, 14, (1500, 3)).astype(np.float32)
+    rays = make_rays(orc, org, rng.uniform(-9, 9, (1500, 3)).astype(np.float32) - org, time=rng.random(1500, dtype=np.float32))
+    want = ob.trace_hits(rays, np.full(len(rays), 0.5, dtype=np.float32))
+    for form in (ref_ops, ops):
+        hit, t, prim = trace_stream(form, rays, nodes)
+        assert np.array_equal(hit, want["hit"] == 1)
+        m = want["hit"] == 1
+        assert m.sum() > 80 and np.array_equal(prim[m], want["prim_id"][m]) and np.allclose(t[m], want["t"][m], rtol=1e-5, atol=0)
+
+
 def test_medium_records_name_their_boundary_shape(pkg, orc):
     """A ConstantMedium whose boundary is one plain sphere / one cuboid (bare or inside one run of ray-space pushes) is
     flagged for the closed-form paths (hrt_types.h OP_MEDIUM_SPHERE / OP_MEDIUM_CUBOID); its sub-stream stays in place."""
