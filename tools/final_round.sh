@@ -1,4 +1,5 @@
 #!/bin/bash
+# (Superseded by tools/final_bench.sh + tools/final_profiles.sh, which fit a smaller GPU budget.)
 # Round-end evidence on one GPU (run under gpurun): full GPU test suite, smoke, both bench arms, all configs, the launch
 # list of the bench command, the per-kernel window and DRAM-traffic pass of the wavefront render, one `ncu --set full`
 # capture per wave kernel (steady-state iteration) and of the persistent kernel on Cornell.  Everything lands in gpurun_out/.
