@@ -239,8 +239,12 @@ __global__ void __launch_bounds__(kBlock, 2) render_interp_kernel(const __grid_c
 // `no_instruction`, growing with the kernel's size (profiles/r02_*).  Here N path slots live in global memory and one
 // iteration is
 //   wave_logic_kernel   shade the segment traced last (emitted + scatter, application.rs:486-494), accumulate finished
-//                       paths, start the next camera sample in every free slot (application.rs:443-448)
-//   wave_trace_kernel   world.hit for every slot's ray segment (warp-uniform walk + tree walks)
+//                       paths, start the next camera sample in every free slot (application.rs:443-448), test the next
+//                       ray against the root box of every tree that is walked ahead and queue it
+//   wave_noise_kernel   the NoiseTexture albedos the logic pass deferred, one evaluation per thread
+//   wave_tree_kernel    the queued tree walks of all pre-walked trees, compacted over the whole wave
+//   wave_trace_kernel   world.hit for every slot's ray segment: the warp-uniform walk of the WAVE form of the stream,
+//                       which takes the trees' answers at their OP_BVH_PRE records (hrt_types.h)
 // each a fraction of the code, each run by the whole GPU at once, so the instruction caches hold what is running.
 // Same Philox streams and arithmetic as the other kernels: the same paths, summed in a different order.
 constexpr int kWaveBlock = 256;
