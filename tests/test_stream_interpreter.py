@@ -179,11 +179,13 @@ def _apply_push(ops, f, q, o, d):
     return o, d
 
 
-def trace_stream(ops, rays, nodes=None, stats=None, spans=None):
+def trace_stream(ops, rays, nodes=None, stats=None, spans=None, xi=None, pc_begin=0, pc_end=None):
     """Closest hit of every ray against the op stream; returns (hit mask, t, prim id).  `nodes`: the tree-node table of
     the fast form; `stats[0]` counts box tests.  `spans` (hrt_scene_get_tree_spans) with the WAVE form of the stream: walk
     as the wavefront render's stream walk does — at an OP_BVH_PRE record the tree's closest hit over [tmin, +inf), computed
-    on its own (the tree stage), is merged, and the walk goes on behind the records that exist only for the tree."""
+    on its own (the tree stage), is merged, and the walk goes on behind the records that exist only for the tree.
+    `xi`: one uniform per ray for ConstantMedium::hit (constant_medium.rs:34-76, restated below); without it media are
+    stepped over.  `[pc_begin, pc_end)`: the part of the stream to walk (a medium's boundary sub-stream)."""
     f = ops.view(np.float32)
     n = len(rays)
     o = rays["o"].astype(F).copy()
@@ -193,11 +195,12 @@ def trace_stream(ops, rays, nodes=None, stats=None, spans=None):
     closest = rays["tmax"].astype(F).copy()
     prim = np.full(n, -1, dtype=np.int64)
     best_pc = np.full(n, -1, dtype=np.int64)
-    pc_of = np.zeros(n, dtype=np.int64)
+    pc_of = np.full(n, pc_begin, dtype=np.int64)
     saved = []  # ray-space stack: (ray indices, their o, their d) per pushed level
-    pc = 0
+    pc = pc_begin
+    pc_stop = len(ops) if pc_end is None else pc_end
     with np.errstate(all="ignore"):
-        while pc < len(ops):
+        while pc < pc_stop:
             idx = np.nonzero(pc_of == pc)[0]
             w7 = int(ops[pc, 7])
             op, payload = w7 & 0xFF, w7 >> 8
@@ -295,7 +298,27 @@ def trace_stream(ops, rays, nodes=None, stats=None, spans=None):
                     pc += 1
                     continue
                 elif op in (OP_MEDIUM, OP_MEDIUM_SPHERE, OP_MEDIUM_CUBOID):
-                    pc_of[idx] = payload  # skip the boundary sub-stream
+                    if xi is not None:  # constant_medium.rs:34-76 on the boundary sub-stream [pc + 1, payload)
+                        sub = rays[idx].copy()
+                        sub["o"], sub["d"] = oo, dd  # the ray in the ray space the medium lives in
+                        sub["tmin"], sub["tmax"] = -np.inf, np.inf
+                        h1, t1, _ = trace_stream(ops, sub, nodes, stats, None, None, pc + 1, payload)
+                        sub["tmin"] = t1 + F(0.0001)
+                        h2, t2, _ = trace_stream(ops, sub, nodes, stats, None, None, pc + 1, payload)
+                        r1 = np.where(t1 < tm, tm, t1)
+                        r2 = np.where(t2 > cl, cl, t2)
+                        ok = h1 & h2 & ~(r1 >= r2)
+                        r1 = np.where(r1 < 0, F(0), r1)
+                        length = np.sqrt((dd[:, 0] * dd[:, 0] + dd[:, 1] * dd[:, 1]) + dd[:, 2] * dd[:, 2])
+                        inside = (r2 - r1) * length
+                        hit_distance = f[pc, 0] * np.log(xi[idx].astype(F))  # w0 = -1 / density
+                        ok &= ~(hit_distance > inside)
+                        t = r1 + hit_distance / length
+                        sel = idx[ok]
+                        closest[sel] = t[ok]
+                        prim[sel] = int(ops[pc, 3])
+                        best_pc[sel] = pc
+                    pc_of[idx] = payload  # go on behind the boundary sub-stream
                     pc += 1
                     continue
                 else:
@@ -380,6 +403,31 @@ def test_fast_form_finds_the_same_hits(pkg, orc, name):
     m = keep & (want["hit"] == 1)
     assert m.sum() > len(rays) // 10
     assert np.array_equal(prim[m], want["prim_id"][m]), (name, int((prim[m] != want["prim_id"][m]).sum()))
+    assert np.allclose(t[m], want["t"][m], rtol=1e-5, atol=0)
+
+
+@pytest.mark.parametrize("name,form", [("cornell-smoke", "reference"), ("cornell-smoke", "fast"), ("final", "fast"), ("final", "wave")])
+def test_medium_semantics_match_the_oracle(pkg, orc, name, form):
+    """ConstantMedium::hit restated in the numpy interpreter (two boundary queries over the medium's sub-stream, the
+    clamps, the exponential free path with an injected uniform) against the oracle with the same uniforms: every hit —
+    surfaces AND media — names the same primitive at the same t, on each form of the stream.  (logf differs by an ulp
+    between numpy and glibc: media get 1e-5.)"""
+    N = pkg.native
+    spec = pkg.make_scene(name, seed=4)
+    gb, ob, ref_ops, fast_ops, nodes = _both_forms(pkg, orc, spec.world)
+    ops = {"reference": ref_ops, "fast": fast_ops, "wave": gb.ops(N.HRT_STREAM_WAVE)}[form]
+    rays = _rays(orc, ob, spec, n=400)
+    rng = np.random.default_rng(12)
+    xi = rng.uniform(0.02, 0.98, len(rays)).astype(np.float32)
+    want = ob.trace_hits(rays, xi)
+    hit, t, prim = trace_stream(ops, rays, nodes, spans=gb.tree_spans(), xi=xi)
+    fin = np.isfinite(want["t"]) | (want["hit"] == 0)
+    assert fin.sum() > len(rays) * 0.9
+    assert np.array_equal(hit[fin], want["hit"][fin] == 1)
+    m = fin & (want["hit"] == 1)
+    medium = m & np.all(want["n"] == 0.0, axis=1)
+    assert medium.sum() > 10, int(medium.sum())
+    assert np.array_equal(prim[m], want["prim_id"][m]), (name, form, int((prim[m] != want["prim_id"][m]).sum()))
     assert np.allclose(t[m], want["t"][m], rtol=1e-5, atol=0)
 
 
